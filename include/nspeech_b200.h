@@ -1,0 +1,143 @@
+/*
+ * nspeech_b200 - C ABI of the B200-native spectrogram / Griffin-Lim hot path.
+ *
+ * The reference (MLCogUP/nspeech) has no FFI layer: the boundary of this path is the module-level
+ * Python API of neural_speech/utils/audio.py plus neural_speech/hparams.get_hparams().  Each entry
+ * point below names the reference function(s) it replaces (file:line relative to /root/reference).
+ * The Python mirror that binds these with ctypes is nspeech_b200/audio.py; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes, no framework types; every call returns an nsb_status (0 = OK) and
+ *    nsb_last_error() gives the thread-local message of the last failure;
+ *  - `space` says where ALL data buffers of the call live: NSB_HOST (the library copies in/out and
+ *    synchronises before returning) or NSB_DEVICE (pointers into the handle's GPU; the call is
+ *    stream-ordered on `stream` and returns without synchronising);
+ *  - `stream` is a cudaStream_t (NULL = the handle's own stream);
+ *  - ragged batches: per-utterance lengths are a HOST int array; utterance blocks are packed back to
+ *    back in every buffer (a uniform [N,T,F] or [N,n] C-contiguous array is already in that form);
+ *  - spectra are float32, 1025 = num_freq bins per frame; layout NSB_FRAME_MAJOR = [T][F] per
+ *    utterance (the memory order of the reference's Fortran-ordered [F,T] arrays and of Tacotron's
+ *    [T,F] outputs), NSB_BIN_MAJOR = [F][T] per utterance (a C-contiguous numpy [F,T]);
+ *  - complex data is interleaved float32 (re, im) = numpy complex64;
+ *  - no CPU fallback: without an sm_100 device nsb_create fails with NSB_ERR_NODEVICE.
+ */
+#ifndef NSPEECH_B200_H
+#define NSPEECH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSB_ABI_VERSION 1
+
+typedef struct nsb_handle_s* nsb_handle_t;
+
+/* the audio keys of the hparams yaml (neural_speech/hparams/audio.yaml:6-18) */
+typedef struct nsb_hparams {
+    int32_t num_freq;
+    int32_t num_mels;
+    int32_t sample_rate;
+    int32_t griffin_lim_iters;
+    double frame_shift_ms;
+    double frame_length_ms;
+    double preemphasis;
+    double ref_level_db;
+    double min_level_db;
+    double power;
+} nsb_hparams;
+
+typedef enum nsb_status {
+    NSB_OK = 0,
+    NSB_ERR_INVALID = 1,      /* bad argument (null pointer, wrong length, T < 2 for inversion, ...) */
+    NSB_ERR_CUDA = 2,         /* a CUDA runtime call failed */
+    NSB_ERR_UNSUPPORTED = 3,  /* hparams outside what the kernels implement (n_fft != 2048, win > n_fft) */
+    NSB_ERR_NONFINITE = 4,    /* NaN/Inf in the audio or spectrogram (librosa.util.valid_audio's ParameterError) */
+    NSB_ERR_NODEVICE = 5,     /* no usable sm_100 GPU */
+    NSB_ERR_OOM = 6
+} nsb_status;
+
+enum { NSB_HOST = 0, NSB_DEVICE = 1 };
+enum { NSB_FRAME_MAJOR = 0, NSB_BIN_MAJOR = 1 };
+enum { NSB_F32 = 0, NSB_F64 = 1 };
+enum { NSB_EW_AMP_TO_DB = 0, NSB_EW_DB_TO_AMP = 1, NSB_EW_NORMALIZE = 2, NSB_EW_DENORMALIZE = 3 };
+
+/* flags of nsb_griffin_lim */
+enum {
+    NSB_GL_DENORMALIZE = 1,   /* input is a normalised dB spectrogram: apply audio.py:47-48 first */
+    NSB_GL_DEEMPHASIS = 2     /* apply inv_preemphasis (audio.py:35-36) to the result */
+};
+
+int nsb_abi_version(void);
+const char* nsb_last_error(void);
+int nsb_device_count(int* count);
+
+/* handle = hparams + device tables (window, twiddles, sparse mel basis) + grow-only workspaces.
+ * Replaces the module-global state of the reference: get_hparams() (hparams/__init__.py:25-26) and the
+ * cached _mel_basis (utils/audio.py:135-147). Thread-safe; calls on one handle serialise. */
+int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out);
+int nsb_destroy(nsb_handle_t h);
+int nsb_synchronize(nsb_handle_t h, void* stream);
+
+/* _stft_parameters (utils/audio.py:126-130): n_fft, hop_length, win_length with the truncating int() */
+int nsb_stft_parameters(nsb_handle_t h, int32_t* n_fft, int32_t* hop_length, int32_t* win_length);
+/* frames of an n-sample signal (1 + n // hop) and samples of a T-frame inversion (hop * (T - 1)) */
+int64_t nsb_num_frames(nsb_handle_t h, int64_t n_samples);
+int64_t nsb_num_samples(nsb_handle_t h, int64_t n_frames);
+
+/* _stft(y) or _stft(preemphasis(y)) (utils/audio.py:106-108, 31-32): centred, reflect-padded, periodic
+ * Hann STFT.  wav: packed float32 samples; out: complex64, frame-major [sum T][num_freq]. */
+int nsb_stft(nsb_handle_t h, const float* wav, const int64_t* n_samples, int32_t batch, int32_t apply_preemphasis,
+             float* out_complex, int32_t space, void* stream);
+
+/* spectrogram(y) and melspectrogram(y) (utils/audio.py:39-42, 61-64) from ONE STFT pass.
+ * lin_out: [sum T][num_freq] or NULL; mel_out: [sum T][num_mels] or NULL (frame-major float32). */
+int nsb_features(nsb_handle_t h, const float* wav, const int64_t* n_samples, int32_t batch,
+                 float* lin_out, float* mel_out, int32_t space, void* stream);
+
+/* _istft(D) (utils/audio.py:111-113): spec complex64 in `layout`; wav_out float32, hop*(T-1) per utterance. */
+int nsb_istft(nsb_handle_t h, const float* spec_complex, int32_t layout, const int32_t* n_frames, int32_t batch,
+              float* wav_out, int32_t space, void* stream);
+
+/* _griffin_lim(S) / inv_spectrogram(spectrogram) (utils/audio.py:77-87, 45-48).
+ *   spec        float32 magnitudes S (flags without NSB_GL_DENORMALIZE) or normalised spectrogram in [0,1]
+ *   init_phase  complex64 unit phasors exp(i*phi) in the same layout, or NULL: then the phase is drawn on
+ *               the device (Philox-4x32 keyed by `seed`) in place of np.random.rand (utils/audio.py:81)
+ *   iters       < 0 -> hparams.griffin_lim_iters
+ *   wav_out     out_dtype NSB_F32 (what _griffin_lim returns) or NSB_F64 (what inv_preemphasis returns) */
+int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout, const int32_t* n_frames, int32_t batch,
+                    const float* init_phase_complex, uint64_t seed, int32_t iters, int32_t flags,
+                    void* wav_out, int32_t out_dtype, int32_t space, void* stream);
+
+/* preemphasis(x) / inv_preemphasis(x) (utils/audio.py:31-36): scipy.signal.lfilter with zero initial state. */
+int nsb_preemphasis(nsb_handle_t h, const float* x, const int64_t* n_samples, int32_t batch,
+                    void* out, int32_t out_dtype, int32_t space, void* stream);
+int nsb_inv_preemphasis(nsb_handle_t h, const float* x, const int64_t* n_samples, int32_t batch,
+                        void* out, int32_t out_dtype, int32_t space, void* stream);
+
+/* _linear_to_mel(S) (utils/audio.py:138-147): librosa.filters.mel (Slaney, area-normalised) applied to
+ * linear magnitudes in `layout`; out frame-major [sum T][num_mels]. */
+int nsb_linear_to_mel(nsb_handle_t h, const float* spec, int32_t layout, const int32_t* n_frames, int32_t batch,
+                      void* out, int32_t out_dtype, int32_t space, void* stream);
+/* the dense basis itself, float64 [num_mels][num_freq] into a HOST buffer (_build_mel_basis, utils/audio.py:145-147) */
+int nsb_mel_basis(nsb_handle_t h, double* out_host);
+
+/* _amp_to_db, _db_to_amp, _normalize, _denormalize (utils/audio.py:150-167), element-wise float32 */
+int nsb_elementwise(nsb_handle_t h, int32_t op, const float* in, int64_t n, float* out, int32_t space, void* stream);
+
+/* deferred device-side error flag of NSB_DEVICE calls (bit 0: non-finite data seen); synchronises; clears it */
+int nsb_check_status(nsb_handle_t h, void* stream);
+
+/* tuning / accounting hooks (not in the reference) */
+int nsb_set_tile_hops(nsb_handle_t h, int32_t tile_hops);       /* 0 = automatic */
+uint64_t nsb_kernel_launches(nsb_handle_t h);                    /* kernels launched through this handle so far */
+/* the Griffin-Lim iteration kernel alone on device-resident state, for roofline timing: runs `iters`
+ * iterations on the state left by the last nsb_griffin_lim(NSB_DEVICE) call */
+int nsb_griffin_lim_iterate(nsb_handle_t h, int32_t iters, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSPEECH_B200_H */

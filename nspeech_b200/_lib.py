@@ -1,0 +1,219 @@
+"""ctypes binding of libnspeech_b200.so (the C ABI in include/nspeech_b200.h).
+
+The product loads exactly one file: ``nspeech_b200/libnspeech_b200.so`` built by ``__graft_entry__.build()``
+(nvcc, sm_100a).  If it is missing or cannot be loaded the import of any compute entry point raises - there
+is no CPU fallback.  (``NativeLib(path)`` accepts an explicit path only so that tests can bind the
+CPU-emulated build of the same sources under tests/emu/.)
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(HERE, "libnspeech_b200.so")
+
+NSB_OK, NSB_ERR_INVALID, NSB_ERR_CUDA, NSB_ERR_UNSUPPORTED, NSB_ERR_NONFINITE, NSB_ERR_NODEVICE, NSB_ERR_OOM = range(7)
+HOST, DEVICE = 0, 1
+FRAME_MAJOR, BIN_MAJOR = 0, 1
+F32, F64 = 0, 1
+EW_AMP_TO_DB, EW_DB_TO_AMP, EW_NORMALIZE, EW_DENORMALIZE = range(4)
+GL_DENORMALIZE, GL_DEEMPHASIS = 1, 2
+
+
+class ParameterError(ValueError):
+    """Raised where librosa 0.6.0 raises ``librosa.util.exceptions.ParameterError`` (non-finite audio, bad shapes)."""
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class HParamsStruct(ctypes.Structure):
+    _fields_ = [("num_freq", ctypes.c_int32), ("num_mels", ctypes.c_int32), ("sample_rate", ctypes.c_int32),
+                ("griffin_lim_iters", ctypes.c_int32), ("frame_shift_ms", ctypes.c_double),
+                ("frame_length_ms", ctypes.c_double), ("preemphasis", ctypes.c_double),
+                ("ref_level_db", ctypes.c_double), ("min_level_db", ctypes.c_double), ("power", ctypes.c_double)]
+
+
+_vp, _i32, _i64, _u64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64
+_pi32, _pi64 = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64)
+
+# name -> (restype, argtypes); every symbol declared in include/nspeech_b200.h
+SIGNATURES = {
+    "nsb_abi_version": (ctypes.c_int, []),
+    "nsb_last_error": (ctypes.c_char_p, []),
+    "nsb_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "nsb_create": (ctypes.c_int, [ctypes.POINTER(HParamsStruct), ctypes.c_int, ctypes.POINTER(_vp)]),
+    "nsb_destroy": (ctypes.c_int, [_vp]),
+    "nsb_synchronize": (ctypes.c_int, [_vp, _vp]),
+    "nsb_stft_parameters": (ctypes.c_int, [_vp, _pi32, _pi32, _pi32]),
+    "nsb_num_frames": (_i64, [_vp, _i64]),
+    "nsb_num_samples": (_i64, [_vp, _i64]),
+    "nsb_stft": (ctypes.c_int, [_vp, _vp, _pi64, _i32, _i32, _vp, _i32, _vp]),
+    "nsb_features": (ctypes.c_int, [_vp, _vp, _pi64, _i32, _vp, _vp, _i32, _vp]),
+    "nsb_istft": (ctypes.c_int, [_vp, _vp, _i32, _pi32, _i32, _vp, _i32, _vp]),
+    "nsb_griffin_lim": (ctypes.c_int, [_vp, _vp, _i32, _pi32, _i32, _vp, _u64, _i32, _i32, _vp, _i32, _i32, _vp]),
+    "nsb_preemphasis": (ctypes.c_int, [_vp, _vp, _pi64, _i32, _vp, _i32, _i32, _vp]),
+    "nsb_inv_preemphasis": (ctypes.c_int, [_vp, _vp, _pi64, _i32, _vp, _i32, _i32, _vp]),
+    "nsb_linear_to_mel": (ctypes.c_int, [_vp, _vp, _i32, _pi32, _i32, _vp, _i32, _i32, _vp]),
+    "nsb_mel_basis": (ctypes.c_int, [_vp, _vp]),
+    "nsb_elementwise": (ctypes.c_int, [_vp, _i32, _vp, _i64, _vp, _i32, _vp]),
+    "nsb_check_status": (ctypes.c_int, [_vp, _vp]),
+    "nsb_set_tile_hops": (ctypes.c_int, [_vp, _i32]),
+    "nsb_kernel_launches": (_u64, [_vp]),
+    "nsb_griffin_lim_iterate": (ctypes.c_int, [_vp, _i32, _vp]),
+}
+
+
+class NativeLib(object):
+    def __init__(self, path=None):
+        self.path = DEFAULT_LIB if path is None else path
+        if not os.path.exists(self.path):
+            raise NativeError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(nvcc, sm_100a). There is no CPU fallback." % self.path)
+        self.dll = ctypes.CDLL(self.path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(self.dll, name)       # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        if self.dll.nsb_abi_version() != 1:
+            raise NativeError("ABI version mismatch")
+
+    def check(self, rc):
+        if rc == NSB_OK:
+            return
+        msg = (self.dll.nsb_last_error() or b"").decode("utf-8", "replace")
+        if rc == NSB_ERR_NONFINITE:
+            raise ParameterError(msg)
+        if rc in (NSB_ERR_INVALID, NSB_ERR_UNSUPPORTED):
+            raise ValueError(msg)
+        if rc == NSB_ERR_OOM:
+            raise MemoryError(msg)
+        raise NativeError("nspeech_b200 error %d: %s" % (rc, msg))
+
+    def device_count(self):
+        n = ctypes.c_int(0)
+        rc = self.dll.nsb_device_count(ctypes.byref(n))
+        return n.value if rc == NSB_OK else 0
+
+
+_default = None
+_default_lock = threading.Lock()
+
+
+def default_lib():
+    global _default
+    with _default_lock:
+        if _default is None:
+            _default = NativeLib()
+        return _default
+
+
+def _ptr(a):
+    """void* of a numpy array, a torch tensor, or a raw integer device address."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return ctypes.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return ctypes.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        return ctypes.c_void_p(a.data_ptr())
+    raise TypeError("unsupported buffer type %r" % type(a))
+
+
+class Handle(object):
+    """One native handle = hparams + device + workspaces.  Calls on one handle serialise (internal mutex)."""
+
+    def __init__(self, hp, device=0, lib=None):
+        self.lib = default_lib() if lib is None else lib
+        s = HParamsStruct(int(hp.num_freq), int(hp.num_mels), int(hp.sample_rate), int(hp.griffin_lim_iters),
+                          float(hp.frame_shift_ms), float(hp.frame_length_ms), float(hp.preemphasis),
+                          float(hp.ref_level_db), float(hp.min_level_db), float(hp.power))
+        h = ctypes.c_void_p()
+        self.lib.check(self.lib.dll.nsb_create(ctypes.byref(s), int(device), ctypes.byref(h)))
+        self._h = h
+        self.device = int(device)
+        a, b, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        self.lib.check(self.lib.dll.nsb_stft_parameters(h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        self.n_fft, self.hop, self.win = a.value, b.value, c.value
+        self.num_freq = int(hp.num_freq)
+        self.num_mels = int(hp.num_mels)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.dll.nsb_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers ----
+    def num_frames(self, n):
+        return 1 + int(n) // self.hop
+
+    def num_samples(self, T):
+        return self.hop * (int(T) - 1)
+
+    @staticmethod
+    def _lens(lengths, ctype):
+        arr = (ctype * len(lengths))(*[int(v) for v in lengths])
+        return arr
+
+    def _call(self, name, *args):
+        self.lib.check(getattr(self.lib.dll, name)(self._h, *args))
+
+    # ---- raw entry points (buffers: numpy arrays for HOST, torch tensors / int addresses for DEVICE) ----
+    def stft(self, wav, n_samples, out, preemphasis=False, space=HOST, stream=None):
+        self._call("nsb_stft", _ptr(wav), self._lens(n_samples, ctypes.c_int64), len(n_samples), int(bool(preemphasis)),
+                   _ptr(out), space, _ptr(stream))
+
+    def features(self, wav, n_samples, lin_out, mel_out, space=HOST, stream=None):
+        self._call("nsb_features", _ptr(wav), self._lens(n_samples, ctypes.c_int64), len(n_samples), _ptr(lin_out),
+                   _ptr(mel_out), space, _ptr(stream))
+
+    def istft(self, spec, layout, n_frames, out, space=HOST, stream=None):
+        self._call("nsb_istft", _ptr(spec), layout, self._lens(n_frames, ctypes.c_int32), len(n_frames), _ptr(out), space,
+                   _ptr(stream))
+
+    def griffin_lim(self, spec, layout, n_frames, out, init_phase=None, seed=0, iters=-1, flags=0, out_dtype=F32,
+                    space=HOST, stream=None):
+        self._call("nsb_griffin_lim", _ptr(spec), layout, self._lens(n_frames, ctypes.c_int32), len(n_frames),
+                   _ptr(init_phase), ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), int(iters), int(flags), _ptr(out),
+                   out_dtype, space, _ptr(stream))
+
+    def griffin_lim_iterate(self, iters, stream=None):
+        self._call("nsb_griffin_lim_iterate", int(iters), _ptr(stream))
+
+    def preemphasis(self, x, n_samples, out, out_dtype=F64, space=HOST, stream=None, inverse=False):
+        self._call("nsb_inv_preemphasis" if inverse else "nsb_preemphasis", _ptr(x), self._lens(n_samples, ctypes.c_int64),
+                   len(n_samples), _ptr(out), out_dtype, space, _ptr(stream))
+
+    def linear_to_mel(self, spec, layout, n_frames, out, out_dtype=F64, space=HOST, stream=None):
+        self._call("nsb_linear_to_mel", _ptr(spec), layout, self._lens(n_frames, ctypes.c_int32), len(n_frames), _ptr(out),
+                   out_dtype, space, _ptr(stream))
+
+    def mel_basis(self):
+        out = np.empty((self.num_mels, self.num_freq), dtype=np.float64)
+        self._call("nsb_mel_basis", _ptr(out))
+        return out
+
+    def elementwise(self, op, x, out, space=HOST, stream=None, n=None):
+        self._call("nsb_elementwise", int(op), _ptr(x), int(x.size if n is None else n), _ptr(out), space, _ptr(stream))
+
+    def synchronize(self, stream=None):
+        self._call("nsb_synchronize", _ptr(stream))
+
+    def check_status(self, stream=None):
+        self._call("nsb_check_status", _ptr(stream))
+
+    def set_tile_hops(self, t):
+        self._call("nsb_set_tile_hops", int(t))
+
+    def kernel_launches(self):
+        return int(self.lib.dll.nsb_kernel_launches(self._h))

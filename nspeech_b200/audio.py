@@ -1,0 +1,234 @@
+"""Drop-in mirror of the reference's ``neural_speech/utils/audio.py`` hot path on B200.
+
+Same names, signatures, dtypes, shapes and hparams-driven behaviour as the reference module
+(``/root/reference/neural_speech/utils/audio.py``, cited per function), but every function body marshals
+its numpy buffers through ctypes into ``libnspeech_b200.so`` (hand-written sm_100a kernels).  No librosa,
+scipy, cuFFT or CPU arithmetic on the path; if the native library or a B200 is missing the call raises.
+
+Like the reference, every call reads the global hparams (``nspeech_b200.hparams.get_hparams()``).  Native
+handles are cached per (audio hparams, device, thread), so changing an hparam can never hit a stale plan
+(the reference's ``_mel_basis`` global is never invalidated, ``audio.py:135-142``) and feeder threads
+(``datasets/datafeeder.py:110-116``) do not serialise on one handle.
+
+Additions that the reference does not have (all optional keyword arguments or new names):
+``inv_spectrogram(..., init_phase=, seed=, iters=)``, ``spectrogram_and_mel``, the ``*_batch`` functions in
+``nspeech_b200.batch``.
+"""
+import threading
+
+import numpy as np
+
+from . import _lib
+from ._lib import ParameterError  # noqa: F401  (re-exported)
+from .hparams import get_hparams
+
+# device used by the module-level functions (one process per GPU: set from LOCAL_RANK by the caller)
+DEVICE = 0
+# how inv_spectrogram/_griffin_lim draw the initial phase when none is supplied:
+#   "numpy"  - np.random.rand(*S.shape) from the global numpy RNG, exactly as the reference (audio.py:81)
+#   "device" - Philox-4x32 on the GPU keyed by `seed` (fast path; no host RNG, no phase upload)
+RANDOM_PHASE = "numpy"
+
+_tls = threading.local()
+_lib_override = None     # tests bind the CPU-emulated build of the same sources here; never set by product code
+
+
+def _handle(device=None):
+    hp = get_hparams()
+    dev = DEVICE if device is None else device
+    key = (tuple(getattr(hp, k) for k in ("num_freq", "num_mels", "sample_rate", "griffin_lim_iters", "frame_shift_ms",
+                                            "frame_length_ms", "preemphasis", "ref_level_db", "min_level_db", "power")),
+           dev, id(_lib_override))
+    cache = getattr(_tls, "handles", None)
+    if cache is None:
+        cache = _tls.handles = {}
+    h = cache.get(key)
+    if h is None:
+        if len(cache) > 8:
+            for old in cache.values():
+                old.close()
+            cache.clear()
+        h = cache[key] = _lib.Handle(hp, dev, lib=_lib_override)
+    return h
+
+
+def _as_wav(y):
+    y = np.asarray(y)
+    if y.ndim != 1:
+        raise ParameterError('Invalid shape for monophonic audio: ndim={:d}, shape={}'.format(y.ndim, y.shape))
+    if not np.issubdtype(y.dtype, np.floating):
+        raise ParameterError('data must be floating-point')
+    if y.size == 0:
+        raise ParameterError('empty audio buffer')
+    return np.ascontiguousarray(y, dtype=np.float32)
+
+
+def _spec_layout(S, dtype):
+    """Return (buffer, layout) for a [F, T] array without copying when it is either Fortran- or C-ordered."""
+    S = np.asarray(S)
+    if S.ndim != 2:
+        raise ValueError("expected a [num_freq, T] array, got shape %r" % (S.shape,))
+    if S.dtype != dtype:
+        S = S.astype(dtype)
+    if S.T.flags.c_contiguous:
+        return S, _lib.FRAME_MAJOR
+    if S.flags.c_contiguous:
+        return S, _lib.BIN_MAJOR
+    return np.asfortranarray(S), _lib.FRAME_MAJOR
+
+
+def _stft_parameters():
+    # reference audio.py:126-130
+    h = _handle()
+    return h.n_fft, h.hop, h.win
+
+
+def preemphasis(x):
+    # reference audio.py:31-32 -> float64, like scipy.signal.lfilter
+    x = _as_wav(x)
+    out = np.empty(x.shape, dtype=np.float64)
+    _handle().preemphasis(x, [x.size], out, _lib.F64)
+    return out
+
+
+def inv_preemphasis(x):
+    # reference audio.py:35-36
+    x = _as_wav(x)
+    out = np.empty(x.shape, dtype=np.float64)
+    _handle().preemphasis(x, [x.size], out, _lib.F64, inverse=True)
+    return out
+
+
+def _stft(y):
+    # reference audio.py:106-108 -> complex64 [F, T], Fortran-ordered like librosa.stft
+    y = _as_wav(y)
+    h = _handle()
+    T = h.num_frames(y.size)
+    out = np.empty((T, h.num_freq), dtype=np.complex64)
+    h.stft(y, [y.size], out, preemphasis=False)
+    return out.T
+
+
+def _istft(D):
+    # reference audio.py:111-113 -> float32, hop*(T-1) samples
+    D, layout = _spec_layout(D, np.complex64)
+    h = _handle()
+    if D.shape[0] != h.num_freq:
+        raise ValueError("expected %d frequency bins, got %d" % (h.num_freq, D.shape[0]))
+    T = D.shape[1]
+    out = np.empty(h.num_samples(T), dtype=np.float32)
+    h.istft(D, layout, [T], out)
+    return out
+
+
+def spectrogram_and_mel(y):
+    """``(spectrogram(y), melspectrogram(y))`` from ONE pass (the reference runs the STFT twice:
+    ``datasets/process.py:30,33`` -> ``audio.py:40,62``)."""
+    y = _as_wav(y)
+    h = _handle()
+    T = h.num_frames(y.size)
+    lin = np.empty((T, h.num_freq), dtype=np.float32)
+    mel = np.empty((T, h.num_mels), dtype=np.float32)
+    h.features(y, [y.size], lin, mel)
+    return lin.T, mel.T
+
+
+def spectrogram(y):
+    # reference audio.py:39-42 -> float32 [F, T]
+    y = _as_wav(y)
+    h = _handle()
+    lin = np.empty((h.num_frames(y.size), h.num_freq), dtype=np.float32)
+    h.features(y, [y.size], lin, None)
+    return lin.T
+
+
+def melspectrogram(y):
+    # reference audio.py:61-64 -> float32 [M, T]
+    y = _as_wav(y)
+    h = _handle()
+    mel = np.empty((h.num_frames(y.size), h.num_mels), dtype=np.float32)
+    h.features(y, [y.size], None, mel)
+    return mel.T
+
+
+def _draw_phase(shape, layout):
+    # reference audio.py:81: angles = exp(2j*pi*rand(*S.shape)) from the global numpy RNG
+    u = np.random.rand(*shape)
+    ang = np.exp(2j * np.pi * u).astype(np.complex64)
+    return np.asfortranarray(ang) if layout == _lib.FRAME_MAJOR else np.ascontiguousarray(ang)
+
+
+def _run_gl(S, flags, out_dtype, init_phase, seed, iters):
+    S, layout = _spec_layout(S, np.float32)
+    h = _handle()
+    if S.shape[0] != h.num_freq:
+        raise ValueError("expected %d frequency bins, got %d" % (h.num_freq, S.shape[0]))
+    T = S.shape[1]
+    if init_phase is None and RANDOM_PHASE == "numpy" and seed is None:
+        init_phase = _draw_phase(S.shape, layout)
+    if init_phase is not None:
+        init_phase = np.asarray(init_phase)
+        if init_phase.shape != S.shape:
+            raise ValueError("init_phase shape %r != spectrogram shape %r" % (init_phase.shape, S.shape))
+        if layout == _lib.FRAME_MAJOR:
+            init_phase = np.asfortranarray(init_phase, dtype=np.complex64)
+        else:
+            init_phase = np.ascontiguousarray(init_phase, dtype=np.complex64)
+    out = np.empty(h.num_samples(T), dtype=np.float64 if out_dtype == _lib.F64 else np.float32)
+    h.griffin_lim(S, layout, [T], out, init_phase=init_phase, seed=0 if seed is None else seed,
+                  iters=-1 if iters is None else iters, flags=flags, out_dtype=out_dtype)
+    return out
+
+
+def _griffin_lim(S, init_phase=None, seed=None, iters=None):
+    # reference audio.py:77-87 -> float32 waveform (no de-emphasis)
+    return _run_gl(S, 0, _lib.F32, init_phase, seed, iters)
+
+
+def inv_spectrogram(spectrogram, init_phase=None, seed=None, iters=None):
+    '''Converts spectrogram to waveform (reference audio.py:45-48) -> float64, hop*(T-1) samples'''
+    return _run_gl(spectrogram, _lib.GL_DENORMALIZE | _lib.GL_DEEMPHASIS, _lib.F64, init_phase, seed, iters)
+
+
+def _build_mel_basis():
+    # reference audio.py:145-147 -> float64 [num_mels, num_freq]
+    return _handle().mel_basis()
+
+
+def _linear_to_mel(spectrogram):
+    # reference audio.py:138-142 -> float64 [num_mels, T] (np.dot with the float64 basis)
+    S, layout = _spec_layout(spectrogram, np.float32)
+    h = _handle()
+    T = S.shape[1]
+    out = np.empty((T, h.num_mels), dtype=np.float64)
+    h.linear_to_mel(S, layout, [T], out, _lib.F64)
+    return out.T
+
+
+def _elementwise(op, x):
+    x = np.asarray(x)
+    flat = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+    out = np.empty_like(flat)
+    if flat.size:
+        _handle().elementwise(op, flat, out)
+    return out.reshape(x.shape)
+
+
+def _amp_to_db(x):
+    # reference audio.py:150-151
+    return _elementwise(_lib.EW_AMP_TO_DB, x)
+
+
+def _db_to_amp(x):
+    # reference audio.py:154-155
+    return _elementwise(_lib.EW_DB_TO_AMP, x)
+
+
+def _normalize(S):
+    # reference audio.py:162-163
+    return _elementwise(_lib.EW_NORMALIZE, S)
+
+
+def _denormalize(S):
+    # reference audio.py:166-167
+    return _elementwise(_lib.EW_DENORMALIZE, S)

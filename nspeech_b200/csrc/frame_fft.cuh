@@ -1,0 +1,115 @@
+// One warp = one 2048-point real frame transform, as 64 x 32:
+//
+//   n = 32*m + r   (r = lane, m = 0..63)          k = q + 64*p   (q = lane, p = 0..31)
+//
+//   pass 1 (lane r): real 64-point FFT over m, done as a packed complex 32-point FFT in registers
+//                    + the real64 split (fft_core.cuh)                        -> Y_r[q], q = 0..32
+//   twiddle        : Y_r[q] *= w2048^(r*q)   (table in shared memory, conflict-free columns)
+//   transpose      : one trip through a per-warp 32x33 float2 scratch tile
+//   pass 2 (lane q): complex 32-point FFT over r                               -> X[q + 64*p]
+//
+// Hermitian symmetry keeps every pair (k, 2048-k) inside ONE lane: lane q >= 1 ends up with the 32
+// bins  k = q + 64p (p < 16, value Z[p])  and  k = (64-q) + 64(31-p) (p >= 16, value conj Z[p]).
+// Rows q = 0 and q = 32 only carry real data; they are packed into row 0 (64 floats) and lane 0
+// turns them into the 33 bins k = 32*j with one more real64 split.  So the per-bin Griffin-Lim
+// update (phase renormalisation times magnitude) needs no cross-lane exchange at all, and the
+// inverse transform is the same pipeline run backwards.
+//
+// Scale conventions (validated by tests/emu): fwd gives 2*rfft(x); inv gives 2048*irfft(X).
+// Callers fold the 1/2 and 1/2048 into their window tables.
+//
+// Lane-0 packing of the "register spectrum": slot 0 = (X[0], X[1024]) (both real), slot j = X[32 j].
+#pragma once
+#include "fft_core.cuh"
+
+namespace nsb {
+
+#if defined(__CUDACC__) || defined(NSB_EMULATE)
+typedef float2 f2;
+#else
+struct alignas(8) f2 { float x, y; };
+#endif
+
+constexpr int kNfft = 2048;
+constexpr int kBins = 1025;
+constexpr int kRowStride = 33;                      // float2 units; keeps row and column access conflict-free
+constexpr int kScratchF2 = 32 * kRowStride;         // per-warp scratch tile (8448 B)
+constexpr int kTwF2 = 31 * 32;                      // twiddle table, tw[(j-1)*32 + l] = exp(-2*pi*i*j*l/2048)
+
+// frequency bin held in slot p of lane `lane` (lane 0 slot 0 is the packed DC/Nyquist pair -> returns 0)
+NSB_HD int bin_of(int lane, int p) {
+    if (lane == 0) return 32 * p;
+    return p < 16 ? lane + 64 * p : (64 - lane) + 64 * (31 - p);
+}
+// true if slot p of lane holds the conjugate of the bin's value
+NSB_HD bool slot_is_conj(int lane, int p) { return lane != 0 && p >= 16; }
+
+// ---- forward -------------------------------------------------------------------------------
+// in : re[t] = x[64 t + lane], im[t] = x[64 t + 32 + lane]
+NSB_HD void fwd_phase1(float (&re)[32], float (&im)[32], int lane, f2* scratch, const f2* tw) {
+    fft32<-1>(re, im);
+    real64_post(re, im);
+    float* row0 = reinterpret_cast<float*>(scratch);
+    row0[lane] = re[0];
+    row0[lane + 32] = im[0];
+#pragma unroll
+    for (int q = 1; q < 32; ++q) {
+        f2 w = tw[(q - 1) * 32 + lane];
+        f2 v;
+        v.x = re[q] * w.x - im[q] * w.y;
+        v.y = re[q] * w.y + im[q] * w.x;
+        scratch[q * kRowStride + lane] = v;
+    }
+}
+// out: register spectrum (2 * rfft), see header comment
+NSB_HD void fwd_phase2(float (&re)[32], float (&im)[32], int lane, const f2* scratch) {
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+        f2 v = scratch[lane * kRowStride + t];
+        re[t] = v.x; im[t] = v.y;
+    }
+    fft32<-1>(re, im);
+    if (lane == 0) {
+        real64_post(re, im);
+        float a = re[0], b = im[0];
+        re[0] = 2.0f * (a + b);
+        im[0] = 2.0f * (a - b);
+    }
+}
+
+// ---- inverse -------------------------------------------------------------------------------
+// in : register spectrum X (Im of DC / Nyquist do not exist in the packing, as in irfft)
+NSB_HD void inv_phase1(float (&re)[32], float (&im)[32], int lane, f2* scratch, const f2* tw) {
+    if (lane == 0) {
+        float a = re[0], b = im[0];
+        re[0] = a + b;
+        im[0] = a - b;
+        real64_pre(re, im);
+    }
+    fft32<+1>(re, im);
+    f2 v0; v0.x = re[0]; v0.y = im[0];
+    scratch[lane * kRowStride] = v0;
+#pragma unroll
+    for (int r = 1; r < 32; ++r) {
+        f2 w = tw[(r - 1) * 32 + lane];     // table is symmetric in (j, l): conj(w2048^(lane*r))
+        f2 v;
+        v.x = re[r] * w.x + im[r] * w.y;
+        v.y = im[r] * w.x - re[r] * w.y;
+        scratch[lane * kRowStride + r] = v;
+    }
+}
+// out: re[t] = 2048 * x[64 t + lane], im[t] = 2048 * x[64 t + 32 + lane]
+NSB_HD void inv_phase2(float (&re)[32], float (&im)[32], int lane, const f2* scratch) {
+    const float* row0 = reinterpret_cast<const float*>(scratch);
+    re[0] = row0[lane];
+    im[0] = row0[lane + 32];
+#pragma unroll
+    for (int q = 1; q < 32; ++q) {
+        f2 v = scratch[q * kRowStride + lane];
+        re[q] = v.x; im[q] = v.y;
+    }
+    real64_pre(re, im);
+    fft32<+1>(re, im);
+}
+
+}  // namespace nsb

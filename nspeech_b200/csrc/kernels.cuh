@@ -1,0 +1,671 @@
+// CUDA kernels of the spectrogram / Griffin-Lim hot path (sm_100a).
+//
+//   k_analysis<MODE>  : framing + (pre-emphasis) + reflect padding + Hann window + 2048-pt real FFT
+//                       -> complex64 STFT, or |.| -> dB -> normalise (+ sparse mel) features
+//                       replaces audio.py:31-32,39-42,61-64,106-108,138-151,162-163
+//   k_synth<SRC>      : (STFT of y -> phase renormalise x magnitude | given spectrum | magnitude x
+//                       given phase) -> inverse real FFT -> window -> overlap-add -> / window-sum
+//                       one launch = one `_istft`, or one whole Griffin-Lim iteration
+//                       replaces audio.py:77-87,111-113
+//   k_prepare_mag     : _denormalize + ref_level_db, _db_to_amp, **power (audio.py:47-48,154-155,166-167)
+//   k_deemphasis      : inv_preemphasis (audio.py:35-36) as a blocked scan
+//   k_preemphasis, k_elementwise, k_linear_to_mel : the small helpers of the same module
+//
+// One warp owns one frame; see frame_fft.cuh for the transform itself.
+#pragma once
+#ifdef NSB_EMULATE            // tests/emu: the same source on CPU threads (test infrastructure, never shipped)
+#include "cuda_emu.h"
+#define NSB_DYN_SMEM(name) unsigned char* name = nsb_emu::dyn_smem()
+#else
+#include <cuda_runtime.h>
+#define NSB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+#include <stdint.h>
+#include "frame_fft.cuh"
+
+namespace nsb {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreads = kWarpsPerCta * 32;
+constexpr int kMagPitch = 1056;  // floats per frame in the permuted magnitude buffer (1024 slots + Nyquist + pad)
+
+// ragged batch: utterance b owns frames [frame_off[b], frame_off[b+1]) and samples [samp_off[b], samp_off[b+1])
+struct Batch {
+    const int* frame_off;        // [batch+1]
+    const long long* samp_off;   // [batch+1]
+    const int* tile_off;         // [batch+1] (synthesis tiles), may be null for analysis
+    int batch;
+};
+
+struct Plan {                    // device tables owned by the handle
+    const float2* tw;            // [31*32]
+    const float* win;            // [2048] window padded centrally to n_fft (unscaled)
+    const float* mel_w;          // mel weights, rows concatenated
+    const int* mel_lo;           // [num_mels] first bin of row
+    const int* mel_n;            // [num_mels] row length
+    const int* mel_ptr;          // [num_mels] offset into mel_w
+    int n_fft, hop, win_len, lo; // lo = (n_fft - win_len)/2
+    int num_mels;
+    int prune;                   // window support inside n in [512,1536)
+};
+
+__device__ __forceinline__ int find_segment(const int* __restrict__ off, int n, int v) {
+    // largest b in [0,n) with off[b] <= v
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(off + mid) <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// np.pad(mode='reflect') index map for a signal of length L (any i, multiple reflections)
+__device__ __forceinline__ long long reflect_index(long long i, long long L) {
+    if (L == 1) return 0;
+    long long period = 2 * (L - 1);
+    long long m = i % period;
+    if (m < 0) m += period;
+    return m < L ? m : period - m;
+}
+
+// ---- frame load: windowed samples of frame k into the lane registers -----------------------
+// re[t] = w[n] * s(start + n), n = 64 t + lane ; im[t] likewise with n + 32.   s = (pre-emphasised) signal
+template <bool PREEMPH>
+__device__ __forceinline__ float sample_at(const float* __restrict__ x, long long L, long long i, float p) {
+    long long m = reflect_index(i, L);
+    float v = __ldg(x + m);
+    if (PREEMPH) { if (m > 0) v = fmaf(-p, __ldg(x + m - 1), v); }
+    return v;
+}
+
+template <bool PREEMPH, bool PRUNE>
+__device__ __forceinline__ void load_frame(float (&re)[32], float (&im)[32], const float* __restrict__ x, long long L,
+                                           long long start, const float* __restrict__ win_s, int lane, float p,
+                                           float scale) {
+    constexpr int t0 = PRUNE ? 8 : 0, t1 = PRUNE ? 24 : 32;
+    const long long first = start + 64 * t0, last = start + 64 * t1;   // [first, last) touched
+    const bool interior = (first >= (PREEMPH ? 1 : 0)) && (last <= L);
+    if (interior) {
+        const float* xs = x + start + lane;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+            if (t >= t0 && t < t1) {
+                float a = __ldg(xs + 64 * t), b = __ldg(xs + 64 * t + 32);
+                if (PREEMPH) {
+                    a = fmaf(-p, __ldg(xs + 64 * t - 1), a);
+                    b = fmaf(-p, __ldg(xs + 64 * t + 31), b);
+                }
+                re[t] = a * (win_s[64 * t + lane] * scale);
+                im[t] = b * (win_s[64 * t + 32 + lane] * scale);
+            } else { re[t] = 0.f; im[t] = 0.f; }
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+            if (t >= t0 && t < t1) {
+                float a = sample_at<PREEMPH>(x, L, start + 64 * t + lane, p);
+                float b = sample_at<PREEMPH>(x, L, start + 64 * t + 32 + lane, p);
+                re[t] = a * (win_s[64 * t + lane] * scale);
+                im[t] = b * (win_s[64 * t + 32 + lane] * scale);
+            } else { re[t] = 0.f; im[t] = 0.f; }
+        }
+    }
+}
+
+// =============================================================================================
+// analysis
+// =============================================================================================
+enum { ANALYSIS_COMPLEX = 0, ANALYSIS_FEATURES = 1 };
+
+struct AnalysisParams {
+    Plan plan;
+    Batch batch;
+    const float* wav;      // packed samples
+    float2* out_complex;   // [frames][1025]
+    float* out_lin;        // [frames][1025] or null
+    float* out_mel;        // [frames][num_mels] or null
+    int total_frames;
+    float preemph;         // coefficient (only read when PREEMPH)
+    float ref_level_db, min_level_db;
+    int* status;           // device flag: bit0 = non-finite input
+};
+
+__device__ __forceinline__ float amp_to_db_norm(float amp, float ref_db, float min_db) {
+    // _normalize(_amp_to_db(amp) - ref): 20*log10(max(1e-5, amp)), (S - min)/(-min), clip [0,1]
+    float db = 20.0f * log10f(fmaxf(1e-5f, amp)) - ref_db;
+    float v = (db - min_db) / (-min_db);
+    return fminf(fmaxf(v, 0.f), 1.f);
+}
+
+template <int MODE, bool PREEMPH, bool PRUNE>
+__global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
+    NSB_DYN_SMEM(smem_raw);
+    float2* tw_s = reinterpret_cast<float2*>(smem_raw);
+    float* win_s = reinterpret_cast<float*>(tw_s + kTwF2);
+    float2* scratch_all = reinterpret_cast<float2*>(win_s + kNfft);
+    for (int i = threadIdx.x; i < kTwF2; i += kThreads) tw_s[i] = P.plan.tw[i];
+    for (int i = threadIdx.x; i < kNfft; i += kThreads) win_s[i] = P.plan.win[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2* scratch = scratch_all + warp * kScratchF2;
+    const int hop = P.plan.hop;
+    bool bad = false;
+    int b = 0;
+    for (int f = blockIdx.x * kWarpsPerCta + warp; f < P.total_frames; f += gridDim.x * kWarpsPerCta) {
+        if (!(f >= __ldg(P.batch.frame_off + b) && f < __ldg(P.batch.frame_off + b + 1)))
+            b = find_segment(P.batch.frame_off, P.batch.batch, f);
+        const int k = f - __ldg(P.batch.frame_off + b);
+        const long long s_off = __ldg(P.batch.samp_off + b);
+        const long long L = __ldg(P.batch.samp_off + b + 1) - s_off;
+        float re[32], im[32];
+        // 0.5 folds the forward transform's factor 2 (frame_fft.cuh) so the registers hold rfft exactly
+        load_frame<PREEMPH, PRUNE>(re, im, P.wav + s_off, L, (long long)k * hop - kNfft / 2, win_s, lane, P.preemph, 0.5f);
+        fwd_phase1(re, im, lane, scratch, tw_s);
+        __syncwarp();
+        fwd_phase2(re, im, lane, scratch);
+        __syncwarp();
+        if (MODE == ANALYSIS_COMPLEX) {
+            float2* o = P.out_complex + (size_t)f * kBins;
+#pragma unroll
+            for (int p = 0; p < 32; ++p) {
+                bad |= !(isfinite(re[p]) && isfinite(im[p]));
+                if (lane == 0 && p == 0) {
+                    o[0] = make_float2(re[0], 0.f);
+                    o[1024] = make_float2(im[0], 0.f);
+                } else {
+                    int kb = bin_of(lane, p);
+                    o[kb] = make_float2(re[p], (lane != 0 && p >= 16) ? -im[p] : im[p]);
+                }
+            }
+        } else {
+            // magnitudes -> scratch (as floats, 1025 <= 2112), then linear dB and sparse mel
+            float* magrow = reinterpret_cast<float*>(scratch);
+#pragma unroll
+            for (int p = 0; p < 32; ++p) {
+                bad |= !(isfinite(re[p]) && isfinite(im[p]));
+                if (lane == 0 && p == 0) {
+                    magrow[0] = fabsf(re[0]);
+                    magrow[1024] = fabsf(im[0]);
+                } else {
+                    magrow[bin_of(lane, p)] = sqrtf(fmaf(re[p], re[p], im[p] * im[p]));
+                }
+            }
+            __syncwarp();
+            if (P.out_lin) {
+                float* o = P.out_lin + (size_t)f * kBins;
+                for (int kb = lane; kb < kBins; kb += 32) o[kb] = amp_to_db_norm(magrow[kb], P.ref_level_db, P.min_level_db);
+            }
+            if (P.out_mel) {
+                float* o = P.out_mel + (size_t)f * P.plan.num_mels;
+                for (int m = lane; m < P.plan.num_mels; m += 32) {
+                    const int lo = __ldg(P.plan.mel_lo + m), n = __ldg(P.plan.mel_n + m);
+                    const float* w = P.plan.mel_w + __ldg(P.plan.mel_ptr + m);
+                    float acc = 0.f;
+                    for (int i = 0; i < n; ++i) acc = fmaf(__ldg(w + i), magrow[lo + i], acc);
+                    o[m] = amp_to_db_norm(acc, 0.f, P.min_level_db);   // melspectrogram subtracts no ref_level_db (audio.py:63)
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (bad) atomicOr(P.status, 1);
+}
+
+// =============================================================================================
+// synthesis: istft / Griffin-Lim iteration
+// =============================================================================================
+enum { SRC_Y = 0, SRC_SPEC = 1, SRC_MAGPHASE = 2, SRC_MAGRAND = 3 };
+
+struct SynthParams {
+    Plan plan;
+    Batch batch;
+    const float* y_in;        // SRC_Y: packed waveform estimate
+    const float* mag;         // permuted magnitudes [frames][kMagPitch]   (SRC_Y, SRC_MAGPHASE, SRC_MAGRAND)
+    const float2* spec;       // SRC_SPEC: spectrum, SRC_MAGPHASE: unit phase; utterance b's block of 1025*T_b elements
+    int spec_bin_major;       //   starts at 1025*frame_off[b]; inside it [T_b][1025] (0) or [1025][T_b] (1)
+    float* y_out;             // packed
+    int tile_hops;            // H
+    int colours;              // ceil(win/hop)
+    unsigned long long seed;
+    int* status;
+};
+
+__device__ __forceinline__ uint32_t mulhilo(uint32_t a, uint32_t b, uint32_t& hi) {
+    unsigned long long r = (unsigned long long)a * b;
+    hi = (uint32_t)(r >> 32);
+    return (uint32_t)r;
+}
+// Philox-4x32-10 (Salmon et al. 2011), counter-based: one call -> four 32-bit words
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, hi1;
+        uint32_t lo0 = mulhilo(0xD2511F53u, ctr.x, hi0);
+        uint32_t lo1 = mulhilo(0xCD9E8D57u, ctr.z, hi1);
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+
+// phase renormalisation of one slot: z <- S * z/|z| ; z == 0 -> S (np.angle(0) = 0, audio.py:85)
+__device__ __forceinline__ void renorm(float& re, float& im, float S) {
+    float m2 = fmaf(re, re, im * im);
+    if (m2 < 1e-30f || m2 > 1e30f) {              // rare: rescale to dodge under/overflow of the square
+        float sc = (m2 < 1e-30f) ? 1.8446744e19f : 5.4210109e-20f;   // 2^64, 2^-64
+        float a = re * sc, b = im * sc;
+        m2 = fmaf(a, a, b * b);
+        if (m2 == 0.f) { re = S; im = 0.f; return; }
+        float inv = rsqrtf(m2) * S;
+        re = a * inv; im = b * inv;
+        return;
+    }
+    float inv = rsqrtf(m2) * S;
+    re *= inv; im *= inv;
+}
+
+template <int SRC, bool PRUNE>
+__global__ void __launch_bounds__(kThreads, 2) k_synth(SynthParams P) {
+    NSB_DYN_SMEM(smem_raw);
+    float2* tw_s = reinterpret_cast<float2*>(smem_raw);
+    float* win_s = reinterpret_cast<float*>(tw_s + kTwF2);
+    float* rinv_s = win_s + kNfft;                                   // [hop] interior 1/window-sum
+    float* acc = rinv_s + P.plan.hop;                                // [H*hop]
+    // scratch must be 8-byte aligned: hop and H*hop are arbitrary, so round up
+    size_t acc_end = (size_t)(acc + (size_t)P.tile_hops * P.plan.hop - reinterpret_cast<float*>(smem_raw));
+    acc_end = (acc_end + 3) & ~(size_t)3;
+    float2* scratch_all = reinterpret_cast<float2*>(reinterpret_cast<float*>(smem_raw) + acc_end);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2* scratch = scratch_all + warp * kScratchF2;
+    const int hop = P.plan.hop, win = P.plan.win_len, lo = P.plan.lo;
+    const int a = kNfft / 2 - lo;          // frame k's window support starts at sample k*hop - a
+    const int C = P.colours, H = P.tile_hops;
+
+    const int b = find_segment(P.batch.tile_off, P.batch.batch, (int)blockIdx.x);
+    const int tile = blockIdx.x - __ldg(P.batch.tile_off + b);
+    const int f_off = __ldg(P.batch.frame_off + b);
+    const int T = __ldg(P.batch.frame_off + b + 1) - f_off;
+    const long long s_off = __ldg(P.batch.samp_off + b);
+    const long long L = (long long)hop * (T - 1);
+    const int h0 = tile * H, h1 = min(h0 + H, T - 1);
+    const long long s0 = (long long)h0 * hop, s1 = (long long)h1 * hop;
+    const int n_out = (int)(s1 - s0);
+
+    for (int i = threadIdx.x; i < kTwF2; i += kThreads) tw_s[i] = P.plan.tw[i];
+    for (int i = threadIdx.x; i < kNfft; i += kThreads) win_s[i] = P.plan.win[i];
+    for (int i = threadIdx.x; i < n_out; i += kThreads) acc[i] = 0.f;
+    __syncthreads();
+    // interior reciprocal window-sum for each offset j inside a hop (all covering frames exist)
+    for (int j = threadIdx.x; j < hop; j += kThreads) {
+        float s = 0.f;
+        for (int idx = (j + a) % hop; idx < win; idx += hop) { float w = win_s[lo + idx]; s = fmaf(w, w, s); }
+        rinv_s[j] = s > 1.17549435e-38f ? 1.0f / s : 1.0f;
+    }
+
+    // frames whose window support [k*hop - a, k*hop - a + win) meets [s0, s1)
+    long long num = s0 + a - win;                       // k*hop > num
+    int k_min = (int)(num >= 0 ? num / hop + 1 : -((-num - 1) / hop + 1) + 1);
+    if (k_min < 0) k_min = 0;
+    int k_max = (int)((s1 + a + hop - 1) / hop - 1);     // k*hop < s1 + a
+    if (k_max > T - 1) k_max = T - 1;
+
+    bool bad = false;
+    for (int c = 0; c < C; ++c) {
+        // first frame >= k_min with k % C == c
+        int kf = k_min + ((c - k_min % C) + C) % C;
+        for (int k = kf + C * warp; k <= k_max; k += C * kWarpsPerCta) {
+            const int fg = f_off + k;                   // global frame index
+            float re[32], im[32];
+            if (SRC == SRC_Y) {
+                load_frame<false, PRUNE>(re, im, P.y_in + s_off, L, (long long)k * hop - kNfft / 2, win_s, lane, 0.f, 1.0f);
+                fwd_phase1(re, im, lane, scratch, tw_s);
+                __syncwarp();
+                fwd_phase2(re, im, lane, scratch);
+                __syncwarp();
+                const float4* mp = reinterpret_cast<const float4*>(P.mag + (size_t)fg * kMagPitch);
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    float4 S = __ldg(mp + g * 32 + lane);
+                    if (g == 0) {
+                        if (lane == 0) {    // packed real DC / Nyquist: phase of a real number is its sign
+                            float Sn = __ldg(P.mag + (size_t)fg * kMagPitch + 1024);
+                            re[0] = (re[0] < 0.f) ? -S.x : S.x;
+                            im[0] = (im[0] < 0.f) ? -Sn : Sn;
+                        } else {
+                            renorm(re[0], im[0], S.x);
+                        }
+                    } else {
+                        renorm(re[4 * g], im[4 * g], S.x);
+                    }
+                    renorm(re[4 * g + 1], im[4 * g + 1], S.y);
+                    renorm(re[4 * g + 2], im[4 * g + 2], S.z);
+                    renorm(re[4 * g + 3], im[4 * g + 3], S.w);
+                }
+            } else if (SRC == SRC_SPEC || SRC == SRC_MAGPHASE) {
+                const float2* sp;
+                long long st_f;
+                if (P.spec_bin_major) { sp = P.spec + (size_t)f_off * kBins + k; st_f = T; }
+                else { sp = P.spec + (size_t)f_off * kBins + (size_t)k * kBins; st_f = 1; }
+                const float* mrow = P.mag + (size_t)fg * kMagPitch;
+#pragma unroll
+                for (int p = 0; p < 32; ++p) {
+                    if (lane == 0 && p == 0) {
+                        float2 v0 = __ldg(sp), v1 = __ldg(sp + 1024 * st_f);
+                        re[0] = v0.x; im[0] = v1.x;          // imaginary parts of DC / Nyquist are dropped (irfft semantics)
+                        if (SRC == SRC_MAGPHASE) { re[0] *= __ldg(mrow); im[0] *= __ldg(mrow + 1024); }
+                    } else {
+                        float2 v = __ldg(sp + (long long)bin_of(lane, p) * st_f);
+                        if (lane != 0 && p >= 16) v.y = -v.y;
+                        if (SRC == SRC_MAGPHASE) { float S = __ldg(mrow + ((p >> 2) * 32 + lane) * 4 + (p & 3)); v.x *= S; v.y *= S; }
+                        re[p] = v.x; im[p] = v.y;
+                    }
+                }
+            } else {  // SRC_MAGRAND: magnitude x exp(2*pi*i*u), u ~ Philox keyed by seed, counter = (frame, lane, group)
+                const float* mrow = P.mag + (size_t)fg * kMagPitch;
+                uint2 key = make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    uint4 r = philox4x32(make_uint4((uint32_t)fg, (uint32_t)(lane * 8 + g), 0x6e737062u, 0u), key);
+                    float4 S = __ldg(reinterpret_cast<const float4*>(mrow) + g * 32 + lane);
+                    uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+                    float SS[4] = {S.x, S.y, S.z, S.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float u = (float)(rr[e] >> 8) * (1.0f / 16777216.0f);
+                        float sn, cs;
+                        sincospif(2.0f * u, &sn, &cs);
+                        re[4 * g + e] = SS[e] * cs; im[4 * g + e] = SS[e] * sn;
+                    }
+                }
+                if (lane == 0) {   // packed DC / Nyquist keep only the real part of S*exp(i*phi)
+                    uint4 r = philox4x32(make_uint4((uint32_t)fg, 0xffffffffu, 0x6e737062u, 0u), key);
+                    float sn, cs;
+                    sincospif(2.0f * (float)(r.x >> 8) * (1.0f / 16777216.0f), &sn, &cs);
+                    im[0] = __ldg(mrow + 1024) * cs;
+                }
+            }
+            inv_phase1(re, im, lane, scratch, tw_s);
+            __syncwarp();
+            inv_phase2(re, im, lane, scratch);
+            __syncwarp();
+            // windowed overlap-add into the tile.  Same-colour frames have disjoint window SUPPORTS, so a plain
+            // read-modify-write is race-free only if each warp touches nothing outside its support: per-lane
+            // bitmasks of the valid t (n = 64 t + lane [+32] inside [lo, lo + win)).
+            const long long base = (long long)k * hop - kNfft / 2 - s0;      // tile-local index of n = 0
+            constexpr int t0 = PRUNE ? 8 : 0, t1 = PRUNE ? 24 : 32;
+            unsigned mre, mim;
+            {
+                int a0 = max((lo - lane + 63) >> 6, 0), a1 = min(max((lo + win - lane + 63) >> 6, 0), 32);
+                int b0 = max((lo - lane - 32 + 63) >> 6, 0), b1 = min(max((lo + win - lane - 32 + 63) >> 6, 0), 32);
+                mre = (a1 > a0) ? ((0xffffffffu >> (32 - (a1 - a0))) << a0) : 0u;
+                mim = (b1 > b0) ? ((0xffffffffu >> (32 - (b1 - b0))) << b0) : 0u;
+            }
+            const bool inside = (base + lo >= 0) && (base + lo + win <= n_out);
+            if (inside) {
+                float* ap = acc + base + lane;
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    if (t >= t0 && t < t1) {
+                        if (mre & (1u << t)) ap[64 * t] = fmaf(re[t], win_s[64 * t + lane], ap[64 * t]);
+                        if (mim & (1u << t)) ap[64 * t + 32] = fmaf(im[t], win_s[64 * t + 32 + lane], ap[64 * t + 32]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    if (t >= t0 && t < t1) {
+                        long long i0 = base + 64 * t + lane, i1 = i0 + 32;
+                        if ((mre & (1u << t)) && i0 >= 0 && i0 < n_out) acc[i0] = fmaf(re[t], win_s[64 * t + lane], acc[i0]);
+                        if ((mim & (1u << t)) && i1 >= 0 && i1 < n_out) acc[i1] = fmaf(im[t], win_s[64 * t + 32 + lane], acc[i1]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // normalise by the summed squared window and store
+    float* yo = P.y_out + s_off + s0;
+    for (int j = threadIdx.x; j < hop; j += kThreads) {
+        const int dj = (j + a) / hop, rj = (j + a) - dj * hop;     // newest covering frame is h + dj, window index rj
+        const float ri = rinv_s[j];
+        int ncover = 0;
+        for (int idx = rj; idx < win; idx += hop) ++ncover;
+        for (int h = h0; h < h1; ++h) {
+            const int k_hi = h + dj, k_lo = k_hi - (ncover - 1);
+            float v = acc[(h - h0) * hop + j] * (1.0f / (float)kNfft);
+            bad |= !isfinite(v);
+            if (k_lo >= 0 && k_hi <= T - 1) {
+                v *= ri;
+            } else {
+                float s = 0.f;
+                int kk = k_hi;
+                for (int idx = rj; idx < win; idx += hop, --kk)
+                    if (kk >= 0 && kk <= T - 1) { float w = win_s[lo + idx]; s = fmaf(w, w, s); }
+                if (s > 1.17549435e-38f) v /= s;
+            }
+            yo[(size_t)(h - h0) * hop + j] = v;
+        }
+    }
+    if (bad) atomicOr(P.status, 1);
+}
+
+// =============================================================================================
+// magnitude preparation: normalised spectrogram (or raw magnitude) -> permuted float32 magnitudes
+// =============================================================================================
+struct PrepParams {
+    Batch batch;
+    const float* in;          // packed per utterance (block of F*T_b elements at F*frame_off[b])
+    int bin_major;            // 0: [T][F] frame-major, 1: [F][T] bin-major (per utterance)
+    int denorm;               // 1: apply _denormalize + ref, _db_to_amp, **power ; 0: |S| as is
+    double min_level_db, ref_level_db, power;
+    float* mag;               // [frames][kMagPitch]
+    int total_frames;
+    int* status;
+};
+
+__device__ __forceinline__ int slot_index(int bin) {
+    // position of `bin` inside a permuted magnitude row (inverse of bin_of); bin 1024 -> 1024
+    if (bin == 1024) return 1024;
+    int q = bin & 63, pp = bin >> 6;
+    int lane, p;
+    if ((bin & 31) == 0) { lane = 0; p = bin >> 5; }
+    else if (q < 32) { lane = q; p = pp; }
+    else { lane = 64 - q; p = 31 - pp; }
+    return ((p >> 2) * 32 + lane) * 4 + (p & 3);
+}
+
+__global__ void __launch_bounds__(256) k_prepare_mag(PrepParams P) {
+    // one block per (utterance-local) tile of 32 frames x 32 bins, through a padded smem tile so that both the
+    // read (contiguous along the input's fast axis) and the per-frame scatter stay inside a few cache lines
+    __shared__ float tile[32][33];
+    const int f0 = blockIdx.x * 32;                 // global frame index base
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    bool bad = false;
+    for (int kb0 = 0; kb0 < kBins; kb0 += 32) {
+        // load: tile[frame][bin]
+        for (int r = ty; r < 32; r += 8) {
+            int f, kb;
+            if (P.bin_major) { f = f0 + tx; kb = kb0 + r; } else { f = f0 + r; kb = kb0 + tx; }
+            float v = 0.f;
+            if (f < P.total_frames && kb < kBins) {
+                int b = find_segment(P.batch.frame_off, P.batch.batch, f);
+                int fo = __ldg(P.batch.frame_off + b);
+                int T = __ldg(P.batch.frame_off + b + 1) - fo;
+                size_t base = (size_t)fo * kBins;
+                v = P.bin_major ? __ldg(P.in + base + (size_t)kb * T + (f - fo)) : __ldg(P.in + base + (size_t)(f - fo) * kBins + kb);
+            }
+            if (P.bin_major) tile[tx][r] = v; else tile[r][tx] = v;
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            int f = f0 + r, kb = kb0 + tx;
+            if (f < P.total_frames && kb < kBins) {
+                float v = tile[r][tx];
+                bad |= !isfinite(v);
+                float S;
+                if (P.denorm) {
+                    double c = fmin(fmax((double)v, 0.0), 1.0);
+                    double db = c * (-P.min_level_db) + P.min_level_db + P.ref_level_db;
+                    S = (float)pow(pow(10.0, db * 0.05), P.power);
+                } else {
+                    S = fabsf(v);
+                }
+                P.mag[(size_t)f * kMagPitch + slot_index(kb)] = S;
+            }
+        }
+        __syncthreads();
+    }
+    if (bad) atomicOr(P.status, 1);
+}
+
+// =============================================================================================
+// (de-)emphasis
+// =============================================================================================
+struct EmphParams {
+    Batch batch;
+    const float* in;      // packed float32
+    double* out64;        // one of the two outputs is non-null
+    float* out32;
+    double p;
+};
+
+// y[n] = x[n] + p*y[n-1] per utterance (scipy.signal.lfilter([1],[1,-p]), zero initial state), in double.
+// One CTA walks one utterance chunk by chunk; inside a chunk each thread owns kPerThread consecutive
+// samples and the carries are combined with a warp/CTA scan of the constant-ratio recurrence.
+constexpr int kDeemphThreads = 256;
+constexpr int kPerThread = 8;
+
+__global__ void __launch_bounds__(kDeemphThreads) k_deemphasis(EmphParams P) {
+    __shared__ double warp_tot[kDeemphThreads / 32];
+    __shared__ double carry_s;
+    const int b = blockIdx.x;
+    const long long s_off = __ldg(P.batch.samp_off + b);
+    const long long L = __ldg(P.batch.samp_off + b + 1) - s_off;
+    const float* x = P.in + s_off;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double p = P.p;
+    double ppow[kPerThread + 1];             // p^1 .. p^kPerThread
+    ppow[0] = 1.0;
+#pragma unroll
+    for (int i = 1; i <= kPerThread; ++i) ppow[i] = ppow[i - 1] * p;
+    const double pT = ppow[kPerThread];      // decay across one thread's span
+    // pT^(2^d) for the warp scan, and pT^32 for the cross-warp step
+    double pw[6];
+    pw[0] = pT;
+#pragma unroll
+    for (int d = 1; d < 6; ++d) pw[d] = pw[d - 1] * pw[d - 1];
+    if (tid == 0) carry_s = 0.0;
+    __syncthreads();
+    const long long chunk = (long long)kDeemphThreads * kPerThread;
+    for (long long c0 = 0; c0 < L; c0 += chunk) {
+        const long long i0 = c0 + (long long)tid * kPerThread;
+        double loc[kPerThread];
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < kPerThread; ++i) {
+            double v = (i0 + i < L) ? (double)__ldg(x + i0 + i) : 0.0;
+            s = fma(p, s, v);
+            loc[i] = s;
+        }
+        // inclusive scan of the thread totals: S_i = e_i + pT * S_{i-1}
+        double S = s;
+#pragma unroll
+        for (int d = 0; d < 5; ++d) {
+            double o = __shfl_up_sync(0xffffffffu, S, 1 << d);
+            if (lane >= (1 << d)) S = fma(pw[d], o, S);
+        }
+        if (lane == 31) warp_tot[warp] = S;
+        __syncthreads();
+        // state entering this warp = combination of previous warps' totals and the chunk carry
+        double enter = carry_s;
+        for (int w = 0; w < warp; ++w) enter = fma(pw[5], enter, warp_tot[w]);
+        // state entering this thread = (exclusive) scan value within the warp + decayed warp-entry state
+        double prev = __shfl_up_sync(0xffffffffu, S, 1);
+        if (lane == 0) prev = 0.0;
+        // enter decays by pT per preceding lane
+        double dec = 1.0;
+        {
+            int l = lane;
+#pragma unroll
+            for (int d = 0; d < 5; ++d) { if (l & 1) dec *= pw[d]; l >>= 1; }
+        }
+        const double cin = fma(dec, enter, prev);
+#pragma unroll
+        for (int i = 0; i < kPerThread; ++i) {
+            if (i0 + i < L) {
+                double v = fma(ppow[i + 1], cin, loc[i]);
+                if (P.out64) P.out64[s_off + i0 + i] = v; else P.out32[s_off + i0 + i] = (float)v;
+            }
+        }
+        __syncthreads();
+        if (tid == kDeemphThreads - 1) carry_s = fma(ppow[kPerThread], cin, loc[kPerThread - 1]);
+        __syncthreads();
+    }
+}
+
+// y[n] = x[n] - p*x[n-1] (lfilter([1,-p],[1])), double arithmetic like scipy
+__global__ void __launch_bounds__(256) k_preemphasis(EmphParams P, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        // utterance start lookup by binary search on the 64-bit offsets
+        int lo = 0, hi = P.batch.batch;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (__ldg(P.batch.samp_off + mid) <= i) lo = mid; else hi = mid; }
+        const long long s_off = __ldg(P.batch.samp_off + lo);
+        double v = (double)__ldg(P.in + i);
+        if (i > s_off) v -= P.p * (double)__ldg(P.in + i - 1);
+        if (P.out64) P.out64[i] = v; else P.out32[i] = (float)v;
+    }
+}
+
+// =============================================================================================
+// element-wise helpers and stand-alone mel projection
+// =============================================================================================
+enum { EW_AMP_TO_DB = 0, EW_DB_TO_AMP = 1, EW_NORMALIZE = 2, EW_DENORMALIZE = 3 };
+
+__global__ void __launch_bounds__(256) k_elementwise(int op, const float* __restrict__ in, float* __restrict__ out,
+                                                     long long n, float min_level_db) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float x = __ldg(in + i), y;
+        switch (op) {
+            case EW_AMP_TO_DB: y = 20.0f * log10f(fmaxf(1e-5f, x)); break;
+            case EW_DB_TO_AMP: y = (float)pow(10.0, (double)x * 0.05); break;
+            case EW_NORMALIZE: y = fminf(fmaxf((x - min_level_db) / (-min_level_db), 0.f), 1.f); break;
+            default: y = fminf(fmaxf(x, 0.f), 1.f) * (-min_level_db) + min_level_db; break;
+        }
+        out[i] = y;
+    }
+}
+
+struct MelParams {
+    Plan plan;
+    Batch batch;
+    const float* in;     // linear magnitudes, packed per utterance, frame-major or bin-major
+    int bin_major;
+    double* out64;       // [frames][num_mels] frame-major (np.dot(basis f64, S) is float64)
+    float* out32;
+    int total_frames;
+};
+
+__global__ void __launch_bounds__(kThreads) k_linear_to_mel(MelParams P) {
+    __shared__ float row[kWarpsPerCta][kBins + 3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int f = blockIdx.x * kWarpsPerCta + warp; f < P.total_frames; f += gridDim.x * kWarpsPerCta) {
+        const int b = find_segment(P.batch.frame_off, P.batch.batch, f);
+        const int fo = __ldg(P.batch.frame_off + b);
+        const int T = __ldg(P.batch.frame_off + b + 1) - fo;
+        const float* base = P.in + (size_t)fo * kBins;
+        for (int kb = lane; kb < kBins; kb += 32)
+            row[warp][kb] = P.bin_major ? __ldg(base + (size_t)kb * T + (f - fo)) : __ldg(base + (size_t)(f - fo) * kBins + kb);
+        __syncwarp();
+        for (int m = lane; m < P.plan.num_mels; m += 32) {
+            const int lo = __ldg(P.plan.mel_lo + m), n = __ldg(P.plan.mel_n + m);
+            const float* w = P.plan.mel_w + __ldg(P.plan.mel_ptr + m);
+            double acc = 0.0;
+            for (int i = 0; i < n; ++i) acc = fma((double)__ldg(w + i), (double)row[warp][lo + i], acc);
+            if (P.out64) P.out64[(size_t)f * P.plan.num_mels + m] = acc; else P.out32[(size_t)f * P.plan.num_mels + m] = (float)acc;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace nsb

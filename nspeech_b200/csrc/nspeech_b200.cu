@@ -1,0 +1,724 @@
+// C-ABI implementation: handle, plans, workspaces, launches.  See include/nspeech_b200.h.
+#include <cmath>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/nspeech_b200.h"
+#include "kernels.cuh"
+
+using namespace nsb;
+
+// kernel launch: <<<>>> on the GPU; under NSB_EMULATE (tests/emu only) the CPU thread emulator
+#ifdef NSB_EMULATE
+#define NSB_LAUNCH(kern, grid, block, smem, st, ...) nsb_emu::launch((grid), (block), (smem), [&] { (kern)(__VA_ARGS__); })
+#else
+#define NSB_LAUNCH(kern, grid, block, smem, st, ...) (kern)<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__)
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? NSB_ERR_OOM : NSB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return NSB_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return fail(NSB_ERR_OOM, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e)); }
+        cap = want;
+        return NSB_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct nsb_handle_s {
+    int device = 0;
+    nsb_hparams hp{};
+    int n_fft = 0, hop = 0, win = 0, lo = 0, colours = 0, prune = 0, num_mels = 0;
+    int num_sms = 0;
+    int user_tile_hops = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t desc_done = nullptr;
+    // tables
+    float2* d_tw = nullptr;
+    float* d_win = nullptr;
+    float* d_mel_w = nullptr;
+    int *d_mel_lo = nullptr, *d_mel_n = nullptr, *d_mel_ptr = nullptr;
+    int* d_status = nullptr;
+    std::vector<double> mel_dense;   // [num_mels][num_freq]
+    // descriptors
+    DevBuf d_desc;
+    void* h_desc = nullptr;          // pinned
+    size_t h_desc_cap = 0;
+    // workspaces
+    DevBuf ws_mag, ws_y0, ws_y1, ws_in, ws_in2, ws_out, ws_out2;
+    // state of the last device-resident Griffin-Lim (for nsb_griffin_lim_iterate)
+    struct { bool valid = false; Batch batch{}; int total_frames = 0; int tile_hops = 0; int total_tiles = 0; int cur = 0; } gl;
+    unsigned long long launches = 0;
+    std::mutex mu;
+};
+
+static Plan make_plan(nsb_handle_s* h) {
+    Plan p;
+    p.tw = h->d_tw; p.win = h->d_win; p.mel_w = h->d_mel_w; p.mel_lo = h->d_mel_lo; p.mel_n = h->d_mel_n; p.mel_ptr = h->d_mel_ptr;
+    p.n_fft = h->n_fft; p.hop = h->hop; p.win_len = h->win; p.lo = h->lo; p.num_mels = h->num_mels; p.prune = h->prune;
+    return p;
+}
+
+// ---- librosa.filters.mel restated (Slaney scale, area normalisation) ---------------------------
+static double hz_to_mel(double f) {
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+    return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+static double mel_to_hz(double m) {
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+    return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+static void build_mel(int sr, int n_fft, int n_mels, std::vector<double>& dense) {
+    const int F = 1 + n_fft / 2;
+    dense.assign((size_t)n_mels * F, 0.0);
+    std::vector<double> mel_f(n_mels + 2), fftf(F);
+    const double fmax = sr / 2.0, mmin = hz_to_mel(0.0), mmax = hz_to_mel(fmax);
+    for (int i = 0; i < n_mels + 2; ++i) mel_f[i] = mel_to_hz(mmin + (mmax - mmin) * i / (n_mels + 1));
+    for (int k = 0; k < F; ++k) fftf[k] = fmax * k / (F - 1);
+    for (int i = 0; i < n_mels; ++i) {
+        const double fd0 = mel_f[i + 1] - mel_f[i], fd1 = mel_f[i + 2] - mel_f[i + 1];
+        const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+        for (int k = 0; k < F; ++k) {
+            double lower = -(mel_f[i] - fftf[k]) / fd0, upper = (mel_f[i + 2] - fftf[k]) / fd1;
+            double w = std::fmax(0.0, std::fmin(lower, upper));
+            dense[(size_t)i * F + k] = w * enorm;
+        }
+    }
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return NSB_OK;
+}
+
+static size_t analysis_smem() { return sizeof(float2) * kTwF2 + sizeof(float) * kNfft + sizeof(float2) * kScratchF2 * kWarpsPerCta; }
+static size_t synth_smem(int hop, int H) {
+    size_t fl = 2 * kTwF2 + kNfft + hop + (size_t)H * hop;
+    fl = (fl + 3) & ~(size_t)3;
+    return fl * sizeof(float) + sizeof(float2) * kScratchF2 * kWarpsPerCta;
+}
+static const size_t kSmemPerCtaTwoResident = (227 * 1024) / 2 - 1024;   // two CTAs per SM, 1 KB reserved each
+
+static int max_tile_hops(const nsb_handle_s* h) {
+    int H = 8 * h->colours - (h->colours - 1);           // one frame per warp per colour round
+    while (H > 1 && synth_smem(h->hop, H) > kSmemPerCtaTwoResident) --H;
+    return H;
+}
+
+extern "C" int nsb_abi_version(void) { return NSB_ABI_VERSION; }
+extern "C" const char* nsb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int nsb_device_count(int* count) {
+    if (!count) return fail(NSB_ERR_INVALID, "count is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; return fail(NSB_ERR_NODEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *count = n;
+    return NSB_OK;
+}
+
+extern "C" int nsb_destroy(nsb_handle_t h) {
+    if (!h) return NSB_OK;
+    cudaSetDevice(h->device);
+    if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
+    if (h->desc_done) cudaEventDestroy(h->desc_done);
+    cudaFree(h->d_tw); cudaFree(h->d_win); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo); cudaFree(h->d_mel_n); cudaFree(h->d_mel_ptr);
+    cudaFree(h->d_status);
+    if (h->h_desc) cudaFreeHost(h->h_desc);
+    h->d_desc.release(); h->ws_mag.release(); h->ws_y0.release(); h->ws_y1.release();
+    h->ws_in.release(); h->ws_in2.release(); h->ws_out.release(); h->ws_out2.release();
+    delete h;
+    return NSB_OK;
+}
+
+extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) {
+    if (!hp || !out) return fail(NSB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    // _stft_parameters, audio.py:126-130 (truncating int())
+    const int n_fft = (hp->num_freq - 1) * 2;
+    const int hop = (int)(hp->frame_shift_ms / 1000 * hp->sample_rate);
+    const int win = (int)(hp->frame_length_ms / 1000 * hp->sample_rate);
+    if (n_fft != kNfft) return fail(NSB_ERR_UNSUPPORTED, "num_freq=%d (n_fft=%d): only n_fft=2048 is implemented", hp->num_freq, n_fft);
+    if (win < 1 || win > n_fft) return fail(NSB_ERR_UNSUPPORTED, "win_length=%d must be in [1, n_fft]", win);
+    if (hop < 1) return fail(NSB_ERR_INVALID, "hop_length=%d must be >= 1", hop);
+    if (hp->num_mels < 1 || hp->num_mels > 1024) return fail(NSB_ERR_INVALID, "num_mels=%d out of range", hp->num_mels);
+    if (hp->min_level_db == 0.0) return fail(NSB_ERR_INVALID, "min_level_db must be non-zero");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(NSB_ERR_NODEVICE, "no CUDA device (%s); this library has no CPU path", e != cudaSuccess ? cudaGetErrorString(e) : "count=0");
+    if (device < 0 || device >= ndev) return fail(NSB_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(NSB_ERR_NODEVICE, "device %d is sm_%d%d; the kernels are built for sm_100a only", device, prop.major, prop.minor);
+    CU(cudaSetDevice(device));
+
+    nsb_handle_s* h = new nsb_handle_s();
+    h->device = device; h->hp = *hp; h->n_fft = n_fft; h->hop = hop; h->win = win; h->lo = (n_fft - win) / 2;
+    h->colours = (win + hop - 1) / hop;
+    h->prune = (h->lo >= 512 && h->lo + win <= 1536) ? 1 : 0;
+    h->num_mels = hp->num_mels;
+    h->num_sms = prop.multiProcessorCount;
+    int rc = NSB_OK;
+    auto bail = [&](int code) { nsb_destroy(h); return code; };
+#define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(NSB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); return bail(NSB_ERR_CUDA); } } while (0)
+    CUB(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&h->desc_done, cudaEventDisableTiming));
+    // twiddles w2048^(j*l), j = 1..31, l = 0..31, rounded from double
+    {
+        std::vector<float2> tw(kTwF2);
+        for (int j = 1; j < 32; ++j)
+            for (int l = 0; l < 32; ++l) {
+                double a = -2.0 * M_PI * (double)(j * l) / (double)kNfft;
+                tw[(j - 1) * 32 + l] = make_float2((float)std::cos(a), (float)std::sin(a));
+            }
+        CUB(cudaMalloc(&h->d_tw, sizeof(float2) * kTwF2));
+        CUB(cudaMemcpy(h->d_tw, tw.data(), sizeof(float2) * kTwF2, cudaMemcpyHostToDevice));
+    }
+    // periodic Hann (scipy.signal.get_window('hann', win, fftbins=True)) padded centrally (librosa.util.pad_center)
+    {
+        std::vector<float> w(kNfft, 0.f);
+        for (int i = 0; i < win; ++i) w[h->lo + i] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * i / win));
+        CUB(cudaMalloc(&h->d_win, sizeof(float) * kNfft));
+        CUB(cudaMemcpy(h->d_win, w.data(), sizeof(float) * kNfft, cudaMemcpyHostToDevice));
+    }
+    // sparse mel rows
+    {
+        build_mel(hp->sample_rate, n_fft, hp->num_mels, h->mel_dense);
+        std::vector<float> wts; std::vector<int> lo(hp->num_mels), n(hp->num_mels), ptr(hp->num_mels);
+        for (int m = 0; m < hp->num_mels; ++m) {
+            int first = -1, last = -1;
+            for (int k = 0; k < kBins; ++k) if (h->mel_dense[(size_t)m * kBins + k] != 0.0) { if (first < 0) first = k; last = k; }
+            if (first < 0) { first = 0; last = -1; }
+            lo[m] = first; n[m] = last - first + 1; ptr[m] = (int)wts.size();
+            for (int k = first; k <= last; ++k) wts.push_back((float)h->mel_dense[(size_t)m * kBins + k]);
+        }
+        if (wts.empty()) wts.push_back(0.f);
+        CUB(cudaMalloc(&h->d_mel_w, sizeof(float) * wts.size()));
+        CUB(cudaMemcpy(h->d_mel_w, wts.data(), sizeof(float) * wts.size(), cudaMemcpyHostToDevice));
+        CUB(cudaMalloc(&h->d_mel_lo, sizeof(int) * lo.size()));
+        CUB(cudaMemcpy(h->d_mel_lo, lo.data(), sizeof(int) * lo.size(), cudaMemcpyHostToDevice));
+        CUB(cudaMalloc(&h->d_mel_n, sizeof(int) * n.size()));
+        CUB(cudaMemcpy(h->d_mel_n, n.data(), sizeof(int) * n.size(), cudaMemcpyHostToDevice));
+        CUB(cudaMalloc(&h->d_mel_ptr, sizeof(int) * ptr.size()));
+        CUB(cudaMemcpy(h->d_mel_ptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice));
+    }
+    CUB(cudaMalloc(&h->d_status, sizeof(int)));
+    CUB(cudaMemset(h->d_status, 0, sizeof(int)));
+    // opt in to the large dynamic shared memory of every instantiation
+    const size_t as = analysis_smem(), ss = synth_smem(hop, max_tile_hops(h));
+#define SET(k, b) do { rc = set_smem(k, b); if (rc) return bail(rc); } while (0)
+    SET((k_analysis<ANALYSIS_COMPLEX, false, false>), as); SET((k_analysis<ANALYSIS_COMPLEX, false, true>), as);
+    SET((k_analysis<ANALYSIS_COMPLEX, true, false>), as);  SET((k_analysis<ANALYSIS_COMPLEX, true, true>), as);
+    SET((k_analysis<ANALYSIS_FEATURES, true, false>), as); SET((k_analysis<ANALYSIS_FEATURES, true, true>), as);
+    SET((k_synth<SRC_Y, false>), ss);        SET((k_synth<SRC_Y, true>), ss);
+    SET((k_synth<SRC_SPEC, false>), ss);     SET((k_synth<SRC_SPEC, true>), ss);
+    SET((k_synth<SRC_MAGPHASE, false>), ss); SET((k_synth<SRC_MAGPHASE, true>), ss);
+    SET((k_synth<SRC_MAGRAND, false>), ss);  SET((k_synth<SRC_MAGRAND, true>), ss);
+#undef SET
+#undef CUB
+    *out = h;
+    return NSB_OK;
+}
+
+extern "C" int nsb_stft_parameters(nsb_handle_t h, int32_t* n_fft, int32_t* hop, int32_t* win) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    if (n_fft) *n_fft = h->n_fft;
+    if (hop) *hop = h->hop;
+    if (win) *win = h->win;
+    return NSB_OK;
+}
+extern "C" int64_t nsb_num_frames(nsb_handle_t h, int64_t n) { return h ? 1 + n / h->hop : -1; }
+extern "C" int64_t nsb_num_samples(nsb_handle_t h, int64_t T) { return h ? (int64_t)h->hop * (T - 1) : -1; }
+extern "C" uint64_t nsb_kernel_launches(nsb_handle_t h) { return h ? h->launches : 0; }
+extern "C" int nsb_set_tile_hops(nsb_handle_t h, int32_t t) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    if (t < 0 || t > max_tile_hops(h)) return fail(NSB_ERR_INVALID, "tile_hops %d outside [0,%d]", t, max_tile_hops(h));
+    h->user_tile_hops = t;
+    return NSB_OK;
+}
+extern "C" int nsb_mel_basis(nsb_handle_t h, double* out) {
+    if (!h || !out) return fail(NSB_ERR_INVALID, "null argument");
+    memcpy(out, h->mel_dense.data(), sizeof(double) * h->mel_dense.size());
+    return NSB_OK;
+}
+
+static cudaStream_t pick_stream(nsb_handle_s* h, void* stream) { return stream ? (cudaStream_t)stream : h->own_stream; }
+
+extern "C" int nsb_synchronize(nsb_handle_t h, void* stream) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(pick_stream(h, stream)));
+    return NSB_OK;
+}
+
+static int read_status(nsb_handle_s* h, cudaStream_t st) {
+    int flag = 0;
+    CU(cudaMemcpyAsync(&flag, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (flag) {
+        CU(cudaMemsetAsync(h->d_status, 0, sizeof(int), st));
+        return fail(NSB_ERR_NONFINITE, "Audio buffer is not finite everywhere");
+    }
+    return NSB_OK;
+}
+extern "C" int nsb_check_status(nsb_handle_t h, void* stream) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    return read_status(h, pick_stream(h, stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// ragged-batch descriptors: frame_off[B+1] (int), tile_off[B+1] (int), samp_off[B+1] (int64)
+// ---------------------------------------------------------------------------------------------
+struct Desc {
+    Batch dev;
+    long long total_samples = 0;
+    int total_frames = 0;
+    int total_tiles = 0;
+};
+
+static int upload_desc(nsb_handle_s* h, cudaStream_t st, const std::vector<int>& frames, const std::vector<long long>& samples,
+                       int tile_hops, Desc* d) {
+    const int B = (int)frames.size();
+    const size_t n_int = 2 * (size_t)(B + 1);
+    const size_t bytes = ((n_int * sizeof(int) + 7) & ~(size_t)7) + (size_t)(B + 1) * sizeof(long long);
+    if (bytes > h->h_desc_cap) {
+        if (h->h_desc) { CU(cudaEventSynchronize(h->desc_done)); cudaFreeHost(h->h_desc); h->h_desc = nullptr; h->h_desc_cap = 0; }
+        CU(cudaHostAlloc(&h->h_desc, bytes * 2, cudaHostAllocDefault));
+        h->h_desc_cap = bytes * 2;
+    } else {
+        CU(cudaEventSynchronize(h->desc_done));   // the previous upload must have left the pinned buffer
+    }
+    int rc = h->d_desc.reserve(bytes);
+    if (rc) return rc;
+    int* fo = reinterpret_cast<int*>(h->h_desc);
+    int* to = fo + (B + 1);
+    long long* so = reinterpret_cast<long long*>(reinterpret_cast<char*>(h->h_desc) + ((n_int * sizeof(int) + 7) & ~(size_t)7));
+    fo[0] = 0; to[0] = 0; so[0] = 0;
+    for (int b = 0; b < B; ++b) {
+        long long nf = (long long)fo[b] + frames[b];
+        if (nf > 2000000000LL) return fail(NSB_ERR_INVALID, "batch too large: more than 2e9 frames");
+        fo[b + 1] = (int)nf;
+        int tiles = 0;
+        if (tile_hops > 0) { int hops = frames[b] - 1; tiles = hops > 0 ? (hops + tile_hops - 1) / tile_hops : 0; }
+        to[b + 1] = to[b] + tiles;
+        so[b + 1] = so[b] + samples[b];
+    }
+    CU(cudaMemcpyAsync(h->d_desc.p, h->h_desc, bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(h->desc_done, st));
+    d->dev.frame_off = reinterpret_cast<const int*>(h->d_desc.p);
+    d->dev.tile_off = d->dev.frame_off + (B + 1);
+    d->dev.samp_off = reinterpret_cast<const long long*>(reinterpret_cast<const char*>(h->d_desc.p) + ((n_int * sizeof(int) + 7) & ~(size_t)7));
+    d->dev.batch = B;
+    d->total_frames = fo[B];
+    d->total_tiles = to[B];
+    d->total_samples = so[B];
+    return NSB_OK;
+}
+
+static int check_launch(nsb_handle_s* h, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(NSB_ERR_CUDA, "launch %s: %s", what, cudaGetErrorString(e));
+    ++h->launches;
+    return NSB_OK;
+}
+
+static int grid_1d(long long n, int threads, int max_blocks) {
+    long long g = (n + threads - 1) / threads;
+    if (g < 1) g = 1;
+    if (g > max_blocks) g = max_blocks;
+    return (int)g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// analysis entry points
+// ---------------------------------------------------------------------------------------------
+static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wav, const int64_t* n_samples, int batch,
+                        float* out_complex, float* lin_out, float* mel_out, int space, void* stream) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    if (!wav || !n_samples || batch < 1) return fail(NSB_ERR_INVALID, "null/empty input");
+    if (mode == ANALYSIS_COMPLEX && !out_complex) return fail(NSB_ERR_INVALID, "out_complex is null");
+    if (mode == ANALYSIS_FEATURES && !lin_out && !mel_out) return fail(NSB_ERR_INVALID, "both outputs are null");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = pick_stream(h, stream);
+    std::vector<int> frames(batch);
+    std::vector<long long> samples(batch);
+    for (int b = 0; b < batch; ++b) {
+        if (n_samples[b] < 1) return fail(NSB_ERR_INVALID, "utterance %d is empty", b);
+        samples[b] = n_samples[b];
+        frames[b] = (int)(1 + n_samples[b] / h->hop);
+    }
+    Desc d;
+    int rc = upload_desc(h, st, frames, samples, 0, &d);
+    if (rc) return rc;
+    const size_t F = kBins, M = h->num_mels;
+    const float* d_wav = wav;
+    float2* d_c = reinterpret_cast<float2*>(out_complex);
+    float *d_lin = lin_out, *d_mel = mel_out;
+    if (space == NSB_HOST) {
+        if ((rc = h->ws_in.reserve(sizeof(float) * d.total_samples))) return rc;
+        CU(cudaMemcpyAsync(h->ws_in.p, wav, sizeof(float) * d.total_samples, cudaMemcpyHostToDevice, st));
+        d_wav = reinterpret_cast<const float*>(h->ws_in.p);
+        if (mode == ANALYSIS_COMPLEX) {
+            if ((rc = h->ws_out.reserve(sizeof(float2) * F * d.total_frames))) return rc;
+            d_c = reinterpret_cast<float2*>(h->ws_out.p);
+        } else {
+            if (lin_out) { if ((rc = h->ws_out.reserve(sizeof(float) * F * d.total_frames))) return rc; d_lin = reinterpret_cast<float*>(h->ws_out.p); }
+            if (mel_out) { if ((rc = h->ws_out2.reserve(sizeof(float) * M * d.total_frames))) return rc; d_mel = reinterpret_cast<float*>(h->ws_out2.p); }
+        }
+    }
+    AnalysisParams P;
+    P.plan = make_plan(h); P.batch = d.dev; P.wav = d_wav; P.out_complex = d_c; P.out_lin = d_lin; P.out_mel = d_mel;
+    P.total_frames = d.total_frames; P.preemph = (float)h->hp.preemphasis;
+    P.ref_level_db = (float)h->hp.ref_level_db; P.min_level_db = (float)h->hp.min_level_db; P.status = h->d_status;
+    const int grid = grid_1d(d.total_frames, kWarpsPerCta, 2 * h->num_sms);
+    const size_t smem = analysis_smem();
+    if (mode == ANALYSIS_COMPLEX) {
+        if (preemph) {
+            if (h->prune) NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, true, true>), grid, kThreads, smem, st, P);
+            else NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, true, false>), grid, kThreads, smem, st, P);
+        } else {
+            if (h->prune) NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, false, true>), grid, kThreads, smem, st, P);
+            else NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, false, false>), grid, kThreads, smem, st, P);
+        }
+    } else {
+        if (h->prune) NSB_LAUNCH((k_analysis<ANALYSIS_FEATURES, true, true>), grid, kThreads, smem, st, P);
+        else NSB_LAUNCH((k_analysis<ANALYSIS_FEATURES, true, false>), grid, kThreads, smem, st, P);
+    }
+    if ((rc = check_launch(h, "k_analysis"))) return rc;
+    if (space == NSB_HOST) {
+        if (mode == ANALYSIS_COMPLEX) CU(cudaMemcpyAsync(out_complex, d_c, sizeof(float2) * F * d.total_frames, cudaMemcpyDeviceToHost, st));
+        else {
+            if (lin_out) CU(cudaMemcpyAsync(lin_out, d_lin, sizeof(float) * F * d.total_frames, cudaMemcpyDeviceToHost, st));
+            if (mel_out) CU(cudaMemcpyAsync(mel_out, d_mel, sizeof(float) * M * d.total_frames, cudaMemcpyDeviceToHost, st));
+        }
+        return read_status(h, st);
+    }
+    return NSB_OK;
+}
+
+extern "C" int nsb_stft(nsb_handle_t h, const float* wav, const int64_t* n_samples, int32_t batch, int32_t apply_preemphasis,
+                        float* out_complex, int32_t space, void* stream) {
+    return run_analysis(h, ANALYSIS_COMPLEX, apply_preemphasis != 0, wav, n_samples, batch, out_complex, nullptr, nullptr, space, stream);
+}
+extern "C" int nsb_features(nsb_handle_t h, const float* wav, const int64_t* n_samples, int32_t batch,
+                            float* lin_out, float* mel_out, int32_t space, void* stream) {
+    return run_analysis(h, ANALYSIS_FEATURES, true, wav, n_samples, batch, nullptr, lin_out, mel_out, space, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// synthesis entry points
+// ---------------------------------------------------------------------------------------------
+static int choose_tile_hops(nsb_handle_s* h, const int32_t* n_frames, int batch) {
+    const int Hmax = max_tile_hops(h);
+    if (h->user_tile_hops > 0) return h->user_tile_hops < Hmax ? h->user_tile_hops : Hmax;
+    long long hops = 0;
+    for (int b = 0; b < batch; ++b) hops += n_frames[b] - 1;
+    // enough tiles to cover every SM twice when the batch is small; never below one colour cycle
+    long long want = 2LL * h->num_sms;
+    int H = (int)((hops + want - 1) / want);
+    if (H < h->colours) H = h->colours;
+    if (H > Hmax) H = Hmax;
+    return H;
+}
+
+template <int SRC>
+static void launch_synth(nsb_handle_s* h, const SynthParams& P, int grid, size_t smem, cudaStream_t st) {
+    if (h->prune) NSB_LAUNCH((k_synth<SRC, true>), grid, kThreads, smem, st, P);
+    else NSB_LAUNCH((k_synth<SRC, false>), grid, kThreads, smem, st, P);
+}
+
+static int validate_frames(nsb_handle_s* h, const int32_t* n_frames, int batch, std::vector<int>& frames, std::vector<long long>& samples) {
+    frames.resize(batch); samples.resize(batch);
+    for (int b = 0; b < batch; ++b) {
+        if (n_frames[b] < 2) return fail(NSB_ERR_INVALID, "utterance %d has %d frame(s); inversion needs at least 2", b, n_frames[b]);
+        frames[b] = n_frames[b];
+        samples[b] = (long long)h->hop * (n_frames[b] - 1);
+    }
+    return NSB_OK;
+}
+
+extern "C" int nsb_istft(nsb_handle_t h, const float* spec, int32_t layout, const int32_t* n_frames, int32_t batch,
+                         float* wav_out, int32_t space, void* stream) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    if (!spec || !n_frames || !wav_out || batch < 1) return fail(NSB_ERR_INVALID, "null/empty argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = pick_stream(h, stream);
+    std::vector<int> frames; std::vector<long long> samples;
+    int rc = validate_frames(h, n_frames, batch, frames, samples);
+    if (rc) return rc;
+    const int H = choose_tile_hops(h, n_frames, batch);
+    Desc d;
+    if ((rc = upload_desc(h, st, frames, samples, H, &d))) return rc;
+    const float2* d_spec = reinterpret_cast<const float2*>(spec);
+    float* d_out = wav_out;
+    if (space == NSB_HOST) {
+        if ((rc = h->ws_in.reserve(sizeof(float2) * kBins * (size_t)d.total_frames))) return rc;
+        if ((rc = h->ws_out.reserve(sizeof(float) * d.total_samples))) return rc;
+        CU(cudaMemcpyAsync(h->ws_in.p, spec, sizeof(float2) * kBins * (size_t)d.total_frames, cudaMemcpyHostToDevice, st));
+        d_spec = reinterpret_cast<const float2*>(h->ws_in.p);
+        d_out = reinterpret_cast<float*>(h->ws_out.p);
+    }
+    h->gl.valid = false;
+    SynthParams P{};
+    P.plan = make_plan(h); P.batch = d.dev; P.spec = d_spec; P.spec_bin_major = (layout == NSB_BIN_MAJOR);
+    P.y_out = d_out; P.tile_hops = H; P.colours = h->colours; P.status = h->d_status; P.mag = nullptr;
+    launch_synth<SRC_SPEC>(h, P, d.total_tiles, synth_smem(h->hop, H), st);
+    if ((rc = check_launch(h, "k_synth<SPEC>"))) return rc;
+    if (space == NSB_HOST) {
+        CU(cudaMemcpyAsync(wav_out, d_out, sizeof(float) * d.total_samples, cudaMemcpyDeviceToHost, st));
+        return read_status(h, st);
+    }
+    return NSB_OK;
+}
+
+static int gl_iterations(nsb_handle_s* h, int iters, cudaStream_t st) {
+    SynthParams P{};
+    P.plan = make_plan(h); P.batch = h->gl.batch; P.mag = reinterpret_cast<const float*>(h->ws_mag.p);
+    P.tile_hops = h->gl.tile_hops; P.colours = h->colours; P.status = h->d_status;
+    const size_t smem = synth_smem(h->hop, h->gl.tile_hops);
+    float* y[2] = {reinterpret_cast<float*>(h->ws_y0.p), reinterpret_cast<float*>(h->ws_y1.p)};
+    for (int it = 0; it < iters; ++it) {
+        P.y_in = y[h->gl.cur]; P.y_out = y[h->gl.cur ^ 1];
+        launch_synth<SRC_Y>(h, P, h->gl.total_tiles, smem, st);
+        int rc = check_launch(h, "k_synth<Y>");
+        if (rc) return rc;
+        h->gl.cur ^= 1;
+    }
+    return NSB_OK;
+}
+
+extern "C" int nsb_griffin_lim_iterate(nsb_handle_t h, int32_t iters, void* stream) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->gl.valid) return fail(NSB_ERR_INVALID, "no device-resident Griffin-Lim state (call nsb_griffin_lim with NSB_DEVICE first)");
+    CU(cudaSetDevice(h->device));
+    return gl_iterations(h, iters, pick_stream(h, stream));
+}
+
+extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout, const int32_t* n_frames, int32_t batch,
+                               const float* init_phase, uint64_t seed, int32_t iters, int32_t flags,
+                               void* wav_out, int32_t out_dtype, int32_t space, void* stream) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    if (!spec || !n_frames || !wav_out || batch < 1) return fail(NSB_ERR_INVALID, "null/empty argument");
+    if (out_dtype != NSB_F32 && out_dtype != NSB_F64) return fail(NSB_ERR_INVALID, "bad out_dtype");
+    if (iters < 0) iters = h->hp.griffin_lim_iters;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = pick_stream(h, stream);
+    std::vector<int> frames; std::vector<long long> samples;
+    int rc = validate_frames(h, n_frames, batch, frames, samples);
+    if (rc) return rc;
+    const int H = choose_tile_hops(h, n_frames, batch);
+    Desc d;
+    if ((rc = upload_desc(h, st, frames, samples, H, &d))) return rc;
+    const size_t n_spec = (size_t)kBins * d.total_frames;
+    const float* d_spec = spec;
+    const float2* d_phase = reinterpret_cast<const float2*>(init_phase);
+    const size_t out_elt = out_dtype == NSB_F64 ? sizeof(double) : sizeof(float);
+    void* d_out = wav_out;
+    if (space == NSB_HOST) {
+        if ((rc = h->ws_in.reserve(sizeof(float) * n_spec))) return rc;
+        CU(cudaMemcpyAsync(h->ws_in.p, spec, sizeof(float) * n_spec, cudaMemcpyHostToDevice, st));
+        d_spec = reinterpret_cast<const float*>(h->ws_in.p);
+        if (init_phase) {
+            if ((rc = h->ws_in2.reserve(sizeof(float2) * n_spec))) return rc;
+            CU(cudaMemcpyAsync(h->ws_in2.p, init_phase, sizeof(float2) * n_spec, cudaMemcpyHostToDevice, st));
+            d_phase = reinterpret_cast<const float2*>(h->ws_in2.p);
+        }
+        if ((rc = h->ws_out.reserve(out_elt * d.total_samples))) return rc;
+        d_out = h->ws_out.p;
+    }
+    if ((rc = h->ws_mag.reserve(sizeof(float) * kMagPitch * (size_t)d.total_frames))) return rc;
+    if ((rc = h->ws_y0.reserve(sizeof(float) * d.total_samples))) return rc;
+    if ((rc = h->ws_y1.reserve(sizeof(float) * d.total_samples))) return rc;
+
+    // S = _db_to_amp(_denormalize(spec) + ref_level_db) ** power   (or |S| for _griffin_lim), permuted layout
+    PrepParams Q{};
+    Q.batch = d.dev; Q.in = d_spec; Q.bin_major = (layout == NSB_BIN_MAJOR); Q.denorm = (flags & NSB_GL_DENORMALIZE) ? 1 : 0;
+    Q.min_level_db = h->hp.min_level_db; Q.ref_level_db = h->hp.ref_level_db; Q.power = h->hp.power;
+    Q.mag = reinterpret_cast<float*>(h->ws_mag.p); Q.total_frames = d.total_frames; Q.status = h->d_status;
+    CU(cudaMemsetAsync(h->ws_mag.p, 0, sizeof(float) * kMagPitch * (size_t)d.total_frames, st));
+    NSB_LAUNCH(k_prepare_mag, (d.total_frames + 31) / 32, 256, 0, st, Q);
+    if ((rc = check_launch(h, "k_prepare_mag"))) return rc;
+
+    // y0 = _istft(S * angles)
+    h->gl.valid = true; h->gl.batch = d.dev; h->gl.total_frames = d.total_frames; h->gl.tile_hops = H;
+    h->gl.total_tiles = d.total_tiles; h->gl.cur = 0;
+    SynthParams P{};
+    P.plan = make_plan(h); P.batch = d.dev; P.mag = Q.mag; P.spec = d_phase; P.spec_bin_major = (layout == NSB_BIN_MAJOR);
+    P.y_out = reinterpret_cast<float*>(h->ws_y0.p); P.tile_hops = H; P.colours = h->colours; P.seed = seed; P.status = h->d_status;
+    const size_t smem = synth_smem(h->hop, H);
+    if (init_phase) launch_synth<SRC_MAGPHASE>(h, P, d.total_tiles, smem, st);
+    else launch_synth<SRC_MAGRAND>(h, P, d.total_tiles, smem, st);
+    if ((rc = check_launch(h, "k_synth<init>"))) return rc;
+
+    if ((rc = gl_iterations(h, iters, st))) return rc;
+    const float* y_fin = reinterpret_cast<const float*>(h->gl.cur ? h->ws_y1.p : h->ws_y0.p);
+
+    if (flags & NSB_GL_DEEMPHASIS) {
+        EmphParams E{};
+        E.batch = d.dev; E.in = y_fin; E.p = h->hp.preemphasis;
+        if (out_dtype == NSB_F64) E.out64 = reinterpret_cast<double*>(d_out); else E.out32 = reinterpret_cast<float*>(d_out);
+        NSB_LAUNCH(k_deemphasis, batch, kDeemphThreads, 0, st, E);
+        if ((rc = check_launch(h, "k_deemphasis"))) return rc;
+    } else if (out_dtype == NSB_F32) {
+        CU(cudaMemcpyAsync(d_out, y_fin, sizeof(float) * d.total_samples, cudaMemcpyDeviceToDevice, st));
+    } else {
+        return fail(NSB_ERR_INVALID, "NSB_F64 output without NSB_GL_DEEMPHASIS is not provided (_griffin_lim returns float32)");
+    }
+    if (space == NSB_HOST) {
+        CU(cudaMemcpyAsync(wav_out, d_out, out_elt * d.total_samples, cudaMemcpyDeviceToHost, st));
+        return read_status(h, st);
+    }
+    return NSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small helpers of the module
+// ---------------------------------------------------------------------------------------------
+static int run_emph(nsb_handle_s* h, bool inverse, const float* x, const int64_t* n_samples, int batch, void* out, int out_dtype,
+                    int space, void* stream) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    if (!x || !n_samples || !out || batch < 1) return fail(NSB_ERR_INVALID, "null/empty argument");
+    if (out_dtype != NSB_F32 && out_dtype != NSB_F64) return fail(NSB_ERR_INVALID, "bad out_dtype");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = pick_stream(h, stream);
+    std::vector<int> frames(batch, 1);
+    std::vector<long long> samples(batch);
+    for (int b = 0; b < batch; ++b) { if (n_samples[b] < 0) return fail(NSB_ERR_INVALID, "negative length"); samples[b] = n_samples[b]; }
+    Desc d;
+    int rc = upload_desc(h, st, frames, samples, 0, &d);
+    if (rc) return rc;
+    if (d.total_samples == 0) return NSB_OK;
+    const size_t out_elt = out_dtype == NSB_F64 ? sizeof(double) : sizeof(float);
+    const float* d_x = x;
+    void* d_out = out;
+    if (space == NSB_HOST) {
+        if ((rc = h->ws_in.reserve(sizeof(float) * d.total_samples))) return rc;
+        if ((rc = h->ws_out.reserve(out_elt * d.total_samples))) return rc;
+        CU(cudaMemcpyAsync(h->ws_in.p, x, sizeof(float) * d.total_samples, cudaMemcpyHostToDevice, st));
+        d_x = reinterpret_cast<const float*>(h->ws_in.p);
+        d_out = h->ws_out.p;
+    }
+    EmphParams E{};
+    E.batch = d.dev; E.in = d_x; E.p = h->hp.preemphasis;
+    if (out_dtype == NSB_F64) E.out64 = reinterpret_cast<double*>(d_out); else E.out32 = reinterpret_cast<float*>(d_out);
+    if (inverse) NSB_LAUNCH(k_deemphasis, batch, kDeemphThreads, 0, st, E);
+    else NSB_LAUNCH(k_preemphasis, grid_1d(d.total_samples, 256, 4 * h->num_sms), 256, 0, st, E, d.total_samples);
+    if ((rc = check_launch(h, inverse ? "k_deemphasis" : "k_preemphasis"))) return rc;
+    if (space == NSB_HOST) {
+        CU(cudaMemcpyAsync(out, d_out, out_elt * d.total_samples, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return NSB_OK;
+}
+extern "C" int nsb_preemphasis(nsb_handle_t h, const float* x, const int64_t* n, int32_t batch, void* out, int32_t dt, int32_t space, void* stream) {
+    return run_emph(h, false, x, n, batch, out, dt, space, stream);
+}
+extern "C" int nsb_inv_preemphasis(nsb_handle_t h, const float* x, const int64_t* n, int32_t batch, void* out, int32_t dt, int32_t space, void* stream) {
+    return run_emph(h, true, x, n, batch, out, dt, space, stream);
+}
+
+extern "C" int nsb_linear_to_mel(nsb_handle_t h, const float* spec, int32_t layout, const int32_t* n_frames, int32_t batch,
+                                 void* out, int32_t out_dtype, int32_t space, void* stream) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    if (!spec || !n_frames || !out || batch < 1) return fail(NSB_ERR_INVALID, "null/empty argument");
+    if (out_dtype != NSB_F32 && out_dtype != NSB_F64) return fail(NSB_ERR_INVALID, "bad out_dtype");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = pick_stream(h, stream);
+    std::vector<int> frames(batch);
+    std::vector<long long> samples(batch, 0);
+    for (int b = 0; b < batch; ++b) { if (n_frames[b] < 1) return fail(NSB_ERR_INVALID, "utterance %d has no frames", b); frames[b] = n_frames[b]; }
+    Desc d;
+    int rc = upload_desc(h, st, frames, samples, 0, &d);
+    if (rc) return rc;
+    const size_t out_elt = out_dtype == NSB_F64 ? sizeof(double) : sizeof(float);
+    const size_t n_in = (size_t)kBins * d.total_frames, n_out = (size_t)h->num_mels * d.total_frames;
+    const float* d_in = spec;
+    void* d_out = out;
+    if (space == NSB_HOST) {
+        if ((rc = h->ws_in.reserve(sizeof(float) * n_in))) return rc;
+        if ((rc = h->ws_out.reserve(out_elt * n_out))) return rc;
+        CU(cudaMemcpyAsync(h->ws_in.p, spec, sizeof(float) * n_in, cudaMemcpyHostToDevice, st));
+        d_in = reinterpret_cast<const float*>(h->ws_in.p);
+        d_out = h->ws_out.p;
+    }
+    MelParams M{};
+    M.plan = make_plan(h); M.batch = d.dev; M.in = d_in; M.bin_major = (layout == NSB_BIN_MAJOR); M.total_frames = d.total_frames;
+    if (out_dtype == NSB_F64) M.out64 = reinterpret_cast<double*>(d_out); else M.out32 = reinterpret_cast<float*>(d_out);
+    NSB_LAUNCH(k_linear_to_mel, grid_1d(d.total_frames, kWarpsPerCta, 4 * h->num_sms), kThreads, 0, st, M);
+    if ((rc = check_launch(h, "k_linear_to_mel"))) return rc;
+    if (space == NSB_HOST) {
+        CU(cudaMemcpyAsync(out, d_out, out_elt * n_out, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return NSB_OK;
+}
+
+extern "C" int nsb_elementwise(nsb_handle_t h, int32_t op, const float* in, int64_t n, float* out, int32_t space, void* stream) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    if (op < 0 || op > 3) return fail(NSB_ERR_INVALID, "bad op %d", op);
+    if (n < 0 || (n > 0 && (!in || !out))) return fail(NSB_ERR_INVALID, "null/negative argument");
+    if (n == 0) return NSB_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = pick_stream(h, stream);
+    const float* d_in = in;
+    float* d_out = out;
+    int rc;
+    if (space == NSB_HOST) {
+        if ((rc = h->ws_in.reserve(sizeof(float) * n))) return rc;
+        if ((rc = h->ws_out.reserve(sizeof(float) * n))) return rc;
+        CU(cudaMemcpyAsync(h->ws_in.p, in, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+        d_in = reinterpret_cast<const float*>(h->ws_in.p);
+        d_out = reinterpret_cast<float*>(h->ws_out.p);
+    }
+    NSB_LAUNCH(k_elementwise, grid_1d(n, 256, 8 * h->num_sms), 256, 0, st, op, d_in, d_out, n, (float)h->hp.min_level_db);
+    if ((rc = check_launch(h, "k_elementwise"))) return rc;
+    if (space == NSB_HOST) {
+        CU(cudaMemcpyAsync(out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return NSB_OK;
+}
