@@ -130,6 +130,11 @@ int nsb_elementwise(nsb_handle_t h, int32_t op, const float* in, int64_t n, floa
 /* deferred device-side error flag of NSB_DEVICE calls (bit 0: non-finite data seen); synchronises; clears it */
 int nsb_check_status(nsb_handle_t h, void* stream);
 
+/* page-locked host buffers for the NSB_HOST entry points (plain cudaHostAlloc / cudaFreeHost): copies from
+ * pageable numpy memory are staged by the driver and reach only a fraction of PCIe bandwidth */
+int nsb_alloc_pinned(uint64_t bytes, void** out);
+int nsb_free_pinned(void* p);
+
 /* tuning / accounting hooks (not in the reference) */
 int nsb_set_tile_hops(nsb_handle_t h, int32_t tile_hops);       /* 0 = automatic */
 uint64_t nsb_kernel_launches(nsb_handle_t h);                    /* kernels launched through this handle so far */

@@ -64,6 +64,8 @@ SIGNATURES = {
     "nsb_set_tile_hops": (ctypes.c_int, [_vp, _i32]),
     "nsb_kernel_launches": (_u64, [_vp]),
     "nsb_griffin_lim_iterate": (ctypes.c_int, [_vp, _i32, _vp]),
+    "nsb_alloc_pinned": (ctypes.c_int, [_u64, ctypes.POINTER(_vp)]),
+    "nsb_free_pinned": (ctypes.c_int, [_vp]),
 }
 
 
@@ -97,6 +99,32 @@ class NativeLib(object):
         n = ctypes.c_int(0)
         rc = self.dll.nsb_device_count(ctypes.byref(n))
         return n.value if rc == NSB_OK else 0
+
+
+class PinnedArray(object):
+    """numpy view of a cudaHostAlloc'ed buffer; keep the object alive as long as the view is used."""
+
+    def __init__(self, shape, dtype, lib=None):
+        self.lib = default_lib() if lib is None else lib
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = ctypes.c_void_p()
+        self.lib.check(self.lib.dll.nsb_alloc_pinned(ctypes.c_uint64(n), ctypes.byref(p)))
+        self._p = p
+        buf = (ctypes.c_char * max(n, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._p is not None and self._p.value:
+            self.array = None
+            self.lib.dll.nsb_free_pinned(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 _default = None

@@ -151,6 +151,17 @@ extern "C" int nsb_device_count(int* count) {
     return NSB_OK;
 }
 
+extern "C" int nsb_alloc_pinned(uint64_t bytes, void** out) {
+    if (!out) return fail(NSB_ERR_INVALID, "out is null");
+    *out = nullptr;
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return NSB_OK;
+}
+extern "C" int nsb_free_pinned(void* p) {
+    if (p) CU(cudaFreeHost(p));
+    return NSB_OK;
+}
+
 extern "C" int nsb_destroy(nsb_handle_t h) {
     if (!h) return NSB_OK;
     cudaSetDevice(h->device);

@@ -1,0 +1,169 @@
+"""Parity checks shared by the CPU-emulated run (tests/test_emulated_kernels.py) and the real-GPU run
+(tests/test_gpu_parity.py).  Each function drives the product's Python mirror (nspeech_b200.audio) - which
+binds whichever native library the caller selected - and compares with the oracle on the same inputs."""
+import numpy as np
+import pytest
+
+from conftest import make_hp, speechlike
+from nspeech_b200 import _lib, audio, hparams
+from oracle import audio_oracle as ao
+
+CONFIGS = [{"min_level_db": -100}, {}, {"min_level_db": -100, "sample_rate": 22050}]
+
+
+def _load(**over):
+    hp = hparams.load()
+    if over:
+        hp.parse(",".join("%s=%s" % kv for kv in over.items()))
+    return make_hp(**over)
+
+
+def check_single_ops_vs_oracle(over):
+    ohp = _load(**over)
+    assert audio._stft_parameters() == ao._stft_parameters(ohp)
+    wav = speechlike(4100, 1)
+    D = audio._stft(wav)
+    Dref = ao._stft(wav.astype(np.float64), ohp)
+    assert D.shape == Dref.shape and D.dtype == np.complex64 and D.flags.f_contiguous
+    assert ao.rel_l2(D, Dref) < 1e-5            # BASELINE.json: single STFT within 1e-5 rel L2
+    y = audio._istft(Dref)
+    yref = ao._istft(Dref, ohp)
+    assert y.dtype == np.float32 and y.shape == yref.shape
+    assert ao.rel_l2(y, yref) < 1e-5
+    assert ao.rel_l2(audio._istft(np.ascontiguousarray(Dref)), yref) < 1e-5   # bin-major input
+    lin, mel = audio.spectrogram_and_mel(wav)
+    assert lin.shape == (1025, D.shape[1]) and mel.shape == (80, D.shape[1]) and lin.dtype == np.float32
+    assert ao.rel_l2(lin, ao.spectrogram(wav, ohp)) < 1e-5
+    assert ao.rel_l2(mel, ao.melspectrogram(wav, ohp)) < 1e-5
+    np.testing.assert_array_equal(audio.spectrogram(wav), lin)
+    np.testing.assert_array_equal(audio.melspectrogram(wav), mel)
+    M = np.abs(Dref)
+    assert ao.rel_l2(audio._linear_to_mel(M), ao._linear_to_mel(M, ohp)) < 1e-6
+    assert np.abs(audio._build_mel_basis() - ao._build_mel_basis(ohp)).max() < 1e-12
+    x = speechlike(7001, 3)
+    pe, de = audio.preemphasis(x), audio.inv_preemphasis(x)
+    assert pe.dtype == np.float64 and de.dtype == np.float64
+    assert ao.rel_l2(pe, ao.preemphasis(x, ohp)) < 1e-12
+    assert ao.rel_l2(de, ao.inv_preemphasis(x, ohp)) < 1e-12
+    v = (np.random.RandomState(5).randn(777) * 50).astype(np.float32)
+    assert ao.rel_l2(audio._amp_to_db(np.abs(v)), ao._amp_to_db(np.abs(v))) < 1e-6
+    assert ao.rel_l2(audio._db_to_amp(v), ao._db_to_amp(v)) < 1e-6
+    assert ao.rel_l2(audio._normalize(v), ao._normalize(v, ohp)) < 1e-6
+    assert ao.rel_l2(audio._denormalize(v / 50), ao._denormalize(v / 50, ohp)) < 1e-6
+
+
+def check_griffin_lim_vs_oracle(over):
+    ohp = _load(**over)
+    wav = speechlike(6000, 2)
+    S = ao.spectrogram(wav, ohp)
+    F, T = S.shape
+    rs = np.random.RandomState(0)
+    ang = np.exp(2j * np.pi * rs.rand(F, T))
+    y = audio.inv_spectrogram(S, init_phase=ang, iters=5)
+    yref = ao.inv_spectrogram(S, ohp, angles=ang, iters=5)
+    assert y.dtype == np.float64 and y.shape == yref.shape == (audio._stft_parameters()[1] * (T - 1),)
+    assert ao.snr_db(y, yref) > 60          # bar is 40 dB (BASELINE.json); fp32 pipeline sits far above
+    y2 = audio.inv_spectrogram(np.ascontiguousarray(S), init_phase=np.ascontiguousarray(ang), iters=5)
+    np.testing.assert_array_equal(y, y2)    # layout must not change a single bit (also a determinism check)
+    S2 = rs.rand(F, 9).astype(np.float32)   # inconsistent (random) spectrogram, Tacotron-at-init like
+    a2 = np.exp(2j * np.pi * rs.rand(F, 9))
+    assert ao.snr_db(audio.inv_spectrogram(S2, init_phase=a2, iters=4), ao.inv_spectrogram(S2, ohp, angles=a2, iters=4)) > 60
+    g = audio._griffin_lim(S2 * 3, init_phase=a2, iters=3)
+    assert g.dtype == np.float32
+    assert ao.snr_db(g, ao._griffin_lim(S2.astype(np.float64) * 3, ohp, angles=a2, iters=3)) > 60
+
+
+def check_golden_fixtures_through_kernels(golden):
+    """The committed fixtures came from the reference's own audio.py (tests/golden/make_golden.py)."""
+    for tag, mn in (("yaml", 100), ("neg", -100)):
+        _load(min_level_db=mn)
+        wav = golden[tag + "_wav"]
+        assert ao.rel_l2(audio._stft(audio.preemphasis(wav).astype(np.float32)), golden[tag + "_stft"]) < 1e-5
+        lin, mel = audio.spectrogram_and_mel(wav)
+        # rel-L2 is the stated bar; bins ~80 dB below the frame peak carry fp32-FFT noise of ~1e-2 dB, so the
+        # element-wise bound is looser
+        assert ao.rel_l2(lin, golden[tag + "_spec"]) < 1e-5 and np.abs(lin - golden[tag + "_spec"]).max() < 1e-3
+        assert ao.rel_l2(mel, golden[tag + "_mel"]) < 1e-5 and np.abs(mel - golden[tag + "_mel"]).max() < 1e-3
+        assert ao.rel_l2(audio._istft(golden[tag + "_stft"]), golden[tag + "_istft"]) < 1e-5
+        F, T = golden[tag + "_gl_in"].shape
+        np.random.seed(1234)       # the reference drew its phase from the global numpy RNG (audio.py:81)
+        y = audio.inv_spectrogram(golden[tag + "_gl_in"], iters=4)
+        assert ao.snr_db(y, golden[tag + "_gl_wav"]) > 60
+
+
+def check_ragged_batch_and_tiles():
+    """Ragged batch through the raw handle, several tile sizes: every tiling must give the same waveform."""
+    ohp = _load(min_level_db=-100)
+    h = audio._handle()
+    rs = np.random.RandomState(3)
+    Ts = [2, 3, 9, 41, 5]
+    specs = [rs.rand(T, 1025).astype(np.float32) for T in Ts]
+    phases = [np.exp(2j * np.pi * rs.rand(T, 1025)).astype(np.complex64) for T in Ts]
+    packed, pph = np.concatenate(specs), np.concatenate(phases)
+    refs = [ao.inv_spectrogram(s.T, ohp, angles=p.T, iters=3) for s, p in zip(specs, phases)]
+    outs = []
+    for tile in (0, 1, 4, 7, 29):
+        h.set_tile_hops(tile)
+        out = np.empty(sum(h.num_samples(T) for T in Ts), dtype=np.float64)
+        h.griffin_lim(packed, _lib.FRAME_MAJOR, Ts, out, init_phase=pph, iters=3,
+                      flags=_lib.GL_DENORMALIZE | _lib.GL_DEEMPHASIS, out_dtype=_lib.F64)
+        outs.append(out)
+        off = 0
+        for T, ref in zip(Ts, refs):
+            n = h.num_samples(T)
+            assert ao.snr_db(out[off:off + n], ref) > 60, (tile, T)
+            off += n
+    h.set_tile_hops(0)
+    for o in outs[1:]:
+        assert ao.snr_db(o, outs[0]) > 100
+    # ragged analysis batch
+    wavs = [speechlike(n, i) for i, n in enumerate((300, 5118, 1, 2049))]
+    ns = [len(w) for w in wavs]
+    Tn = [h.num_frames(n) for n in ns]
+    lin = np.empty((sum(Tn), 1025), np.float32)
+    mel = np.empty((sum(Tn), 80), np.float32)
+    h.features(np.concatenate(wavs), ns, lin, mel)
+    off = 0
+    for w, T in zip(wavs, Tn):
+        # the 1-sample "utterance" is a constant after reflect padding: its spectrum spans > 130 dB, so bins
+        # at 1e-4 of the peak sit inside the fp32 FFT's noise and only a loose dB bound is meaningful there
+        tol = 1e-5 if len(w) > 100 else 5e-3
+        assert ao.rel_l2(lin[off:off + T].T, ao.spectrogram(w, ohp)) < tol
+        assert ao.rel_l2(mel[off:off + T].T, ao.melspectrogram(w, ohp)) < tol
+        off += T
+
+
+def check_errors_and_edge_cases():
+    _load(min_level_db=-100)
+    wav = speechlike(3000, 1)
+    bad = wav.copy()
+    bad[100] = np.nan
+    with pytest.raises(audio.ParameterError):
+        audio.spectrogram(bad)
+    with pytest.raises(audio.ParameterError):
+        audio._stft(np.zeros((2, 100), np.float32))
+    with pytest.raises(ValueError):
+        audio.inv_spectrogram(np.zeros((1025, 1), np.float32))
+    with pytest.raises(ValueError):
+        audio.inv_spectrogram(np.zeros((513, 10), np.float32))
+    S = np.full((1025, 4), np.inf, np.float32)
+    with pytest.raises(audio.ParameterError):
+        audio.inv_spectrogram(S, iters=1)
+    # silence: phase of an all-zero STFT is 0 (np.angle(0) == 0) -> finite output, no NaN from 0/0
+    y = audio._griffin_lim(np.zeros((1025, 6), np.float32), init_phase=np.ones((1025, 6), np.complex64), iters=2)
+    assert np.all(y == 0)
+    hp = hparams.load()
+    hp.parse("num_freq=513")
+    with pytest.raises(ValueError):
+        audio._stft(wav)
+    hparams.load()
+
+
+def check_device_random_phase_is_deterministic_per_seed():
+    _load(min_level_db=-100)
+    S = np.random.RandomState(1).rand(1025, 7).astype(np.float32)
+    a = audio.inv_spectrogram(S, seed=7, iters=2)
+    b = audio.inv_spectrogram(S, seed=7, iters=2)
+    c = audio.inv_spectrogram(S, seed=8, iters=2)
+    np.testing.assert_array_equal(a, b)
+    assert np.isfinite(a).all() and not np.array_equal(a, c)

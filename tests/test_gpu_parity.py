@@ -1,0 +1,169 @@
+"""Parity tests proper: the sm_100a kernels, called through the C ABI (ctypes) on a real B200, against the
+CPU oracle on the same seeded inputs, the committed golden fixtures, and - at BASELINE.json's full sizes -
+through size-independent properties.  Tolerances are BASELINE.json's: single STFT / iSTFT / mel call within
+1e-5 relative L2; Griffin-Lim waveform SNR >= 40 dB vs the oracle and spectral convergence within 1 %."""
+import numpy as np
+import pytest
+
+import parity_checks as pc
+from conftest import make_hp, speechlike
+from nspeech_b200 import _lib, audio, batch, hparams
+from oracle import audio_oracle as ao
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _native():
+    assert audio._lib_override is None
+    lib = _lib.default_lib()                       # raises if libnspeech_b200.so is missing: no fallback
+    assert lib.device_count() >= 1
+    yield
+    hparams.load()
+
+
+@pytest.mark.parametrize("over", pc.CONFIGS)
+def test_single_ops_vs_oracle(over):
+    pc.check_single_ops_vs_oracle(over)
+
+
+@pytest.mark.parametrize("over", pc.CONFIGS)
+def test_griffin_lim_vs_oracle(over):
+    pc.check_griffin_lim_vs_oracle(over)
+
+
+def test_golden_fixtures_through_kernels(golden):
+    pc.check_golden_fixtures_through_kernels(golden)
+
+
+def test_ragged_batch_and_tiles():
+    pc.check_ragged_batch_and_tiles()
+
+
+def test_errors_and_edge_cases():
+    pc.check_errors_and_edge_cases()
+
+
+def test_device_random_phase_is_deterministic_per_seed():
+    pc.check_device_random_phase_is_deterministic_per_seed()
+
+
+@pytest.mark.parametrize("mn", [100, -100])
+def test_config1_full_griffin_lim(mn):
+    """BASELINE config 1: one 5 s spectrogram [1025,401], 60 iterations, identical supplied initial phase."""
+    ohp = pc._load(min_level_db=mn)
+    wav = speechlike(100000, 11)
+    S = ao.spectrogram(wav, ohp)
+    assert S.shape == (1025, 401)
+    ang = np.exp(2j * np.pi * np.random.default_rng(0).random((1025, 401)))
+    y = audio.inv_spectrogram(S, init_phase=ang)            # griffin_lim_iters = 60 from hparams
+    yref = ao.inv_spectrogram(S, ohp, angles=ang)
+    assert y.shape == yref.shape == (100000,)
+    assert ao.snr_db(y, yref) >= 40.0
+    mag = ao._db_to_amp(ao._denormalize(S, ohp) + ohp.ref_level_db) ** ohp.power
+    sc = ao.spectral_convergence(ao.preemphasis(y, ohp), mag, ohp)
+    sc_ref = ao.spectral_convergence(ao.preemphasis(yref, ohp), mag, ohp)
+    assert abs(sc - sc_ref) <= 0.01 * max(sc_ref, 1e-12) + 1e-6
+
+
+def test_random_init_tacotron_like_input():
+    """U(0,1) 'spectrogram' (what a random-init Tacotron emits, BASELINE config 3 variant ii), 60 iterations."""
+    ohp = pc._load()
+    rs = np.random.RandomState(5)
+    S = rs.rand(1025, 120).astype(np.float32)
+    ang = np.exp(2j * np.pi * rs.rand(1025, 120))
+    y = audio.inv_spectrogram(S, init_phase=ang)
+    assert ao.snr_db(y, ao.inv_spectrogram(S, ohp, angles=ang)) >= 40.0
+
+
+def test_full_size_properties():
+    """BASELINE config 3 size (64 x 1000 frames): properties that need no CPU oracle run."""
+    pc._load(min_level_db=-100)
+    h = audio._handle()
+    rs = np.random.RandomState(9)
+    N, T = 64, 1000
+    wavs = [speechlike(h.hop * (T - 1), 100 + i) for i in range(4)]
+    # (1) STFT -> iSTFT round trip at full length
+    for w in wavs[:2]:
+        D = audio._stft(w)
+        assert D.shape == (1025, T)
+        assert ao.rel_l2(audio._istft(D), w) < 1e-5
+    # (2) linearity of the STFT
+    a, b = wavs[0], wavs[1]
+    assert ao.rel_l2(audio._stft(a + 2 * b), audio._stft(a) + 2 * audio._stft(b)) < 1e-5
+    # (3) Parseval on the iSTFT/STFT pair: energy of the re-analysed resynthesis equals the original
+    assert abs(np.sum(audio._istft(audio._stft(a)).astype(np.float64) ** 2) / np.sum(a.astype(np.float64) ** 2) - 1) < 1e-5
+    # (4) a batch gives bit-identical waveforms to one-at-a-time calls (same supplied phase), any tile size
+    feats = [audio.spectrogram(w) for w in wavs]
+    specs = np.stack([feats[i % 4].T for i in range(N)])              # [N,T,F], Tacotron layout
+    phase = np.exp(2j * np.pi * rs.rand(N, T, 1025)).astype(np.complex64)
+    outs = batch.inv_spectrogram_batch(specs, init_phase=phase, iters=8)
+    assert len(outs) == N and all(o.shape == (h.hop * (T - 1),) and o.dtype == np.float64 for o in outs)
+    for i in (0, 5, 63):
+        single = audio.inv_spectrogram(specs[i].T, init_phase=phase[i].T, iters=8)
+        np.testing.assert_array_equal(outs[i], single)
+    # (5) Griffin-Lim reduces the spectral inconsistency monotonically-ish: more iterations -> lower error
+    ohp = make_hp(min_level_db=-100)
+    mag = ao._db_to_amp(ao._denormalize(feats[0], ohp) + ohp.ref_level_db) ** ohp.power
+    errs = []
+    for it in (0, 10, 60):
+        y = audio.inv_spectrogram(feats[0], init_phase=phase[0].T, iters=it)
+        D = np.abs(audio._stft(audio.preemphasis(y).astype(np.float32)))
+        errs.append(np.linalg.norm(D - mag) / np.linalg.norm(mag))
+    assert errs[2] < errs[1] < errs[0]
+
+
+def test_device_pointer_api_with_torch():
+    """NSB_DEVICE entry points on torch-owned memory and torch's current stream."""
+    torch = pytest.importorskip("torch")
+    ohp = pc._load(min_level_db=-100)
+    h = audio._handle()
+    rs = np.random.RandomState(2)
+    Ts = [50, 31]
+    specs = [rs.rand(T, 1025).astype(np.float32) for T in Ts]
+    phases = [np.exp(2j * np.pi * rs.rand(T, 1025)).astype(np.complex64) for T in Ts]
+    d_spec = torch.from_numpy(np.concatenate(specs)).cuda()
+    d_ph = torch.view_as_real(torch.from_numpy(np.concatenate(phases))).contiguous().cuda()
+    d_out = torch.empty(sum(h.num_samples(T) for T in Ts), dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    h.griffin_lim(d_spec, _lib.FRAME_MAJOR, Ts, d_out, init_phase=d_ph, iters=5,
+                  flags=_lib.GL_DENORMALIZE | _lib.GL_DEEMPHASIS, out_dtype=_lib.F64, space=_lib.DEVICE, stream=st)
+    h.check_status(st)
+    out = d_out.cpu().numpy()
+    off = 0
+    for s, p, T in zip(specs, phases, Ts):
+        n = h.num_samples(T)
+        assert ao.snr_db(out[off:off + n], ao.inv_spectrogram(s.T, ohp, angles=p.T, iters=5)) > 60
+        off += n
+    # device-resident features
+    wav = speechlike(20000, 4)
+    d_wav = torch.from_numpy(wav).cuda()
+    T = h.num_frames(wav.size)
+    d_lin = torch.empty((T, 1025), dtype=torch.float32, device="cuda")
+    d_mel = torch.empty((T, 80), dtype=torch.float32, device="cuda")
+    h.features(d_wav, [wav.size], d_lin, d_mel, space=_lib.DEVICE, stream=st)
+    h.check_status(st)
+    assert ao.rel_l2(d_lin.cpu().numpy().T, ao.spectrogram(wav, ohp)) < 1e-5
+    assert ao.rel_l2(d_mel.cpu().numpy().T, ao.melspectrogram(wav, ohp)) < 1e-5
+
+
+def test_threads_share_nothing():
+    """Feeder-style concurrency (datasets/datafeeder.py:110-116): N python threads call the module API at once."""
+    import threading
+    ohp = pc._load(min_level_db=-100)
+    wavs = [speechlike(8000 + 500 * i, i) for i in range(6)]
+    refs = [ao.melspectrogram(w, ohp) for w in wavs]
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                m = audio.melspectrogram(wavs[i])
+                assert ao.rel_l2(m, refs[i]) < 1e-5
+        except Exception as e:
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(wavs))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
