@@ -13,7 +13,8 @@
  *  - `space` says where ALL data buffers of the call live: NSB_HOST (the library copies in/out and
  *    synchronises before returning) or NSB_DEVICE (pointers into the handle's GPU; the call is
  *    stream-ordered on `stream` and returns without synchronising);
- *  - `stream` is a cudaStream_t (NULL = the handle's own stream);
+ *  - `stream` is a cudaStream_t used as given; NULL means CUDA's default stream for NSB_DEVICE calls and the
+ *    handle's private non-blocking stream for the (synchronous) NSB_HOST calls;
  *  - ragged batches: per-utterance lengths are a HOST int array; utterance blocks are packed back to
  *    back in every buffer (a uniform [N,T,F] or [N,n] C-contiguous array is already in that form);
  *  - spectra are float32, 1025 = num_freq bins per frame; layout NSB_FRAME_MAJOR = [T][F] per

@@ -288,12 +288,19 @@ extern "C" int nsb_mel_basis(nsb_handle_t h, double* out) {
     return NSB_OK;
 }
 
-static cudaStream_t pick_stream(nsb_handle_s* h, void* stream) { return stream ? (cudaStream_t)stream : h->own_stream; }
+// NSB_DEVICE calls are stream-ordered on exactly the cudaStream_t given (NULL = CUDA's default stream, as in the
+// runtime API), so that they compose with the caller's own work and events.  NSB_HOST calls are synchronous; with
+// NULL they run on the handle's private non-blocking stream so that host threads with separate handles overlap.
+static cudaStream_t pick_stream(nsb_handle_s* h, void* stream, int space = NSB_DEVICE) {
+    if (stream) return (cudaStream_t)stream;
+    return space == NSB_HOST ? h->own_stream : (cudaStream_t)0;
+}
 
 extern "C" int nsb_synchronize(nsb_handle_t h, void* stream) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");
     CU(cudaSetDevice(h->device));
-    CU(cudaStreamSynchronize(pick_stream(h, stream)));
+    if (stream) CU(cudaStreamSynchronize((cudaStream_t)stream));
+    else { CU(cudaStreamSynchronize(h->own_stream)); CU(cudaStreamSynchronize((cudaStream_t)0)); }
     return NSB_OK;
 }
 
@@ -388,7 +395,7 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
     if (mode == ANALYSIS_FEATURES && !lin_out && !mel_out) return fail(NSB_ERR_INVALID, "both outputs are null");
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
-    cudaStream_t st = pick_stream(h, stream);
+    cudaStream_t st = pick_stream(h, stream, space);
     std::vector<int> frames(batch);
     std::vector<long long> samples(batch);
     for (int b = 0; b < batch; ++b) {
@@ -492,7 +499,7 @@ extern "C" int nsb_istft(nsb_handle_t h, const float* spec, int32_t layout, cons
     if (!spec || !n_frames || !wav_out || batch < 1) return fail(NSB_ERR_INVALID, "null/empty argument");
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
-    cudaStream_t st = pick_stream(h, stream);
+    cudaStream_t st = pick_stream(h, stream, space);
     std::vector<int> frames; std::vector<long long> samples;
     int rc = validate_frames(h, n_frames, batch, frames, samples);
     if (rc) return rc;
@@ -554,7 +561,7 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
     if (iters < 0) iters = h->hp.griffin_lim_iters;
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
-    cudaStream_t st = pick_stream(h, stream);
+    cudaStream_t st = pick_stream(h, stream, space);
     std::vector<int> frames; std::vector<long long> samples;
     int rc = validate_frames(h, n_frames, batch, frames, samples);
     if (rc) return rc;
@@ -633,7 +640,7 @@ static int run_emph(nsb_handle_s* h, bool inverse, const float* x, const int64_t
     if (out_dtype != NSB_F32 && out_dtype != NSB_F64) return fail(NSB_ERR_INVALID, "bad out_dtype");
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
-    cudaStream_t st = pick_stream(h, stream);
+    cudaStream_t st = pick_stream(h, stream, space);
     std::vector<int> frames(batch, 1);
     std::vector<long long> samples(batch);
     for (int b = 0; b < batch; ++b) { if (n_samples[b] < 0) return fail(NSB_ERR_INVALID, "negative length"); samples[b] = n_samples[b]; }
@@ -677,7 +684,7 @@ extern "C" int nsb_linear_to_mel(nsb_handle_t h, const float* spec, int32_t layo
     if (out_dtype != NSB_F32 && out_dtype != NSB_F64) return fail(NSB_ERR_INVALID, "bad out_dtype");
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
-    cudaStream_t st = pick_stream(h, stream);
+    cudaStream_t st = pick_stream(h, stream, space);
     std::vector<int> frames(batch);
     std::vector<long long> samples(batch, 0);
     for (int b = 0; b < batch; ++b) { if (n_frames[b] < 1) return fail(NSB_ERR_INVALID, "utterance %d has no frames", b); frames[b] = n_frames[b]; }
@@ -714,7 +721,7 @@ extern "C" int nsb_elementwise(nsb_handle_t h, int32_t op, const float* in, int6
     if (n == 0) return NSB_OK;
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
-    cudaStream_t st = pick_stream(h, stream);
+    cudaStream_t st = pick_stream(h, stream, space);
     const float* d_in = in;
     float* d_out = out;
     int rc;
