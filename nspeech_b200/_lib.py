@@ -62,6 +62,7 @@ SIGNATURES = {
     "nsb_elementwise": (ctypes.c_int, [_vp, _i32, _vp, _i64, _vp, _i32, _vp]),
     "nsb_check_status": (ctypes.c_int, [_vp, _vp]),
     "nsb_set_tile_hops": (ctypes.c_int, [_vp, _i32]),
+    "nsb_set_generic_iteration": (ctypes.c_int, [_vp, _i32]),
     "nsb_kernel_launches": (_u64, [_vp]),
     "nsb_griffin_lim_iterate": (ctypes.c_int, [_vp, _i32, _vp]),
     "nsb_alloc_pinned": (ctypes.c_int, [_u64, ctypes.POINTER(_vp)]),
@@ -242,6 +243,9 @@ class Handle(object):
 
     def set_tile_hops(self, t):
         self._call("nsb_set_tile_hops", int(t))
+
+    def set_generic_iteration(self, on):
+        self._call("nsb_set_generic_iteration", int(bool(on)))
 
     def kernel_launches(self):
         return int(self.lib.dll.nsb_kernel_launches(self._h))

@@ -460,6 +460,7 @@ struct PrepParams {
     int denorm;               // 1: apply _denormalize + ref, _db_to_amp, **power ; 0: |S| as is
     double min_level_db, ref_level_db, power;
     float* mag;               // [frames][kMagPitch]
+    float scale;              // power-of-two pre-scale of the magnitudes (undone on output; Griffin-Lim is linear in S)
     int total_frames;
     int* status;
 };
@@ -511,7 +512,7 @@ __global__ void __launch_bounds__(256) k_prepare_mag(PrepParams P) {
                 } else {
                     S = fabsf(v);
                 }
-                P.mag[(size_t)f * kMagPitch + slot_index(kb)] = S;
+                P.mag[(size_t)f * kMagPitch + slot_index(kb)] = S * P.scale;
             }
         }
         __syncthreads();
@@ -528,6 +529,7 @@ struct EmphParams {
     double* out64;        // one of the two outputs is non-null
     float* out32;
     double p;
+    double scale;         // output multiplier (undoes the magnitude pre-scale); 0 is treated as 1
 };
 
 // y[n] = x[n] + p*y[n-1] per utterance (scipy.signal.lfilter([1],[1,-p]), zero initial state), in double.
@@ -545,6 +547,7 @@ __global__ void __launch_bounds__(kDeemphThreads) k_deemphasis(EmphParams P) {
     const float* x = P.in + s_off;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double p = P.p;
+    const double oscale = P.scale == 0.0 ? 1.0 : P.scale;
     double ppow[kPerThread + 1];             // p^1 .. p^kPerThread
     ppow[0] = 1.0;
 #pragma unroll
@@ -564,7 +567,7 @@ __global__ void __launch_bounds__(kDeemphThreads) k_deemphasis(EmphParams P) {
         double s = 0.0;
 #pragma unroll
         for (int i = 0; i < kPerThread; ++i) {
-            double v = (i0 + i < L) ? (double)__ldg(x + i0 + i) : 0.0;
+            double v = (i0 + i < L) ? (double)__ldg(x + i0 + i) * oscale : 0.0;
             s = fma(p, s, v);
             loc[i] = s;
         }

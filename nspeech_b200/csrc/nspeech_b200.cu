@@ -9,6 +9,7 @@
 
 #include "../../include/nspeech_b200.h"
 #include "kernels.cuh"
+#include "gl_iter.cuh"
 
 using namespace nsb;
 
@@ -61,7 +62,7 @@ struct DevBuf {
 struct nsb_handle_s {
     int device = 0;
     nsb_hparams hp{};
-    int n_fft = 0, hop = 0, win = 0, lo = 0, colours = 0, prune = 0, num_mels = 0;
+    int n_fft = 0, hop = 0, win = 0, lo = 0, colours = 0, prune = 0, defcfg = 0, num_mels = 0;
     int num_sms = 0;
     int user_tile_hops = 0;
     cudaStream_t own_stream = nullptr;
@@ -81,6 +82,7 @@ struct nsb_handle_s {
     DevBuf ws_mag, ws_y0, ws_y1, ws_in, ws_in2, ws_out, ws_out2;
     // state of the last device-resident Griffin-Lim (for nsb_griffin_lim_iterate)
     struct { bool valid = false; Batch batch{}; int total_frames = 0; int tile_hops = 0; int total_tiles = 0; int cur = 0; } gl;
+    int use_generic_iter = 0;        // debugging / A-B hook: run the iterations with k_synth<SRC_Y> instead of k_gl_iter
     unsigned long long launches = 0;
     std::mutex mu;
 };
@@ -131,11 +133,18 @@ static size_t synth_smem(int hop, int H) {
     fl = (fl + 3) & ~(size_t)3;
     return fl * sizeof(float) + sizeof(float2) * kScratchF2 * kWarpsPerCta;
 }
+static size_t gl_smem(int hop, int H) { return synth_smem(hop, H) + 64; }   // + neighbour progress flags
 static const size_t kSmemPerCtaTwoResident = (227 * 1024) / 2 - 1024;   // two CTAs per SM, 1 KB reserved each
 
 static int max_tile_hops(const nsb_handle_s* h) {
-    int H = 8 * h->colours - (h->colours - 1);           // one frame per warp per colour round
-    while (H > 1 && synth_smem(h->hop, H) > kSmemPerCtaTwoResident) --H;
+    // k_gl_iter gives each of its 8 warps C consecutive frames, so a tile may meet at most 8*C frames.  The frames
+    // meeting H hops are the multiples of hop inside an open interval of length H*hop + win: at most H + C of them,
+    // or H + C - 1 when win is a multiple of hop and the interval ends fall on multiples of hop (the default config).
+    const int a = kNfft / 2 - h->lo;
+    const bool aligned = (h->win % h->hop == 0) && ((a - h->win) % h->hop == 0);
+    int H = 8 * h->colours - h->colours + (aligned ? 1 : 0);
+    if (H < 1) H = 1;
+    while (H > 1 && gl_smem(h->hop, H) > kSmemPerCtaTwoResident) --H;
     return H;
 }
 
@@ -251,7 +260,8 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
     CUB(cudaMalloc(&h->d_status, sizeof(int)));
     CUB(cudaMemset(h->d_status, 0, sizeof(int)));
     // opt in to the large dynamic shared memory of every instantiation
-    const size_t as = analysis_smem(), ss = synth_smem(hop, max_tile_hops(h));
+    const size_t as = analysis_smem(), ss = synth_smem(hop, max_tile_hops(h)), gs = gl_smem(hop, max_tile_hops(h));
+    h->defcfg = (hop == 250 && win == 1000 && h->lo == 524) ? 1 : 0;
 #define SET(k, b) do { rc = set_smem(k, b); if (rc) return bail(rc); } while (0)
     SET((k_analysis<ANALYSIS_COMPLEX, false, false>), as); SET((k_analysis<ANALYSIS_COMPLEX, false, true>), as);
     SET((k_analysis<ANALYSIS_COMPLEX, true, false>), as);  SET((k_analysis<ANALYSIS_COMPLEX, true, true>), as);
@@ -260,6 +270,7 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
     SET((k_synth<SRC_SPEC, false>), ss);     SET((k_synth<SRC_SPEC, true>), ss);
     SET((k_synth<SRC_MAGPHASE, false>), ss); SET((k_synth<SRC_MAGPHASE, true>), ss);
     SET((k_synth<SRC_MAGRAND, false>), ss);  SET((k_synth<SRC_MAGRAND, true>), ss);
+    SET((k_gl_iter<true, true>), gs); SET((k_gl_iter<true, false>), gs); SET((k_gl_iter<false, false>), gs);
 #undef SET
 #undef CUB
     *out = h;
@@ -276,6 +287,11 @@ extern "C" int nsb_stft_parameters(nsb_handle_t h, int32_t* n_fft, int32_t* hop,
 extern "C" int64_t nsb_num_frames(nsb_handle_t h, int64_t n) { return h ? 1 + n / h->hop : -1; }
 extern "C" int64_t nsb_num_samples(nsb_handle_t h, int64_t T) { return h ? (int64_t)h->hop * (T - 1) : -1; }
 extern "C" uint64_t nsb_kernel_launches(nsb_handle_t h) { return h ? h->launches : 0; }
+extern "C" int nsb_set_generic_iteration(nsb_handle_t h, int32_t on) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    h->use_generic_iter = on ? 1 : 0;
+    return NSB_OK;
+}
 extern "C" int nsb_set_tile_hops(nsb_handle_t h, int32_t t) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");
     if (t < 0 || t > max_tile_hops(h)) return fail(NSB_ERR_INVALID, "tile_hops %d outside [0,%d]", t, max_tile_hops(h));
@@ -529,15 +545,32 @@ extern "C" int nsb_istft(nsb_handle_t h, const float* spec, int32_t layout, cons
 }
 
 static int gl_iterations(nsb_handle_s* h, int iters, cudaStream_t st) {
-    SynthParams P{};
-    P.plan = make_plan(h); P.batch = h->gl.batch; P.mag = reinterpret_cast<const float*>(h->ws_mag.p);
-    P.tile_hops = h->gl.tile_hops; P.colours = h->colours; P.status = h->d_status;
-    const size_t smem = synth_smem(h->hop, h->gl.tile_hops);
     float* y[2] = {reinterpret_cast<float*>(h->ws_y0.p), reinterpret_cast<float*>(h->ws_y1.p)};
+    if (h->use_generic_iter) {
+        SynthParams P{};
+        P.plan = make_plan(h); P.batch = h->gl.batch; P.mag = reinterpret_cast<const float*>(h->ws_mag.p);
+        P.tile_hops = h->gl.tile_hops; P.colours = h->colours; P.status = h->d_status;
+        const size_t smem = synth_smem(h->hop, h->gl.tile_hops);
+        for (int it = 0; it < iters; ++it) {
+            P.y_in = y[h->gl.cur]; P.y_out = y[h->gl.cur ^ 1];
+            launch_synth<SRC_Y>(h, P, h->gl.total_tiles, smem, st);
+            int rc = check_launch(h, "k_synth<Y>");
+            if (rc) return rc;
+            h->gl.cur ^= 1;
+        }
+        return NSB_OK;
+    }
+    GlParams G{};
+    G.plan = make_plan(h); G.batch = h->gl.batch; G.mag = reinterpret_cast<const float*>(h->ws_mag.p);
+    G.tile_hops = h->gl.tile_hops; G.colours = h->colours; G.total_tiles = h->gl.total_tiles; G.status = h->d_status;
+    const size_t smem = gl_smem(h->hop, h->gl.tile_hops);
+    const int grid = h->gl.total_tiles < 2 * h->num_sms ? h->gl.total_tiles : 2 * h->num_sms;   // persistent: 2 CTAs per SM
     for (int it = 0; it < iters; ++it) {
-        P.y_in = y[h->gl.cur]; P.y_out = y[h->gl.cur ^ 1];
-        launch_synth<SRC_Y>(h, P, h->gl.total_tiles, smem, st);
-        int rc = check_launch(h, "k_synth<Y>");
+        G.y_in = y[h->gl.cur]; G.y_out = y[h->gl.cur ^ 1];
+        if (h->defcfg) NSB_LAUNCH((k_gl_iter<true, true>), grid, kThreads, smem, st, G);
+        else if (h->prune) NSB_LAUNCH((k_gl_iter<true, false>), grid, kThreads, smem, st, G);
+        else NSB_LAUNCH((k_gl_iter<false, false>), grid, kThreads, smem, st, G);
+        int rc = check_launch(h, "k_gl_iter");
         if (rc) return rc;
         h->gl.cur ^= 1;
     }
@@ -594,6 +627,16 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
     Q.batch = d.dev; Q.in = d_spec; Q.bin_major = (layout == NSB_BIN_MAJOR); Q.denorm = (flags & NSB_GL_DENORMALIZE) ? 1 : 0;
     Q.min_level_db = h->hp.min_level_db; Q.ref_level_db = h->hp.ref_level_db; Q.power = h->hp.power;
     Q.mag = reinterpret_cast<float*>(h->ws_mag.p); Q.total_frames = d.total_frames; Q.status = h->d_status;
+    // Griffin-Lim is linear in S: run it on g*S with g a power of two that brings the largest possible magnitude
+    // below 1 (the yaml's +100 dB floor gives S up to 1e9 whose squares would overflow fp32), undo g on output.
+    double gscale = 1.0;
+    if (flags & NSB_GL_DENORMALIZE) {
+        const double e0 = (h->hp.min_level_db + h->hp.ref_level_db) * 0.05 * h->hp.power, e1 = h->hp.ref_level_db * 0.05 * h->hp.power;
+        const double smax = std::pow(10.0, e0 > e1 ? e0 : e1);
+        gscale = std::ldexp(1.0, -(int)std::ceil(std::log2(smax)));
+        if (!(gscale > 0.0) || !std::isfinite(gscale)) gscale = 1.0;
+    }
+    Q.scale = (float)gscale;
     CU(cudaMemsetAsync(h->ws_mag.p, 0, sizeof(float) * kMagPitch * (size_t)d.total_frames, st));
     NSB_LAUNCH(k_prepare_mag, (d.total_frames + 31) / 32, 256, 0, st, Q);
     if ((rc = check_launch(h, "k_prepare_mag"))) return rc;
@@ -612,9 +655,11 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
     if ((rc = gl_iterations(h, iters, st))) return rc;
     const float* y_fin = reinterpret_cast<const float*>(h->gl.cur ? h->ws_y1.p : h->ws_y0.p);
 
-    if (flags & NSB_GL_DEEMPHASIS) {
+    if ((flags & NSB_GL_DEEMPHASIS) || gscale != 1.0) {
+        if (!(flags & NSB_GL_DEEMPHASIS) && out_dtype != NSB_F32)
+            return fail(NSB_ERR_INVALID, "NSB_F64 output without NSB_GL_DEEMPHASIS is not provided (_griffin_lim returns float32)");
         EmphParams E{};
-        E.batch = d.dev; E.in = y_fin; E.p = h->hp.preemphasis;
+        E.batch = d.dev; E.in = y_fin; E.p = (flags & NSB_GL_DEEMPHASIS) ? h->hp.preemphasis : 0.0; E.scale = 1.0 / gscale;
         if (out_dtype == NSB_F64) E.out64 = reinterpret_cast<double*>(d_out); else E.out32 = reinterpret_cast<float*>(d_out);
         NSB_LAUNCH(k_deemphasis, batch, kDeemphThreads, 0, st, E);
         if ((rc = check_launch(h, "k_deemphasis"))) return rc;

@@ -1,4 +1,4 @@
-"""Timing sweep of the Griffin-Lim iteration kernel (device-resident, CUDA events): tile size x batch."""
+"""Timing sweep of the Griffin-Lim iteration kernel (device-resident, CUDA events): kernel variant x tile x batch."""
 import os
 import sys
 
@@ -11,22 +11,26 @@ hparams.load()
 h = audio._handle()
 T = 1000
 st = torch.cuda.current_stream().cuda_stream
-for batch in (64, 8, 1, 256):
+cases = [(64, 0, 0), (64, 0, 1), (64, 21, 0), (8, 0, 0), (1, 0, 0), (256, 0, 0)]
+if len(sys.argv) > 1:
+    cases = [tuple(int(v) for v in c.split(",")) for c in sys.argv[1:]]
+for batch, tile, generic in cases:
     spec = torch.rand((batch, T, 1025), device="cuda")
     out = torch.empty(batch * h.num_samples(T), dtype=torch.float64, device="cuda")
-    for tile in (0, 29, 21, 13, 5):
-        h.set_tile_hops(tile)
-        h.griffin_lim(spec, _lib.FRAME_MAJOR, [T] * batch, out, seed=1, iters=2, flags=3, out_dtype=_lib.F64, space=_lib.DEVICE, stream=st)
-        h.griffin_lim_iterate(20, st)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n = 100
-        e0.record()
-        h.griffin_lim_iterate(n, st)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / n
-        print("batch %4d tile %2d: %.4f ms/iter  %.2f ns/frame-iter  -> %.0f audio-s/s at 61 passes" % (
-            batch, tile, ms, ms * 1e6 / (batch * T), batch * T * 0.0125 / (ms * 1e-3 * 61)), flush=True)
+    h.set_tile_hops(tile)
+    h.set_generic_iteration(generic)
+    h.griffin_lim(spec, _lib.FRAME_MAJOR, [T] * batch, out, seed=1, iters=2, flags=3, out_dtype=_lib.F64, space=_lib.DEVICE, stream=st)
+    h.griffin_lim_iterate(20, st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 100
+    e0.record()
+    h.griffin_lim_iterate(n, st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    print("batch %4d tile %2d %s: %.4f ms/iter  %.2f ns/frame-iter  -> %.0f audio-s/s at 61 passes" % (
+        batch, tile, "k_synth<Y> " if generic else "k_gl_iter  ", ms, ms * 1e6 / (batch * T), batch * T * 0.0125 / (ms * 1e-3 * 61)), flush=True)
     del spec, out
 h.set_tile_hops(0)
+h.set_generic_iteration(0)
