@@ -8,8 +8,9 @@
 //   * the frame's magnitude row is prefetched with cp.async into the warp's own scratch tile while the
 //     second FFT pass runs (the scratch tile is idle exactly then), so the renormalisation never waits on HBM/L2;
 //   * overlap-add ordering uses per-warp progress flags between NEIGHBOUR warps instead of one CTA barrier
-//     per colour: warp w owns the C consecutive frames kb + C*w .. kb + C*w + C-1 and may add frame number s
-//     once both neighbours have added their frames < s (frames of non-neighbour warps never overlap);
+//     per colour: warp w owns the C consecutive frames kb + C*w .. kb + C*w + C-1, adds them in the order of the
+//     global colour k mod C, and may add its colour-s frame once both neighbours have added their colours < s
+//     (frames of non-neighbour warps never overlap; equal colours never overlap);
 //   * the lane-0 real-64 split (rows 0/32 of the 64x32 decomposition) is spread over lanes 1..16 through a
 //     256-byte exchange area instead of running on one lane while 31 idle;
 //   * branch-free renormalisation (the magnitudes are pre-scaled by a power of two in k_prepare_mag so the
@@ -142,7 +143,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
         __syncthreads();
 
         for (int s = 0; s < C; ++s) {
-            const int k = k_min + C * warp + s;
+            // the warp's group is the C consecutive frames kg .. kg+C-1; it adds them in the order of the GLOBAL colour
+            // k mod C (step s takes the frame with k % C == s), so the summation order of every output sample is
+            // independent of how the utterance was tiled: a batch is bit-identical to one-at-a-time calls
+            const int kg = k_min + C * warp;
+            const int k = kg + ((s - kg % C) + C) % C;
             const bool active = (k <= k_max);        // warp-uniform
             float re[32], im[32];
             if (active) {

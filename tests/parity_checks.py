@@ -115,7 +115,7 @@ def check_ragged_batch_and_tiles():
             off += n
     h.set_tile_hops(0)
     for o in outs[1:]:
-        assert ao.snr_db(o, outs[0]) > 100
+        np.testing.assert_array_equal(o, outs[0])      # the tiling must not change a single bit
     # ragged analysis batch
     wavs = [speechlike(n, i) for i, n in enumerate((300, 5118, 1, 2049))]
     ns = [len(w) for w in wavs]
