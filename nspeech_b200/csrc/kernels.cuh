@@ -59,11 +59,12 @@ __device__ __forceinline__ int find_segment(const int* __restrict__ off, int n, 
     return lo;
 }
 
-// np.pad(mode='reflect') index map for a signal of length L (any i, multiple reflections)
-__device__ __forceinline__ long long reflect_index(long long i, long long L) {
+// np.pad(mode='reflect') index map for a signal of length L (any i, multiple reflections); 32-bit on purpose
+// (utterances are far below 2^31 samples; 64-bit division is a subroutine call on the GPU)
+__device__ __forceinline__ int reflect_index(int i, int L) {
     if (L == 1) return 0;
-    long long period = 2 * (L - 1);
-    long long m = i % period;
+    int period = 2 * (L - 1);
+    int m = i % period;
     if (m < 0) m += period;
     return m < L ? m : period - m;
 }
@@ -71,17 +72,20 @@ __device__ __forceinline__ long long reflect_index(long long i, long long L) {
 // ---- frame load: windowed samples of frame k into the lane registers -----------------------
 // re[t] = w[n] * s(start + n), n = 64 t + lane ; im[t] likewise with n + 32.   s = (pre-emphasised) signal
 template <bool PREEMPH>
-__device__ __forceinline__ float sample_at(const float* __restrict__ x, long long L, long long i, float p) {
-    long long m = reflect_index(i, L);
+__device__ __forceinline__ float sample_at(const float* __restrict__ x, int L, int i, float p) {
+    int m = reflect_index(i, L);
     float v = __ldg(x + m);
     if (PREEMPH) { if (m > 0) v = fmaf(-p, __ldg(x + m - 1), v); }
     return v;
 }
 
+// `stage` is the warp's scratch tile (>= 2048 floats): frames that touch the utterance's ends (reflect padding)
+// are gathered through it by a rolled loop, so the rare path costs a few dozen instructions of code instead of
+// an unrolled copy of the index arithmetic per register
 template <bool PREEMPH, bool PRUNE>
 __device__ __forceinline__ void load_frame(float (&re)[32], float (&im)[32], const float* __restrict__ x, long long L,
                                            long long start, const float* __restrict__ win_s, int lane, float p,
-                                           float scale) {
+                                           float scale, float* stage) {
     constexpr int t0 = PRUNE ? 8 : 0, t1 = PRUNE ? 24 : 32;
     const long long first = start + 64 * t0, last = start + 64 * t1;   // [first, last) touched
     const bool interior = (first >= (PREEMPH ? 1 : 0)) && (last <= L);
@@ -100,15 +104,17 @@ __device__ __forceinline__ void load_frame(float (&re)[32], float (&im)[32], con
             } else { re[t] = 0.f; im[t] = 0.f; }
         }
     } else {
+#pragma unroll 1
+        for (int n = 64 * t0 + lane; n < 64 * t1; n += 32) stage[n] = sample_at<PREEMPH>(x, (int)L, (int)start + n, p);
+        __syncwarp();
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
             if (t >= t0 && t < t1) {
-                float a = sample_at<PREEMPH>(x, L, start + 64 * t + lane, p);
-                float b = sample_at<PREEMPH>(x, L, start + 64 * t + 32 + lane, p);
-                re[t] = a * (win_s[64 * t + lane] * scale);
-                im[t] = b * (win_s[64 * t + 32 + lane] * scale);
+                re[t] = stage[64 * t + lane] * (win_s[64 * t + lane] * scale);
+                im[t] = stage[64 * t + 32 + lane] * (win_s[64 * t + 32 + lane] * scale);
             } else { re[t] = 0.f; im[t] = 0.f; }
         }
+        __syncwarp();
     }
 }
 
@@ -159,7 +165,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
         const long long L = __ldg(P.batch.samp_off + b + 1) - s_off;
         float re[32], im[32];
         // 0.5 folds the forward transform's factor 2 (frame_fft.cuh) so the registers hold rfft exactly
-        load_frame<PREEMPH, PRUNE>(re, im, P.wav + s_off, L, (long long)k * hop - kNfft / 2, win_s, lane, P.preemph, 0.5f);
+        load_frame<PREEMPH, PRUNE>(re, im, P.wav + s_off, L, (long long)k * hop - kNfft / 2, win_s, lane, P.preemph, 0.5f,
+                                   reinterpret_cast<float*>(scratch));
         fwd_phase1(re, im, lane, scratch, tw_s);
         __syncwarp();
         fwd_phase2(re, im, lane, scratch);
@@ -318,7 +325,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_synth(SynthParams P) {
             const int fg = f_off + k;                   // global frame index
             float re[32], im[32];
             if (SRC == SRC_Y) {
-                load_frame<false, PRUNE>(re, im, P.y_in + s_off, L, (long long)k * hop - kNfft / 2, win_s, lane, 0.f, 1.0f);
+                load_frame<false, PRUNE>(re, im, P.y_in + s_off, L, (long long)k * hop - kNfft / 2, win_s, lane, 0.f, 1.0f,
+                                         reinterpret_cast<float*>(scratch));
                 fwd_phase1(re, im, lane, scratch, tw_s);
                 __syncwarp();
                 fwd_phase2(re, im, lane, scratch);

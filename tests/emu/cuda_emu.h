@@ -36,6 +36,7 @@ static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) {
 #define __device__
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
+#define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __align__(n) alignas(n)
