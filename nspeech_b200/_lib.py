@@ -245,7 +245,7 @@ class Handle(object):
         self._call("nsb_set_tile_hops", int(t))
 
     def set_generic_iteration(self, on):
-        self._call("nsb_set_generic_iteration", int(bool(on)))
+        self._call("nsb_set_generic_iteration", int(on))
 
     def kernel_launches(self):
         return int(self.lib.dll.nsb_kernel_launches(self._h))

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
     const int win = DEFCFG ? 1000 : P.plan.win_len;
     const int lo = DEFCFG ? 524 : P.plan.lo;
     const int C = DEFCFG ? 4 : P.colours;
-    const int H = P.tile_hops;
+    const int H = P.tile_hops;                       // a multiple of C (host guarantees it)
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
     float* win_s = reinterpret_cast<float*>(tw_s + kTwF2);
     float* rinv_s = win_s + kNfft;
@@ -130,6 +130,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float2* scratch = scratch_all + warp * kScratchF2;
     const int a = kNfft / 2 - lo;
+    // first frame (possibly negative = does not exist) whose window support can reach hop h is h + kfirst0
+    const int kfirst0 = (a - win >= 0) ? (a - win) / hop + 1 : -((win - a - 1) / hop + 1) + 1;
 
     for (int i = threadIdx.x; i < kTwF2; i += kThreads) tw_s[i] = P.plan.tw[i];
     for (int i = threadIdx.x; i < kNfft; i += kThreads) win_s[i] = P.plan.win[i];
@@ -150,31 +152,31 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
         const long long s_off = __ldg(P.batch.samp_off + b);
         const long long L = (long long)hop * (T - 1);
         const int h0 = tile * H, h1 = min(h0 + H, T - 1);
-        const long long s0 = (long long)h0 * hop, s1 = (long long)h1 * hop;
-        const int n_out = (int)(s1 - s0);
-        long long num = s0 + a - win;
-        int k_min = (int)(num >= 0 ? num / hop + 1 : -((-num - 1) / hop + 1) + 1);
-        if (k_min < 0) k_min = 0;
-        int k_max = (int)((s1 + a + hop - 1) / hop - 1);
+        const int s0 = h0 * hop;
+        const int n_out = (h1 - h0) * hop;
+        // Frames are grouped from the VIRTUAL first frame h0 + kfirst0 (negative frames simply do not exist).  Because
+        // H is a multiple of C, every tile's groups start at the same residue mod C: the warp adds its frames in
+        // increasing order AND that order is the global colour (k - kfirst0) mod C, so the summation order of every
+        // output sample is independent of the tiling (a batch is bit-identical to one-at-a-time calls).
+        const int k_first = h0 + kfirst0;
+        int k_max = (s0 + n_out + a + hop - 1) / hop - 1;      // last frame with k*hop - a < s1
         if (k_max > T - 1) k_max = T - 1;
-        if (k_max - k_min + 1 > kWarpsPerCta * C) bad = true;   // host sizes tiles so this cannot happen; never drop frames silently
+        if (k_max - k_first + 1 > kWarpsPerCta * C) bad = true;   // host sizes tiles so this cannot happen; never drop frames silently
+        const int kg = k_first + C * warp;
 
         for (int s = 0; s < C; ++s) {
-            // the warp's group is the C consecutive frames kg .. kg+C-1; it adds them in the order of the GLOBAL colour
-            // k mod C (step s takes the frame with k % C == s), so the summation order of every output sample is
-            // independent of how the utterance was tiled: a batch is bit-identical to one-at-a-time calls
-            const int kg = k_min + C * warp;
-            const int k = kg + ((s - kg % C) + C) % C;
-            const bool active = (k <= k_max);        // warp-uniform
-            // A/B are the (real-role, imag-role) inputs of the ONE shared forward FFT32 below.  The inverse passes
-            // run the same code with the roles swapped (ifft(re,im) = swap(fft(im,re))); the swaps are folded into
-            // the loads/stores around the FFT, so the frame's four FFT passes share one copy of the butterfly code
-            // (the fully inlined version was ~98 KB of SASS and instruction-fetch bound).
-            float A[32], B[32];
-            if (active) {
-                const int fg = f_off + k;
+            const int k = kg + s;
+            const bool active = (k >= 0 && k <= k_max);        // warp-uniform
+            const int fg = f_off + k;
+            // One shared copy of the forward FFT32 serves the frame's four passes: every pass is
+            //   load (global / scratch) -> FFT32 -> post-process -> store (scratch / accumulator)
+            // so nothing array-sized is live across the loop's back edge; the inverse passes run the same butterflies
+            // with the real/imaginary roles swapped (ifft(re, im) = swap(fft(im, re))), the swap folded into the
+            // loads and stores.  (Four inlined copies made ~98 KB of SASS and the kernel instruction-fetch bound.)
 #pragma unroll 1
-                for (int pass = 0; pass < 4; ++pass) {
+            for (int pass = 0; pass < 4; ++pass) {
+                float A[32], B[32];
+                if (active) {
                     if (pass == 0) {
                         load_frame<false, PRUNE>(A, B, P.y_in + s_off, L, (long long)k * hop - kNfft / 2, win_s, lane, 0.f, 1.0f,
                                                  reinterpret_cast<float*>(scratch));
@@ -187,7 +189,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
 #pragma unroll
                         for (int g = 0; g < 8; ++g) cp_async16(dst + (g * 32 + lane) * 16, src + (g * 32 + lane) * 16);
                         if (lane == 0) cp_async16(dst + 4096, src + 4096);
-                    } else if (pass == 3) {
+                    } else if (pass == 2) {
+                        // own row back, roles swapped (stored as (im, re) by pass 1)
+#pragma unroll
+                        for (int t = 0; t < 32; ++t) { float2 v = scratch[lane * kRowStride + t]; A[t] = v.x; B[t] = v.y; }
+                    } else {
                         // column load with swapped roles (B = re, A = im), then the inverse real-64 pre-split
                         const float* row0 = reinterpret_cast<const float*>(scratch);
                         B[0] = row0[lane];
@@ -221,18 +227,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                         const float4* mrow = reinterpret_cast<const float4*>(scratch);
                         const float* mflt = reinterpret_cast<const float*>(scratch);
                         bool zero = false;
-                        // (a) every lane renormalises its 32 slots and leaves them role-swapped (A <- im, B <- re) for the
-                        //     inverse passes (lane 0's registers hold the packed-row FFT, not bins: overwritten below)
+                        // (a) every lane renormalises its 32 slots (lane 0's registers hold the packed-row FFT, not bins:
+                        //     replaced below)
 #pragma unroll
                         for (int g = 0; g < 8; ++g) {
                             float4 S = mrow[g * 32 + lane];
-                            const float Ss[4] = {S.x, S.y, S.z, S.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                float re = A[4 * g + e], im = B[4 * g + e];
-                                renorm_fast(re, im, Ss[e], zero);
-                                A[4 * g + e] = im; B[4 * g + e] = re;
-                            }
+                            renorm_fast(A[4 * g], B[4 * g], S.x, zero);
+                            renorm_fast(A[4 * g + 1], B[4 * g + 1], S.y, zero);
+                            renorm_fast(A[4 * g + 2], B[4 * g + 2], S.z, zero);
+                            renorm_fast(A[4 * g + 3], B[4 * g + 3], S.w, zero);
                         }
                         if (lane == 0) zero = false;
                         if (warp_any(zero)) {        // rare: some bin of y's STFT is exactly 0 -> phase 0 (np.angle(0))
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                                     const float Ss[4] = {S.x, S.y, S.z, S.w};
 #pragma unroll
                                     for (int e = 0; e < 4; ++e)
-                                        if (A[4 * g + e] == 0.f && B[4 * g + e] == 0.f) B[4 * g + e] = Ss[e];
+                                        if (A[4 * g + e] == 0.f && B[4 * g + e] == 0.f) A[4 * g + e] = Ss[e];
                                 }
                             }
                         }
@@ -284,9 +287,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                         __syncwarp();
                         if (lane == 0) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) { float2 v = xch[j]; B[j] = v.x; A[j] = v.y; }
+                            for (int j = 0; j < 32; ++j) { float2 v = xch[j]; A[j] = v.x; B[j] = v.y; }
                         }
-                        __syncwarp();                // magnitude row and exchange area fully consumed
+                        __syncwarp();                // magnitude row and exchange area fully consumed: the tile is free again
+                        // park the renormalised row, roles swapped, for pass 2 (each lane re-reads only what it wrote)
+#pragma unroll
+                        for (int t = 0; t < 32; ++t) scratch[lane * kRowStride + t] = make_float2(B[t], A[t]);
                     } else if (pass == 2) {
                         // inverse pass 1 result: re = B, im = A; conjugate twiddle, row store
                         scratch[lane * kRowStride] = make_float2(B[0], A[0]);
@@ -298,47 +304,48 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                         __syncwarp();
                     }
                 }
-                __syncwarp();                        // the scratch tile may be rewritten by this warp's next frame
-            }
-            // ---- overlap-add of the frame held in (re = B, im = A) ----
-            if (s == 0) {
-                // software-pipelined tile hand-over: this warp has already computed its first frame of the new tile, so
-                // waiting here for the slowest warp of the previous tile costs (almost) nothing
-                __syncthreads();                     // (A) every warp has added its last frame of the previous tile
-                if (prev_tile >= 0) gl_store_tile<DEFCFG>(P, prev_tile, acc, win_s, rinv_s, hop, win, lo, H, bad);
-                __syncthreads();
-                for (int i = threadIdx.x; i < n_out; i += kThreads) acc[i] = 0.f;
-                if (threadIdx.x < 16) progress[threadIdx.x] = 0;
-                __syncthreads();                     // (B)
-            } else {
-                // my colour-s frame overlaps only frames of the two neighbour warps; those of colour < s must be in
-                if (lane == 0) {
-                    if (warp > 0) while (flag_load(progress + warp - 1) < s) spin_pause();
-                    if (warp < kWarpsPerCta - 1) while (flag_load(progress + warp + 1) < s) spin_pause();
-                }
-                __syncwarp();
-            }
-            if (active) {
-                // window support [lo, lo+win) clipped to the tile -> per-lane bitmasks of the valid t (n = 64 t + lane [+32]).
-                // Touching nothing outside the support is what makes the plain read-modify-write race-free.
-                const int base = (int)((long long)k * hop - kNfft / 2 - s0);      // tile-local index of n = 0
-                const int nlo = max(lo, -base), nhi = min(lo + win, n_out - base);
-                const int a0 = min(max((nlo - lane + 63) >> 6, 0), 32), a1 = min(max((nhi - lane + 63) >> 6, 0), 32);
-                const int b0 = min(max((nlo - lane - 32 + 63) >> 6, 0), 32), b1 = min(max((nhi - lane - 32 + 63) >> 6, 0), 32);
-                const unsigned mre = (a1 > a0) ? ((0xffffffffu >> (32 - (a1 - a0))) << a0) : 0u;
-                const unsigned mim = (b1 > b0) ? ((0xffffffffu >> (32 - (b1 - b0))) << b0) : 0u;
-                constexpr int t0 = PRUNE ? 8 : 0, t1 = PRUNE ? 24 : 32;
-                float* ap = acc + base + lane;
-#pragma unroll
-                for (int t = 0; t < 32; ++t) {
-                    if (t >= t0 && t < t1) {
-                        if ((mre >> t) & 1u) ap[64 * t] = fmaf(B[t], win_s[64 * t + lane], ap[64 * t]);
-                        if ((mim >> t) & 1u) ap[64 * t + 32] = fmaf(A[t], win_s[64 * t + 32 + lane], ap[64 * t + 32]);
+                if (pass == 3) {
+                    // ---- overlap-add of the frame now held in (re = B, im = A) ----
+                    if (s == 0) {
+                        // software-pipelined tile hand-over: this warp has already computed its first frame of the new
+                        // tile, so waiting here for the slowest warp of the previous tile costs (almost) nothing
+                        __syncthreads();             // every warp has added its last frame of the previous tile
+                        if (prev_tile >= 0) gl_store_tile<DEFCFG>(P, prev_tile, acc, win_s, rinv_s, hop, win, lo, H, bad);
+                        __syncthreads();
+                        for (int i = threadIdx.x; i < n_out; i += kThreads) acc[i] = 0.f;
+                        if (threadIdx.x < 16) progress[threadIdx.x] = 0;
+                        __syncthreads();
+                    } else {
+                        // my colour-s frame overlaps only frames of the two neighbour warps; those of colour < s must be in
+                        if (lane == 0) {
+                            if (warp > 0) while (flag_load(progress + warp - 1) < s) spin_pause();
+                            if (warp < kWarpsPerCta - 1) while (flag_load(progress + warp + 1) < s) spin_pause();
+                        }
+                        __syncwarp();
                     }
+                    if (active) {
+                        // window support [lo, lo+win) clipped to the tile -> per-lane bitmasks of the valid t
+                        // (n = 64 t + lane [+32]).  Touching nothing outside the support makes the plain RMW race-free.
+                        const int base = k * hop - kNfft / 2 - s0;            // tile-local index of n = 0
+                        const int nlo = max(lo, -base), nhi = min(lo + win, n_out - base);
+                        const int a0 = min(max((nlo - lane + 63) >> 6, 0), 32), a1 = min(max((nhi - lane + 63) >> 6, 0), 32);
+                        const int b0 = min(max((nlo - lane - 32 + 63) >> 6, 0), 32), b1 = min(max((nhi - lane - 32 + 63) >> 6, 0), 32);
+                        const unsigned mre = (a1 > a0) ? ((0xffffffffu >> (32 - (a1 - a0))) << a0) : 0u;
+                        const unsigned mim = (b1 > b0) ? ((0xffffffffu >> (32 - (b1 - b0))) << b0) : 0u;
+                        constexpr int t0 = PRUNE ? 8 : 0, t1 = PRUNE ? 24 : 32;
+                        float* ap = acc + base + lane;
+#pragma unroll
+                        for (int t = 0; t < 32; ++t) {
+                            if (t >= t0 && t < t1) {
+                                if ((mre >> t) & 1u) ap[64 * t] = fmaf(B[t], win_s[64 * t + lane], ap[64 * t]);
+                                if ((mim >> t) & 1u) ap[64 * t + 32] = fmaf(A[t], win_s[64 * t + 32 + lane], ap[64 * t + 32]);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) flag_store(progress + warp, s + 1);
                 }
             }
-            __syncwarp();
-            if (lane == 0) flag_store(progress + warp, s + 1);
         }
         prev_tile = tile_g;
     }

@@ -10,6 +10,7 @@
 #include "../../include/nspeech_b200.h"
 #include "kernels.cuh"
 #include "gl_iter.cuh"
+#include "gl_iter_v1.cuh"
 
 using namespace nsb;
 
@@ -137,14 +138,17 @@ static size_t gl_smem(int hop, int H) { return synth_smem(hop, H) + 64; }   // +
 static const size_t kSmemPerCtaTwoResident = (227 * 1024) / 2 - 1024;   // two CTAs per SM, 1 KB reserved each
 
 static int max_tile_hops(const nsb_handle_s* h) {
-    // k_gl_iter gives each of its 8 warps C consecutive frames, so a tile may meet at most 8*C frames.  The frames
-    // meeting H hops are the multiples of hop inside an open interval of length H*hop + win: at most H + C of them,
-    // or H + C - 1 when win is a multiple of hop and the interval ends fall on multiples of hop (the default config).
+    // k_gl_iter gives each of its 8 warps C consecutive frames starting from the tile's (virtual) first frame, so a
+    // tile may span at most 8*C frame indices.  The frames meeting H hops are the multiples of hop inside an open
+    // interval of length H*hop + win: at most H + C of them (H + C - 1 when win is a multiple of hop and the interval
+    // ends fall on multiples of hop, the default config).  H is kept a multiple of C: then every tile's frame groups
+    // start at the same residue mod C and the summation order of the overlap-add does not depend on the tiling.
     const int a = kNfft / 2 - h->lo;
     const bool aligned = (h->win % h->hop == 0) && ((a - h->win) % h->hop == 0);
     int H = 8 * h->colours - h->colours + (aligned ? 1 : 0);
-    if (H < 1) H = 1;
-    while (H > 1 && gl_smem(h->hop, H) > kSmemPerCtaTwoResident) --H;
+    H -= H % h->colours;
+    if (H < h->colours) H = h->colours;
+    while (H > h->colours && gl_smem(h->hop, H) > kSmemPerCtaTwoResident) H -= h->colours;
     return H;
 }
 
@@ -270,6 +274,7 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
     SET((k_synth<SRC_SPEC, false>), ss);     SET((k_synth<SRC_SPEC, true>), ss);
     SET((k_synth<SRC_MAGPHASE, false>), ss); SET((k_synth<SRC_MAGPHASE, true>), ss);
     SET((k_synth<SRC_MAGRAND, false>), ss);  SET((k_synth<SRC_MAGRAND, true>), ss);
+    SET((k_gl_iter_v1<true, true, true>), gs); SET((k_gl_iter_v1<true, true, false>), gs);
     SET((k_gl_iter<true, true>), gs); SET((k_gl_iter<true, false>), gs); SET((k_gl_iter<false, false>), gs);
 #undef SET
 #undef CUB
@@ -289,7 +294,7 @@ extern "C" int64_t nsb_num_samples(nsb_handle_t h, int64_t T) { return h ? (int6
 extern "C" uint64_t nsb_kernel_launches(nsb_handle_t h) { return h ? h->launches : 0; }
 extern "C" int nsb_set_generic_iteration(nsb_handle_t h, int32_t on) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");
-    h->use_generic_iter = on ? 1 : 0;
+    h->use_generic_iter = on;
     return NSB_OK;
 }
 extern "C" int nsb_set_tile_hops(nsb_handle_t h, int32_t t) {
@@ -481,15 +486,20 @@ extern "C" int nsb_features(nsb_handle_t h, const float* wav, const int64_t* n_s
 // synthesis entry points
 // ---------------------------------------------------------------------------------------------
 static int choose_tile_hops(nsb_handle_s* h, const int32_t* n_frames, int batch) {
-    const int Hmax = max_tile_hops(h);
-    if (h->user_tile_hops > 0) return h->user_tile_hops < Hmax ? h->user_tile_hops : Hmax;
-    long long hops = 0;
-    for (int b = 0; b < batch; ++b) hops += n_frames[b] - 1;
-    // enough tiles to cover every SM twice when the batch is small; never below one colour cycle
-    long long want = 2LL * h->num_sms;
-    int H = (int)((hops + want - 1) / want);
-    if (H < h->colours) H = h->colours;
-    if (H > Hmax) H = Hmax;
+    const int Hmax = max_tile_hops(h), C = h->colours;
+    int H;
+    if (h->user_tile_hops > 0) {
+        H = h->user_tile_hops < Hmax ? h->user_tile_hops : Hmax;
+    } else {
+        long long hops = 0;
+        for (int b = 0; b < batch; ++b) hops += n_frames[b] - 1;
+        // enough tiles to cover every SM twice when the batch is small
+        long long want = 2LL * h->num_sms;
+        H = (int)((hops + want - 1) / want);
+        if (H > Hmax) H = Hmax;
+    }
+    H -= H % C;                      // multiples of C only (tiling-independent summation order, see max_tile_hops)
+    if (H < C) H = C;
     return H;
 }
 
@@ -546,7 +556,7 @@ extern "C" int nsb_istft(nsb_handle_t h, const float* spec, int32_t layout, cons
 
 static int gl_iterations(nsb_handle_s* h, int iters, cudaStream_t st) {
     float* y[2] = {reinterpret_cast<float*>(h->ws_y0.p), reinterpret_cast<float*>(h->ws_y1.p)};
-    if (h->use_generic_iter) {
+    if (h->use_generic_iter == 1) {
         SynthParams P{};
         P.plan = make_plan(h); P.batch = h->gl.batch; P.mag = reinterpret_cast<const float*>(h->ws_mag.p);
         P.tile_hops = h->gl.tile_hops; P.colours = h->colours; P.status = h->d_status;
@@ -567,7 +577,9 @@ static int gl_iterations(nsb_handle_s* h, int iters, cudaStream_t st) {
     const int grid = h->gl.total_tiles < 2 * h->num_sms ? h->gl.total_tiles : 2 * h->num_sms;   // persistent: 2 CTAs per SM
     for (int it = 0; it < iters; ++it) {
         G.y_in = y[h->gl.cur]; G.y_out = y[h->gl.cur ^ 1];
-        if (h->defcfg) NSB_LAUNCH((k_gl_iter<true, true>), grid, kThreads, smem, st, G);
+        if (h->defcfg && h->use_generic_iter == 2) NSB_LAUNCH((k_gl_iter_v1<true, true, true>), grid, kThreads, smem, st, G);
+        else if (h->defcfg && h->use_generic_iter == 3) NSB_LAUNCH((k_gl_iter_v1<true, true, false>), grid, kThreads, smem, st, G);
+        else if (h->defcfg) NSB_LAUNCH((k_gl_iter<true, true>), grid, kThreads, smem, st, G);
         else if (h->prune) NSB_LAUNCH((k_gl_iter<true, false>), grid, kThreads, smem, st, G);
         else NSB_LAUNCH((k_gl_iter<false, false>), grid, kThreads, smem, st, G);
         int rc = check_launch(h, "k_gl_iter");

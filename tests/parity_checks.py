@@ -102,7 +102,7 @@ def check_ragged_batch_and_tiles():
     packed, pph = np.concatenate(specs), np.concatenate(phases)
     refs = [ao.inv_spectrogram(s.T, ohp, angles=p.T, iters=3) for s, p in zip(specs, phases)]
     outs = []
-    for tile in (0, 1, 4, 7, 29):
+    for tile in (0, 4, 8, 16, 28):
         h.set_tile_hops(tile)
         out = np.empty(sum(h.num_samples(T) for T in Ts), dtype=np.float64)
         h.griffin_lim(packed, _lib.FRAME_MAJOR, Ts, out, init_phase=pph, iters=3,
