@@ -264,7 +264,9 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
     CUB(cudaMalloc(&h->d_status, sizeof(int)));
     CUB(cudaMemset(h->d_status, 0, sizeof(int)));
     // opt in to the large dynamic shared memory of every instantiation
-    const size_t as = analysis_smem(), ss = synth_smem(hop, max_tile_hops(h)), gs = gl_smem(hop, max_tile_hops(h));
+    // The opt-in limit is a per-FUNCTION attribute shared by every handle of the process: always raise it to the
+    // device maximum (a handle with a smaller hop must not lower it under another handle's launches).
+    const size_t as = prop.sharedMemPerBlockOptin, ss = prop.sharedMemPerBlockOptin, gs = prop.sharedMemPerBlockOptin;
     h->defcfg = (hop == 250 && win == 1000 && h->lo == 524) ? 1 : 0;
 #define SET(k, b) do { rc = set_smem(k, b); if (rc) return bail(rc); } while (0)
     SET((k_analysis<ANALYSIS_COMPLEX, false, false>), as); SET((k_analysis<ANALYSIS_COMPLEX, false, true>), as);
