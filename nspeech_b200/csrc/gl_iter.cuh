@@ -110,7 +110,9 @@ __device__ __noinline__ void gl_store_tile(const GlParams& P, int tile_g, const 
     }
 }
 
-template <bool PRUNE, bool DEFCFG>
+// PIPE: software-pipelined tile hand-over (the previous tile is normalised/stored after the warp has computed the
+// first frame of the next one) instead of a barrier pair at the end of every tile.
+template <bool PRUNE, bool DEFCFG, bool PIPE>
 __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
     NSB_DYN_SMEM(smem_raw);
     const int hop = DEFCFG ? 250 : P.plan.hop;
@@ -163,194 +165,183 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
         if (k_max > T - 1) k_max = T - 1;
         if (k_max - k_first + 1 > kWarpsPerCta * C) bad = true;   // host sizes tiles so this cannot happen; never drop frames silently
         const int kg = k_first + C * warp;
+        if (!PIPE) {
+            for (int i = threadIdx.x; i < n_out; i += kThreads) acc[i] = 0.f;
+            if (threadIdx.x < 16) progress[threadIdx.x] = 0;
+            __syncthreads();
+        }
 
         for (int s = 0; s < C; ++s) {
             const int k = kg + s;
             const bool active = (k >= 0 && k <= k_max);        // warp-uniform
-            const int fg = f_off + k;
-            // One shared copy of the forward FFT32 serves the frame's four passes: every pass is
-            //   load (global / scratch) -> FFT32 -> post-process -> store (scratch / accumulator)
-            // so nothing array-sized is live across the loop's back edge; the inverse passes run the same butterflies
-            // with the real/imaginary roles swapped (ifft(re, im) = swap(fft(im, re))), the swap folded into the
-            // loads and stores.  (Four inlined copies made ~98 KB of SASS and the kernel instruction-fetch bound.)
-#pragma unroll 1
-            for (int pass = 0; pass < 4; ++pass) {
-                float A[32], B[32];
-                if (active) {
-                    if (pass == 0) {
-                        load_frame<false, PRUNE>(A, B, P.y_in + s_off, L, (long long)k * hop - kNfft / 2, win_s, lane, 0.f, 1.0f,
-                                                 reinterpret_cast<float*>(scratch));
-                    } else if (pass == 1) {
+            float re[32], im[32];
+            if (active) {
+                const int fg = f_off + k;
+                load_frame<false, PRUNE>(re, im, P.y_in + s_off, L, (long long)k * hop - kNfft / 2, win_s, lane, 0.f, 1.0f,
+                                         reinterpret_cast<float*>(scratch));
+                fwd_phase1(re, im, lane, scratch, tw_s);
+                __syncwarp();
 #pragma unroll
-                        for (int t = 0; t < 32; ++t) { float2 v = scratch[lane * kRowStride + t]; A[t] = v.x; B[t] = v.y; }
-                        __syncwarp();                // every lane has its row: the scratch tile is free
-                        const char* src = reinterpret_cast<const char*>(P.mag + (size_t)fg * kMagPitch);
-                        char* dst = reinterpret_cast<char*>(scratch);
+                for (int t = 0; t < 32; ++t) { float2 v = scratch[lane * kRowStride + t]; re[t] = v.x; im[t] = v.y; }
+                __syncwarp();                        // every lane has its row: the scratch tile is free
+                {
+                    const char* src = reinterpret_cast<const char*>(P.mag + (size_t)fg * kMagPitch);
+                    char* dst = reinterpret_cast<char*>(scratch);
 #pragma unroll
-                        for (int g = 0; g < 8; ++g) cp_async16(dst + (g * 32 + lane) * 16, src + (g * 32 + lane) * 16);
-                        if (lane == 0) cp_async16(dst + 4096, src + 4096);
-                    } else if (pass == 2) {
-                        // own row back, roles swapped (stored as (im, re) by pass 1)
+                    for (int g = 0; g < 8; ++g) cp_async16(dst + (g * 32 + lane) * 16, src + (g * 32 + lane) * 16);
+                    if (lane == 0) cp_async16(dst + 4096, src + 4096);
+                }
+                fft32<-1>(re, im);
+                float2* xch = scratch + kXchOffsetF2;
+                if (lane == 0) {
 #pragma unroll
-                        for (int t = 0; t < 32; ++t) { float2 v = scratch[lane * kRowStride + t]; A[t] = v.x; B[t] = v.y; }
-                    } else {
-                        // column load with swapped roles (B = re, A = im), then the inverse real-64 pre-split
-                        const float* row0 = reinterpret_cast<const float*>(scratch);
-                        B[0] = row0[lane];
-                        A[0] = row0[lane + 32];
+                    for (int j = 0; j < 32; ++j) xch[j] = make_float2(re[j], im[j]);
+                }
+                cp_async_wait_all();
+                __syncwarp();
+                const float4* mrow = reinterpret_cast<const float4*>(scratch);
+                const float* mflt = reinterpret_cast<const float*>(scratch);
+                bool zero = false;
+                // (a) every lane renormalises its 32 slots (lane 0's registers hold the packed-row FFT, not bins:
+                //     replaced below)
 #pragma unroll
-                        for (int q = 1; q < 32; ++q) { float2 v = scratch[q * kRowStride + lane]; B[q] = v.x; A[q] = v.y; }
-                        real64_pre(B, A);
-                    }
-
-                    fft32<-1>(A, B);
-
-                    if (pass == 0) {
-                        real64_post(A, B);
-                        float* row0 = reinterpret_cast<float*>(scratch);
-                        row0[lane] = A[0];
-                        row0[lane + 32] = B[0];
-#pragma unroll
-                        for (int q = 1; q < 32; ++q) {
-                            float2 w = tw_s[(q - 1) * 32 + lane];
-                            scratch[q * kRowStride + lane] = make_float2(A[q] * w.x - B[q] * w.y, A[q] * w.y + B[q] * w.x);
-                        }
-                        __syncwarp();
-                    } else if (pass == 1) {
-                        float2* xch = scratch + kXchOffsetF2;
-                        if (lane == 0) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) xch[j] = make_float2(A[j], B[j]);
-                        }
-                        cp_async_wait_all();
-                        __syncwarp();
-                        const float4* mrow = reinterpret_cast<const float4*>(scratch);
-                        const float* mflt = reinterpret_cast<const float*>(scratch);
-                        bool zero = false;
-                        // (a) every lane renormalises its 32 slots (lane 0's registers hold the packed-row FFT, not bins:
-                        //     replaced below)
+                for (int g = 0; g < 8; ++g) {
+                    float4 S = mrow[g * 32 + lane];
+                    renorm_fast(re[4 * g], im[4 * g], S.x, zero);
+                    renorm_fast(re[4 * g + 1], im[4 * g + 1], S.y, zero);
+                    renorm_fast(re[4 * g + 2], im[4 * g + 2], S.z, zero);
+                    renorm_fast(re[4 * g + 3], im[4 * g + 3], S.w, zero);
+                }
+                if (lane == 0) zero = false;
+                if (warp_any(zero)) {                // rare: some bin of y's STFT is exactly 0 -> phase 0 (np.angle(0))
+                    if (lane != 0) {
 #pragma unroll
                         for (int g = 0; g < 8; ++g) {
                             float4 S = mrow[g * 32 + lane];
-                            renorm_fast(A[4 * g], B[4 * g], S.x, zero);
-                            renorm_fast(A[4 * g + 1], B[4 * g + 1], S.y, zero);
-                            renorm_fast(A[4 * g + 2], B[4 * g + 2], S.z, zero);
-                            renorm_fast(A[4 * g + 3], B[4 * g + 3], S.w, zero);
-                        }
-                        if (lane == 0) zero = false;
-                        if (warp_any(zero)) {        // rare: some bin of y's STFT is exactly 0 -> phase 0 (np.angle(0))
-                            if (lane != 0) {
+                            const float Ss[4] = {S.x, S.y, S.z, S.w};
 #pragma unroll
-                                for (int g = 0; g < 8; ++g) {
-                                    float4 S = mrow[g * 32 + lane];
-                                    const float Ss[4] = {S.x, S.y, S.z, S.w};
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e)
-                                        if (A[4 * g + e] == 0.f && B[4 * g + e] == 0.f) A[4 * g + e] = Ss[e];
-                                }
-                            }
+                            for (int e = 0; e < 4; ++e)
+                                if (re[4 * g + e] == 0.f && im[4 * g + e] == 0.f) re[4 * g + e] = Ss[e];
                         }
-                        // (b) bins k = 32 j (rows 0/32): lane j in 1..16 does pair (j, 32-j); lane 0 the real DC/Nyquist pair
-                        if (lane <= 16) {
-                            if (lane == 0) {
-                                float2 g0 = xch[0];
-                                float x0 = g0.x + g0.y, xn = g0.x - g0.y;      // (X[0], X[1024]) up to the factor 2
-                                float S0 = mflt[0], Sn = mflt[1024];
-                                x0 = (x0 < 0.f) ? -S0 : S0;                     // phase of a real number is its sign
-                                xn = (xn < 0.f) ? -Sn : Sn;
-                                xch[0] = make_float2(x0 + xn, x0 - xn);
-                            } else {
-                                const int j = lane, jj = 32 - lane;
-                                // u = -i * w64^j with w64^j = w2048^(16 * 2j) from the twiddle table (j = 16: w = -i)
-                                const float2 wj = (j <= 15) ? tw_s[15 * 32 + 2 * j] : make_float2(0.f, -1.f);
-                                const float ur = wj.y, ui = -wj.x;
-                                float2 Aj = xch[j], Bj = xch[jj];
-                                float sr = Aj.x + Bj.x, si = Aj.y - Bj.y, dr = Aj.x - Bj.x, di = Aj.y + Bj.y;
-                                float tr = dr * ur - di * ui, ti = dr * ui + di * ur;
-                                float c1r = sr + tr, c1i = si + ti;             // 2*X[32 j]
-                                float c2r = sr - tr, c2i = -(si - ti);          // 2*X[32 (32-j)]
-                                bool z2 = false;
-                                renorm_fast(c1r, c1i, mflt[(j >> 2) * 128 + (j & 3)], z2);
-                                renorm_fast(c2r, c2i, mflt[(jj >> 2) * 128 + (jj & 3)], z2);
-                                if (z2) {
-                                    if (c1r == 0.f && c1i == 0.f) c1r = mflt[(j >> 2) * 128 + (j & 3)];
-                                    if (c2r == 0.f && c2i == 0.f) c2r = mflt[(jj >> 2) * 128 + (jj & 3)];
-                                }
-                                // inverse split: S' = V[j] + conj V[32-j], D' = V[j] - conj V[32-j], P = D' * conj(u)
-                                float s2r = c1r + c2r, s2i = c1i - c2i, d2r = c1r - c2r, d2i = c1i + c2i;
-                                float pr = d2r * ur + d2i * ui, pi = d2i * ur - d2r * ui;
-                                // lane j reads and writes only xch[j] and xch[32-j]: no cross-lane hazard inside this block
-                                xch[j] = make_float2(s2r + pr, s2i + pi);
-                                if (j != 16) xch[jj] = make_float2(s2r - pr, -s2i + pi);
-                            }
-                        }
-                        __syncwarp();
-                        if (lane == 0) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) { float2 v = xch[j]; A[j] = v.x; B[j] = v.y; }
-                        }
-                        __syncwarp();                // magnitude row and exchange area fully consumed: the tile is free again
-                        // park the renormalised row, roles swapped, for pass 2 (each lane re-reads only what it wrote)
-#pragma unroll
-                        for (int t = 0; t < 32; ++t) scratch[lane * kRowStride + t] = make_float2(B[t], A[t]);
-                    } else if (pass == 2) {
-                        // inverse pass 1 result: re = B, im = A; conjugate twiddle, row store
-                        scratch[lane * kRowStride] = make_float2(B[0], A[0]);
-#pragma unroll
-                        for (int r = 1; r < 32; ++r) {
-                            float2 w = tw_s[(r - 1) * 32 + lane];
-                            scratch[lane * kRowStride + r] = make_float2(B[r] * w.x + A[r] * w.y, A[r] * w.x - B[r] * w.y);
-                        }
-                        __syncwarp();
                     }
                 }
-                if (pass == 3) {
-                    // ---- overlap-add of the frame now held in (re = B, im = A) ----
-                    if (s == 0) {
-                        // software-pipelined tile hand-over: this warp has already computed its first frame of the new
-                        // tile, so waiting here for the slowest warp of the previous tile costs (almost) nothing
-                        __syncthreads();             // every warp has added its last frame of the previous tile
-                        if (prev_tile >= 0) gl_store_tile<DEFCFG>(P, prev_tile, acc, win_s, rinv_s, hop, win, lo, H, bad);
-                        __syncthreads();
-                        for (int i = threadIdx.x; i < n_out; i += kThreads) acc[i] = 0.f;
-                        if (threadIdx.x < 16) progress[threadIdx.x] = 0;
-                        __syncthreads();
+                // (b) bins k = 32 j (rows 0/32): lane j in 1..16 does pair (j, 32-j); lane 0 the real DC/Nyquist pair
+                if (lane <= 16) {
+                    if (lane == 0) {
+                        float2 g0 = xch[0];
+                        float x0 = g0.x + g0.y, xn = g0.x - g0.y;          // (X[0], X[1024]) up to the factor 2
+                        float S0 = mflt[0], Sn = mflt[1024];
+                        x0 = (x0 < 0.f) ? -S0 : S0;                         // phase of a real number is its sign
+                        xn = (xn < 0.f) ? -Sn : Sn;
+                        xch[0] = make_float2(x0 + xn, x0 - xn);
                     } else {
-                        // my colour-s frame overlaps only frames of the two neighbour warps; those of colour < s must be in
-                        if (lane == 0) {
-                            if (warp > 0) while (flag_load(progress + warp - 1) < s) spin_pause();
-                            if (warp < kWarpsPerCta - 1) while (flag_load(progress + warp + 1) < s) spin_pause();
+                        const int j = lane, jj = 32 - lane;
+                        // u = -i * w64^j with w64^j = w2048^(16 * 2j) from the twiddle table (j = 16: w = -i)
+                        const float2 wj = (j <= 15) ? tw_s[15 * 32 + 2 * j] : make_float2(0.f, -1.f);
+                        const float ur = wj.y, ui = -wj.x;
+                        float2 Aj = xch[j], Bj = xch[jj];
+                        float sr = Aj.x + Bj.x, si = Aj.y - Bj.y, dr = Aj.x - Bj.x, di = Aj.y + Bj.y;
+                        float tr = dr * ur - di * ui, ti = dr * ui + di * ur;
+                        float c1r = sr + tr, c1i = si + ti;                 // 2*X[32 j]
+                        float c2r = sr - tr, c2i = -(si - ti);              // 2*X[32 (32-j)]
+                        bool z2 = false;
+                        renorm_fast(c1r, c1i, mflt[(j >> 2) * 128 + (j & 3)], z2);
+                        renorm_fast(c2r, c2i, mflt[(jj >> 2) * 128 + (jj & 3)], z2);
+                        if (z2) {
+                            if (c1r == 0.f && c1i == 0.f) c1r = mflt[(j >> 2) * 128 + (j & 3)];
+                            if (c2r == 0.f && c2i == 0.f) c2r = mflt[(jj >> 2) * 128 + (jj & 3)];
                         }
-                        __syncwarp();
+                        // inverse split: S' = V[j] + conj V[32-j], D' = V[j] - conj V[32-j], P = D' * conj(u)
+                        float s2r = c1r + c2r, s2i = c1i - c2i, d2r = c1r - c2r, d2i = c1i + c2i;
+                        float pr = d2r * ur + d2i * ui, pi = d2i * ur - d2r * ui;
+                        // lane j reads and writes only xch[j] and xch[32-j]: no cross-lane hazard inside this block
+                        xch[j] = make_float2(s2r + pr, s2i + pi);
+                        if (j != 16) xch[jj] = make_float2(s2r - pr, -s2i + pi);
                     }
-                    if (active) {
-                        // window support [lo, lo+win) clipped to the tile -> per-lane bitmasks of the valid t
-                        // (n = 64 t + lane [+32]).  Touching nothing outside the support makes the plain RMW race-free.
-                        const int base = k * hop - kNfft / 2 - s0;            // tile-local index of n = 0
-                        const int nlo = max(lo, -base), nhi = min(lo + win, n_out - base);
-                        const int a0 = min(max((nlo - lane + 63) >> 6, 0), 32), a1 = min(max((nhi - lane + 63) >> 6, 0), 32);
-                        const int b0 = min(max((nlo - lane - 32 + 63) >> 6, 0), 32), b1 = min(max((nhi - lane - 32 + 63) >> 6, 0), 32);
-                        const unsigned mre = (a1 > a0) ? ((0xffffffffu >> (32 - (a1 - a0))) << a0) : 0u;
-                        const unsigned mim = (b1 > b0) ? ((0xffffffffu >> (32 - (b1 - b0))) << b0) : 0u;
-                        constexpr int t0 = PRUNE ? 8 : 0, t1 = PRUNE ? 24 : 32;
-                        float* ap = acc + base + lane;
+                }
+                __syncwarp();
+                if (lane == 0) {
 #pragma unroll
-                        for (int t = 0; t < 32; ++t) {
-                            if (t >= t0 && t < t1) {
-                                if ((mre >> t) & 1u) ap[64 * t] = fmaf(B[t], win_s[64 * t + lane], ap[64 * t]);
-                                if ((mim >> t) & 1u) ap[64 * t + 32] = fmaf(A[t], win_s[64 * t + 32 + lane], ap[64 * t + 32]);
-                            }
+                    for (int j = 0; j < 32; ++j) { float2 v = xch[j]; re[j] = v.x; im[j] = v.y; }
+                }
+                __syncwarp();                        // magnitude row and exchange area fully consumed
+                // inverse pass 1 (the lane-0 pre-split already happened above)
+                fft32<+1>(re, im);
+                scratch[lane * kRowStride] = make_float2(re[0], im[0]);
+#pragma unroll
+                for (int r = 1; r < 32; ++r) {
+                    float2 w = tw_s[(r - 1) * 32 + lane];
+                    scratch[lane * kRowStride + r] = make_float2(re[r] * w.x + im[r] * w.y, im[r] * w.x - re[r] * w.y);
+                }
+                __syncwarp();
+                inv_phase2(re, im, lane, scratch);
+                __syncwarp();                        // the scratch tile may be rewritten by this warp's next frame
+            }
+            // ---- overlap-add ordering ----
+            if (PIPE && s == 0) {
+                // this warp has already computed its first frame of the new tile, so waiting here for the slowest
+                // warp of the previous tile costs (almost) nothing
+                __syncthreads();                     // every warp has added its last frame of the previous tile
+                if (prev_tile >= 0) gl_store_tile<DEFCFG>(P, prev_tile, acc, win_s, rinv_s, hop, win, lo, H, bad);
+                __syncthreads();
+                for (int i = threadIdx.x; i < n_out; i += kThreads) acc[i] = 0.f;
+                if (threadIdx.x < 16) progress[threadIdx.x] = 0;
+                __syncthreads();
+            } else if (s > 0) {
+                // my colour-s frame overlaps only frames of the two neighbour warps; those of colour < s must be in
+                if (lane == 0) {
+                    if (warp > 0) while (flag_load(progress + warp - 1) < s) spin_pause();
+                    if (warp < kWarpsPerCta - 1) while (flag_load(progress + warp + 1) < s) spin_pause();
+                }
+                __syncwarp();
+            }
+            if (active) {
+                const int base = k * hop - kNfft / 2 - s0;                    // tile-local index of n = 0
+                constexpr int t0 = PRUNE ? 8 : 0, t1 = PRUNE ? 24 : 32;
+                const bool inside = (base + lo >= 0) && (base + lo + win <= n_out);
+                if (DEFCFG && inside) {
+                    // default hparams: the support n in [524, 1524) is known at compile time
+                    float* ap = acc + base + lane;
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) {
+                        if (t >= t0 && t < t1) {
+                            if (t > 8 || lane >= 12) ap[64 * t] = fmaf(re[t], win_s[64 * t + lane], ap[64 * t]);
+                            if (t < 23 || lane < 20) ap[64 * t + 32] = fmaf(im[t], win_s[64 * t + 32 + lane], ap[64 * t + 32]);
                         }
                     }
-                    __syncwarp();
-                    if (lane == 0) flag_store(progress + warp, s + 1);
+                } else {
+                    // window support [lo, lo+win) clipped to the tile -> per-lane bitmasks of the valid t
+                    // (n = 64 t + lane [+32]).  Touching nothing outside the support makes the plain RMW race-free.
+                    const int nlo = max(lo, -base), nhi = min(lo + win, n_out - base);
+                    const int a0 = min(max((nlo - lane + 63) >> 6, 0), 32), a1 = min(max((nhi - lane + 63) >> 6, 0), 32);
+                    const int b0 = min(max((nlo - lane - 32 + 63) >> 6, 0), 32), b1 = min(max((nhi - lane - 32 + 63) >> 6, 0), 32);
+                    const unsigned mre = (a1 > a0) ? ((0xffffffffu >> (32 - (a1 - a0))) << a0) : 0u;
+                    const unsigned mim = (b1 > b0) ? ((0xffffffffu >> (32 - (b1 - b0))) << b0) : 0u;
+                    float* ap = acc + base + lane;
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) {
+                        if (t >= t0 && t < t1) {
+                            if ((mre >> t) & 1u) ap[64 * t] = fmaf(re[t], win_s[64 * t + lane], ap[64 * t]);
+                            if ((mim >> t) & 1u) ap[64 * t + 32] = fmaf(im[t], win_s[64 * t + 32 + lane], ap[64 * t + 32]);
+                        }
+                    }
                 }
             }
+            __syncwarp();
+            if (lane == 0) flag_store(progress + warp, s + 1);
         }
-        prev_tile = tile_g;
+        if (PIPE) {
+            prev_tile = tile_g;
+        } else {
+            __syncthreads();
+            gl_store_tile<DEFCFG>(P, tile_g, acc, win_s, rinv_s, hop, win, lo, H, bad);
+            __syncthreads();
+        }
     }
-    __syncthreads();
-    if (prev_tile >= 0) gl_store_tile<DEFCFG>(P, prev_tile, acc, win_s, rinv_s, hop, win, lo, H, bad);
+    if (PIPE) {
+        __syncthreads();
+        if (prev_tile >= 0) gl_store_tile<DEFCFG>(P, prev_tile, acc, win_s, rinv_s, hop, win, lo, H, bad);
+    }
     if (bad) atomicOr(P.status, 1);
 }
 

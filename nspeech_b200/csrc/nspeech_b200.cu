@@ -276,8 +276,8 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
     SET((k_synth<SRC_SPEC, false>), ss);     SET((k_synth<SRC_SPEC, true>), ss);
     SET((k_synth<SRC_MAGPHASE, false>), ss); SET((k_synth<SRC_MAGPHASE, true>), ss);
     SET((k_synth<SRC_MAGRAND, false>), ss);  SET((k_synth<SRC_MAGRAND, true>), ss);
-    SET((k_gl_iter_v1<true, true, true>), gs); SET((k_gl_iter_v1<true, true, false>), gs);
-    SET((k_gl_iter<true, true>), gs); SET((k_gl_iter<true, false>), gs); SET((k_gl_iter<false, false>), gs);
+    SET((k_gl_iter_v1<true, true, false>), gs); SET((k_gl_iter<true, true, false>), gs);
+    SET((k_gl_iter<true, true, true>), gs); SET((k_gl_iter<true, false, true>), gs); SET((k_gl_iter<false, false, true>), gs);
 #undef SET
 #undef CUB
     *out = h;
@@ -579,11 +579,11 @@ static int gl_iterations(nsb_handle_s* h, int iters, cudaStream_t st) {
     const int grid = h->gl.total_tiles < 2 * h->num_sms ? h->gl.total_tiles : 2 * h->num_sms;   // persistent: 2 CTAs per SM
     for (int it = 0; it < iters; ++it) {
         G.y_in = y[h->gl.cur]; G.y_out = y[h->gl.cur ^ 1];
-        if (h->defcfg && h->use_generic_iter == 2) NSB_LAUNCH((k_gl_iter_v1<true, true, true>), grid, kThreads, smem, st, G);
+        if (h->defcfg && h->use_generic_iter == 2) NSB_LAUNCH((k_gl_iter<true, true, false>), grid, kThreads, smem, st, G);
         else if (h->defcfg && h->use_generic_iter == 3) NSB_LAUNCH((k_gl_iter_v1<true, true, false>), grid, kThreads, smem, st, G);
-        else if (h->defcfg) NSB_LAUNCH((k_gl_iter<true, true>), grid, kThreads, smem, st, G);
-        else if (h->prune) NSB_LAUNCH((k_gl_iter<true, false>), grid, kThreads, smem, st, G);
-        else NSB_LAUNCH((k_gl_iter<false, false>), grid, kThreads, smem, st, G);
+        else if (h->defcfg) NSB_LAUNCH((k_gl_iter<true, true, true>), grid, kThreads, smem, st, G);
+        else if (h->prune) NSB_LAUNCH((k_gl_iter<true, false, true>), grid, kThreads, smem, st, G);
+        else NSB_LAUNCH((k_gl_iter<false, false, true>), grid, kThreads, smem, st, G);
         int rc = check_launch(h, "k_gl_iter");
         if (rc) return rc;
         h->gl.cur ^= 1;
