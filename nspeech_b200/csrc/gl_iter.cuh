@@ -110,9 +110,11 @@ __device__ __noinline__ void gl_store_tile(const GlParams& P, int tile_g, const 
     }
 }
 
-// PIPE: software-pipelined tile hand-over (the previous tile is normalised/stored after the warp has computed the
-// first frame of the next one) instead of a barrier pair at the end of every tile.
-template <bool PRUNE, bool DEFCFG, bool PIPE>
+// Rejected variants (measured on B200, batch 64 x 1000 frames, see profiles/README.md): one shared FFT32 copy for
+// the four passes through a rolled pass loop (i-cache stalls 23% -> 6% but +12% instructions from loop-carried
+// register shuffling: no gain); software-pipelined tile hand-over (4% slower); global-colour order that rotates
+// the warp's frames (12% slower than increasing order, hence the aligned tiles below).
+template <bool PRUNE, bool DEFCFG>
 __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
     NSB_DYN_SMEM(smem_raw);
     const int hop = DEFCFG ? 250 : P.plan.hop;
@@ -144,7 +146,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
         rinv_s[j] = s > 1.17549435e-38f ? 1.0f / s : 1.0f;
     }
     bool bad = false;
-    int prev_tile = -1;
 
     for (int tile_g = blockIdx.x; tile_g < P.total_tiles; tile_g += gridDim.x) {
         const int b = find_segment(P.batch.tile_off, P.batch.batch, tile_g);
@@ -165,11 +166,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
         if (k_max > T - 1) k_max = T - 1;
         if (k_max - k_first + 1 > kWarpsPerCta * C) bad = true;   // host sizes tiles so this cannot happen; never drop frames silently
         const int kg = k_first + C * warp;
-        if (!PIPE) {
-            for (int i = threadIdx.x; i < n_out; i += kThreads) acc[i] = 0.f;
-            if (threadIdx.x < 16) progress[threadIdx.x] = 0;
-            __syncthreads();
-        }
+        for (int i = threadIdx.x; i < n_out; i += kThreads) acc[i] = 0.f;
+        if (threadIdx.x < 16) progress[threadIdx.x] = 0;
+        __syncthreads();
 
         for (int s = 0; s < C; ++s) {
             const int k = kg + s;
@@ -278,16 +277,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                 __syncwarp();                        // the scratch tile may be rewritten by this warp's next frame
             }
             // ---- overlap-add ordering ----
-            if (PIPE && s == 0) {
-                // this warp has already computed its first frame of the new tile, so waiting here for the slowest
-                // warp of the previous tile costs (almost) nothing
-                __syncthreads();                     // every warp has added its last frame of the previous tile
-                if (prev_tile >= 0) gl_store_tile<DEFCFG>(P, prev_tile, acc, win_s, rinv_s, hop, win, lo, H, bad);
-                __syncthreads();
-                for (int i = threadIdx.x; i < n_out; i += kThreads) acc[i] = 0.f;
-                if (threadIdx.x < 16) progress[threadIdx.x] = 0;
-                __syncthreads();
-            } else if (s > 0) {
+            if (s > 0) {
                 // my colour-s frame overlaps only frames of the two neighbour warps; those of colour < s must be in
                 if (lane == 0) {
                     if (warp > 0) while (flag_load(progress + warp - 1) < s) spin_pause();
@@ -330,17 +320,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
             __syncwarp();
             if (lane == 0) flag_store(progress + warp, s + 1);
         }
-        if (PIPE) {
-            prev_tile = tile_g;
-        } else {
-            __syncthreads();
-            gl_store_tile<DEFCFG>(P, tile_g, acc, win_s, rinv_s, hop, win, lo, H, bad);
-            __syncthreads();
-        }
-    }
-    if (PIPE) {
         __syncthreads();
-        if (prev_tile >= 0) gl_store_tile<DEFCFG>(P, prev_tile, acc, win_s, rinv_s, hop, win, lo, H, bad);
+        gl_store_tile<DEFCFG>(P, tile_g, acc, win_s, rinv_s, hop, win, lo, H, bad);
+        __syncthreads();                             // acc and progress are reused by the next tile
     }
     if (bad) atomicOr(P.status, 1);
 }

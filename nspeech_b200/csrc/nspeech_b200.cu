@@ -10,7 +10,6 @@
 #include "../../include/nspeech_b200.h"
 #include "kernels.cuh"
 #include "gl_iter.cuh"
-#include "gl_iter_v1.cuh"
 
 using namespace nsb;
 
@@ -276,8 +275,7 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
     SET((k_synth<SRC_SPEC, false>), ss);     SET((k_synth<SRC_SPEC, true>), ss);
     SET((k_synth<SRC_MAGPHASE, false>), ss); SET((k_synth<SRC_MAGPHASE, true>), ss);
     SET((k_synth<SRC_MAGRAND, false>), ss);  SET((k_synth<SRC_MAGRAND, true>), ss);
-    SET((k_gl_iter_v1<true, true, false>), gs); SET((k_gl_iter<true, true, false>), gs);
-    SET((k_gl_iter<true, true, true>), gs); SET((k_gl_iter<true, false, true>), gs); SET((k_gl_iter<false, false, true>), gs);
+    SET((k_gl_iter<true, true>), gs); SET((k_gl_iter<true, false>), gs); SET((k_gl_iter<false, false>), gs);
 #undef SET
 #undef CUB
     *out = h;
@@ -489,20 +487,24 @@ extern "C" int nsb_features(nsb_handle_t h, const float* wav, const int64_t* n_s
 // ---------------------------------------------------------------------------------------------
 static int choose_tile_hops(nsb_handle_s* h, const int32_t* n_frames, int batch) {
     const int Hmax = max_tile_hops(h), C = h->colours;
-    int H;
     if (h->user_tile_hops > 0) {
-        H = h->user_tile_hops < Hmax ? h->user_tile_hops : Hmax;
-    } else {
-        long long hops = 0;
-        for (int b = 0; b < batch; ++b) hops += n_frames[b] - 1;
-        // enough tiles to cover every SM twice when the batch is small
-        long long want = 2LL * h->num_sms;
-        H = (int)((hops + want - 1) / want);
-        if (H > Hmax) H = Hmax;
+        int H = h->user_tile_hops < Hmax ? h->user_tile_hops : Hmax;
+        H -= H % C;                  // multiples of C only (tiling-independent summation order, see max_tile_hops)
+        return H < C ? C : H;
     }
-    H -= H % C;                      // multiples of C only (tiling-independent summation order, see max_tile_hops)
-    if (H < C) H = C;
-    return H;
+    // persistent grid of 2*#SMs CTAs; a CTA spends ~C frame-times per tile whatever H is (one frame per warp and
+    // colour), so the launch takes ceil(tiles / CTAs) * C frame-times: pick the multiple of C that minimises the number
+    // of waves, and among equals the largest tile (least halo recomputation)
+    const long long ctas = 2LL * h->num_sms;
+    int best = C;
+    long long best_waves = -1;
+    for (int H = C; H <= Hmax; H += C) {
+        long long tiles = 0;
+        for (int b = 0; b < batch; ++b) tiles += (n_frames[b] - 1 + H - 1) / H;
+        const long long waves = (tiles + ctas - 1) / ctas;
+        if (best_waves < 0 || waves <= best_waves) { best = H; best_waves = waves; }
+    }
+    return best;
 }
 
 template <int SRC>
@@ -579,11 +581,9 @@ static int gl_iterations(nsb_handle_s* h, int iters, cudaStream_t st) {
     const int grid = h->gl.total_tiles < 2 * h->num_sms ? h->gl.total_tiles : 2 * h->num_sms;   // persistent: 2 CTAs per SM
     for (int it = 0; it < iters; ++it) {
         G.y_in = y[h->gl.cur]; G.y_out = y[h->gl.cur ^ 1];
-        if (h->defcfg && h->use_generic_iter == 2) NSB_LAUNCH((k_gl_iter<true, true, false>), grid, kThreads, smem, st, G);
-        else if (h->defcfg && h->use_generic_iter == 3) NSB_LAUNCH((k_gl_iter_v1<true, true, false>), grid, kThreads, smem, st, G);
-        else if (h->defcfg) NSB_LAUNCH((k_gl_iter<true, true, true>), grid, kThreads, smem, st, G);
-        else if (h->prune) NSB_LAUNCH((k_gl_iter<true, false, true>), grid, kThreads, smem, st, G);
-        else NSB_LAUNCH((k_gl_iter<false, false, true>), grid, kThreads, smem, st, G);
+        if (h->defcfg) NSB_LAUNCH((k_gl_iter<true, true>), grid, kThreads, smem, st, G);
+        else if (h->prune) NSB_LAUNCH((k_gl_iter<true, false>), grid, kThreads, smem, st, G);
+        else NSB_LAUNCH((k_gl_iter<false, false>), grid, kThreads, smem, st, G);
         int rc = check_launch(h, "k_gl_iter");
         if (rc) return rc;
         h->gl.cur ^= 1;

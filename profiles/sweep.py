@@ -30,7 +30,7 @@ for batch, tile, generic in cases:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     print("batch %4d tile %2d %s: %.4f ms/iter  %.2f ns/frame-iter  -> %.0f audio-s/s at 61 passes" % (
-        batch, tile, {0: "k_gl_iter pipe", 1: "k_synth<Y>    ", 2: "k_gl_iter nopipe", 3: "gl_v1 seq (ref)"}[generic], ms, ms * 1e6 / (batch * T), batch * T * 0.0125 / (ms * 1e-3 * 61)), flush=True)
+        batch, tile, {0: "k_gl_iter ", 1: "k_synth<Y>"}[generic], ms, ms * 1e6 / (batch * T), batch * T * 0.0125 / (ms * 1e-3 * 61)), flush=True)
     del spec, out
 h.set_tile_hops(0)
 h.set_generic_iteration(0)
