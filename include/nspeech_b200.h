@@ -138,6 +138,7 @@ int nsb_free_pinned(void* p);
 
 /* tuning / accounting hooks (not in the reference) */
 int nsb_set_tile_hops(nsb_handle_t h, int32_t tile_hops);       /* 0 = automatic */
+int nsb_set_host_chunks(nsb_handle_t h, int32_t n);             /* NSB_HOST Griffin-Lim pipelining: 0 = automatic (4 chunks above 8 MB), n = force n chunks */
 int nsb_set_generic_iteration(nsb_handle_t h, int32_t on);     /* A/B hook: iterate with the generic k_synth<SRC_Y> kernel instead of k_gl_iter */
 uint64_t nsb_kernel_launches(nsb_handle_t h);                    /* kernels launched through this handle so far */
 /* the Griffin-Lim iteration kernel alone on device-resident state, for roofline timing: runs `iters`

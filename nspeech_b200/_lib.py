@@ -63,6 +63,7 @@ SIGNATURES = {
     "nsb_check_status": (ctypes.c_int, [_vp, _vp]),
     "nsb_set_tile_hops": (ctypes.c_int, [_vp, _i32]),
     "nsb_set_generic_iteration": (ctypes.c_int, [_vp, _i32]),
+    "nsb_set_host_chunks": (ctypes.c_int, [_vp, _i32]),
     "nsb_kernel_launches": (_u64, [_vp]),
     "nsb_griffin_lim_iterate": (ctypes.c_int, [_vp, _i32, _vp]),
     "nsb_alloc_pinned": (ctypes.c_int, [_u64, ctypes.POINTER(_vp)]),
@@ -243,6 +244,9 @@ class Handle(object):
 
     def set_tile_hops(self, t):
         self._call("nsb_set_tile_hops", int(t))
+
+    def set_host_chunks(self, n):
+        self._call("nsb_set_host_chunks", int(n))
 
     def set_generic_iteration(self, on):
         self._call("nsb_set_generic_iteration", int(on))

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
     }
     bool bad = false;
 
-    for (int tile_g = blockIdx.x; tile_g < P.total_tiles; tile_g += gridDim.x) {
+    for (int tile_g = P.batch.tile_base + blockIdx.x; tile_g < P.batch.tile_base + P.total_tiles; tile_g += gridDim.x) {
         const int b = find_segment(P.batch.tile_off, P.batch.batch, tile_g);
         const int tile = tile_g - __ldg(P.batch.tile_off + b);
         const int f_off = __ldg(P.batch.frame_off + b);

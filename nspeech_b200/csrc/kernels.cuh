@@ -35,6 +35,8 @@ struct Batch {
     const long long* samp_off;   // [batch+1]
     const int* tile_off;         // [batch+1] (synthesis tiles), may be null for analysis
     int batch;
+    int frame_base, tile_base;   // global index of this (sub-)batch's first frame / tile: the arrays hold GLOBAL prefix
+                                 // sums, so a chunk of a batch is just a pointer offset + these bases (host-side pipelining)
 };
 
 struct Plan {                    // device tables owned by the handle
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
     const int hop = P.plan.hop;
     bool bad = false;
     int b = 0;
-    for (int f = blockIdx.x * kWarpsPerCta + warp; f < P.total_frames; f += gridDim.x * kWarpsPerCta) {
+    for (int f = P.batch.frame_base + blockIdx.x * kWarpsPerCta + warp; f < P.batch.frame_base + P.total_frames; f += gridDim.x * kWarpsPerCta) {
         if (!(f >= __ldg(P.batch.frame_off + b) && f < __ldg(P.batch.frame_off + b + 1)))
             b = find_segment(P.batch.frame_off, P.batch.batch, f);
         const int k = f - __ldg(P.batch.frame_off + b);
@@ -289,8 +291,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_synth(SynthParams P) {
     const int a = kNfft / 2 - lo;          // frame k's window support starts at sample k*hop - a
     const int C = P.colours, H = P.tile_hops;
 
-    const int b = find_segment(P.batch.tile_off, P.batch.batch, (int)blockIdx.x);
-    const int tile = blockIdx.x - __ldg(P.batch.tile_off + b);
+    const int tile_g = P.batch.tile_base + (int)blockIdx.x;
+    const int b = find_segment(P.batch.tile_off, P.batch.batch, tile_g);
+    const int tile = tile_g - __ldg(P.batch.tile_off + b);
     const int f_off = __ldg(P.batch.frame_off + b);
     const int T = __ldg(P.batch.frame_off + b + 1) - f_off;
     const long long s_off = __ldg(P.batch.samp_off + b);
@@ -484,11 +487,44 @@ __device__ __forceinline__ int slot_index(int bin) {
     return ((p >> 2) * 32 + lane) * 4 + (p & 3);
 }
 
+// S = (10 ** ((clip(v,0,1) * -min + min + ref) * 0.05)) ** power, evaluated as one double exp10 and rounded once
+__device__ __forceinline__ float prep_magnitude(const PrepParams& P, float v) {
+    if (!P.denorm) return fabsf(v) * P.scale;
+    double c = fmin(fmax((double)v, 0.0), 1.0);
+    double db = c * (-P.min_level_db) + P.min_level_db + P.ref_level_db;
+    return (float)(exp10(db * 0.05 * P.power) * (double)P.scale);
+}
+
+// frame-major input: one warp per frame, row staged in shared memory in slot order, written back as float4
+__global__ void __launch_bounds__(kThreads) k_prepare_mag_rows(PrepParams P) {
+    __align__(16) __shared__ float row[kWarpsPerCta][kMagPitch];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool bad = false;
+    int b = 0;
+    for (int f = P.batch.frame_base + blockIdx.x * kWarpsPerCta + warp; f < P.batch.frame_base + P.total_frames; f += gridDim.x * kWarpsPerCta) {
+        if (!(f >= __ldg(P.batch.frame_off + b) && f < __ldg(P.batch.frame_off + b + 1)))
+            b = find_segment(P.batch.frame_off, P.batch.batch, f);
+        const float* in = P.in + (size_t)f * kBins;            // frame-major blocks are packed: global frame index addresses the row
+        for (int i = 1025 + lane; i < kMagPitch; i += 32) row[warp][i] = 0.f;
+        for (int kb = lane; kb < kBins; kb += 32) {
+            float v = __ldg(in + kb);
+            bad |= !isfinite(v);
+            row[warp][slot_index(kb)] = prep_magnitude(P, v);
+        }
+        __syncwarp();
+        float4* out = reinterpret_cast<float4*>(P.mag + (size_t)f * kMagPitch);
+        const float4* r4 = reinterpret_cast<const float4*>(row[warp]);
+        for (int i = lane; i < kMagPitch / 4; i += 32) out[i] = r4[i];
+        __syncwarp();
+    }
+    if (bad) atomicOr(P.status, 1);
+}
+
 __global__ void __launch_bounds__(256) k_prepare_mag(PrepParams P) {
     // one block per (utterance-local) tile of 32 frames x 32 bins, through a padded smem tile so that both the
     // read (contiguous along the input's fast axis) and the per-frame scatter stay inside a few cache lines
     __shared__ float tile[32][33];
-    const int f0 = blockIdx.x * 32;                 // global frame index base
+    const int f0 = P.batch.frame_base + blockIdx.x * 32;   // global frame index base
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
     bool bad = false;
     for (int kb0 = 0; kb0 < kBins; kb0 += 32) {
@@ -497,7 +533,7 @@ __global__ void __launch_bounds__(256) k_prepare_mag(PrepParams P) {
             int f, kb;
             if (P.bin_major) { f = f0 + tx; kb = kb0 + r; } else { f = f0 + r; kb = kb0 + tx; }
             float v = 0.f;
-            if (f < P.total_frames && kb < kBins) {
+            if (f < P.batch.frame_base + P.total_frames && kb < kBins) {
                 int b = find_segment(P.batch.frame_off, P.batch.batch, f);
                 int fo = __ldg(P.batch.frame_off + b);
                 int T = __ldg(P.batch.frame_off + b + 1) - fo;
@@ -509,18 +545,10 @@ __global__ void __launch_bounds__(256) k_prepare_mag(PrepParams P) {
         __syncthreads();
         for (int r = ty; r < 32; r += 8) {
             int f = f0 + r, kb = kb0 + tx;
-            if (f < P.total_frames && kb < kBins) {
+            if (f < P.batch.frame_base + P.total_frames && kb < kBins) {
                 float v = tile[r][tx];
                 bad |= !isfinite(v);
-                float S;
-                if (P.denorm) {
-                    double c = fmin(fmax((double)v, 0.0), 1.0);
-                    double db = c * (-P.min_level_db) + P.min_level_db + P.ref_level_db;
-                    S = (float)pow(pow(10.0, db * 0.05), P.power);
-                } else {
-                    S = fabsf(v);
-                }
-                P.mag[(size_t)f * kMagPitch + slot_index(kb)] = S * P.scale;
+                P.mag[(size_t)f * kMagPitch + slot_index(kb)] = prep_magnitude(P, v);
             }
         }
         __syncthreads();
@@ -660,7 +688,7 @@ struct MelParams {
 __global__ void __launch_bounds__(kThreads) k_linear_to_mel(MelParams P) {
     __shared__ float row[kWarpsPerCta][kBins + 3];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int f = blockIdx.x * kWarpsPerCta + warp; f < P.total_frames; f += gridDim.x * kWarpsPerCta) {
+    for (int f = P.batch.frame_base + blockIdx.x * kWarpsPerCta + warp; f < P.batch.frame_base + P.total_frames; f += gridDim.x * kWarpsPerCta) {
         const int b = find_segment(P.batch.frame_off, P.batch.batch, f);
         const int fo = __ldg(P.batch.frame_off + b);
         const int T = __ldg(P.batch.frame_off + b + 1) - fo;

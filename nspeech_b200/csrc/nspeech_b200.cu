@@ -65,7 +65,7 @@ struct nsb_handle_s {
     int n_fft = 0, hop = 0, win = 0, lo = 0, colours = 0, prune = 0, defcfg = 0, num_mels = 0;
     int num_sms = 0;
     int user_tile_hops = 0;
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr, copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t desc_done = nullptr;
     // tables
     float2* d_tw = nullptr;
@@ -82,6 +82,9 @@ struct nsb_handle_s {
     DevBuf ws_mag, ws_y0, ws_y1, ws_in, ws_in2, ws_out, ws_out2;
     // state of the last device-resident Griffin-Lim (for nsb_griffin_lim_iterate)
     struct { bool valid = false; Batch batch{}; int total_frames = 0; int tile_hops = 0; int total_tiles = 0; int cur = 0; } gl;
+    std::vector<int> h_frame_off, h_tile_off;       // host copies of the last descriptors (chunking)
+    std::vector<long long> h_samp_off;
+    int host_chunks = 0;             // 0 = automatic chunking of NSB_HOST Griffin-Lim calls, n > 0 = force n chunks
     int use_generic_iter = 0;        // debugging / A-B hook: run the iterations with k_synth<SRC_Y> instead of k_gl_iter
     unsigned long long launches = 0;
     std::mutex mu;
@@ -178,6 +181,8 @@ extern "C" int nsb_destroy(nsb_handle_t h) {
     if (!h) return NSB_OK;
     cudaSetDevice(h->device);
     if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
+    if (h->copy_in) cudaStreamDestroy(h->copy_in);
+    if (h->copy_out) cudaStreamDestroy(h->copy_out);
     if (h->desc_done) cudaEventDestroy(h->desc_done);
     cudaFree(h->d_tw); cudaFree(h->d_win); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo); cudaFree(h->d_mel_n); cudaFree(h->d_mel_ptr);
     cudaFree(h->d_status);
@@ -220,6 +225,8 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
     auto bail = [&](int code) { nsb_destroy(h); return code; };
 #define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(NSB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); return bail(NSB_ERR_CUDA); } } while (0)
     CUB(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
     CUB(cudaEventCreateWithFlags(&h->desc_done, cudaEventDisableTiming));
     // twiddles w2048^(j*l), j = 1..31, l = 0..31, rounded from double
     {
@@ -292,6 +299,12 @@ extern "C" int nsb_stft_parameters(nsb_handle_t h, int32_t* n_fft, int32_t* hop,
 extern "C" int64_t nsb_num_frames(nsb_handle_t h, int64_t n) { return h ? 1 + n / h->hop : -1; }
 extern "C" int64_t nsb_num_samples(nsb_handle_t h, int64_t T) { return h ? (int64_t)h->hop * (T - 1) : -1; }
 extern "C" uint64_t nsb_kernel_launches(nsb_handle_t h) { return h ? h->launches : 0; }
+extern "C" int nsb_set_host_chunks(nsb_handle_t h, int32_t n) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    if (n < 0 || n > 64) return fail(NSB_ERR_INVALID, "host_chunks %d outside [0,64]", n);
+    h->host_chunks = n;
+    return NSB_OK;
+}
 extern "C" int nsb_set_generic_iteration(nsb_handle_t h, int32_t on) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");
     h->use_generic_iter = on;
@@ -379,12 +392,14 @@ static int upload_desc(nsb_handle_s* h, cudaStream_t st, const std::vector<int>&
         to[b + 1] = to[b] + tiles;
         so[b + 1] = so[b] + samples[b];
     }
+    h->h_frame_off.assign(fo, fo + B + 1); h->h_tile_off.assign(to, to + B + 1); h->h_samp_off.assign(so, so + B + 1);
     CU(cudaMemcpyAsync(h->d_desc.p, h->h_desc, bytes, cudaMemcpyHostToDevice, st));
     CU(cudaEventRecord(h->desc_done, st));
     d->dev.frame_off = reinterpret_cast<const int*>(h->d_desc.p);
     d->dev.tile_off = d->dev.frame_off + (B + 1);
     d->dev.samp_off = reinterpret_cast<const long long*>(reinterpret_cast<const char*>(h->d_desc.p) + ((n_int * sizeof(int) + 7) & ~(size_t)7));
     d->dev.batch = B;
+    d->dev.frame_base = 0; d->dev.tile_base = 0;
     d->total_frames = fo[B];
     d->total_tiles = to[B];
     d->total_samples = so[B];
@@ -558,35 +573,37 @@ extern "C" int nsb_istft(nsb_handle_t h, const float* spec, int32_t layout, cons
     return NSB_OK;
 }
 
-static int gl_iterations(nsb_handle_s* h, int iters, cudaStream_t st) {
+// `iters` Griffin-Lim iterations on the (sub-)batch B; y ping-pongs between ws_y0 / ws_y1, `cur` says which holds y
+static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int H, int& cur, int iters, cudaStream_t st) {
     float* y[2] = {reinterpret_cast<float*>(h->ws_y0.p), reinterpret_cast<float*>(h->ws_y1.p)};
+    if (total_tiles <= 0) return NSB_OK;
     if (h->use_generic_iter == 1) {
         SynthParams P{};
-        P.plan = make_plan(h); P.batch = h->gl.batch; P.mag = reinterpret_cast<const float*>(h->ws_mag.p);
-        P.tile_hops = h->gl.tile_hops; P.colours = h->colours; P.status = h->d_status;
-        const size_t smem = synth_smem(h->hop, h->gl.tile_hops);
+        P.plan = make_plan(h); P.batch = B; P.mag = reinterpret_cast<const float*>(h->ws_mag.p);
+        P.tile_hops = H; P.colours = h->colours; P.status = h->d_status;
+        const size_t smem = synth_smem(h->hop, H);
         for (int it = 0; it < iters; ++it) {
-            P.y_in = y[h->gl.cur]; P.y_out = y[h->gl.cur ^ 1];
-            launch_synth<SRC_Y>(h, P, h->gl.total_tiles, smem, st);
+            P.y_in = y[cur]; P.y_out = y[cur ^ 1];
+            launch_synth<SRC_Y>(h, P, total_tiles, smem, st);
             int rc = check_launch(h, "k_synth<Y>");
             if (rc) return rc;
-            h->gl.cur ^= 1;
+            cur ^= 1;
         }
         return NSB_OK;
     }
     GlParams G{};
-    G.plan = make_plan(h); G.batch = h->gl.batch; G.mag = reinterpret_cast<const float*>(h->ws_mag.p);
-    G.tile_hops = h->gl.tile_hops; G.colours = h->colours; G.total_tiles = h->gl.total_tiles; G.status = h->d_status;
-    const size_t smem = gl_smem(h->hop, h->gl.tile_hops);
-    const int grid = h->gl.total_tiles < 2 * h->num_sms ? h->gl.total_tiles : 2 * h->num_sms;   // persistent: 2 CTAs per SM
+    G.plan = make_plan(h); G.batch = B; G.mag = reinterpret_cast<const float*>(h->ws_mag.p);
+    G.tile_hops = H; G.colours = h->colours; G.total_tiles = total_tiles; G.status = h->d_status;
+    const size_t smem = gl_smem(h->hop, H);
+    const int grid = total_tiles < 2 * h->num_sms ? total_tiles : 2 * h->num_sms;   // persistent: 2 CTAs per SM
     for (int it = 0; it < iters; ++it) {
-        G.y_in = y[h->gl.cur]; G.y_out = y[h->gl.cur ^ 1];
+        G.y_in = y[cur]; G.y_out = y[cur ^ 1];
         if (h->defcfg) NSB_LAUNCH((k_gl_iter<true, true>), grid, kThreads, smem, st, G);
         else if (h->prune) NSB_LAUNCH((k_gl_iter<true, false>), grid, kThreads, smem, st, G);
         else NSB_LAUNCH((k_gl_iter<false, false>), grid, kThreads, smem, st, G);
         int rc = check_launch(h, "k_gl_iter");
         if (rc) return rc;
-        h->gl.cur ^= 1;
+        cur ^= 1;
     }
     return NSB_OK;
 }
@@ -596,7 +613,7 @@ extern "C" int nsb_griffin_lim_iterate(nsb_handle_t h, int32_t iters, void* stre
     std::lock_guard<std::mutex> lk(h->mu);
     if (!h->gl.valid) return fail(NSB_ERR_INVALID, "no device-resident Griffin-Lim state (call nsb_griffin_lim with NSB_DEVICE first)");
     CU(cudaSetDevice(h->device));
-    return gl_iterations(h, iters, pick_stream(h, stream));
+    return gl_iterations(h, h->gl.batch, h->gl.total_tiles, h->gl.tile_hops, h->gl.cur, iters, pick_stream(h, stream));
 }
 
 extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout, const int32_t* n_frames, int32_t batch,
@@ -615,32 +632,27 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
     const int H = choose_tile_hops(h, n_frames, batch);
     Desc d;
     if ((rc = upload_desc(h, st, frames, samples, H, &d))) return rc;
+    const size_t out_elt = out_dtype == NSB_F64 ? sizeof(double) : sizeof(float);
+    if (!(flags & NSB_GL_DEEMPHASIS) && out_dtype != NSB_F32)
+        return fail(NSB_ERR_INVALID, "NSB_F64 output without NSB_GL_DEEMPHASIS is not provided (_griffin_lim returns float32)");
     const size_t n_spec = (size_t)kBins * d.total_frames;
     const float* d_spec = spec;
     const float2* d_phase = reinterpret_cast<const float2*>(init_phase);
-    const size_t out_elt = out_dtype == NSB_F64 ? sizeof(double) : sizeof(float);
-    void* d_out = wav_out;
+    char* d_out = reinterpret_cast<char*>(wav_out);
     if (space == NSB_HOST) {
         if ((rc = h->ws_in.reserve(sizeof(float) * n_spec))) return rc;
-        CU(cudaMemcpyAsync(h->ws_in.p, spec, sizeof(float) * n_spec, cudaMemcpyHostToDevice, st));
         d_spec = reinterpret_cast<const float*>(h->ws_in.p);
         if (init_phase) {
             if ((rc = h->ws_in2.reserve(sizeof(float2) * n_spec))) return rc;
-            CU(cudaMemcpyAsync(h->ws_in2.p, init_phase, sizeof(float2) * n_spec, cudaMemcpyHostToDevice, st));
             d_phase = reinterpret_cast<const float2*>(h->ws_in2.p);
         }
         if ((rc = h->ws_out.reserve(out_elt * d.total_samples))) return rc;
-        d_out = h->ws_out.p;
+        d_out = reinterpret_cast<char*>(h->ws_out.p);
     }
     if ((rc = h->ws_mag.reserve(sizeof(float) * kMagPitch * (size_t)d.total_frames))) return rc;
     if ((rc = h->ws_y0.reserve(sizeof(float) * d.total_samples))) return rc;
     if ((rc = h->ws_y1.reserve(sizeof(float) * d.total_samples))) return rc;
 
-    // S = _db_to_amp(_denormalize(spec) + ref_level_db) ** power   (or |S| for _griffin_lim), permuted layout
-    PrepParams Q{};
-    Q.batch = d.dev; Q.in = d_spec; Q.bin_major = (layout == NSB_BIN_MAJOR); Q.denorm = (flags & NSB_GL_DENORMALIZE) ? 1 : 0;
-    Q.min_level_db = h->hp.min_level_db; Q.ref_level_db = h->hp.ref_level_db; Q.power = h->hp.power;
-    Q.mag = reinterpret_cast<float*>(h->ws_mag.p); Q.total_frames = d.total_frames; Q.status = h->d_status;
     // Griffin-Lim is linear in S: run it on g*S with g a power of two that brings the largest possible magnitude
     // below 1 (the yaml's +100 dB floor gives S up to 1e9 whose squares would overflow fp32), undo g on output.
     double gscale = 1.0;
@@ -650,42 +662,106 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
         gscale = std::ldexp(1.0, -(int)std::ceil(std::log2(smax)));
         if (!(gscale > 0.0) || !std::isfinite(gscale)) gscale = 1.0;
     }
-    Q.scale = (float)gscale;
-    CU(cudaMemsetAsync(h->ws_mag.p, 0, sizeof(float) * kMagPitch * (size_t)d.total_frames, st));
-    NSB_LAUNCH(k_prepare_mag, (d.total_frames + 31) / 32, 256, 0, st, Q);
-    if ((rc = check_launch(h, "k_prepare_mag"))) return rc;
 
-    // y0 = _istft(S * angles)
-    h->gl.valid = true; h->gl.batch = d.dev; h->gl.total_frames = d.total_frames; h->gl.tile_hops = H;
-    h->gl.total_tiles = d.total_tiles; h->gl.cur = 0;
-    SynthParams P{};
-    P.plan = make_plan(h); P.batch = d.dev; P.mag = Q.mag; P.spec = d_phase; P.spec_bin_major = (layout == NSB_BIN_MAJOR);
-    P.y_out = reinterpret_cast<float*>(h->ws_y0.p); P.tile_hops = H; P.colours = h->colours; P.seed = seed; P.status = h->d_status;
-    const size_t smem = synth_smem(h->hop, H);
-    if (init_phase) launch_synth<SRC_MAGPHASE>(h, P, d.total_tiles, smem, st);
-    else launch_synth<SRC_MAGRAND>(h, P, d.total_tiles, smem, st);
-    if ((rc = check_launch(h, "k_synth<init>"))) return rc;
-
-    if ((rc = gl_iterations(h, iters, st))) return rc;
-    const float* y_fin = reinterpret_cast<const float*>(h->gl.cur ? h->ws_y1.p : h->ws_y0.p);
-
-    if ((flags & NSB_GL_DEEMPHASIS) || gscale != 1.0) {
-        if (!(flags & NSB_GL_DEEMPHASIS) && out_dtype != NSB_F32)
-            return fail(NSB_ERR_INVALID, "NSB_F64 output without NSB_GL_DEEMPHASIS is not provided (_griffin_lim returns float32)");
-        EmphParams E{};
-        E.batch = d.dev; E.in = y_fin; E.p = (flags & NSB_GL_DEEMPHASIS) ? h->hp.preemphasis : 0.0; E.scale = 1.0 / gscale;
-        if (out_dtype == NSB_F64) E.out64 = reinterpret_cast<double*>(d_out); else E.out32 = reinterpret_cast<float*>(d_out);
-        NSB_LAUNCH(k_deemphasis, batch, kDeemphThreads, 0, st, E);
-        if ((rc = check_launch(h, "k_deemphasis"))) return rc;
-    } else if (out_dtype == NSB_F32) {
-        CU(cudaMemcpyAsync(d_out, y_fin, sizeof(float) * d.total_samples, cudaMemcpyDeviceToDevice, st));
-    } else {
-        return fail(NSB_ERR_INVALID, "NSB_F64 output without NSB_GL_DEEMPHASIS is not provided (_griffin_lim returns float32)");
+    // Host buffers: cut the batch into a few chunks of whole utterances and pipeline them - chunk c+1 is copied in
+    // (copy_in stream) and chunk c-1 copied out (copy_out stream) while chunk c computes.  Device buffers: one chunk.
+    std::vector<int> cuts;           // utterance index where each chunk starts, plus the end
+    cuts.push_back(0);
+    if (space == NSB_HOST && batch > 1 && (h->host_chunks > 0 || n_spec * sizeof(float) > (8u << 20))) {
+        const int want_cfg = h->host_chunks > 0 ? h->host_chunks : 4;
+        const int want = batch < want_cfg ? batch : want_cfg;
+        for (int c = 1; c < want; ++c) {
+            const long long target = (long long)d.total_frames * c / want;
+            int b = cuts.back() + 1;
+            while (b < batch && h->h_frame_off[b] < target) ++b;
+            if (b < batch && b > cuts.back()) cuts.push_back(b);
+        }
     }
+    cuts.push_back(batch);
+    const int n_chunks = (int)cuts.size() - 1;
+    std::vector<cudaEvent_t> ev_in(n_chunks, nullptr), ev_done(n_chunks, nullptr);
+    auto cleanup = [&]() { for (auto e : ev_in) if (e) cudaEventDestroy(e); for (auto e : ev_done) if (e) cudaEventDestroy(e); };
+#define CUE(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(NSB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
     if (space == NSB_HOST) {
-        CU(cudaMemcpyAsync(wav_out, d_out, out_elt * d.total_samples, cudaMemcpyDeviceToHost, st));
+        for (int c = 0; c < n_chunks; ++c) {
+            CUE(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
+            CUE(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
+        }
+        // all input copies are queued up front on the copy-in stream, in chunk order
+        for (int c = 0; c < n_chunks; ++c) {
+            const size_t f0 = h->h_frame_off[cuts[c]], f1 = h->h_frame_off[cuts[c + 1]];
+            CUE(cudaMemcpyAsync(reinterpret_cast<float*>(h->ws_in.p) + f0 * kBins, spec + f0 * kBins, sizeof(float) * (f1 - f0) * kBins,
+                                cudaMemcpyHostToDevice, h->copy_in));
+            if (init_phase)
+                CUE(cudaMemcpyAsync(reinterpret_cast<float2*>(h->ws_in2.p) + f0 * kBins, reinterpret_cast<const float2*>(init_phase) + f0 * kBins,
+                                    sizeof(float2) * (f1 - f0) * kBins, cudaMemcpyHostToDevice, h->copy_in));
+            CUE(cudaEventRecord(ev_in[c], h->copy_in));
+        }
+    }
+    h->gl.valid = false;
+    int cur = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int b0 = cuts[c], b1 = cuts[c + 1];
+        Batch B = d.dev;
+        B.frame_off += b0; B.tile_off += b0; B.samp_off += b0; B.batch = b1 - b0;
+        B.frame_base = h->h_frame_off[b0]; B.tile_base = h->h_tile_off[b0];
+        const int n_frames_c = h->h_frame_off[b1] - h->h_frame_off[b0];
+        const int n_tiles_c = h->h_tile_off[b1] - h->h_tile_off[b0];
+        if (space == NSB_HOST) CUE(cudaStreamWaitEvent(st, ev_in[c], 0));
+
+        // S = _db_to_amp(_denormalize(spec) + ref_level_db) ** power   (or |S| for _griffin_lim), permuted layout
+        PrepParams Q{};
+        Q.batch = B; Q.in = d_spec; Q.bin_major = (layout == NSB_BIN_MAJOR); Q.denorm = (flags & NSB_GL_DENORMALIZE) ? 1 : 0;
+        Q.min_level_db = h->hp.min_level_db; Q.ref_level_db = h->hp.ref_level_db; Q.power = h->hp.power;
+        Q.mag = reinterpret_cast<float*>(h->ws_mag.p); Q.total_frames = n_frames_c; Q.status = h->d_status; Q.scale = (float)gscale;
+        if (Q.bin_major) {
+            CUE(cudaMemsetAsync(Q.mag + (size_t)B.frame_base * kMagPitch, 0, sizeof(float) * kMagPitch * (size_t)n_frames_c, st));
+            NSB_LAUNCH(k_prepare_mag, (n_frames_c + 31) / 32, 256, 0, st, Q);
+        } else {
+            NSB_LAUNCH(k_prepare_mag_rows, grid_1d(n_frames_c, kWarpsPerCta, 8 * h->num_sms), kThreads, 0, st, Q);
+        }
+        if ((rc = check_launch(h, "k_prepare_mag"))) { cleanup(); return rc; }
+
+        // y0 = _istft(S * angles)
+        SynthParams P{};
+        P.plan = make_plan(h); P.batch = B; P.mag = Q.mag; P.spec = d_phase; P.spec_bin_major = (layout == NSB_BIN_MAJOR);
+        P.y_out = reinterpret_cast<float*>(h->ws_y0.p); P.tile_hops = H; P.colours = h->colours; P.seed = seed; P.status = h->d_status;
+        const size_t smem = synth_smem(h->hop, H);
+        if (init_phase) launch_synth<SRC_MAGPHASE>(h, P, n_tiles_c, smem, st);
+        else launch_synth<SRC_MAGRAND>(h, P, n_tiles_c, smem, st);
+        if ((rc = check_launch(h, "k_synth<init>"))) { cleanup(); return rc; }
+
+        cur = 0;
+        if ((rc = gl_iterations(h, B, n_tiles_c, H, cur, iters, st))) { cleanup(); return rc; }
+        const float* y_fin = reinterpret_cast<const float*>(cur ? h->ws_y1.p : h->ws_y0.p);
+
+        const long long s_base = h->h_samp_off[b0], s_cnt = h->h_samp_off[b1] - s_base;
+        if ((flags & NSB_GL_DEEMPHASIS) || gscale != 1.0) {
+            EmphParams E{};
+            E.batch = B; E.in = y_fin; E.p = (flags & NSB_GL_DEEMPHASIS) ? h->hp.preemphasis : 0.0; E.scale = 1.0 / gscale;
+            if (out_dtype == NSB_F64) E.out64 = reinterpret_cast<double*>(d_out); else E.out32 = reinterpret_cast<float*>(d_out);
+            NSB_LAUNCH(k_deemphasis, b1 - b0, kDeemphThreads, 0, st, E);
+            if ((rc = check_launch(h, "k_deemphasis"))) { cleanup(); return rc; }
+        } else {
+            CUE(cudaMemcpyAsync(d_out + s_base * sizeof(float), y_fin + s_base, sizeof(float) * s_cnt, cudaMemcpyDeviceToDevice, st));
+        }
+        if (space == NSB_HOST) {
+            CUE(cudaEventRecord(ev_done[c], st));
+            CUE(cudaStreamWaitEvent(h->copy_out, ev_done[c], 0));
+            CUE(cudaMemcpyAsync(reinterpret_cast<char*>(wav_out) + s_base * out_elt, d_out + s_base * out_elt, out_elt * s_cnt,
+                                cudaMemcpyDeviceToHost, h->copy_out));
+        }
+    }
+    // device-resident state for nsb_griffin_lim_iterate: the whole batch
+    h->gl.valid = true; h->gl.batch = d.dev; h->gl.total_frames = d.total_frames; h->gl.tile_hops = H;
+    h->gl.total_tiles = d.total_tiles; h->gl.cur = cur;
+    if (space == NSB_HOST) {
+        CUE(cudaStreamSynchronize(h->copy_out));
+        cleanup();
         return read_status(h, st);
     }
+#undef CUE
+    cleanup();
     return NSB_OK;
 }
 

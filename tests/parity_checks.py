@@ -114,6 +114,14 @@ def check_ragged_batch_and_tiles():
             assert ao.snr_db(out[off:off + n], ref) > 60, (tile, T)
             off += n
     h.set_tile_hops(0)
+    # host-side pipelining: cutting the batch into chunks (H2D / compute / D2H overlap) must not change a bit either
+    for chunks in (2, 3, 5):
+        h.set_host_chunks(chunks)
+        out = np.empty_like(outs[0])
+        h.griffin_lim(packed, _lib.FRAME_MAJOR, Ts, out, init_phase=pph, iters=3,
+                      flags=_lib.GL_DENORMALIZE | _lib.GL_DEEMPHASIS, out_dtype=_lib.F64)
+        outs.append(out)
+    h.set_host_chunks(0)
     for o in outs[1:]:
         np.testing.assert_array_equal(o, outs[0])      # the tiling must not change a single bit
     # ragged analysis batch
