@@ -1,14 +1,20 @@
-// In-register FFT building blocks for the 2048-point real frame transform.
+// In-register FFT building blocks for the 2048-point real frame transform, in COMPLEX-PACKED form.
 //
-// Everything here is straight-line code on register arrays with compile-time indices and
-// compile-time twiddles (they become FFMA/FMUL immediates), so one lane runs a whole 32-point
-// complex FFT without touching memory.  The file is plain C++17 behind NSB_HD so that the same
-// source is compiled by g++ into the warp-emulation harness (tests/emu/) - that is how the index
-// algebra is validated in the GPU-less build container.  It is not a CPU fallback: nothing in the
-// product links the harness.
+// Every complex value lives in one float2 = one aligned 64-bit register pair (x = re, y = im) and all
+// arithmetic goes through Blackwell's packed fp32 instructions (FADD2 / FMUL2 / FFMA2, CUDA intrinsics
+// __fadd2_rn / __fmul2_rn / __ffma2_rn, sm_100+).  Their operands can be swizzled for free in SASS
+// (R.F32x2.LO_HI = halves swapped, per-half negation, R.F32 = scalar broadcast, 32-bit immediate broadcast),
+// so a complex add is ONE instruction, a multiplication by +-i costs nothing (it folds into the next add) and a
+// complex multiplication is two (FMUL2 + FFMA2) instead of four.  A 32-point complex FFT is 216 instructions
+// instead of 420 scalar ones; the packed ops run at the same flop rate in half the issue slots
+// (profiles/r1/microbench_fp32_pipes.txt), and issue slots are what bounds the Griffin-Lim kernel.
 //
-// Replaces (together with frame_fft.cuh): scipy.fftpack.fft / ifft as called by librosa.stft /
-// librosa.istft, reference call sites neural_speech/utils/audio.py:108 and :113.
+// Everything is straight-line code on register arrays with compile-time indices and twiddles.  The file is
+// plain C++17 behind NSB_HD: the same source is compiled by g++ into the warp-emulation harness (tests/emu/),
+// where the pair operations fall back to two scalar ones.  That is test infrastructure, not a CPU fallback.
+//
+// Replaces (together with frame_fft.cuh): scipy.fftpack.fft / ifft as called by librosa.stft / librosa.istft,
+// reference call sites neural_speech/utils/audio.py:108 and :113.
 #pragma once
 
 #if defined(__CUDACC__)
@@ -20,6 +26,48 @@
 #endif
 
 namespace nsb {
+
+#if !defined(__CUDACC__) && !defined(NSB_EMULATE)
+struct alignas(8) float2 { float x, y; };
+#endif
+typedef float2 c2;   // complex: x = re, y = im
+
+NSB_HD c2 mk2(float x, float y) { c2 r; r.x = x; r.y = y; return r; }
+
+// ---- element-wise pair operations (one SASS instruction each on sm_100) -------------------------------------
+NSB_HD c2 p_add(c2 a, c2 b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd2_rn(a, b);
+#else
+    return mk2(a.x + b.x, a.y + b.y);
+#endif
+}
+NSB_HD c2 p_mul(c2 a, c2 b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul2_rn(a, b);
+#else
+    return mk2(a.x * b.x, a.y * b.y);
+#endif
+}
+NSB_HD c2 p_fma(c2 a, c2 b, c2 c) {
+#if defined(__CUDA_ARCH__)
+    return __ffma2_rn(a, b, c);
+#else
+    return mk2(__builtin_fmaf(a.x, b.x, c.x), __builtin_fmaf(a.y, b.y, c.y));
+#endif
+}
+
+// ---- complex helpers; swaps / negations / broadcasts become operand modifiers ---------------------------------
+NSB_HD c2 cadd(c2 a, c2 b) { return p_add(a, b); }
+NSB_HD c2 csub(c2 a, c2 b) { return p_add(a, mk2(-b.x, -b.y)); }
+NSB_HD c2 cadd_i(c2 a, c2 b) { return p_add(a, mk2(-b.y, b.x)); }            // a + i*b
+NSB_HD c2 csub_i(c2 a, c2 b) { return p_add(a, mk2(b.y, -b.x)); }            // a - i*b
+NSB_HD c2 cconj(c2 a) { return mk2(a.x, -a.y); }
+NSB_HD c2 cadd_conj(c2 a, c2 b) { return p_add(a, mk2(b.x, -b.y)); }         // a + conj(b)
+NSB_HD c2 csub_conj(c2 a, c2 b) { return p_add(a, mk2(-b.x, b.y)); }         // a - conj(b)
+NSB_HD c2 cscale(c2 a, float s) { return p_mul(a, mk2(s, s)); }
+NSB_HD c2 cmul(c2 z, c2 w) { return p_fma(mk2(-z.y, z.x), mk2(w.y, w.y), p_mul(z, mk2(w.x, w.x))); }        // z * w
+NSB_HD c2 cmul_conj(c2 z, c2 w) { return p_fma(mk2(z.y, -z.x), mk2(w.y, w.y), p_mul(z, mk2(w.x, w.x))); }   // z * conj(w)
 
 // ---------------------------------------------------------------------------------------------
 // compile-time cos/sin of 2*pi*k/n (double precision Taylor after octant reduction)
@@ -54,89 +102,68 @@ NSB_HDC double sin2pi(long long k, long long n) {
 }
 }  // namespace cx
 
-// multiply (r,i) by exp(DIR * 2*pi*i * K / N), K and N compile-time; trivial cases cost no multiplies
+// z * exp(DIR * 2*pi*i * K / N), K and N compile-time; quarter turns cost nothing
 template <int K, int N, int DIR>
-NSB_HD void tw_mul(float& r, float& i) {
+NSB_HD c2 ctw(c2 z) {
     constexpr int k = ((K % N) + N) % N;
     if constexpr (k == 0) {
+        return z;
     } else if constexpr (2 * k == N) {
-        r = -r; i = -i;
+        return mk2(-z.x, -z.y);
     } else if constexpr (4 * k == N) {          // exp(DIR*i*pi/2) = DIR*i
-        float t = r;
-        if constexpr (DIR > 0) { r = -i; i = t; } else { r = i; i = -t; }
+        if constexpr (DIR > 0) return mk2(-z.y, z.x); else return mk2(z.y, -z.x);
     } else if constexpr (4 * k == 3 * N) {      // exp(DIR*i*3pi/2) = -DIR*i
-        float t = r;
-        if constexpr (DIR > 0) { r = i; i = -t; } else { r = -i; i = t; }
+        if constexpr (DIR > 0) return mk2(z.y, -z.x); else return mk2(-z.y, z.x);
     } else {
         constexpr float c = float(cx::cos2pi(k, N));
         constexpr float s = float(double(DIR) * cx::sin2pi(k, N));
-        float nr = r * c - i * s;
-        float ni = r * s + i * c;
-        r = nr; i = ni;
+        return p_fma(mk2(-z.y, z.x), mk2(s, s), p_mul(z, mk2(c, c)));
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// out-of-place decimation-in-time FFT on register arrays: y[k] = sum_j x[IS*j] exp(DIR*2*pi*i*j*k/N)
+// out-of-place radix-4 decimation-in-time FFT on register arrays: y[k] = sum_j x[IS*j] exp(DIR*2*pi*i*j*k/N)
 // ---------------------------------------------------------------------------------------------
 template <int N, int DIR, int IS>
-struct FftRec {
-    static NSB_HD void run(const float* xr, const float* xi, float* yr, float* yi) {
+struct FftC {
+    static NSB_HD void run(const c2* x, c2* y) {
         static_assert(N % 4 == 0, "radix-4 step");
         constexpr int Q = N / 4;
-        float fr[4][Q], fi[4][Q];
+        c2 f[4][Q];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) FftRec<Q, DIR, IS * 4>::run(xr + IS * j, xi + IS * j, fr[j], fi[j]);
-        combine<0>(fr, fi, yr, yi);
+        for (int j = 0; j < 4; ++j) FftC<Q, DIR, IS * 4>::run(x + IS * j, f[j]);
+        combine<0>(f, y);
     }
     template <int K>
-    static NSB_HD void combine(float (&fr)[4][N / 4], float (&fi)[4][N / 4], float* yr, float* yi) {
+    static NSB_HD void combine(c2 (&f)[4][N / 4], c2* y) {
         constexpr int Q = N / 4;
         if constexpr (K < Q) {
-            float ar = fr[0][K], ai = fi[0][K];
-            float br = fr[1][K], bi = fi[1][K];
-            float cr = fr[2][K], ci = fi[2][K];
-            float dr = fr[3][K], di = fi[3][K];
-            tw_mul<K, N, DIR>(br, bi);
-            tw_mul<2 * K, N, DIR>(cr, ci);
-            tw_mul<3 * K, N, DIR>(dr, di);
-            float t0r = ar + cr, t0i = ai + ci;
-            float t1r = ar - cr, t1i = ai - ci;
-            float t2r = br + dr, t2i = bi + di;
-            float t3r = br - dr, t3i = bi - di;
-            yr[K] = t0r + t2r;         yi[K] = t0i + t2i;
-            yr[K + 2 * Q] = t0r - t2r; yi[K + 2 * Q] = t0i - t2i;
-            if constexpr (DIR < 0) {   // forward: y[k+Q] = t1 - i*t3, y[k+3Q] = t1 + i*t3
-                yr[K + Q] = t1r + t3i;     yi[K + Q] = t1i - t3r;
-                yr[K + 3 * Q] = t1r - t3i; yi[K + 3 * Q] = t1i + t3r;
-            } else {
-                yr[K + Q] = t1r - t3i;     yi[K + Q] = t1i + t3r;
-                yr[K + 3 * Q] = t1r + t3i; yi[K + 3 * Q] = t1i - t3r;
-            }
-            combine<K + 1>(fr, fi, yr, yi);
+            c2 a = f[0][K], b = ctw<K, N, DIR>(f[1][K]), c = ctw<2 * K, N, DIR>(f[2][K]), d = ctw<3 * K, N, DIR>(f[3][K]);
+            c2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = csub(b, d);
+            y[K] = cadd(t0, t2);
+            y[K + 2 * Q] = csub(t0, t2);
+            if constexpr (DIR < 0) { y[K + Q] = csub_i(t1, t3); y[K + 3 * Q] = cadd_i(t1, t3); }   // forward: t1 -+ i*t3
+            else { y[K + Q] = cadd_i(t1, t3); y[K + 3 * Q] = csub_i(t1, t3); }
+            combine<K + 1>(f, y);
         }
     }
 };
 template <int DIR, int IS>
-struct FftRec<1, DIR, IS> {
-    static NSB_HD void run(const float* xr, const float* xi, float* yr, float* yi) { yr[0] = xr[0]; yi[0] = xi[0]; }
+struct FftC<1, DIR, IS> {
+    static NSB_HD void run(const c2* x, c2* y) { y[0] = x[0]; }
 };
 template <int DIR, int IS>
-struct FftRec<2, DIR, IS> {
-    static NSB_HD void run(const float* xr, const float* xi, float* yr, float* yi) {
-        float ar = xr[0], ai = xi[0], br = xr[IS], bi = xi[IS];
-        yr[0] = ar + br; yi[0] = ai + bi;
-        yr[1] = ar - br; yi[1] = ai - bi;
-    }
+struct FftC<2, DIR, IS> {
+    static NSB_HD void run(const c2* x, c2* y) { c2 a = x[0], b = x[IS]; y[0] = cadd(a, b); y[1] = csub(a, b); }
 };
 
-// in-place convenience wrapper: 32-point complex FFT of (re, im)
+// in-place convenience wrapper: 32-point complex FFT (DIR = -1 forward, +1 inverse, unnormalised)
 template <int DIR>
-NSB_HD void fft32(float (&re)[32], float (&im)[32]) {
-    float yr[32], yi[32];
-    FftRec<32, DIR, 1>::run(re, im, yr, yi);
+NSB_HD void fft32(c2 (&z)[32]) {
+    c2 y[32];
+    FftC<32, DIR, 1>::run(z, y);
 #pragma unroll
-    for (int k = 0; k < 32; ++k) { re[k] = yr[k]; im[k] = yi[k]; }
+    for (int k = 0; k < 32; ++k) z[k] = y[k];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -144,55 +171,30 @@ NSB_HD void fft32(float (&re)[32], float (&im)[32]) {
 //
 // g[t] = x[2t] + i x[2t+1] (t<32), G = FFT32(g).  The 64-point spectrum of x is
 //   Y[q] = E[q] + w64^q O[q],  E[q] = (G[q] + conj G[32-q])/2,  O[q] = (G[q] - conj G[32-q])/(2i).
-// real64_post turns G (in re/im) into 2*Y[q] for q = 1..31 in place; slot 0 keeps (Re G[0], Im G[0])
-// = (sum of even samples, sum of odd samples), i.e. Y[0] = re0 + im0 and Y[32] = re0 - im0.
+// real64_post turns G into 2*Y[q] for q = 1..31 in place; slot 0 keeps (Re G[0], Im G[0]) = (sum of even
+// samples, sum of odd samples), i.e. Y[0] = x0 + y0 and Y[32] = x0 - y0.
 // real64_pre is the inverse map: from V[q] (q = 1..31, Hermitian 64-spectrum) and slot 0 holding
-// (V[0] + V[32], V[0] - V[32]) it builds 2*G so that IFFT32 gives 2*64/... (see frame_fft.cuh for
-// the overall scale bookkeeping).
+// (V[0] + V[32], V[0] - V[32]) it builds the G' whose inverse FFT32 is the packed real sequence (times 64).
 // ---------------------------------------------------------------------------------------------
-template <int Q>
-NSB_HD void real64_post_pair(float (&re)[32], float (&im)[32]) {
-    // A = G[Q], B = conj(G[32-Q]);  S = A + B, D = A - B;  2Y[Q] = S - i*w^Q*D ; 2Y[32-Q] = conj(S + i*w^Q*D)
-    float ar = re[Q], ai = im[Q], br = re[32 - Q], bi = -im[32 - Q];
-    float sr = ar + br, si = ai + bi;
-    float dr = ar - br, di = ai - bi;
-    // T = -i * w64^Q * D with w64^Q = exp(-2*pi*i*Q/64):  -i*w = exp(-i*(pi/2 + 2*pi*Q/64)) = exp(-2*pi*i*(Q+16)/64)
-    tw_mul<Q + 16, 64, -1>(dr, di);
-    re[Q] = sr + dr;      im[Q] = si + di;
-    re[32 - Q] = sr - dr; im[32 - Q] = -(si - di);
+template <int Q, int DIR>
+NSB_HD void real64_pair(c2 (&z)[32]) {
+    // S = A + conj(B), D = A - conj(B), T = D * exp(DIR * 2*pi*i*(Q+16)/64)   (= -+i * w64^(-+Q) * D)
+    // out[Q] = S + T, out[32-Q] = conj(S - T)
+    c2 A = z[Q], B = z[32 - Q];
+    c2 S = cadd_conj(A, B), D = csub_conj(A, B);
+    c2 T = ctw<Q + 16, 64, DIR>(D);
+    z[Q] = cadd(S, T);
+    z[32 - Q] = cconj(csub(S, T));
 }
-NSB_HD void real64_post(float (&re)[32], float (&im)[32]) {
-    real64_post_pair<1>(re, im);  real64_post_pair<2>(re, im);  real64_post_pair<3>(re, im);
-    real64_post_pair<4>(re, im);  real64_post_pair<5>(re, im);  real64_post_pair<6>(re, im);
-    real64_post_pair<7>(re, im);  real64_post_pair<8>(re, im);  real64_post_pair<9>(re, im);
-    real64_post_pair<10>(re, im); real64_post_pair<11>(re, im); real64_post_pair<12>(re, im);
-    real64_post_pair<13>(re, im); real64_post_pair<14>(re, im); real64_post_pair<15>(re, im);
-    // Q = 16: 2Y[16] = 2*conj(G[16])
-    re[16] = 2.0f * re[16]; im[16] = -2.0f * im[16];
+template <int DIR>
+NSB_HD void real64_split(c2 (&z)[32]) {
+    real64_pair<1, DIR>(z);  real64_pair<2, DIR>(z);  real64_pair<3, DIR>(z);  real64_pair<4, DIR>(z);
+    real64_pair<5, DIR>(z);  real64_pair<6, DIR>(z);  real64_pair<7, DIR>(z);  real64_pair<8, DIR>(z);
+    real64_pair<9, DIR>(z);  real64_pair<10, DIR>(z); real64_pair<11, DIR>(z); real64_pair<12, DIR>(z);
+    real64_pair<13, DIR>(z); real64_pair<14, DIR>(z); real64_pair<15, DIR>(z);
+    z[16] = mk2(2.0f * z[16].x, -2.0f * z[16].y);     // Q = 16: 2 * conj
 }
-
-template <int Q>
-NSB_HD void real64_pre_pair(float (&re)[32], float (&im)[32]) {
-    // inputs V[Q], V[32-Q];  S = V[Q] + conj V[32-Q] (=2E), D = (V[Q] - conj V[32-Q]) * conj(w64^Q) (=2O)
-    // G'[Q] = S + i*D ;  G'[32-Q] = conj(S) + i*conj(D) ... derived from E,O being spectra of real sequences:
-    // E[32-Q] = conj E[Q], O[32-Q] = conj O[Q]  =>  G'[32-Q] = conj(S) + i*conj(D)
-    float ar = re[Q], ai = im[Q], br = re[32 - Q], bi = -im[32 - Q];
-    float sr = ar + br, si = ai + bi;
-    float dr = ar - br, di = ai - bi;
-    // i * conj(w64^Q) = exp(+i*(pi/2 + 2*pi*Q/64)) = exp(+2*pi*i*(Q+16)/64)
-    tw_mul<Q + 16, 64, +1>(dr, di);    // now (dr,di) = i*D
-    re[Q] = sr + dr;      im[Q] = si + di;
-    // i*conj(D) = conj(-i*D) = -conj(i*D)
-    re[32 - Q] = sr - dr; im[32 - Q] = -si + di;
-}
-NSB_HD void real64_pre(float (&re)[32], float (&im)[32]) {
-    real64_pre_pair<1>(re, im);  real64_pre_pair<2>(re, im);  real64_pre_pair<3>(re, im);
-    real64_pre_pair<4>(re, im);  real64_pre_pair<5>(re, im);  real64_pre_pair<6>(re, im);
-    real64_pre_pair<7>(re, im);  real64_pre_pair<8>(re, im);  real64_pre_pair<9>(re, im);
-    real64_pre_pair<10>(re, im); real64_pre_pair<11>(re, im); real64_pre_pair<12>(re, im);
-    real64_pre_pair<13>(re, im); real64_pre_pair<14>(re, im); real64_pre_pair<15>(re, im);
-    // Q = 16: G'[16] = 2*conj(V[16])
-    re[16] = 2.0f * re[16]; im[16] = -2.0f * im[16];
-}
+NSB_HD void real64_post(c2 (&z)[32]) { real64_split<-1>(z); }
+NSB_HD void real64_pre(c2 (&z)[32]) { real64_split<+1>(z); }
 
 }  // namespace nsb

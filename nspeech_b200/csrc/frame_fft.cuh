@@ -24,11 +24,7 @@
 
 namespace nsb {
 
-#if defined(__CUDACC__) || defined(NSB_EMULATE)
 typedef float2 f2;
-#else
-struct alignas(8) f2 { float x, y; };
-#endif
 
 constexpr int kNfft = 2048;
 constexpr int kBins = 1025;
@@ -45,71 +41,50 @@ NSB_HD int bin_of(int lane, int p) {
 NSB_HD bool slot_is_conj(int lane, int p) { return lane != 0 && p >= 16; }
 
 // ---- forward -------------------------------------------------------------------------------
-// in : re[t] = x[64 t + lane], im[t] = x[64 t + 32 + lane]
-NSB_HD void fwd_phase1(float (&re)[32], float (&im)[32], int lane, f2* scratch, const f2* tw) {
-    fft32<-1>(re, im);
-    real64_post(re, im);
+// in : z[t] = (x[64 t + lane], x[64 t + 32 + lane])
+NSB_HD void fwd_phase1(c2 (&z)[32], int lane, f2* scratch, const f2* tw) {
+    fft32<-1>(z);
+    real64_post(z);
     float* row0 = reinterpret_cast<float*>(scratch);
-    row0[lane] = re[0];
-    row0[lane + 32] = im[0];
+    row0[lane] = z[0].x;
+    row0[lane + 32] = z[0].y;
 #pragma unroll
-    for (int q = 1; q < 32; ++q) {
-        f2 w = tw[(q - 1) * 32 + lane];
-        f2 v;
-        v.x = re[q] * w.x - im[q] * w.y;
-        v.y = re[q] * w.y + im[q] * w.x;
-        scratch[q * kRowStride + lane] = v;
-    }
+    for (int q = 1; q < 32; ++q) scratch[q * kRowStride + lane] = cmul(z[q], tw[(q - 1) * 32 + lane]);
 }
 // out: register spectrum (2 * rfft), see header comment
-NSB_HD void fwd_phase2(float (&re)[32], float (&im)[32], int lane, const f2* scratch) {
+NSB_HD void fwd_phase2(c2 (&z)[32], int lane, const f2* scratch) {
 #pragma unroll
-    for (int t = 0; t < 32; ++t) {
-        f2 v = scratch[lane * kRowStride + t];
-        re[t] = v.x; im[t] = v.y;
-    }
-    fft32<-1>(re, im);
+    for (int t = 0; t < 32; ++t) z[t] = scratch[lane * kRowStride + t];
+    fft32<-1>(z);
     if (lane == 0) {
-        real64_post(re, im);
-        float a = re[0], b = im[0];
-        re[0] = 2.0f * (a + b);
-        im[0] = 2.0f * (a - b);
+        real64_post(z);
+        float a = z[0].x, b = z[0].y;
+        z[0] = mk2(2.0f * (a + b), 2.0f * (a - b));
     }
 }
 
 // ---- inverse -------------------------------------------------------------------------------
 // in : register spectrum X (Im of DC / Nyquist do not exist in the packing, as in irfft)
-NSB_HD void inv_phase1(float (&re)[32], float (&im)[32], int lane, f2* scratch, const f2* tw) {
+NSB_HD void inv_phase1(c2 (&z)[32], int lane, f2* scratch, const f2* tw) {
     if (lane == 0) {
-        float a = re[0], b = im[0];
-        re[0] = a + b;
-        im[0] = a - b;
-        real64_pre(re, im);
+        float a = z[0].x, b = z[0].y;
+        z[0] = mk2(a + b, a - b);
+        real64_pre(z);
     }
-    fft32<+1>(re, im);
-    f2 v0; v0.x = re[0]; v0.y = im[0];
-    scratch[lane * kRowStride] = v0;
+    fft32<+1>(z);
+    scratch[lane * kRowStride] = z[0];
 #pragma unroll
-    for (int r = 1; r < 32; ++r) {
-        f2 w = tw[(r - 1) * 32 + lane];     // table is symmetric in (j, l): conj(w2048^(lane*r))
-        f2 v;
-        v.x = re[r] * w.x + im[r] * w.y;
-        v.y = im[r] * w.x - re[r] * w.y;
-        scratch[lane * kRowStride + r] = v;
-    }
+    for (int r = 1; r < 32; ++r)      // table is symmetric in (j, l): conj(w2048^(lane*r))
+        scratch[lane * kRowStride + r] = cmul_conj(z[r], tw[(r - 1) * 32 + lane]);
 }
-// out: re[t] = 2048 * x[64 t + lane], im[t] = 2048 * x[64 t + 32 + lane]
-NSB_HD void inv_phase2(float (&re)[32], float (&im)[32], int lane, const f2* scratch) {
+// out: z[t] = 2048 * (x[64 t + lane], x[64 t + 32 + lane])
+NSB_HD void inv_phase2(c2 (&z)[32], int lane, const f2* scratch) {
     const float* row0 = reinterpret_cast<const float*>(scratch);
-    re[0] = row0[lane];
-    im[0] = row0[lane + 32];
+    z[0] = mk2(row0[lane], row0[lane + 32]);
 #pragma unroll
-    for (int q = 1; q < 32; ++q) {
-        f2 v = scratch[q * kRowStride + lane];
-        re[q] = v.x; im[q] = v.y;
-    }
-    real64_pre(re, im);
-    fft32<+1>(re, im);
+    for (int q = 1; q < 32; ++q) z[q] = scratch[q * kRowStride + lane];
+    real64_pre(z);
+    fft32<+1>(z);
 }
 
 }  // namespace nsb

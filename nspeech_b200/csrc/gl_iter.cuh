@@ -70,11 +70,10 @@ constexpr int kMagBytes = 4096 + 16;                 // slots + the float4 that 
 constexpr int kXchOffsetF2 = (kMagBytes + 112) / 8;  // exchange area starts at byte 4224 of the scratch tile (8-byte units)
 
 // renormalise one slot, branch-free; `zero` collects exact zeros for the rare fix-up
-__device__ __forceinline__ void renorm_fast(float& re, float& im, float S, bool& zero) {
-    float m2 = fmaf(re, re, im * im);
+__device__ __forceinline__ void renorm_fast(c2& z, float S, bool& zero) {
+    float m2 = fmaf(z.x, z.x, z.y * z.y);
     zero |= (m2 == 0.f);
-    float inv = rsqrtf(fmaxf(m2, 1e-36f)) * S;
-    re *= inv; im *= inv;
+    z = cscale(z, rsqrtf(fmaxf(m2, 1e-36f)) * S);
 }
 
 // normalise the finished tile by the summed squared window and store it (all threads of the CTA)
@@ -173,15 +172,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
         for (int s = 0; s < C; ++s) {
             const int k = kg + s;
             const bool active = (k >= 0 && k <= k_max);        // warp-uniform
-            float re[32], im[32];
+            c2 z[32];
             if (active) {
                 const int fg = f_off + k;
-                load_frame<false, PRUNE>(re, im, P.y_in + s_off, L, (long long)k * hop - kNfft / 2, win_s, lane, 0.f, 1.0f,
+                load_frame<false, PRUNE>(z, P.y_in + s_off, L, (long long)k * hop - kNfft / 2, win_s, lane, 0.f,
                                          reinterpret_cast<float*>(scratch));
-                fwd_phase1(re, im, lane, scratch, tw_s);
+                fwd_phase1(z, lane, scratch, tw_s);
                 __syncwarp();
 #pragma unroll
-                for (int t = 0; t < 32; ++t) { float2 v = scratch[lane * kRowStride + t]; re[t] = v.x; im[t] = v.y; }
+                for (int t = 0; t < 32; ++t) z[t] = scratch[lane * kRowStride + t];
                 __syncwarp();                        // every lane has its row: the scratch tile is free
                 {
                     const char* src = reinterpret_cast<const char*>(P.mag + (size_t)fg * kMagPitch);
@@ -190,11 +189,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                     for (int g = 0; g < 8; ++g) cp_async16(dst + (g * 32 + lane) * 16, src + (g * 32 + lane) * 16);
                     if (lane == 0) cp_async16(dst + 4096, src + 4096);
                 }
-                fft32<-1>(re, im);
+                fft32<-1>(z);
                 float2* xch = scratch + kXchOffsetF2;
                 if (lane == 0) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) xch[j] = make_float2(re[j], im[j]);
+                    for (int j = 0; j < 32; ++j) xch[j] = z[j];
                 }
                 cp_async_wait_all();
                 __syncwarp();
@@ -206,10 +205,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
                     float4 S = mrow[g * 32 + lane];
-                    renorm_fast(re[4 * g], im[4 * g], S.x, zero);
-                    renorm_fast(re[4 * g + 1], im[4 * g + 1], S.y, zero);
-                    renorm_fast(re[4 * g + 2], im[4 * g + 2], S.z, zero);
-                    renorm_fast(re[4 * g + 3], im[4 * g + 3], S.w, zero);
+                    renorm_fast(z[4 * g], S.x, zero);
+                    renorm_fast(z[4 * g + 1], S.y, zero);
+                    renorm_fast(z[4 * g + 2], S.z, zero);
+                    renorm_fast(z[4 * g + 3], S.w, zero);
                 }
                 if (lane == 0) zero = false;
                 if (warp_any(zero)) {                // rare: some bin of y's STFT is exactly 0 -> phase 0 (np.angle(0))
@@ -220,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                             const float Ss[4] = {S.x, S.y, S.z, S.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
-                                if (re[4 * g + e] == 0.f && im[4 * g + e] == 0.f) re[4 * g + e] = Ss[e];
+                                if (z[4 * g + e].x == 0.f && z[4 * g + e].y == 0.f) z[4 * g + e].x = Ss[e];
                         }
                     }
                 }
@@ -237,43 +236,40 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                         const int j = lane, jj = 32 - lane;
                         // u = -i * w64^j with w64^j = w2048^(16 * 2j) from the twiddle table (j = 16: w = -i)
                         const float2 wj = (j <= 15) ? tw_s[15 * 32 + 2 * j] : make_float2(0.f, -1.f);
-                        const float ur = wj.y, ui = -wj.x;
-                        float2 Aj = xch[j], Bj = xch[jj];
-                        float sr = Aj.x + Bj.x, si = Aj.y - Bj.y, dr = Aj.x - Bj.x, di = Aj.y + Bj.y;
-                        float tr = dr * ur - di * ui, ti = dr * ui + di * ur;
-                        float c1r = sr + tr, c1i = si + ti;                 // 2*X[32 j]
-                        float c2r = sr - tr, c2i = -(si - ti);              // 2*X[32 (32-j)]
+                        const c2 u = mk2(wj.y, -wj.x);
+                        const c2 Aj = xch[j], Bj = xch[jj];
+                        const c2 S1 = cadd_conj(Aj, Bj), D1 = csub_conj(Aj, Bj);
+                        const c2 T1 = cmul(D1, u);
+                        c2 c1 = cadd(S1, T1);                               // 2*X[32 j]
+                        c2 c2v = cconj(csub(S1, T1));                       // 2*X[32 (32-j)]
                         bool z2 = false;
-                        renorm_fast(c1r, c1i, mflt[(j >> 2) * 128 + (j & 3)], z2);
-                        renorm_fast(c2r, c2i, mflt[(jj >> 2) * 128 + (jj & 3)], z2);
+                        renorm_fast(c1, mflt[(j >> 2) * 128 + (j & 3)], z2);
+                        renorm_fast(c2v, mflt[(jj >> 2) * 128 + (jj & 3)], z2);
                         if (z2) {
-                            if (c1r == 0.f && c1i == 0.f) c1r = mflt[(j >> 2) * 128 + (j & 3)];
-                            if (c2r == 0.f && c2i == 0.f) c2r = mflt[(jj >> 2) * 128 + (jj & 3)];
+                            if (c1.x == 0.f && c1.y == 0.f) c1.x = mflt[(j >> 2) * 128 + (j & 3)];
+                            if (c2v.x == 0.f && c2v.y == 0.f) c2v.x = mflt[(jj >> 2) * 128 + (jj & 3)];
                         }
                         // inverse split: S' = V[j] + conj V[32-j], D' = V[j] - conj V[32-j], P = D' * conj(u)
-                        float s2r = c1r + c2r, s2i = c1i - c2i, d2r = c1r - c2r, d2i = c1i + c2i;
-                        float pr = d2r * ur + d2i * ui, pi = d2i * ur - d2r * ui;
+                        const c2 S2 = cadd_conj(c1, c2v), D2 = csub_conj(c1, c2v);
+                        const c2 Pv = cmul_conj(D2, u);
                         // lane j reads and writes only xch[j] and xch[32-j]: no cross-lane hazard inside this block
-                        xch[j] = make_float2(s2r + pr, s2i + pi);
-                        if (j != 16) xch[jj] = make_float2(s2r - pr, -s2i + pi);
+                        xch[j] = cadd(S2, Pv);
+                        if (j != 16) xch[jj] = cconj(csub(S2, Pv));
                     }
                 }
                 __syncwarp();
                 if (lane == 0) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { float2 v = xch[j]; re[j] = v.x; im[j] = v.y; }
+                    for (int j = 0; j < 32; ++j) z[j] = xch[j];
                 }
                 __syncwarp();                        // magnitude row and exchange area fully consumed
                 // inverse pass 1 (the lane-0 pre-split already happened above)
-                fft32<+1>(re, im);
-                scratch[lane * kRowStride] = make_float2(re[0], im[0]);
+                fft32<+1>(z);
+                scratch[lane * kRowStride] = z[0];
 #pragma unroll
-                for (int r = 1; r < 32; ++r) {
-                    float2 w = tw_s[(r - 1) * 32 + lane];
-                    scratch[lane * kRowStride + r] = make_float2(re[r] * w.x + im[r] * w.y, im[r] * w.x - re[r] * w.y);
-                }
+                for (int r = 1; r < 32; ++r) scratch[lane * kRowStride + r] = cmul_conj(z[r], tw_s[(r - 1) * 32 + lane]);
                 __syncwarp();
-                inv_phase2(re, im, lane, scratch);
+                inv_phase2(z, lane, scratch);
                 __syncwarp();                        // the scratch tile may be rewritten by this warp's next frame
             }
             // ---- overlap-add ordering ----
@@ -290,13 +286,23 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                 constexpr int t0 = PRUNE ? 8 : 0, t1 = PRUNE ? 24 : 32;
                 const bool inside = (base + lo >= 0) && (base + lo + win <= n_out);
                 if (DEFCFG && inside) {
-                    // default hparams: the support n in [524, 1524) is known at compile time
+                    // default hparams: the support n in [524, 1524) is known at compile time; (acc[n], acc[n+32]) and the
+                    // two window values ride in register pairs so the accumulate is one FFMA2
                     float* ap = acc + base + lane;
 #pragma unroll
                     for (int t = 0; t < 32; ++t) {
                         if (t >= t0 && t < t1) {
-                            if (t > 8 || lane >= 12) ap[64 * t] = fmaf(re[t], win_s[64 * t + lane], ap[64 * t]);
-                            if (t < 23 || lane < 20) ap[64 * t + 32] = fmaf(im[t], win_s[64 * t + 32 + lane], ap[64 * t + 32]);
+                            if (t == 8) {
+                                if (lane >= 12) ap[64 * t] = fmaf(z[t].x, win_s[64 * t + lane], ap[64 * t]);
+                                ap[64 * t + 32] = fmaf(z[t].y, win_s[64 * t + 32 + lane], ap[64 * t + 32]);
+                            } else if (t == 23) {
+                                ap[64 * t] = fmaf(z[t].x, win_s[64 * t + lane], ap[64 * t]);
+                                if (lane < 20) ap[64 * t + 32] = fmaf(z[t].y, win_s[64 * t + 32 + lane], ap[64 * t + 32]);
+                            } else {
+                                c2 r = p_fma(z[t], mk2(win_s[64 * t + lane], win_s[64 * t + 32 + lane]), mk2(ap[64 * t], ap[64 * t + 32]));
+                                ap[64 * t] = r.x;
+                                ap[64 * t + 32] = r.y;
+                            }
                         }
                     }
                 } else {
@@ -311,8 +317,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
 #pragma unroll
                     for (int t = 0; t < 32; ++t) {
                         if (t >= t0 && t < t1) {
-                            if ((mre >> t) & 1u) ap[64 * t] = fmaf(re[t], win_s[64 * t + lane], ap[64 * t]);
-                            if ((mim >> t) & 1u) ap[64 * t + 32] = fmaf(im[t], win_s[64 * t + 32 + lane], ap[64 * t + 32]);
+                            if ((mre >> t) & 1u) ap[64 * t] = fmaf(z[t].x, win_s[64 * t + lane], ap[64 * t]);
+                            if ((mim >> t) & 1u) ap[64 * t + 32] = fmaf(z[t].y, win_s[64 * t + 32 + lane], ap[64 * t + 32]);
                         }
                     }
                 }

@@ -85,9 +85,8 @@ __device__ __forceinline__ float sample_at(const float* __restrict__ x, int L, i
 // are gathered through it by a rolled loop, so the rare path costs a few dozen instructions of code instead of
 // an unrolled copy of the index arithmetic per register
 template <bool PREEMPH, bool PRUNE>
-__device__ __forceinline__ void load_frame(float (&re)[32], float (&im)[32], const float* __restrict__ x, long long L,
-                                           long long start, const float* __restrict__ win_s, int lane, float p,
-                                           float scale, float* stage) {
+__device__ __forceinline__ void load_frame(c2 (&z)[32], const float* __restrict__ x, long long L, long long start,
+                                           const float* __restrict__ win_s, int lane, float p, float* stage) {
     constexpr int t0 = PRUNE ? 8 : 0, t1 = PRUNE ? 24 : 32;
     const long long first = start + 64 * t0, last = start + 64 * t1;   // [first, last) touched
     const bool interior = (first >= (PREEMPH ? 1 : 0)) && (last <= L);
@@ -101,9 +100,8 @@ __device__ __forceinline__ void load_frame(float (&re)[32], float (&im)[32], con
                     a = fmaf(-p, __ldg(xs + 64 * t - 1), a);
                     b = fmaf(-p, __ldg(xs + 64 * t + 31), b);
                 }
-                re[t] = a * (win_s[64 * t + lane] * scale);
-                im[t] = b * (win_s[64 * t + 32 + lane] * scale);
-            } else { re[t] = 0.f; im[t] = 0.f; }
+                z[t] = p_mul(mk2(a, b), mk2(win_s[64 * t + lane], win_s[64 * t + 32 + lane]));
+            } else { z[t] = mk2(0.f, 0.f); }
         }
     } else {
 #pragma unroll 1
@@ -112,9 +110,8 @@ __device__ __forceinline__ void load_frame(float (&re)[32], float (&im)[32], con
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
             if (t >= t0 && t < t1) {
-                re[t] = stage[64 * t + lane] * (win_s[64 * t + lane] * scale);
-                im[t] = stage[64 * t + 32 + lane] * (win_s[64 * t + 32 + lane] * scale);
-            } else { re[t] = 0.f; im[t] = 0.f; }
+                z[t] = p_mul(mk2(stage[64 * t + lane], stage[64 * t + 32 + lane]), mk2(win_s[64 * t + lane], win_s[64 * t + 32 + lane]));
+            } else { z[t] = mk2(0.f, 0.f); }
         }
         __syncwarp();
     }
@@ -152,7 +149,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
     float* win_s = reinterpret_cast<float*>(tw_s + kTwF2);
     float2* scratch_all = reinterpret_cast<float2*>(win_s + kNfft);
     for (int i = threadIdx.x; i < kTwF2; i += kThreads) tw_s[i] = P.plan.tw[i];
-    for (int i = threadIdx.x; i < kNfft; i += kThreads) win_s[i] = P.plan.win[i];
+    // 0.5 folds the forward transform's factor 2 (frame_fft.cuh) so the registers hold rfft exactly
+    for (int i = threadIdx.x; i < kNfft; i += kThreads) win_s[i] = 0.5f * P.plan.win[i];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float2* scratch = scratch_all + warp * kScratchF2;
@@ -165,25 +163,24 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
         const int k = f - __ldg(P.batch.frame_off + b);
         const long long s_off = __ldg(P.batch.samp_off + b);
         const long long L = __ldg(P.batch.samp_off + b + 1) - s_off;
-        float re[32], im[32];
-        // 0.5 folds the forward transform's factor 2 (frame_fft.cuh) so the registers hold rfft exactly
-        load_frame<PREEMPH, PRUNE>(re, im, P.wav + s_off, L, (long long)k * hop - kNfft / 2, win_s, lane, P.preemph, 0.5f,
+        c2 z[32];
+        load_frame<PREEMPH, PRUNE>(z, P.wav + s_off, L, (long long)k * hop - kNfft / 2, win_s, lane, P.preemph,
                                    reinterpret_cast<float*>(scratch));
-        fwd_phase1(re, im, lane, scratch, tw_s);
+        fwd_phase1(z, lane, scratch, tw_s);
         __syncwarp();
-        fwd_phase2(re, im, lane, scratch);
+        fwd_phase2(z, lane, scratch);
         __syncwarp();
         if (MODE == ANALYSIS_COMPLEX) {
             float2* o = P.out_complex + (size_t)f * kBins;
 #pragma unroll
             for (int p = 0; p < 32; ++p) {
-                bad |= !(isfinite(re[p]) && isfinite(im[p]));
+                bad |= !(isfinite(z[p].x) && isfinite(z[p].y));
                 if (lane == 0 && p == 0) {
-                    o[0] = make_float2(re[0], 0.f);
-                    o[1024] = make_float2(im[0], 0.f);
+                    o[0] = make_float2(z[0].x, 0.f);
+                    o[1024] = make_float2(z[0].y, 0.f);
                 } else {
                     int kb = bin_of(lane, p);
-                    o[kb] = make_float2(re[p], (lane != 0 && p >= 16) ? -im[p] : im[p]);
+                    o[kb] = make_float2(z[p].x, (lane != 0 && p >= 16) ? -z[p].y : z[p].y);
                 }
             }
         } else {
@@ -191,12 +188,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
             float* magrow = reinterpret_cast<float*>(scratch);
 #pragma unroll
             for (int p = 0; p < 32; ++p) {
-                bad |= !(isfinite(re[p]) && isfinite(im[p]));
+                bad |= !(isfinite(z[p].x) && isfinite(z[p].y));
                 if (lane == 0 && p == 0) {
-                    magrow[0] = fabsf(re[0]);
-                    magrow[1024] = fabsf(im[0]);
+                    magrow[0] = fabsf(z[0].x);
+                    magrow[1024] = fabsf(z[0].y);
                 } else {
-                    magrow[bin_of(lane, p)] = sqrtf(fmaf(re[p], re[p], im[p] * im[p]));
+                    magrow[bin_of(lane, p)] = sqrtf(fmaf(z[p].x, z[p].x, z[p].y * z[p].y));
                 }
             }
             __syncwarp();
@@ -258,19 +255,17 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 }
 
 // phase renormalisation of one slot: z <- S * z/|z| ; z == 0 -> S (np.angle(0) = 0, audio.py:85)
-__device__ __forceinline__ void renorm(float& re, float& im, float S) {
-    float m2 = fmaf(re, re, im * im);
+__device__ __forceinline__ void renorm(c2& z, float S) {
+    float m2 = fmaf(z.x, z.x, z.y * z.y);
     if (m2 < 1e-30f || m2 > 1e30f) {              // rare: rescale to dodge under/overflow of the square
         float sc = (m2 < 1e-30f) ? 1.8446744e19f : 5.4210109e-20f;   // 2^64, 2^-64
-        float a = re * sc, b = im * sc;
-        m2 = fmaf(a, a, b * b);
-        if (m2 == 0.f) { re = S; im = 0.f; return; }
-        float inv = rsqrtf(m2) * S;
-        re = a * inv; im = b * inv;
+        c2 w = cscale(z, sc);
+        m2 = fmaf(w.x, w.x, w.y * w.y);
+        if (m2 == 0.f) { z = mk2(S, 0.f); return; }
+        z = cscale(w, rsqrtf(m2) * S);
         return;
     }
-    float inv = rsqrtf(m2) * S;
-    re *= inv; im *= inv;
+    z = cscale(z, rsqrtf(m2) * S);
 }
 
 template <int SRC, bool PRUNE>
@@ -326,13 +321,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_synth(SynthParams P) {
         int kf = k_min + ((c - k_min % C) + C) % C;
         for (int k = kf + C * warp; k <= k_max; k += C * kWarpsPerCta) {
             const int fg = f_off + k;                   // global frame index
-            float re[32], im[32];
+            c2 z[32];
             if (SRC == SRC_Y) {
-                load_frame<false, PRUNE>(re, im, P.y_in + s_off, L, (long long)k * hop - kNfft / 2, win_s, lane, 0.f, 1.0f,
+                load_frame<false, PRUNE>(z, P.y_in + s_off, L, (long long)k * hop - kNfft / 2, win_s, lane, 0.f,
                                          reinterpret_cast<float*>(scratch));
-                fwd_phase1(re, im, lane, scratch, tw_s);
+                fwd_phase1(z, lane, scratch, tw_s);
                 __syncwarp();
-                fwd_phase2(re, im, lane, scratch);
+                fwd_phase2(z, lane, scratch);
                 __syncwarp();
                 const float4* mp = reinterpret_cast<const float4*>(P.mag + (size_t)fg * kMagPitch);
 #pragma unroll
@@ -341,17 +336,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_synth(SynthParams P) {
                     if (g == 0) {
                         if (lane == 0) {    // packed real DC / Nyquist: phase of a real number is its sign
                             float Sn = __ldg(P.mag + (size_t)fg * kMagPitch + 1024);
-                            re[0] = (re[0] < 0.f) ? -S.x : S.x;
-                            im[0] = (im[0] < 0.f) ? -Sn : Sn;
+                            z[0] = mk2((z[0].x < 0.f) ? -S.x : S.x, (z[0].y < 0.f) ? -Sn : Sn);
                         } else {
-                            renorm(re[0], im[0], S.x);
+                            renorm(z[0], S.x);
                         }
                     } else {
-                        renorm(re[4 * g], im[4 * g], S.x);
+                        renorm(z[4 * g], S.x);
                     }
-                    renorm(re[4 * g + 1], im[4 * g + 1], S.y);
-                    renorm(re[4 * g + 2], im[4 * g + 2], S.z);
-                    renorm(re[4 * g + 3], im[4 * g + 3], S.w);
+                    renorm(z[4 * g + 1], S.y);
+                    renorm(z[4 * g + 2], S.z);
+                    renorm(z[4 * g + 3], S.w);
                 }
             } else if (SRC == SRC_SPEC || SRC == SRC_MAGPHASE) {
                 const float2* sp;
@@ -363,13 +357,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_synth(SynthParams P) {
                 for (int p = 0; p < 32; ++p) {
                     if (lane == 0 && p == 0) {
                         float2 v0 = __ldg(sp), v1 = __ldg(sp + 1024 * st_f);
-                        re[0] = v0.x; im[0] = v1.x;          // imaginary parts of DC / Nyquist are dropped (irfft semantics)
-                        if (SRC == SRC_MAGPHASE) { re[0] *= __ldg(mrow); im[0] *= __ldg(mrow + 1024); }
+                        z[0] = mk2(v0.x, v1.x);              // imaginary parts of DC / Nyquist are dropped (irfft semantics)
+                        if (SRC == SRC_MAGPHASE) z[0] = p_mul(z[0], mk2(__ldg(mrow), __ldg(mrow + 1024)));
                     } else {
                         float2 v = __ldg(sp + (long long)bin_of(lane, p) * st_f);
                         if (lane != 0 && p >= 16) v.y = -v.y;
-                        if (SRC == SRC_MAGPHASE) { float S = __ldg(mrow + ((p >> 2) * 32 + lane) * 4 + (p & 3)); v.x *= S; v.y *= S; }
-                        re[p] = v.x; im[p] = v.y;
+                        if (SRC == SRC_MAGPHASE) v = cscale(v, __ldg(mrow + ((p >> 2) * 32 + lane) * 4 + (p & 3)));
+                        z[p] = v;
                     }
                 }
             } else {  // SRC_MAGRAND: magnitude x exp(2*pi*i*u), u ~ Philox keyed by seed, counter = (frame, lane, group)
@@ -386,19 +380,19 @@ __global__ void __launch_bounds__(kThreads, 2) k_synth(SynthParams P) {
                         float u = (float)(rr[e] >> 8) * (1.0f / 16777216.0f);
                         float sn, cs;
                         sincospif(2.0f * u, &sn, &cs);
-                        re[4 * g + e] = SS[e] * cs; im[4 * g + e] = SS[e] * sn;
+                        z[4 * g + e] = mk2(SS[e] * cs, SS[e] * sn);
                     }
                 }
                 if (lane == 0) {   // packed DC / Nyquist keep only the real part of S*exp(i*phi)
                     uint4 r = philox4x32(make_uint4((uint32_t)fg, 0xffffffffu, 0x6e737062u, 0u), key);
                     float sn, cs;
                     sincospif(2.0f * (float)(r.x >> 8) * (1.0f / 16777216.0f), &sn, &cs);
-                    im[0] = __ldg(mrow + 1024) * cs;
+                    z[0].y = __ldg(mrow + 1024) * cs;
                 }
             }
-            inv_phase1(re, im, lane, scratch, tw_s);
+            inv_phase1(z, lane, scratch, tw_s);
             __syncwarp();
-            inv_phase2(re, im, lane, scratch);
+            inv_phase2(z, lane, scratch);
             __syncwarp();
             // windowed overlap-add into the tile.  Same-colour frames have disjoint window SUPPORTS, so a plain
             // read-modify-write is race-free only if each warp touches nothing outside its support: per-lane
@@ -418,8 +412,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_synth(SynthParams P) {
 #pragma unroll
                 for (int t = 0; t < 32; ++t) {
                     if (t >= t0 && t < t1) {
-                        if (mre & (1u << t)) ap[64 * t] = fmaf(re[t], win_s[64 * t + lane], ap[64 * t]);
-                        if (mim & (1u << t)) ap[64 * t + 32] = fmaf(im[t], win_s[64 * t + 32 + lane], ap[64 * t + 32]);
+                        if (mre & (1u << t)) ap[64 * t] = fmaf(z[t].x, win_s[64 * t + lane], ap[64 * t]);
+                        if (mim & (1u << t)) ap[64 * t + 32] = fmaf(z[t].y, win_s[64 * t + 32 + lane], ap[64 * t + 32]);
                     }
                 }
             } else {
@@ -427,8 +421,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_synth(SynthParams P) {
                 for (int t = 0; t < 32; ++t) {
                     if (t >= t0 && t < t1) {
                         long long i0 = base + 64 * t + lane, i1 = i0 + 32;
-                        if ((mre & (1u << t)) && i0 >= 0 && i0 < n_out) acc[i0] = fmaf(re[t], win_s[64 * t + lane], acc[i0]);
-                        if ((mim & (1u << t)) && i1 >= 0 && i1 < n_out) acc[i1] = fmaf(im[t], win_s[64 * t + 32 + lane], acc[i1]);
+                        if ((mre & (1u << t)) && i0 >= 0 && i0 < n_out) acc[i0] = fmaf(z[t].x, win_s[64 * t + lane], acc[i0]);
+                        if ((mim & (1u << t)) && i1 >= 0 && i1 < n_out) acc[i1] = fmaf(z[t].y, win_s[64 * t + 32 + lane], acc[i1]);
                     }
                 }
             }

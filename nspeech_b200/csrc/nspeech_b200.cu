@@ -670,8 +670,12 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
     if (space == NSB_HOST && batch > 1 && (h->host_chunks > 0 || n_spec * sizeof(float) > (8u << 20))) {
         const int want_cfg = h->host_chunks > 0 ? h->host_chunks : 4;
         const int want = batch < want_cfg ? batch : want_cfg;
+        // automatic mode: small first and last chunks (1:3:3:1) - only the first copy-in and the last copy-out are
+        // exposed, everything in between hides behind the compute of a neighbouring chunk
+        const bool taper = (h->host_chunks == 0 && want == 4 && batch >= 8);
+        const int weight[4] = {1, 4, 7, 8};
         for (int c = 1; c < want; ++c) {
-            const long long target = (long long)d.total_frames * c / want;
+            const long long target = taper ? (long long)d.total_frames * weight[c - 1] / 8 : (long long)d.total_frames * c / want;
             int b = cuts.back() + 1;
             while (b < batch && h->h_frame_off[b] < target) ++b;
             if (b < batch && b > cuts.back()) cuts.push_back(b);

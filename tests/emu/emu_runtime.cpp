@@ -48,7 +48,7 @@ static void make_tw(std::vector<f2>& tw) {
             tw[(j - 1) * 32 + l].y = float(std::sin(a));
         }
 }
-struct Lane { float re[32], im[32]; };
+struct Lane { c2 z[32]; };
 
 extern "C" {
 // lane-level checks of the frame transform: out = rfft(x), x = irfft(X) (numpy conventions)
@@ -57,15 +57,15 @@ void emu_rfft2048(const float* x, float* out_re, float* out_im) {
     std::vector<f2> scratch(kScratchF2);
     Lane L[32];
     for (int lane = 0; lane < 32; ++lane)
-        for (int t = 0; t < 32; ++t) { L[lane].re[t] = 0.5f * x[64 * t + lane]; L[lane].im[t] = 0.5f * x[64 * t + 32 + lane]; }
-    for (int lane = 0; lane < 32; ++lane) fwd_phase1(L[lane].re, L[lane].im, lane, scratch.data(), tw.data());
-    for (int lane = 0; lane < 32; ++lane) fwd_phase2(L[lane].re, L[lane].im, lane, scratch.data());
+        for (int t = 0; t < 32; ++t) L[lane].z[t] = mk2(0.5f * x[64 * t + lane], 0.5f * x[64 * t + 32 + lane]);
+    for (int lane = 0; lane < 32; ++lane) fwd_phase1(L[lane].z, lane, scratch.data(), tw.data());
+    for (int lane = 0; lane < 32; ++lane) fwd_phase2(L[lane].z, lane, scratch.data());
     for (int lane = 0; lane < 32; ++lane)
         for (int p = 0; p < 32; ++p) {
-            if (lane == 0 && p == 0) { out_re[0] = L[0].re[0]; out_im[0] = 0.f; out_re[1024] = L[0].im[0]; out_im[1024] = 0.f; continue; }
+            if (lane == 0 && p == 0) { out_re[0] = L[0].z[0].x; out_im[0] = 0.f; out_re[1024] = L[0].z[0].y; out_im[1024] = 0.f; continue; }
             int k = bin_of(lane, p);
-            out_re[k] = L[lane].re[p];
-            out_im[k] = slot_is_conj(lane, p) ? -L[lane].im[p] : L[lane].im[p];
+            out_re[k] = L[lane].z[p].x;
+            out_im[k] = slot_is_conj(lane, p) ? -L[lane].z[p].y : L[lane].z[p].y;
         }
 }
 void emu_irfft2048(const float* in_re, const float* in_im, float* x) {
@@ -74,23 +74,22 @@ void emu_irfft2048(const float* in_re, const float* in_im, float* x) {
     Lane L[32];
     for (int lane = 0; lane < 32; ++lane)
         for (int p = 0; p < 32; ++p) {
-            if (lane == 0 && p == 0) { L[0].re[0] = in_re[0]; L[0].im[0] = in_re[1024]; continue; }
+            if (lane == 0 && p == 0) { L[0].z[0] = mk2(in_re[0], in_re[1024]); continue; }
             int k = bin_of(lane, p);
-            L[lane].re[p] = in_re[k];
-            L[lane].im[p] = slot_is_conj(lane, p) ? -in_im[k] : in_im[k];
+            L[lane].z[p] = mk2(in_re[k], slot_is_conj(lane, p) ? -in_im[k] : in_im[k]);
         }
-    for (int lane = 0; lane < 32; ++lane) inv_phase1(L[lane].re, L[lane].im, lane, scratch.data(), tw.data());
-    for (int lane = 0; lane < 32; ++lane) inv_phase2(L[lane].re, L[lane].im, lane, scratch.data());
+    for (int lane = 0; lane < 32; ++lane) inv_phase1(L[lane].z, lane, scratch.data(), tw.data());
+    for (int lane = 0; lane < 32; ++lane) inv_phase2(L[lane].z, lane, scratch.data());
     for (int lane = 0; lane < 32; ++lane)
         for (int t = 0; t < 32; ++t) {
-            x[64 * t + lane] = L[lane].re[t] * (1.0f / 2048.0f);
-            x[64 * t + 32 + lane] = L[lane].im[t] * (1.0f / 2048.0f);
+            x[64 * t + lane] = L[lane].z[t].x * (1.0f / 2048.0f);
+            x[64 * t + 32 + lane] = L[lane].z[t].y * (1.0f / 2048.0f);
         }
 }
 void emu_fft32(float* re, float* im, int dir) {
-    float r[32], i[32];
-    memcpy(r, re, sizeof r); memcpy(i, im, sizeof i);
-    if (dir < 0) fft32<-1>(r, i); else fft32<+1>(r, i);
-    memcpy(re, r, sizeof r); memcpy(im, i, sizeof i);
+    c2 z[32];
+    for (int i = 0; i < 32; ++i) z[i] = mk2(re[i], im[i]);
+    if (dir < 0) fft32<-1>(z); else fft32<+1>(z);
+    for (int i = 0; i < 32; ++i) { re[i] = z[i].x; im[i] = z[i].y; }
 }
 }  // extern "C"
