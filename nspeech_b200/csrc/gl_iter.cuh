@@ -23,6 +23,8 @@ namespace nsb {
 
 #ifdef NSB_EMULATE
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) { memcpy(dst, src, 8); }
+__device__ __forceinline__ void prefetch_l2(const void*) {}
 __device__ __forceinline__ void cp_async_wait_all() {}
 __device__ __forceinline__ int flag_load(const int* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 __device__ __forceinline__ void flag_store(int* p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
@@ -41,6 +43,10 @@ __device__ __forceinline__ bool warp_any(bool p) {
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
@@ -81,7 +87,7 @@ template <bool DEFCFG>
 __device__ __noinline__ void gl_store_tile(const GlParams& P, int tile_g, const float* acc, const float* win_s, const float* rinv_s,
                                               int hop, int win, int lo, int H, bool& bad) {
     const int a = kNfft / 2 - lo;
-    const int b = find_segment(P.batch.tile_off, P.batch.batch, tile_g);
+    const int b = __ldg(P.batch.tile_utt + tile_g) - P.batch.utt_base;
     const int tile = tile_g - __ldg(P.batch.tile_off + b);
     const int T = __ldg(P.batch.frame_off + b + 1) - __ldg(P.batch.frame_off + b);
     const int h0 = tile * H, h1 = min(h0 + H, T - 1);
@@ -147,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
     bool bad = false;
 
     for (int tile_g = P.batch.tile_base + blockIdx.x; tile_g < P.batch.tile_base + P.total_tiles; tile_g += gridDim.x) {
-        const int b = find_segment(P.batch.tile_off, P.batch.batch, tile_g);
+        const int b = __ldg(P.batch.tile_utt + tile_g) - P.batch.utt_base;
         const int tile = tile_g - __ldg(P.batch.tile_off + b);
         const int f_off = __ldg(P.batch.frame_off + b);
         const int T = __ldg(P.batch.frame_off + b + 1) - f_off;
@@ -169,14 +175,34 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
         if (threadIdx.x < 16) progress[threadIdx.x] = 0;
         __syncthreads();
 
+        bool staged = false;                         // this frame's samples were cp.async'ed into the scratch tile already
         for (int s = 0; s < C; ++s) {
             const int k = kg + s;
             const bool active = (k >= 0 && k <= k_max);        // warp-uniform
             c2 z[32];
             if (active) {
                 const int fg = f_off + k;
-                load_frame<false, PRUNE>(z, P.y_in + s_off, L, (long long)k * hop - kNfft / 2, win_s, lane, 0.f,
-                                         reinterpret_cast<float*>(scratch));
+                // pull the NEXT frame's magnitude row towards L2 (it streams from HBM) while this frame computes
+                if (k + 1 <= k_max) {
+                    const char* nm = reinterpret_cast<const char*>(P.mag + (size_t)(fg + 1) * kMagPitch);
+                    prefetch_l2(nm + lane * 128);
+                    if (lane == 0) prefetch_l2(nm + 4096);
+                }
+                if (staged) {
+                    // samples were staged by the previous frame of this warp (see below): window them from shared memory
+                    cp_async_wait_all();
+                    __syncwarp();
+                    const float* stage = reinterpret_cast<const float*>(scratch);
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) {
+                        if (t >= 8 && t < 24) z[t] = p_mul(mk2(stage[64 * t + lane], stage[64 * t + 32 + lane]), mk2(win_s[64 * t + lane], win_s[64 * t + 32 + lane]));
+                        else z[t] = mk2(0.f, 0.f);
+                    }
+                    __syncwarp();
+                } else {
+                    load_frame<false, PRUNE>(z, P.y_in + s_off, L, (long long)k * hop - kNfft / 2, win_s, lane, 0.f,
+                                             reinterpret_cast<float*>(scratch));
+                }
                 fwd_phase1(z, lane, scratch, tw_s);
                 __syncwarp();
 #pragma unroll
@@ -271,6 +297,22 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                 __syncwarp();
                 inv_phase2(z, lane, scratch);
                 __syncwarp();                        // the scratch tile may be rewritten by this warp's next frame
+                // The scratch tile now idles through the overlap-add: stage the warp's NEXT frame (k+1) into it with
+                // cp.async so that its load latency hides behind the neighbour wait and the accumulate.  Only for
+                // frames that need no reflect padding and (8-byte copies) an even sample offset.
+                staged = false;
+                if (PRUNE && s + 1 < C && k + 1 <= k_max) {
+                    const long long nstart = (long long)(k + 1) * hop - kNfft / 2;
+                    if (nstart + 512 >= 0 && nstart + 1536 <= L && ((s_off + nstart) & 1) == 0) {
+                        const float* src = P.y_in + s_off + nstart + 512 + 2 * lane;
+                        float* dst = reinterpret_cast<float*>(scratch) + 512 + 2 * lane;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) cp_async8(dst + 64 * j, src + 64 * j);
+                        staged = true;
+                    }
+                }
+            } else {
+                staged = false;
             }
             // ---- overlap-add ordering ----
             if (s > 0) {

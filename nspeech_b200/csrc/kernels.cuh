@@ -34,7 +34,9 @@ struct Batch {
     const int* frame_off;        // [batch+1]
     const long long* samp_off;   // [batch+1]
     const int* tile_off;         // [batch+1] (synthesis tiles), may be null for analysis
+    const int* tile_utt;         // [total tiles] GLOBAL tile index -> GLOBAL utterance index
     int batch;
+    int utt_base;                // global index of this (sub-)batch's first utterance (pointers above are offset by it)
     int frame_base, tile_base;   // global index of this (sub-)batch's first frame / tile: the arrays hold GLOBAL prefix
                                  // sums, so a chunk of a batch is just a pointer offset + these bases (host-side pipelining)
 };
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_synth(SynthParams P) {
     const int C = P.colours, H = P.tile_hops;
 
     const int tile_g = P.batch.tile_base + (int)blockIdx.x;
-    const int b = find_segment(P.batch.tile_off, P.batch.batch, tile_g);
+    const int b = __ldg(P.batch.tile_utt + tile_g) - P.batch.utt_base;
     const int tile = tile_g - __ldg(P.batch.tile_off + b);
     const int f_off = __ldg(P.batch.frame_off + b);
     const int T = __ldg(P.batch.frame_off + b + 1) - f_off;

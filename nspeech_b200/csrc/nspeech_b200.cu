@@ -368,8 +368,13 @@ struct Desc {
 static int upload_desc(nsb_handle_s* h, cudaStream_t st, const std::vector<int>& frames, const std::vector<long long>& samples,
                        int tile_hops, Desc* d) {
     const int B = (int)frames.size();
+    long long n_tiles = 0;
+    if (tile_hops > 0) for (int b = 0; b < B; ++b) { int hops = frames[b] - 1; if (hops > 0) n_tiles += (hops + tile_hops - 1) / tile_hops; }
+    if (n_tiles > 2000000000LL) return fail(NSB_ERR_INVALID, "batch too large: more than 2e9 tiles");
     const size_t n_int = 2 * (size_t)(B + 1);
-    const size_t bytes = ((n_int * sizeof(int) + 7) & ~(size_t)7) + (size_t)(B + 1) * sizeof(long long);
+    const size_t off_samp = (n_int * sizeof(int) + 7) & ~(size_t)7;
+    const size_t off_tutt = off_samp + (size_t)(B + 1) * sizeof(long long);
+    const size_t bytes = off_tutt + (size_t)(n_tiles > 0 ? n_tiles : 1) * sizeof(int);
     if (bytes > h->h_desc_cap) {
         if (h->h_desc) { CU(cudaEventSynchronize(h->desc_done)); cudaFreeHost(h->h_desc); h->h_desc = nullptr; h->h_desc_cap = 0; }
         CU(cudaHostAlloc(&h->h_desc, bytes * 2, cudaHostAllocDefault));
@@ -379,9 +384,11 @@ static int upload_desc(nsb_handle_s* h, cudaStream_t st, const std::vector<int>&
     }
     int rc = h->d_desc.reserve(bytes);
     if (rc) return rc;
-    int* fo = reinterpret_cast<int*>(h->h_desc);
+    char* hb = reinterpret_cast<char*>(h->h_desc);
+    int* fo = reinterpret_cast<int*>(hb);
     int* to = fo + (B + 1);
-    long long* so = reinterpret_cast<long long*>(reinterpret_cast<char*>(h->h_desc) + ((n_int * sizeof(int) + 7) & ~(size_t)7));
+    long long* so = reinterpret_cast<long long*>(hb + off_samp);
+    int* tu = reinterpret_cast<int*>(hb + off_tutt);
     fo[0] = 0; to[0] = 0; so[0] = 0;
     for (int b = 0; b < B; ++b) {
         long long nf = (long long)fo[b] + frames[b];
@@ -390,16 +397,19 @@ static int upload_desc(nsb_handle_s* h, cudaStream_t st, const std::vector<int>&
         int tiles = 0;
         if (tile_hops > 0) { int hops = frames[b] - 1; tiles = hops > 0 ? (hops + tile_hops - 1) / tile_hops : 0; }
         to[b + 1] = to[b] + tiles;
+        for (int t = to[b]; t < to[b + 1]; ++t) tu[t] = b;       // tile -> utterance (saves a binary search per tile on the GPU)
         so[b + 1] = so[b] + samples[b];
     }
     h->h_frame_off.assign(fo, fo + B + 1); h->h_tile_off.assign(to, to + B + 1); h->h_samp_off.assign(so, so + B + 1);
     CU(cudaMemcpyAsync(h->d_desc.p, h->h_desc, bytes, cudaMemcpyHostToDevice, st));
     CU(cudaEventRecord(h->desc_done, st));
-    d->dev.frame_off = reinterpret_cast<const int*>(h->d_desc.p);
+    const char* db = reinterpret_cast<const char*>(h->d_desc.p);
+    d->dev.frame_off = reinterpret_cast<const int*>(db);
     d->dev.tile_off = d->dev.frame_off + (B + 1);
-    d->dev.samp_off = reinterpret_cast<const long long*>(reinterpret_cast<const char*>(h->d_desc.p) + ((n_int * sizeof(int) + 7) & ~(size_t)7));
+    d->dev.samp_off = reinterpret_cast<const long long*>(db + off_samp);
+    d->dev.tile_utt = reinterpret_cast<const int*>(db + off_tutt);
     d->dev.batch = B;
-    d->dev.frame_base = 0; d->dev.tile_base = 0;
+    d->dev.frame_base = 0; d->dev.tile_base = 0; d->dev.utt_base = 0;
     d->total_frames = fo[B];
     d->total_tiles = to[B];
     d->total_samples = so[B];
@@ -708,7 +718,7 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
         const int b0 = cuts[c], b1 = cuts[c + 1];
         Batch B = d.dev;
         B.frame_off += b0; B.tile_off += b0; B.samp_off += b0; B.batch = b1 - b0;
-        B.frame_base = h->h_frame_off[b0]; B.tile_base = h->h_tile_off[b0];
+        B.frame_base = h->h_frame_off[b0]; B.tile_base = h->h_tile_off[b0]; B.utt_base = b0;
         const int n_frames_c = h->h_frame_off[b1] - h->h_frame_off[b0];
         const int n_tiles_c = h->h_tile_off[b1] - h->h_tile_off[b0];
         if (space == NSB_HOST) CUE(cudaStreamWaitEvent(st, ev_in[c], 0));
