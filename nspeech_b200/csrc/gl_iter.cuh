@@ -83,36 +83,60 @@ __device__ __forceinline__ void renorm_fast(c2& z, float S, bool& zero) {
 }
 
 // normalise the finished tile by the summed squared window and store it (all threads of the CTA)
+// rinv_s[j] already contains 1 / (n_fft * window-sum) for the interior (all covering frames exist).
 template <bool DEFCFG>
 __device__ __noinline__ void gl_store_tile(const GlParams& P, int tile_g, const float* acc, const float* win_s, const float* rinv_s,
-                                              int hop, int win, int lo, int H, bool& bad) {
+                                           int hop, int win, int lo, int H, bool& bad) {
     const int a = kNfft / 2 - lo;
     const int b = __ldg(P.batch.tile_utt + tile_g) - P.batch.utt_base;
     const int tile = tile_g - __ldg(P.batch.tile_off + b);
     const int T = __ldg(P.batch.frame_off + b + 1) - __ldg(P.batch.frame_off + b);
     const int h0 = tile * H, h1 = min(h0 + H, T - 1);
-    float* yo = P.y_out + __ldg(P.batch.samp_off + b) + (long long)h0 * hop;
-    for (int j = threadIdx.x; j < hop; j += kThreads) {
-        const int dj = (j + a) / hop, rj = (j + a) - dj * hop;
-        const float ri = rinv_s[j];
-        int ncover = 0;
-        for (int idx = rj; idx < win; idx += hop) ++ncover;
-        for (int h = h0; h < h1; ++h) {
-            const int k_hi = h + dj, k_lo = k_hi - (ncover - 1);
-            float v = acc[(h - h0) * hop + j] * (1.0f / (float)kNfft);
-            bad |= !isfinite(v);
-            if (k_lo >= 0 && k_hi <= T - 1) {
-                v *= ri;
-            } else {
-                float sm = 0.f;
-                int kk = k_hi;
-                for (int idx = rj; idx < win; idx += hop, --kk)
-                    if (kk >= 0 && kk <= T - 1) { float w = win_s[lo + idx]; sm = fmaf(w, w, sm); }
-                if (sm > 1.17549435e-38f) v /= sm;
+    const long long o0 = __ldg(P.batch.samp_off + b) + (long long)h0 * hop;
+    float* yo = P.y_out + o0;
+    const int n_out = (h1 - h0) * hop;
+    // interior tile: every sample is covered by all of its ceil(win/hop) frames -> no per-sample frame tests
+    const int ncov = (win + hop - 1) / hop;
+    const bool interior = (h0 + a / hop - (ncov - 1) >= 0) && (h1 - 1 + (hop - 1 + a) / hop <= T - 1);
+    float chk = 0.f;                                  // NaN/Inf detector: v*0 accumulates to NaN iff some v is not finite
+    if (interior && (hop & 1) == 0 && (o0 & 1) == 0) {
+        const float2* acc2 = reinterpret_cast<const float2*>(acc);
+        const float2* r2 = reinterpret_cast<const float2*>(rinv_s);
+        float2* yo2 = reinterpret_cast<float2*>(yo);
+        const int hop2 = hop >> 1;
+        c2 chk2 = mk2(0.f, 0.f);
+        for (int i = threadIdx.x; i < (n_out >> 1); i += kThreads) {
+            const int j = i % hop2;
+            c2 v = p_mul(acc2[i], r2[j]);
+            chk2 = p_fma(v, mk2(0.f, 0.f), chk2);
+            yo2[i] = v;
+        }
+        chk = chk2.x + chk2.y;
+    } else {
+        for (int j = threadIdx.x; j < hop; j += kThreads) {
+            const int dj = (j + a) / hop, rj = (j + a) - dj * hop;
+            const float ri = rinv_s[j];
+            int ncover = 0;
+            for (int idx = rj; idx < win; idx += hop) ++ncover;
+            for (int h = h0; h < h1; ++h) {
+                const int k_hi = h + dj, k_lo = k_hi - (ncover - 1);
+                float v = acc[(h - h0) * hop + j];
+                if (k_lo >= 0 && k_hi <= T - 1) {
+                    v *= ri;
+                } else {
+                    v *= (1.0f / (float)kNfft);
+                    float sm = 0.f;
+                    int kk = k_hi;
+                    for (int idx = rj; idx < win; idx += hop, --kk)
+                        if (kk >= 0 && kk <= T - 1) { float w = win_s[lo + idx]; sm = fmaf(w, w, sm); }
+                    if (sm > 1.17549435e-38f) v /= sm;
+                }
+                chk = fmaf(v, 0.f, chk);
+                yo[(size_t)(h - h0) * hop + j] = v;
             }
-            yo[(size_t)(h - h0) * hop + j] = v;
         }
     }
+    bad |= (chk != 0.f);
 }
 
 // Rejected variants (measured on B200, batch 64 x 1000 frames, see profiles/README.md): one shared FFT32 copy for
@@ -130,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
     float* win_s = reinterpret_cast<float*>(tw_s + kTwF2);
     float* rinv_s = win_s + kNfft;
-    float* acc = rinv_s + hop;
+    float* acc = rinv_s + ((hop + 3) & ~3);          // 16-byte aligned (float4 zeroing, float2 epilogue)
     size_t acc_end = (size_t)(acc + (size_t)H * hop - reinterpret_cast<float*>(smem_raw));
     acc_end = (acc_end + 3) & ~(size_t)3;
     int* progress = reinterpret_cast<int*>(reinterpret_cast<float*>(smem_raw) + acc_end);   // [kWarpsPerCta] (+pad to 16 ints)
@@ -148,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
     for (int j = threadIdx.x; j < hop; j += kThreads) {
         float s = 0.f;
         for (int idx = (j + a) % hop; idx < win; idx += hop) { float w = win_s[lo + idx]; s = fmaf(w, w, s); }
-        rinv_s[j] = s > 1.17549435e-38f ? 1.0f / s : 1.0f;
+        rinv_s[j] = (s > 1.17549435e-38f ? 1.0f / s : 1.0f) * (1.0f / (float)kNfft);
     }
     bool bad = false;
 
@@ -171,7 +195,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
         if (k_max > T - 1) k_max = T - 1;
         if (k_max - k_first + 1 > kWarpsPerCta * C) bad = true;   // host sizes tiles so this cannot happen; never drop frames silently
         const int kg = k_first + C * warp;
-        for (int i = threadIdx.x; i < n_out; i += kThreads) acc[i] = 0.f;
+        {
+            float4* a4 = reinterpret_cast<float4*>(acc);            // the tile buffer is 16-byte aligned and a multiple of 4 long (+pad)
+            for (int i = threadIdx.x; i < (n_out + 3) / 4; i += kThreads) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         if (threadIdx.x < 16) progress[threadIdx.x] = 0;
         __syncthreads();
 

@@ -136,7 +136,7 @@ static size_t synth_smem(int hop, int H) {
     fl = (fl + 3) & ~(size_t)3;
     return fl * sizeof(float) + sizeof(float2) * kScratchF2 * kWarpsPerCta;
 }
-static size_t gl_smem(int hop, int H) { return synth_smem(hop, H) + 64; }   // + neighbour progress flags
+static size_t gl_smem(int hop, int H) { return synth_smem(hop, H) + 64 + 16; }   // + neighbour progress flags + rinv padding   // + neighbour progress flags
 static const size_t kSmemPerCtaTwoResident = (227 * 1024) / 2 - 1024;   // two CTAs per SM, 1 KB reserved each
 
 static int max_tile_hops(const nsb_handle_s* h) {
