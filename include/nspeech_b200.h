@@ -68,7 +68,12 @@ enum { NSB_EW_AMP_TO_DB = 0, NSB_EW_DB_TO_AMP = 1, NSB_EW_NORMALIZE = 2, NSB_EW_
 /* flags of nsb_griffin_lim */
 enum {
     NSB_GL_DENORMALIZE = 1,   /* input is a normalised dB spectrogram: apply audio.py:47-48 first */
-    NSB_GL_DEEMPHASIS = 2     /* apply inv_preemphasis (audio.py:35-36) to the result */
+    NSB_GL_DEEMPHASIS = 2,    /* apply inv_preemphasis (audio.py:35-36) to the result */
+    NSB_GL_TF_TWIN = 4        /* the TensorFlow twin's semantics, inv_spectrogram_tensorflow / _griffin_lim_tensorflow
+                               * (audio.py:51-58, 90-103): zero initial phase, tf.contrib.signal framing (frame k =
+                               * samples [k*hop, k*hop+win), window on them, zero-padded at the END to n_fft, no centring,
+                               * no reflect padding), inverse without window-sum normalisation, phase = est/max(1e-8,|est|),
+                               * output win + hop*(T-1) samples per utterance.  init_phase and seed are ignored. */
 };
 
 int nsb_abi_version(void);
@@ -93,6 +98,11 @@ int64_t nsb_num_samples(nsb_handle_t h, int64_t n_frames);
 int nsb_stft(nsb_handle_t h, const float* wav, const int64_t* n_samples, int32_t batch, int32_t apply_preemphasis,
              float* out_complex, int32_t space, void* stream);
 
+/* _stft_tensorflow(signals) (utils/audio.py:116-118): tf.contrib.signal.stft(signals, win, hop, n_fft, pad_end=False);
+ * needs n >= win; T = 1 + (n - win) // hop frames; out complex64 frame-major [sum T][num_freq]. */
+int nsb_stft_tf(nsb_handle_t h, const float* wav, const int64_t* n_samples, int32_t batch, float* out_complex,
+                int32_t space, void* stream);
+
 /* spectrogram(y) and melspectrogram(y) (utils/audio.py:39-42, 61-64) from ONE STFT pass.
  * lin_out: [sum T][num_freq] or NULL; mel_out: [sum T][num_mels] or NULL (frame-major float32). */
 int nsb_features(nsb_handle_t h, const float* wav, const int64_t* n_samples, int32_t batch,
@@ -101,6 +111,11 @@ int nsb_features(nsb_handle_t h, const float* wav, const int64_t* n_samples, int
 /* _istft(D) (utils/audio.py:111-113): spec complex64 in `layout`; wav_out float32, hop*(T-1) per utterance. */
 int nsb_istft(nsb_handle_t h, const float* spec_complex, int32_t layout, const int32_t* n_frames, int32_t batch,
               float* wav_out, int32_t space, void* stream);
+
+/* _istft_tensorflow(stfts) (utils/audio.py:121-123): tf.contrib.signal.inverse_stft(stfts, win, hop, n_fft) with its
+ * TF-1.7 default window (periodic Hann, no normalisation); wav_out float32, win + hop*(T-1) per utterance. */
+int nsb_istft_tf(nsb_handle_t h, const float* spec_complex, int32_t layout, const int32_t* n_frames, int32_t batch,
+                 float* wav_out, int32_t space, void* stream);
 
 /* _griffin_lim(S) / inv_spectrogram(spectrogram) (utils/audio.py:77-87, 45-48).
  *   spec        float32 magnitudes S (flags without NSB_GL_DENORMALIZE) or normalised spectrogram in [0,1]

@@ -19,7 +19,7 @@ HOST, DEVICE = 0, 1
 FRAME_MAJOR, BIN_MAJOR = 0, 1
 F32, F64 = 0, 1
 EW_AMP_TO_DB, EW_DB_TO_AMP, EW_NORMALIZE, EW_DENORMALIZE = range(4)
-GL_DENORMALIZE, GL_DEEMPHASIS = 1, 2
+GL_DENORMALIZE, GL_DEEMPHASIS, GL_TF_TWIN = 1, 2, 4
 
 
 class ParameterError(ValueError):
@@ -52,6 +52,8 @@ SIGNATURES = {
     "nsb_num_frames": (_i64, [_vp, _i64]),
     "nsb_num_samples": (_i64, [_vp, _i64]),
     "nsb_stft": (ctypes.c_int, [_vp, _vp, _pi64, _i32, _i32, _vp, _i32, _vp]),
+    "nsb_stft_tf": (ctypes.c_int, [_vp, _vp, _pi64, _i32, _vp, _i32, _vp]),
+    "nsb_istft_tf": (ctypes.c_int, [_vp, _vp, _i32, _pi32, _i32, _vp, _i32, _vp]),
     "nsb_features": (ctypes.c_int, [_vp, _vp, _pi64, _i32, _vp, _vp, _i32, _vp]),
     "nsb_istft": (ctypes.c_int, [_vp, _vp, _i32, _pi32, _i32, _vp, _i32, _vp]),
     "nsb_griffin_lim": (ctypes.c_int, [_vp, _vp, _i32, _pi32, _i32, _vp, _u64, _i32, _i32, _vp, _i32, _i32, _vp]),
@@ -202,6 +204,19 @@ class Handle(object):
     def stft(self, wav, n_samples, out, preemphasis=False, space=HOST, stream=None):
         self._call("nsb_stft", _ptr(wav), self._lens(n_samples, ctypes.c_int64), len(n_samples), int(bool(preemphasis)),
                    _ptr(out), space, _ptr(stream))
+
+    def stft_tf(self, wav, n_samples, out, space=HOST, stream=None):
+        self._call("nsb_stft_tf", _ptr(wav), self._lens(n_samples, ctypes.c_int64), len(n_samples), _ptr(out), space, _ptr(stream))
+
+    def istft_tf(self, spec, layout, n_frames, out, space=HOST, stream=None):
+        self._call("nsb_istft_tf", _ptr(spec), layout, self._lens(n_frames, ctypes.c_int32), len(n_frames), _ptr(out), space,
+                   _ptr(stream))
+
+    def num_frames_tf(self, n):
+        return 1 + (int(n) - self.win) // self.hop
+
+    def num_samples_tf(self, T):
+        return self.hop * (int(T) - 1) + self.win
 
     def features(self, wav, n_samples, lin_out, mel_out, space=HOST, stream=None):
         self._call("nsb_features", _ptr(wav), self._lens(n_samples, ctypes.c_int64), len(n_samples), _ptr(lin_out),

@@ -232,3 +232,80 @@ def _normalize(S):
 def _denormalize(S):
     # reference audio.py:166-167
     return _elementwise(_lib.EW_DENORMALIZE, S)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The TensorFlow twin (reference audio.py:51-58, 90-103, 116-123, 158-159, 170-171) - the variant the reference's live
+# callers use (synthesizer.py:30, models/tacotron.py:107).  In the reference these build TF-1 graph ops; here they are
+# eager functions on numpy arrays with the same semantics: time-major [T, F] (or batched [N, T, F]) spectrograms,
+# tf.contrib.signal framing (no centring / padding, window on the first win samples, zero-padded at the end),
+# inverse without window-sum normalisation, zero initial phase, est / max(1e-8, |est|), float32 results of
+# win + hop*(T-1) samples, and NO inverse pre-emphasis (the caller applies it, synthesizer.py:52).
+# ---------------------------------------------------------------------------------------------------------------
+
+def _tf_batch(S, dtype):
+    S = np.asarray(S)
+    if S.ndim not in (2, 3):
+        raise ValueError("expected [T, F] or [N, T, F], got shape %r" % (S.shape,))
+    return np.ascontiguousarray(S, dtype=dtype), S.ndim == 3
+
+
+def _run_gl_tf(S, flags, iters):
+    S, batched = _tf_batch(S, np.float32)
+    h = _handle()
+    if S.shape[-1] != h.num_freq:
+        raise ValueError("expected %d frequency bins on the last axis, got %d" % (h.num_freq, S.shape[-1]))
+    N = S.shape[0] if batched else 1
+    T = S.shape[-2]
+    n = h.num_samples_tf(T)
+    out = np.empty((N, n), dtype=np.float32)
+    h.griffin_lim(S, _lib.FRAME_MAJOR, [T] * N, out, iters=-1 if iters is None else iters, flags=flags | _lib.GL_TF_TWIN,
+                  out_dtype=_lib.F32)
+    return out if batched else out[0]
+
+
+def _griffin_lim_tensorflow(S, iters=None):
+    # reference audio.py:90-103
+    return _run_gl_tf(S, 0, iters)
+
+
+def inv_spectrogram_tensorflow(spectrogram, iters=None):
+    '''reference audio.py:51-58; like there, this does NOT invert the preemphasis'''
+    return _run_gl_tf(spectrogram, _lib.GL_DENORMALIZE, iters)
+
+
+def _stft_tensorflow(signals):
+    # reference audio.py:116-118 -> complex64 [T, F] (or [N, T, F])
+    x = np.asarray(signals)
+    batched = x.ndim == 2
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    h = _handle()
+    N = x.shape[0] if batched else 1
+    n = x.shape[-1]
+    if n < h.win:
+        raise ValueError("signal shorter than one frame (%d < %d)" % (n, h.win))
+    T = h.num_frames_tf(n)
+    out = np.empty((N, T, h.num_freq), dtype=np.complex64)
+    h.stft_tf(x, [n] * N, out)
+    return out if batched else out[0]
+
+
+def _istft_tensorflow(stfts):
+    # reference audio.py:121-123 -> float32 [win + hop*(T-1)] (or [N, ...])
+    D, batched = _tf_batch(stfts, np.complex64)
+    h = _handle()
+    N = D.shape[0] if batched else 1
+    T = D.shape[-2]
+    out = np.empty((N, h.num_samples_tf(T)), dtype=np.float32)
+    h.istft_tf(D, _lib.FRAME_MAJOR, [T] * N, out)
+    return out if batched else out[0]
+
+
+def _db_to_amp_tensorflow(x):
+    # reference audio.py:158-159
+    return _db_to_amp(x)
+
+
+def _denormalize_tensorflow(S):
+    # reference audio.py:170-171
+    return _denormalize(S)

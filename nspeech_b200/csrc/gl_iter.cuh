@@ -69,8 +69,16 @@ struct GlParams {
     float* y_out;
     const float* mag;        // permuted, pre-scaled magnitudes [frames][kMagPitch]
     int tile_hops, colours, total_tiles;
+    float inv_thr;           // TF twin: the clamp of est / max(1e-8, |est|) (audio.py:101) for register slots, which hold
+                             // 2 * g * est (g = magnitude pre-scale): 1 / (2 * g * 1e-8)
     int* status;
 };
+
+// TF twin: angles = est / max(1e-8, |est|) -> z * S * min(1/|z|, 1/thr); |z| = 0 gives 0 (not S)
+__device__ __forceinline__ void renorm_tf(c2& z, float S, float inv_thr) {
+    float m2 = fmaf(z.x, z.x, z.y * z.y);
+    z = cscale(z, fminf(rsqrtf(m2), inv_thr) * S);
+}
 
 constexpr int kMagBytes = 4096 + 16;                 // slots + the float4 that carries the Nyquist magnitude
 constexpr int kXchOffsetF2 = (kMagBytes + 112) / 8;  // exchange area starts at byte 4224 of the scratch tile (8-byte units)
@@ -87,17 +95,21 @@ __device__ __forceinline__ void renorm_fast(c2& z, float S, bool& zero) {
 template <bool DEFCFG>
 __device__ __noinline__ void gl_store_tile(const GlParams& P, int tile_g, const float* acc, const float* win_s, const float* rinv_s,
                                            int hop, int win, int lo, int H, bool& bad) {
-    const int a = kNfft / 2 - lo;
+    const int a = P.plan.origin - lo;
     const int b = __ldg(P.batch.tile_utt + tile_g) - P.batch.utt_base;
     const int tile = tile_g - __ldg(P.batch.tile_off + b);
     const int T = __ldg(P.batch.frame_off + b + 1) - __ldg(P.batch.frame_off + b);
-    const int h0 = tile * H, h1 = min(h0 + H, T - 1);
-    const long long o0 = __ldg(P.batch.samp_off + b) + (long long)h0 * hop;
+    const long long s_off = __ldg(P.batch.samp_off + b);
+    const long long L = __ldg(P.batch.samp_off + b + 1) - s_off;
+    const int n_hops = (int)((L + hop - 1) / hop);
+    const int h0 = tile * H, h1 = min(h0 + H, n_hops);
+    const long long o0 = s_off + (long long)h0 * hop;
     float* yo = P.y_out + o0;
-    const int n_out = (h1 - h0) * hop;
+    const int n_out = (int)(min((long long)h1 * hop, L) - (long long)h0 * hop);
     // interior tile: every sample is covered by all of its ceil(win/hop) frames -> no per-sample frame tests
+    // (without window-sum normalisation every tile is "interior": rinv_s is the constant 1/n_fft)
     const int ncov = (win + hop - 1) / hop;
-    const bool interior = (h0 + a / hop - (ncov - 1) >= 0) && (h1 - 1 + (hop - 1 + a) / hop <= T - 1);
+    const bool interior = !P.plan.norm_wss || ((h0 + a / hop - (ncov - 1) >= 0) && (h1 - 1 + (hop - 1 + a) / hop <= T - 1));
     float chk = 0.f;                                  // NaN/Inf detector: v*0 accumulates to NaN iff some v is not finite
     if (interior && (hop & 1) == 0 && (o0 & 1) == 0) {
         const float2* acc2 = reinterpret_cast<const float2*>(acc);
@@ -119,9 +131,10 @@ __device__ __noinline__ void gl_store_tile(const GlParams& P, int tile_g, const 
             int ncover = 0;
             for (int idx = rj; idx < win; idx += hop) ++ncover;
             for (int h = h0; h < h1; ++h) {
+                if ((h - h0) * hop + j >= n_out) break;
                 const int k_hi = h + dj, k_lo = k_hi - (ncover - 1);
                 float v = acc[(h - h0) * hop + j];
-                if (k_lo >= 0 && k_hi <= T - 1) {
+                if (!P.plan.norm_wss || (k_lo >= 0 && k_hi <= T - 1)) {
                     v *= ri;
                 } else {
                     v *= (1.0f / (float)kNfft);
@@ -143,7 +156,7 @@ __device__ __noinline__ void gl_store_tile(const GlParams& P, int tile_g, const 
 // the four passes through a rolled pass loop (i-cache stalls 23% -> 6% but +12% instructions from loop-carried
 // register shuffling: no gain); software-pipelined tile hand-over (4% slower); global-colour order that rotates
 // the warp's frames (12% slower than increasing order, hence the aligned tiles below).
-template <bool PRUNE, bool DEFCFG>
+template <int PRUNE, bool DEFCFG, bool TFM>
 __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
     NSB_DYN_SMEM(smem_raw);
     const int hop = DEFCFG ? 250 : P.plan.hop;
@@ -162,7 +175,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float2* scratch = scratch_all + warp * kScratchF2;
-    const int a = kNfft / 2 - lo;
+    const int origin = DEFCFG ? kNfft / 2 : P.plan.origin;
+    const int a = origin - lo;
     // first frame (possibly negative = does not exist) whose window support can reach hop h is h + kfirst0
     const int kfirst0 = (a - win >= 0) ? (a - win) / hop + 1 : -((win - a - 1) / hop + 1) + 1;
 
@@ -172,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
     for (int j = threadIdx.x; j < hop; j += kThreads) {
         float s = 0.f;
         for (int idx = (j + a) % hop; idx < win; idx += hop) { float w = win_s[lo + idx]; s = fmaf(w, w, s); }
-        rinv_s[j] = (s > 1.17549435e-38f ? 1.0f / s : 1.0f) * (1.0f / (float)kNfft);
+        rinv_s[j] = ((P.plan.norm_wss && s > 1.17549435e-38f) ? 1.0f / s : 1.0f) * (1.0f / (float)kNfft);
     }
     bool bad = false;
 
@@ -182,10 +196,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
         const int f_off = __ldg(P.batch.frame_off + b);
         const int T = __ldg(P.batch.frame_off + b + 1) - f_off;
         const long long s_off = __ldg(P.batch.samp_off + b);
-        const long long L = (long long)hop * (T - 1);
-        const int h0 = tile * H, h1 = min(h0 + H, T - 1);
+        const long long L = __ldg(P.batch.samp_off + b + 1) - s_off;   // hop*(T-1) (librosa) or hop*(T-1)+win (tf)
+        const int n_hops = (int)((L + hop - 1) / hop);
+        const int h0 = tile * H, h1 = min(h0 + H, n_hops);
         const int s0 = h0 * hop;
-        const int n_out = (h1 - h0) * hop;
+        const int n_out = (int)(min((long long)h1 * hop, L) - s0);
         // Frames are grouped from the VIRTUAL first frame h0 + kfirst0 (negative frames simply do not exist).  Because
         // H is a multiple of C, every tile's groups start at the same residue mod C: the warp adds its frames in
         // increasing order AND that order is the global colour (k - kfirst0) mod C, so the summation order of every
@@ -227,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                     }
                     __syncwarp();
                 } else {
-                    load_frame<false, PRUNE>(z, P.y_in + s_off, L, (long long)k * hop - kNfft / 2, win_s, lane, 0.f,
+                    load_frame<false, PRUNE>(z, P.y_in + s_off, L, (long long)k * hop - origin, win_s, lane, 0.f,
                                              reinterpret_cast<float*>(scratch));
                 }
                 fwd_phase1(z, lane, scratch, tw_s);
@@ -258,13 +273,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
                     float4 S = mrow[g * 32 + lane];
-                    renorm_fast(z[4 * g], S.x, zero);
-                    renorm_fast(z[4 * g + 1], S.y, zero);
-                    renorm_fast(z[4 * g + 2], S.z, zero);
-                    renorm_fast(z[4 * g + 3], S.w, zero);
+                    if (TFM) {
+                        renorm_tf(z[4 * g], S.x, P.inv_thr); renorm_tf(z[4 * g + 1], S.y, P.inv_thr);
+                        renorm_tf(z[4 * g + 2], S.z, P.inv_thr); renorm_tf(z[4 * g + 3], S.w, P.inv_thr);
+                    } else {
+                        renorm_fast(z[4 * g], S.x, zero);
+                        renorm_fast(z[4 * g + 1], S.y, zero);
+                        renorm_fast(z[4 * g + 2], S.z, zero);
+                        renorm_fast(z[4 * g + 3], S.w, zero);
+                    }
                 }
                 if (lane == 0) zero = false;
-                if (warp_any(zero)) {                // rare: some bin of y's STFT is exactly 0 -> phase 0 (np.angle(0))
+                if (!TFM && warp_any(zero)) {                // rare: some bin of y's STFT is exactly 0 -> phase 0 (np.angle(0))
                     if (lane != 0) {
 #pragma unroll
                         for (int g = 0; g < 8; ++g) {
@@ -282,8 +302,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                         float2 g0 = xch[0];
                         float x0 = g0.x + g0.y, xn = g0.x - g0.y;          // (X[0], X[1024]) up to the factor 2
                         float S0 = mflt[0], Sn = mflt[1024];
-                        x0 = (x0 < 0.f) ? -S0 : S0;                         // phase of a real number is its sign
-                        xn = (xn < 0.f) ? -Sn : Sn;
+                        if (TFM) {                                          // x / max(1e-8, |x|); x0, xn carry g * est (no factor 2)
+                            x0 = x0 * fminf(1.0f / fabsf(x0), 2.0f * P.inv_thr) * S0;
+                            xn = xn * fminf(1.0f / fabsf(xn), 2.0f * P.inv_thr) * Sn;
+                            if (!(fabsf(x0) <= S0)) x0 = 0.f;               // 0 * inf
+                            if (!(fabsf(xn) <= Sn)) xn = 0.f;
+                        } else {
+                            x0 = (x0 < 0.f) ? -S0 : S0;                     // phase of a real number is its sign
+                            xn = (xn < 0.f) ? -Sn : Sn;
+                        }
                         xch[0] = make_float2(x0 + xn, x0 - xn);
                     } else {
                         const int j = lane, jj = 32 - lane;
@@ -296,8 +323,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                         c2 c1 = cadd(S1, T1);                               // 2*X[32 j]
                         c2 c2v = cconj(csub(S1, T1));                       // 2*X[32 (32-j)]
                         bool z2 = false;
-                        renorm_fast(c1, mflt[(j >> 2) * 128 + (j & 3)], z2);
-                        renorm_fast(c2v, mflt[(jj >> 2) * 128 + (jj & 3)], z2);
+                        if (TFM) {
+                            renorm_tf(c1, mflt[(j >> 2) * 128 + (j & 3)], P.inv_thr);
+                            renorm_tf(c2v, mflt[(jj >> 2) * 128 + (jj & 3)], P.inv_thr);
+                        } else {
+                            renorm_fast(c1, mflt[(j >> 2) * 128 + (j & 3)], z2);
+                            renorm_fast(c2v, mflt[(jj >> 2) * 128 + (jj & 3)], z2);
+                        }
                         if (z2) {
                             if (c1.x == 0.f && c1.y == 0.f) c1.x = mflt[(j >> 2) * 128 + (j & 3)];
                             if (c2v.x == 0.f && c2v.y == 0.f) c2v.x = mflt[(jj >> 2) * 128 + (jj & 3)];
@@ -328,8 +360,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                 // cp.async so that its load latency hides behind the neighbour wait and the accumulate.  Only for
                 // frames that need no reflect padding and (8-byte copies) an even sample offset.
                 staged = false;
-                if (PRUNE && s + 1 < C && k + 1 <= k_max) {
-                    const long long nstart = (long long)(k + 1) * hop - kNfft / 2;
+                if (PRUNE == 1 && s + 1 < C && k + 1 <= k_max) {
+                    const long long nstart = (long long)(k + 1) * hop - origin;
                     if (nstart + 512 >= 0 && nstart + 1536 <= L && ((s_off + nstart) & 1) == 0) {
                         const float* src = P.y_in + s_off + nstart + 512 + 2 * lane;
                         float* dst = reinterpret_cast<float*>(scratch) + 512 + 2 * lane;
@@ -351,8 +383,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                 __syncwarp();
             }
             if (active) {
-                const int base = k * hop - kNfft / 2 - s0;                    // tile-local index of n = 0
-                constexpr int t0 = PRUNE ? 8 : 0, t1 = PRUNE ? 24 : 32;
+                const int base = k * hop - origin - s0;                       // tile-local index of n = 0
+                constexpr int t0 = PruneRange<PRUNE>::t0, t1 = PruneRange<PRUNE>::t1;
                 const bool inside = (base + lo >= 0) && (base + lo + win <= n_out);
                 if (DEFCFG && inside) {
                     // default hparams: the support n in [524, 1524) is known at compile time; (acc[n], acc[n+32]) and the

@@ -48,10 +48,16 @@ struct Plan {                    // device tables owned by the handle
     const int* mel_lo;           // [num_mels] first bin of row
     const int* mel_n;            // [num_mels] row length
     const int* mel_ptr;          // [num_mels] offset into mel_w
-    int n_fft, hop, win_len, lo; // lo = (n_fft - win_len)/2
+    int n_fft, hop, win_len, lo; // window support is n in [lo, lo + win_len) of the n_fft-long frame
+    int origin;                  // frame k starts at sample k*hop - origin
+    int norm_wss;                // 1: divide the overlap-add by the summed squared window (librosa.istft), 0: do not (tf inverse_stft)
     int num_mels;
-    int prune;                   // window support inside n in [512,1536)
+    int prune;                   // 0: none, 1: support inside n in [512,1536), 2: support inside n in [0,1024)
+    // librosa geometry (audio.py:106-113): window padded centrally, lo = (n_fft - win)/2, origin = n_fft/2, reflect padding.
+    // tf.contrib.signal geometry (audio.py:116-123): lo = 0, origin = 0, frames never leave the signal.
 };
+
+template <int PRUNE> struct PruneRange { static constexpr int t0 = PRUNE == 1 ? 8 : 0, t1 = PRUNE == 1 ? 24 : (PRUNE == 2 ? 16 : 32); };
 
 __device__ __forceinline__ int find_segment(const int* __restrict__ off, int n, int v) {
     // largest b in [0,n) with off[b] <= v
@@ -86,10 +92,10 @@ __device__ __forceinline__ float sample_at(const float* __restrict__ x, int L, i
 // `stage` is the warp's scratch tile (>= 2048 floats): frames that touch the utterance's ends (reflect padding)
 // are gathered through it by a rolled loop, so the rare path costs a few dozen instructions of code instead of
 // an unrolled copy of the index arithmetic per register
-template <bool PREEMPH, bool PRUNE>
+template <bool PREEMPH, int PRUNE>
 __device__ __forceinline__ void load_frame(c2 (&z)[32], const float* __restrict__ x, long long L, long long start,
                                            const float* __restrict__ win_s, int lane, float p, float* stage) {
-    constexpr int t0 = PRUNE ? 8 : 0, t1 = PRUNE ? 24 : 32;
+    constexpr int t0 = PruneRange<PRUNE>::t0, t1 = PruneRange<PRUNE>::t1;
     const long long first = start + 64 * t0, last = start + 64 * t1;   // [first, last) touched
     const bool interior = (first >= (PREEMPH ? 1 : 0)) && (last <= L);
     if (interior) {
@@ -144,7 +150,7 @@ __device__ __forceinline__ float amp_to_db_norm(float amp, float ref_db, float m
     return fminf(fmaxf(v, 0.f), 1.f);
 }
 
-template <int MODE, bool PREEMPH, bool PRUNE>
+template <int MODE, bool PREEMPH, int PRUNE>
 __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
     NSB_DYN_SMEM(smem_raw);
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
@@ -166,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
         const long long s_off = __ldg(P.batch.samp_off + b);
         const long long L = __ldg(P.batch.samp_off + b + 1) - s_off;
         c2 z[32];
-        load_frame<PREEMPH, PRUNE>(z, P.wav + s_off, L, (long long)k * hop - kNfft / 2, win_s, lane, P.preemph,
+        load_frame<PREEMPH, PRUNE>(z, P.wav + s_off, L, (long long)k * hop - P.plan.origin, win_s, lane, P.preemph,
                                    reinterpret_cast<float*>(scratch));
         fwd_phase1(z, lane, scratch, tw_s);
         __syncwarp();
@@ -222,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
 // =============================================================================================
 // synthesis: istft / Griffin-Lim iteration
 // =============================================================================================
-enum { SRC_Y = 0, SRC_SPEC = 1, SRC_MAGPHASE = 2, SRC_MAGRAND = 3 };
+enum { SRC_Y = 0, SRC_SPEC = 1, SRC_MAGPHASE = 2, SRC_MAGRAND = 3, SRC_MAGZERO = 4 };
 
 struct SynthParams {
     Plan plan;
@@ -270,7 +276,7 @@ __device__ __forceinline__ void renorm(c2& z, float S) {
     z = cscale(z, rsqrtf(m2) * S);
 }
 
-template <int SRC, bool PRUNE>
+template <int SRC, int PRUNE>
 __global__ void __launch_bounds__(kThreads, 2) k_synth(SynthParams P) {
     NSB_DYN_SMEM(smem_raw);
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
@@ -285,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_synth(SynthParams P) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float2* scratch = scratch_all + warp * kScratchF2;
     const int hop = P.plan.hop, win = P.plan.win_len, lo = P.plan.lo;
-    const int a = kNfft / 2 - lo;          // frame k's window support starts at sample k*hop - a
+    const int a = P.plan.origin - lo;      // frame k's window support starts at sample k*hop - a
     const int C = P.colours, H = P.tile_hops;
 
     const int tile_g = P.batch.tile_base + (int)blockIdx.x;
@@ -294,9 +300,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_synth(SynthParams P) {
     const int f_off = __ldg(P.batch.frame_off + b);
     const int T = __ldg(P.batch.frame_off + b + 1) - f_off;
     const long long s_off = __ldg(P.batch.samp_off + b);
-    const long long L = (long long)hop * (T - 1);
-    const int h0 = tile * H, h1 = min(h0 + H, T - 1);
-    const long long s0 = (long long)h0 * hop, s1 = (long long)h1 * hop;
+    const long long L = __ldg(P.batch.samp_off + b + 1) - s_off;       // hop*(T-1) (librosa) or hop*(T-1)+win (tf)
+    const int n_hops = (int)((L + hop - 1) / hop);
+    const int h0 = tile * H, h1 = min(h0 + H, n_hops);
+    const long long s0 = (long long)h0 * hop, s1 = min((long long)h1 * hop, L);
     const int n_out = (int)(s1 - s0);
 
     for (int i = threadIdx.x; i < kTwF2; i += kThreads) tw_s[i] = P.plan.tw[i];
@@ -325,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_synth(SynthParams P) {
             const int fg = f_off + k;                   // global frame index
             c2 z[32];
             if (SRC == SRC_Y) {
-                load_frame<false, PRUNE>(z, P.y_in + s_off, L, (long long)k * hop - kNfft / 2, win_s, lane, 0.f,
+                load_frame<false, PRUNE>(z, P.y_in + s_off, L, (long long)k * hop - P.plan.origin, win_s, lane, 0.f,
                                          reinterpret_cast<float*>(scratch));
                 fwd_phase1(z, lane, scratch, tw_s);
                 __syncwarp();
@@ -368,6 +375,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_synth(SynthParams P) {
                         z[p] = v;
                     }
                 }
+            } else if (SRC == SRC_MAGZERO) {   // zero phase: S_complex = S + 0j (the TF twin's start, audio.py:97-98)
+                const float4* mp = reinterpret_cast<const float4*>(P.mag + (size_t)fg * kMagPitch);
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    float4 S = __ldg(mp + g * 32 + lane);
+                    z[4 * g] = mk2(S.x, 0.f); z[4 * g + 1] = mk2(S.y, 0.f); z[4 * g + 2] = mk2(S.z, 0.f); z[4 * g + 3] = mk2(S.w, 0.f);
+                }
+                if (lane == 0) z[0].y = __ldg(P.mag + (size_t)fg * kMagPitch + 1024);     // packed (DC, Nyquist)
             } else {  // SRC_MAGRAND: magnitude x exp(2*pi*i*u), u ~ Philox keyed by seed, counter = (frame, lane, group)
                 const float* mrow = P.mag + (size_t)fg * kMagPitch;
                 uint2 key = make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32));
@@ -399,8 +414,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_synth(SynthParams P) {
             // windowed overlap-add into the tile.  Same-colour frames have disjoint window SUPPORTS, so a plain
             // read-modify-write is race-free only if each warp touches nothing outside its support: per-lane
             // bitmasks of the valid t (n = 64 t + lane [+32] inside [lo, lo + win)).
-            const long long base = (long long)k * hop - kNfft / 2 - s0;      // tile-local index of n = 0
-            constexpr int t0 = PRUNE ? 8 : 0, t1 = PRUNE ? 24 : 32;
+            const long long base = (long long)k * hop - P.plan.origin - s0;  // tile-local index of n = 0
+            constexpr int t0 = PruneRange<PRUNE>::t0, t1 = PruneRange<PRUNE>::t1;
             unsigned mre, mim;
             {
                 int a0 = max((lo - lane + 63) >> 6, 0), a1 = min(max((lo + win - lane + 63) >> 6, 0), 32);
@@ -431,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_synth(SynthParams P) {
         }
         __syncthreads();
     }
-    // normalise by the summed squared window and store
+    // normalise by the summed squared window (librosa.istft) or not at all (tf inverse_stft) and store
     float* yo = P.y_out + s_off + s0;
     for (int j = threadIdx.x; j < hop; j += kThreads) {
         const int dj = (j + a) / hop, rj = (j + a) - dj * hop;     // newest covering frame is h + dj, window index rj
@@ -439,19 +454,23 @@ __global__ void __launch_bounds__(kThreads, 2) k_synth(SynthParams P) {
         int ncover = 0;
         for (int idx = rj; idx < win; idx += hop) ++ncover;
         for (int h = h0; h < h1; ++h) {
+            const int i = (h - h0) * hop + j;
+            if (i >= n_out) break;                                  // the last hop of a tf-geometry signal may be partial
             const int k_hi = h + dj, k_lo = k_hi - (ncover - 1);
-            float v = acc[(h - h0) * hop + j] * (1.0f / (float)kNfft);
+            float v = acc[i] * (1.0f / (float)kNfft);
             bad |= !isfinite(v);
-            if (k_lo >= 0 && k_hi <= T - 1) {
-                v *= ri;
-            } else {
-                float s = 0.f;
-                int kk = k_hi;
-                for (int idx = rj; idx < win; idx += hop, --kk)
-                    if (kk >= 0 && kk <= T - 1) { float w = win_s[lo + idx]; s = fmaf(w, w, s); }
-                if (s > 1.17549435e-38f) v /= s;
+            if (P.plan.norm_wss) {
+                if (k_lo >= 0 && k_hi <= T - 1) {
+                    v *= ri;
+                } else {
+                    float s = 0.f;
+                    int kk = k_hi;
+                    for (int idx = rj; idx < win; idx += hop, --kk)
+                        if (kk >= 0 && kk <= T - 1) { float w = win_s[lo + idx]; s = fmaf(w, w, s); }
+                    if (s > 1.17549435e-38f) v /= s;
+                }
             }
-            yo[(size_t)(h - h0) * hop + j] = v;
+            yo[i] = v;
         }
     }
     if (bad) atomicOr(P.status, 1);

@@ -69,7 +69,9 @@ struct nsb_handle_s {
     cudaEvent_t desc_done = nullptr;
     // tables
     float2* d_tw = nullptr;
-    float* d_win = nullptr;
+    float* d_win = nullptr;          // periodic Hann padded centrally to n_fft (librosa geometry)
+    float* d_win_tf = nullptr;       // the same window at n in [0, win) (tf.contrib.signal geometry)
+    int prune_tf = 0, colours_tf = 0;
     float* d_mel_w = nullptr;
     int *d_mel_lo = nullptr, *d_mel_n = nullptr, *d_mel_ptr = nullptr;
     int* d_status = nullptr;
@@ -81,7 +83,7 @@ struct nsb_handle_s {
     // workspaces
     DevBuf ws_mag, ws_y0, ws_y1, ws_in, ws_in2, ws_out, ws_out2;
     // state of the last device-resident Griffin-Lim (for nsb_griffin_lim_iterate)
-    struct { bool valid = false; Batch batch{}; int total_frames = 0; int tile_hops = 0; int total_tiles = 0; int cur = 0; } gl;
+    struct { bool valid = false; Batch batch{}; int total_frames = 0; int tile_hops = 0; int total_tiles = 0; int cur = 0; bool tf = false; float inv_thr = 0.f; } gl;
     std::vector<int> h_frame_off, h_tile_off;       // host copies of the last descriptors (chunking)
     std::vector<long long> h_samp_off;
     int host_chunks = 0;             // 0 = automatic chunking of NSB_HOST Griffin-Lim calls, n > 0 = force n chunks
@@ -90,10 +92,12 @@ struct nsb_handle_s {
     std::mutex mu;
 };
 
-static Plan make_plan(nsb_handle_s* h) {
+static Plan make_plan(nsb_handle_s* h, bool tf = false) {
     Plan p;
-    p.tw = h->d_tw; p.win = h->d_win; p.mel_w = h->d_mel_w; p.mel_lo = h->d_mel_lo; p.mel_n = h->d_mel_n; p.mel_ptr = h->d_mel_ptr;
-    p.n_fft = h->n_fft; p.hop = h->hop; p.win_len = h->win; p.lo = h->lo; p.num_mels = h->num_mels; p.prune = h->prune;
+    p.tw = h->d_tw; p.mel_w = h->d_mel_w; p.mel_lo = h->d_mel_lo; p.mel_n = h->d_mel_n; p.mel_ptr = h->d_mel_ptr;
+    p.n_fft = h->n_fft; p.hop = h->hop; p.win_len = h->win; p.num_mels = h->num_mels;
+    if (tf) { p.win = h->d_win_tf; p.lo = 0; p.origin = 0; p.norm_wss = 0; p.prune = h->prune_tf; }
+    else { p.win = h->d_win; p.lo = h->lo; p.origin = h->n_fft / 2; p.norm_wss = 1; p.prune = h->prune; }
     return p;
 }
 
@@ -139,13 +143,13 @@ static size_t synth_smem(int hop, int H) {
 static size_t gl_smem(int hop, int H) { return synth_smem(hop, H) + 64 + 16; }   // + neighbour progress flags + rinv padding   // + neighbour progress flags
 static const size_t kSmemPerCtaTwoResident = (227 * 1024) / 2 - 1024;   // two CTAs per SM, 1 KB reserved each
 
-static int max_tile_hops(const nsb_handle_s* h) {
+static int max_tile_hops(const nsb_handle_s* h, bool tf = false) {
     // k_gl_iter gives each of its 8 warps C consecutive frames starting from the tile's (virtual) first frame, so a
     // tile may span at most 8*C frame indices.  The frames meeting H hops are the multiples of hop inside an open
     // interval of length H*hop + win: at most H + C of them (H + C - 1 when win is a multiple of hop and the interval
     // ends fall on multiples of hop, the default config).  H is kept a multiple of C: then every tile's frame groups
     // start at the same residue mod C and the summation order of the overlap-add does not depend on the tiling.
-    const int a = kNfft / 2 - h->lo;
+    const int a = tf ? 0 : kNfft / 2 - h->lo;      // frame k's window support starts at sample k*hop - a
     const bool aligned = (h->win % h->hop == 0) && ((a - h->win) % h->hop == 0);
     int H = 8 * h->colours - h->colours + (aligned ? 1 : 0);
     H -= H % h->colours;
@@ -184,7 +188,7 @@ extern "C" int nsb_destroy(nsb_handle_t h) {
     if (h->copy_in) cudaStreamDestroy(h->copy_in);
     if (h->copy_out) cudaStreamDestroy(h->copy_out);
     if (h->desc_done) cudaEventDestroy(h->desc_done);
-    cudaFree(h->d_tw); cudaFree(h->d_win); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo); cudaFree(h->d_mel_n); cudaFree(h->d_mel_ptr);
+    cudaFree(h->d_tw); cudaFree(h->d_win); cudaFree(h->d_win_tf); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo); cudaFree(h->d_mel_n); cudaFree(h->d_mel_ptr);
     cudaFree(h->d_status);
     if (h->h_desc) cudaFreeHost(h->h_desc);
     h->d_desc.release(); h->ws_mag.release(); h->ws_y0.release(); h->ws_y1.release();
@@ -245,6 +249,13 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
         for (int i = 0; i < win; ++i) w[h->lo + i] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * i / win));
         CUB(cudaMalloc(&h->d_win, sizeof(float) * kNfft));
         CUB(cudaMemcpy(h->d_win, w.data(), sizeof(float) * kNfft, cudaMemcpyHostToDevice));
+        // tf.contrib.signal.stft / inverse_stft: the same periodic Hann on the first `win` samples, zero-padded at the END
+        std::vector<float> wt(kNfft, 0.f);
+        for (int i = 0; i < win; ++i) wt[i] = w[h->lo + i];
+        CUB(cudaMalloc(&h->d_win_tf, sizeof(float) * kNfft));
+        CUB(cudaMemcpy(h->d_win_tf, wt.data(), sizeof(float) * kNfft, cudaMemcpyHostToDevice));
+        h->prune_tf = (win <= 1024) ? 2 : 0;
+        h->colours_tf = h->colours;
     }
     // sparse mel rows
     {
@@ -275,14 +286,16 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
     const size_t as = prop.sharedMemPerBlockOptin, ss = prop.sharedMemPerBlockOptin, gs = prop.sharedMemPerBlockOptin;
     h->defcfg = (hop == 250 && win == 1000 && h->lo == 524) ? 1 : 0;
 #define SET(k, b) do { rc = set_smem(k, b); if (rc) return bail(rc); } while (0)
-    SET((k_analysis<ANALYSIS_COMPLEX, false, false>), as); SET((k_analysis<ANALYSIS_COMPLEX, false, true>), as);
-    SET((k_analysis<ANALYSIS_COMPLEX, true, false>), as);  SET((k_analysis<ANALYSIS_COMPLEX, true, true>), as);
-    SET((k_analysis<ANALYSIS_FEATURES, true, false>), as); SET((k_analysis<ANALYSIS_FEATURES, true, true>), as);
-    SET((k_synth<SRC_Y, false>), ss);        SET((k_synth<SRC_Y, true>), ss);
-    SET((k_synth<SRC_SPEC, false>), ss);     SET((k_synth<SRC_SPEC, true>), ss);
-    SET((k_synth<SRC_MAGPHASE, false>), ss); SET((k_synth<SRC_MAGPHASE, true>), ss);
-    SET((k_synth<SRC_MAGRAND, false>), ss);  SET((k_synth<SRC_MAGRAND, true>), ss);
-    SET((k_gl_iter<true, true>), gs); SET((k_gl_iter<true, false>), gs); SET((k_gl_iter<false, false>), gs);
+    SET((k_analysis<ANALYSIS_COMPLEX, false, 0>), as); SET((k_analysis<ANALYSIS_COMPLEX, false, 1>), as); SET((k_analysis<ANALYSIS_COMPLEX, false, 2>), as);
+    SET((k_analysis<ANALYSIS_COMPLEX, true, 0>), as);  SET((k_analysis<ANALYSIS_COMPLEX, true, 1>), as);
+    SET((k_analysis<ANALYSIS_FEATURES, true, 0>), as); SET((k_analysis<ANALYSIS_FEATURES, true, 1>), as);
+    SET((k_synth<SRC_Y, 0>), ss);        SET((k_synth<SRC_Y, 1>), ss);
+    SET((k_synth<SRC_SPEC, 0>), ss);     SET((k_synth<SRC_SPEC, 1>), ss);     SET((k_synth<SRC_SPEC, 2>), ss);
+    SET((k_synth<SRC_MAGPHASE, 0>), ss); SET((k_synth<SRC_MAGPHASE, 1>), ss);
+    SET((k_synth<SRC_MAGRAND, 0>), ss);  SET((k_synth<SRC_MAGRAND, 1>), ss);
+    SET((k_synth<SRC_MAGZERO, 0>), ss);  SET((k_synth<SRC_MAGZERO, 2>), ss);
+    SET((k_gl_iter<1, true, false>), gs); SET((k_gl_iter<1, false, false>), gs); SET((k_gl_iter<0, false, false>), gs);
+    SET((k_gl_iter<2, false, true>), gs); SET((k_gl_iter<0, false, true>), gs);
 #undef SET
 #undef CUB
     *out = h;
@@ -369,7 +382,7 @@ static int upload_desc(nsb_handle_s* h, cudaStream_t st, const std::vector<int>&
                        int tile_hops, Desc* d) {
     const int B = (int)frames.size();
     long long n_tiles = 0;
-    if (tile_hops > 0) for (int b = 0; b < B; ++b) { int hops = frames[b] - 1; if (hops > 0) n_tiles += (hops + tile_hops - 1) / tile_hops; }
+    if (tile_hops > 0) for (int b = 0; b < B; ++b) { long long hops = (samples[b] + h->hop - 1) / h->hop; n_tiles += (hops + tile_hops - 1) / tile_hops; }
     if (n_tiles > 2000000000LL) return fail(NSB_ERR_INVALID, "batch too large: more than 2e9 tiles");
     const size_t n_int = 2 * (size_t)(B + 1);
     const size_t off_samp = (n_int * sizeof(int) + 7) & ~(size_t)7;
@@ -395,7 +408,7 @@ static int upload_desc(nsb_handle_s* h, cudaStream_t st, const std::vector<int>&
         if (nf > 2000000000LL) return fail(NSB_ERR_INVALID, "batch too large: more than 2e9 frames");
         fo[b + 1] = (int)nf;
         int tiles = 0;
-        if (tile_hops > 0) { int hops = frames[b] - 1; tiles = hops > 0 ? (hops + tile_hops - 1) / tile_hops : 0; }
+        if (tile_hops > 0) { long long hops = (samples[b] + h->hop - 1) / h->hop; tiles = (int)((hops + tile_hops - 1) / tile_hops); }
         to[b + 1] = to[b] + tiles;
         for (int t = to[b]; t < to[b + 1]; ++t) tu[t] = b;       // tile -> utterance (saves a binary search per tile on the GPU)
         so[b + 1] = so[b] + samples[b];
@@ -434,7 +447,7 @@ static int grid_1d(long long n, int threads, int max_blocks) {
 // analysis entry points
 // ---------------------------------------------------------------------------------------------
 static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wav, const int64_t* n_samples, int batch,
-                        float* out_complex, float* lin_out, float* mel_out, int space, void* stream) {
+                        float* out_complex, float* lin_out, float* mel_out, int space, void* stream, bool tf = false) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");
     if (!wav || !n_samples || batch < 1) return fail(NSB_ERR_INVALID, "null/empty input");
     if (mode == ANALYSIS_COMPLEX && !out_complex) return fail(NSB_ERR_INVALID, "out_complex is null");
@@ -446,8 +459,9 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
     std::vector<long long> samples(batch);
     for (int b = 0; b < batch; ++b) {
         if (n_samples[b] < 1) return fail(NSB_ERR_INVALID, "utterance %d is empty", b);
+        if (tf && n_samples[b] < h->win) return fail(NSB_ERR_INVALID, "utterance %d is shorter than one frame (%d samples)", b, h->win);
         samples[b] = n_samples[b];
-        frames[b] = (int)(1 + n_samples[b] / h->hop);
+        frames[b] = tf ? (int)(1 + (n_samples[b] - h->win) / h->hop) : (int)(1 + n_samples[b] / h->hop);
     }
     Desc d;
     int rc = upload_desc(h, st, frames, samples, 0, &d);
@@ -469,22 +483,24 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
         }
     }
     AnalysisParams P;
-    P.plan = make_plan(h); P.batch = d.dev; P.wav = d_wav; P.out_complex = d_c; P.out_lin = d_lin; P.out_mel = d_mel;
+    P.plan = make_plan(h, tf); P.batch = d.dev; P.wav = d_wav; P.out_complex = d_c; P.out_lin = d_lin; P.out_mel = d_mel;
     P.total_frames = d.total_frames; P.preemph = (float)h->hp.preemphasis;
     P.ref_level_db = (float)h->hp.ref_level_db; P.min_level_db = (float)h->hp.min_level_db; P.status = h->d_status;
     const int grid = grid_1d(d.total_frames, kWarpsPerCta, 2 * h->num_sms);
     const size_t smem = analysis_smem();
+    const int prune = tf ? h->prune_tf : h->prune;
     if (mode == ANALYSIS_COMPLEX) {
         if (preemph) {
-            if (h->prune) NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, true, true>), grid, kThreads, smem, st, P);
-            else NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, true, false>), grid, kThreads, smem, st, P);
+            if (prune == 1) NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, true, 1>), grid, kThreads, smem, st, P);
+            else NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, true, 0>), grid, kThreads, smem, st, P);
         } else {
-            if (h->prune) NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, false, true>), grid, kThreads, smem, st, P);
-            else NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, false, false>), grid, kThreads, smem, st, P);
+            if (prune == 1) NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, false, 1>), grid, kThreads, smem, st, P);
+            else if (prune == 2) NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, false, 2>), grid, kThreads, smem, st, P);
+            else NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, false, 0>), grid, kThreads, smem, st, P);
         }
     } else {
-        if (h->prune) NSB_LAUNCH((k_analysis<ANALYSIS_FEATURES, true, true>), grid, kThreads, smem, st, P);
-        else NSB_LAUNCH((k_analysis<ANALYSIS_FEATURES, true, false>), grid, kThreads, smem, st, P);
+        if (prune == 1) NSB_LAUNCH((k_analysis<ANALYSIS_FEATURES, true, 1>), grid, kThreads, smem, st, P);
+        else NSB_LAUNCH((k_analysis<ANALYSIS_FEATURES, true, 0>), grid, kThreads, smem, st, P);
     }
     if ((rc = check_launch(h, "k_analysis"))) return rc;
     if (space == NSB_HOST) {
@@ -502,6 +518,9 @@ extern "C" int nsb_stft(nsb_handle_t h, const float* wav, const int64_t* n_sampl
                         float* out_complex, int32_t space, void* stream) {
     return run_analysis(h, ANALYSIS_COMPLEX, apply_preemphasis != 0, wav, n_samples, batch, out_complex, nullptr, nullptr, space, stream);
 }
+extern "C" int nsb_stft_tf(nsb_handle_t h, const float* wav, const int64_t* n_samples, int32_t batch, float* out_complex, int32_t space, void* stream) {
+    return run_analysis(h, ANALYSIS_COMPLEX, false, wav, n_samples, batch, out_complex, nullptr, nullptr, space, stream, true);
+}
 extern "C" int nsb_features(nsb_handle_t h, const float* wav, const int64_t* n_samples, int32_t batch,
                             float* lin_out, float* mel_out, int32_t space, void* stream) {
     return run_analysis(h, ANALYSIS_FEATURES, true, wav, n_samples, batch, nullptr, lin_out, mel_out, space, stream);
@@ -510,8 +529,8 @@ extern "C" int nsb_features(nsb_handle_t h, const float* wav, const int64_t* n_s
 // ---------------------------------------------------------------------------------------------
 // synthesis entry points
 // ---------------------------------------------------------------------------------------------
-static int choose_tile_hops(nsb_handle_s* h, const int32_t* n_frames, int batch) {
-    const int Hmax = max_tile_hops(h), C = h->colours;
+static int choose_tile_hops(nsb_handle_s* h, const std::vector<long long>& samples, bool tf = false) {
+    const int Hmax = max_tile_hops(h, tf), C = h->colours;
     if (h->user_tile_hops > 0) {
         int H = h->user_tile_hops < Hmax ? h->user_tile_hops : Hmax;
         H -= H % C;                  // multiples of C only (tiling-independent summation order, see max_tile_hops)
@@ -525,7 +544,7 @@ static int choose_tile_hops(nsb_handle_s* h, const int32_t* n_frames, int batch)
     long long best_waves = -1;
     for (int H = C; H <= Hmax; H += C) {
         long long tiles = 0;
-        for (int b = 0; b < batch; ++b) tiles += (n_frames[b] - 1 + H - 1) / H;
+        for (size_t b = 0; b < samples.size(); ++b) { long long hops = (samples[b] + h->hop - 1) / h->hop; tiles += (hops + H - 1) / H; }
         const long long waves = (tiles + ctas - 1) / ctas;
         if (best_waves < 0 || waves <= best_waves) { best = H; best_waves = waves; }
     }
@@ -534,31 +553,44 @@ static int choose_tile_hops(nsb_handle_s* h, const int32_t* n_frames, int batch)
 
 template <int SRC>
 static void launch_synth(nsb_handle_s* h, const SynthParams& P, int grid, size_t smem, cudaStream_t st) {
-    if (h->prune) NSB_LAUNCH((k_synth<SRC, true>), grid, kThreads, smem, st, P);
-    else NSB_LAUNCH((k_synth<SRC, false>), grid, kThreads, smem, st, P);
+    if (P.plan.prune == 1) NSB_LAUNCH((k_synth<SRC, 1>), grid, kThreads, smem, st, P);
+    else NSB_LAUNCH((k_synth<SRC, 0>), grid, kThreads, smem, st, P);
+}
+// tf geometry variants exist for the two sources the TF twin needs
+static void launch_synth_tf(nsb_handle_s* h, int src, const SynthParams& P, int grid, size_t smem, cudaStream_t st) {
+    if (src == SRC_SPEC) {
+        if (P.plan.prune == 2) NSB_LAUNCH((k_synth<SRC_SPEC, 2>), grid, kThreads, smem, st, P);
+        else NSB_LAUNCH((k_synth<SRC_SPEC, 0>), grid, kThreads, smem, st, P);
+    } else {
+        if (P.plan.prune == 2) NSB_LAUNCH((k_synth<SRC_MAGZERO, 2>), grid, kThreads, smem, st, P);
+        else NSB_LAUNCH((k_synth<SRC_MAGZERO, 0>), grid, kThreads, smem, st, P);
+    }
 }
 
-static int validate_frames(nsb_handle_s* h, const int32_t* n_frames, int batch, std::vector<int>& frames, std::vector<long long>& samples) {
+// librosa.istft gives hop*(T-1) samples (centre trimmed); tf inverse_stft gives hop*(T-1) + win
+static int validate_frames(nsb_handle_s* h, const int32_t* n_frames, int batch, std::vector<int>& frames, std::vector<long long>& samples,
+                           bool tf = false) {
     frames.resize(batch); samples.resize(batch);
     for (int b = 0; b < batch; ++b) {
-        if (n_frames[b] < 2) return fail(NSB_ERR_INVALID, "utterance %d has %d frame(s); inversion needs at least 2", b, n_frames[b]);
+        if (n_frames[b] < (tf ? 1 : 2))
+            return fail(NSB_ERR_INVALID, "utterance %d has %d frame(s); inversion needs at least %d", b, n_frames[b], tf ? 1 : 2);
         frames[b] = n_frames[b];
-        samples[b] = (long long)h->hop * (n_frames[b] - 1);
+        samples[b] = (long long)h->hop * (n_frames[b] - 1) + (tf ? h->win : 0);
     }
     return NSB_OK;
 }
 
-extern "C" int nsb_istft(nsb_handle_t h, const float* spec, int32_t layout, const int32_t* n_frames, int32_t batch,
-                         float* wav_out, int32_t space, void* stream) {
+static int run_istft(nsb_handle_t h, const float* spec, int32_t layout, const int32_t* n_frames, int32_t batch,
+                     float* wav_out, int32_t space, void* stream, bool tf) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");
     if (!spec || !n_frames || !wav_out || batch < 1) return fail(NSB_ERR_INVALID, "null/empty argument");
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
     cudaStream_t st = pick_stream(h, stream, space);
     std::vector<int> frames; std::vector<long long> samples;
-    int rc = validate_frames(h, n_frames, batch, frames, samples);
+    int rc = validate_frames(h, n_frames, batch, frames, samples, tf);
     if (rc) return rc;
-    const int H = choose_tile_hops(h, n_frames, batch);
+    const int H = choose_tile_hops(h, samples, tf);
     Desc d;
     if ((rc = upload_desc(h, st, frames, samples, H, &d))) return rc;
     const float2* d_spec = reinterpret_cast<const float2*>(spec);
@@ -572,9 +604,10 @@ extern "C" int nsb_istft(nsb_handle_t h, const float* spec, int32_t layout, cons
     }
     h->gl.valid = false;
     SynthParams P{};
-    P.plan = make_plan(h); P.batch = d.dev; P.spec = d_spec; P.spec_bin_major = (layout == NSB_BIN_MAJOR);
+    P.plan = make_plan(h, tf); P.batch = d.dev; P.spec = d_spec; P.spec_bin_major = (layout == NSB_BIN_MAJOR);
     P.y_out = d_out; P.tile_hops = H; P.colours = h->colours; P.status = h->d_status; P.mag = nullptr;
-    launch_synth<SRC_SPEC>(h, P, d.total_tiles, synth_smem(h->hop, H), st);
+    if (tf) launch_synth_tf(h, SRC_SPEC, P, d.total_tiles, synth_smem(h->hop, H), st);
+    else launch_synth<SRC_SPEC>(h, P, d.total_tiles, synth_smem(h->hop, H), st);
     if ((rc = check_launch(h, "k_synth<SPEC>"))) return rc;
     if (space == NSB_HOST) {
         CU(cudaMemcpyAsync(wav_out, d_out, sizeof(float) * d.total_samples, cudaMemcpyDeviceToHost, st));
@@ -582,12 +615,21 @@ extern "C" int nsb_istft(nsb_handle_t h, const float* spec, int32_t layout, cons
     }
     return NSB_OK;
 }
+extern "C" int nsb_istft(nsb_handle_t h, const float* spec, int32_t layout, const int32_t* n_frames, int32_t batch,
+                         float* wav_out, int32_t space, void* stream) {
+    return run_istft(h, spec, layout, n_frames, batch, wav_out, space, stream, false);
+}
+extern "C" int nsb_istft_tf(nsb_handle_t h, const float* spec, int32_t layout, const int32_t* n_frames, int32_t batch,
+                            float* wav_out, int32_t space, void* stream) {
+    return run_istft(h, spec, layout, n_frames, batch, wav_out, space, stream, true);
+}
 
 // `iters` Griffin-Lim iterations on the (sub-)batch B; y ping-pongs between ws_y0 / ws_y1, `cur` says which holds y
-static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int H, int& cur, int iters, cudaStream_t st) {
+static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int H, int& cur, int iters, cudaStream_t st,
+                         bool tf = false, float inv_thr = 0.f) {
     float* y[2] = {reinterpret_cast<float*>(h->ws_y0.p), reinterpret_cast<float*>(h->ws_y1.p)};
     if (total_tiles <= 0) return NSB_OK;
-    if (h->use_generic_iter == 1) {
+    if (h->use_generic_iter == 1 && !tf) {
         SynthParams P{};
         P.plan = make_plan(h); P.batch = B; P.mag = reinterpret_cast<const float*>(h->ws_mag.p);
         P.tile_hops = H; P.colours = h->colours; P.status = h->d_status;
@@ -602,15 +644,18 @@ static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int H
         return NSB_OK;
     }
     GlParams G{};
-    G.plan = make_plan(h); G.batch = B; G.mag = reinterpret_cast<const float*>(h->ws_mag.p);
-    G.tile_hops = H; G.colours = h->colours; G.total_tiles = total_tiles; G.status = h->d_status;
+    G.plan = make_plan(h, tf); G.batch = B; G.mag = reinterpret_cast<const float*>(h->ws_mag.p);
+    G.tile_hops = H; G.colours = h->colours; G.total_tiles = total_tiles; G.status = h->d_status; G.inv_thr = inv_thr;
     const size_t smem = gl_smem(h->hop, H);
     const int grid = total_tiles < 2 * h->num_sms ? total_tiles : 2 * h->num_sms;   // persistent: 2 CTAs per SM
     for (int it = 0; it < iters; ++it) {
         G.y_in = y[cur]; G.y_out = y[cur ^ 1];
-        if (h->defcfg) NSB_LAUNCH((k_gl_iter<true, true>), grid, kThreads, smem, st, G);
-        else if (h->prune) NSB_LAUNCH((k_gl_iter<true, false>), grid, kThreads, smem, st, G);
-        else NSB_LAUNCH((k_gl_iter<false, false>), grid, kThreads, smem, st, G);
+        if (tf) {
+            if (G.plan.prune == 2) NSB_LAUNCH((k_gl_iter<2, false, true>), grid, kThreads, smem, st, G);
+            else NSB_LAUNCH((k_gl_iter<0, false, true>), grid, kThreads, smem, st, G);
+        } else if (h->defcfg) NSB_LAUNCH((k_gl_iter<1, true, false>), grid, kThreads, smem, st, G);
+        else if (h->prune == 1) NSB_LAUNCH((k_gl_iter<1, false, false>), grid, kThreads, smem, st, G);
+        else NSB_LAUNCH((k_gl_iter<0, false, false>), grid, kThreads, smem, st, G);
         int rc = check_launch(h, "k_gl_iter");
         if (rc) return rc;
         cur ^= 1;
@@ -623,7 +668,7 @@ extern "C" int nsb_griffin_lim_iterate(nsb_handle_t h, int32_t iters, void* stre
     std::lock_guard<std::mutex> lk(h->mu);
     if (!h->gl.valid) return fail(NSB_ERR_INVALID, "no device-resident Griffin-Lim state (call nsb_griffin_lim with NSB_DEVICE first)");
     CU(cudaSetDevice(h->device));
-    return gl_iterations(h, h->gl.batch, h->gl.total_tiles, h->gl.tile_hops, h->gl.cur, iters, pick_stream(h, stream));
+    return gl_iterations(h, h->gl.batch, h->gl.total_tiles, h->gl.tile_hops, h->gl.cur, iters, pick_stream(h, stream), h->gl.tf, h->gl.inv_thr);
 }
 
 extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout, const int32_t* n_frames, int32_t batch,
@@ -636,10 +681,12 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
     cudaStream_t st = pick_stream(h, stream, space);
+    const bool tf = (flags & NSB_GL_TF_TWIN) != 0;
+    if (tf) init_phase = nullptr;            // the TF twin always starts from zero phase (audio.py:97-98)
     std::vector<int> frames; std::vector<long long> samples;
-    int rc = validate_frames(h, n_frames, batch, frames, samples);
+    int rc = validate_frames(h, n_frames, batch, frames, samples, tf);
     if (rc) return rc;
-    const int H = choose_tile_hops(h, n_frames, batch);
+    const int H = choose_tile_hops(h, samples, tf);
     Desc d;
     if ((rc = upload_desc(h, st, frames, samples, H, &d))) return rc;
     const size_t out_elt = out_dtype == NSB_F64 ? sizeof(double) : sizeof(float);
@@ -738,15 +785,17 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
 
         // y0 = _istft(S * angles)
         SynthParams P{};
-        P.plan = make_plan(h); P.batch = B; P.mag = Q.mag; P.spec = d_phase; P.spec_bin_major = (layout == NSB_BIN_MAJOR);
+        P.plan = make_plan(h, tf); P.batch = B; P.mag = Q.mag; P.spec = d_phase; P.spec_bin_major = (layout == NSB_BIN_MAJOR);
         P.y_out = reinterpret_cast<float*>(h->ws_y0.p); P.tile_hops = H; P.colours = h->colours; P.seed = seed; P.status = h->d_status;
         const size_t smem = synth_smem(h->hop, H);
-        if (init_phase) launch_synth<SRC_MAGPHASE>(h, P, n_tiles_c, smem, st);
+        if (tf) launch_synth_tf(h, SRC_MAGZERO, P, n_tiles_c, smem, st);
+        else if (init_phase) launch_synth<SRC_MAGPHASE>(h, P, n_tiles_c, smem, st);
         else launch_synth<SRC_MAGRAND>(h, P, n_tiles_c, smem, st);
         if ((rc = check_launch(h, "k_synth<init>"))) { cleanup(); return rc; }
 
         cur = 0;
-        if ((rc = gl_iterations(h, B, n_tiles_c, H, cur, iters, st))) { cleanup(); return rc; }
+        const float inv_thr = (float)(1.0 / (2.0e-8 * gscale));      // est / max(1e-8, |est|) on slots that hold 2*g*est
+        if ((rc = gl_iterations(h, B, n_tiles_c, H, cur, iters, st, tf, inv_thr))) { cleanup(); return rc; }
         const float* y_fin = reinterpret_cast<const float*>(cur ? h->ws_y1.p : h->ws_y0.p);
 
         const long long s_base = h->h_samp_off[b0], s_cnt = h->h_samp_off[b1] - s_base;
@@ -768,7 +817,7 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
     }
     // device-resident state for nsb_griffin_lim_iterate: the whole batch
     h->gl.valid = true; h->gl.batch = d.dev; h->gl.total_frames = d.total_frames; h->gl.tile_hops = H;
-    h->gl.total_tiles = d.total_tiles; h->gl.cur = cur;
+    h->gl.total_tiles = d.total_tiles; h->gl.cur = cur; h->gl.tf = tf; h->gl.inv_thr = (float)(1.0 / (2.0e-8 * gscale));
     if (space == NSB_HOST) {
         CUE(cudaStreamSynchronize(h->copy_out));
         cleanup();

@@ -7,6 +7,7 @@ import pytest
 from conftest import make_hp, speechlike
 from nspeech_b200 import _lib, audio, hparams
 from oracle import audio_oracle as ao
+from oracle import tf_signal17 as tfo
 
 CONFIGS = [{"min_level_db": -100}, {}, {"min_level_db": -100, "sample_rate": 22050}]
 
@@ -175,3 +176,47 @@ def check_device_random_phase_is_deterministic_per_seed():
     c = audio.inv_spectrogram(S, seed=8, iters=2)
     np.testing.assert_array_equal(a, b)
     assert np.isfinite(a).all() and not np.array_equal(a, c)
+
+
+def check_tf_twin_vs_oracle(over):
+    """The TensorFlow twin (reference audio.py:51-58, 90-103, 116-123) that synthesizer.py:30 and
+    models/tacotron.py:107 call: tf.contrib.signal framing, zero initial phase, no window-sum normalisation."""
+    ohp = _load(**over)
+    h = audio._handle()
+    wav = speechlike(5300, 1)
+    D = audio._stft_tensorflow(wav)
+    Dref = tfo._stft_tensorflow(wav, ohp)
+    assert D.shape == Dref.shape == (h.num_frames_tf(wav.size), 1025) and D.dtype == np.complex64
+    assert ao.rel_l2(D, Dref) < 1e-5
+    Db = audio._stft_tensorflow(np.stack([wav, wav[::-1]]))                  # batched [N, n] -> [N, T, F]
+    assert Db.shape == (2,) + Dref.shape
+    np.testing.assert_array_equal(Db[0], D)
+    assert ao.rel_l2(Db[1], tfo._stft_tensorflow(wav[::-1].copy(), ohp)) < 1e-5
+    y = audio._istft_tensorflow(Dref)
+    yref = tfo._istft_tensorflow(Dref, ohp)
+    assert y.dtype == np.float32 and y.shape == yref.shape == (h.num_samples_tf(Dref.shape[0]),)
+    assert ao.rel_l2(y, yref) < 1e-5
+    # Griffin-Lim twin on a random (Tacotron-at-init like) normalised spectrogram, single and batched
+    rs = np.random.RandomState(0)
+    S = rs.rand(12, 1025).astype(np.float32)
+    g = audio.inv_spectrogram_tensorflow(S, iters=4)
+    gref = tfo.inv_spectrogram_tensorflow(S, ohp, iters=4)
+    assert g.dtype == np.float32 and g.shape == gref.shape
+    assert ao.snr_db(g, gref) > 60
+    S3 = rs.rand(3, 9, 1025).astype(np.float32)
+    g3 = audio.inv_spectrogram_tensorflow(S3, iters=3)
+    assert g3.shape == (3, h.num_samples_tf(9))
+    for i in range(3):
+        assert ao.snr_db(g3[i], tfo.inv_spectrogram_tensorflow(S3[i], ohp, iters=3)) > 60
+        np.testing.assert_array_equal(g3[i], audio.inv_spectrogram_tensorflow(S3[i], iters=3))   # batch == single, bitwise
+    # consistent magnitudes (|STFT| of a real signal), raw _griffin_lim_tensorflow
+    Sc = np.abs(Dref)
+    assert ao.snr_db(audio._griffin_lim_tensorflow(Sc, iters=5), tfo._griffin_lim_tensorflow(Sc, ohp, iters=5)) > 60
+    # silence: est = 0 -> angles = 0 / 1e-8 = 0 -> all-zero waveform, no NaN
+    assert np.all(audio._griffin_lim_tensorflow(np.zeros((5, 1025), np.float32), iters=2) == 0)
+    with pytest.raises(ValueError):
+        audio._stft_tensorflow(wav[:10])
+    with pytest.raises(ValueError):
+        audio.inv_spectrogram_tensorflow(np.zeros((4, 513), np.float32))
+    assert ao.rel_l2(audio._db_to_amp_tensorflow(S[0] * 40 - 20), tfo._db_to_amp_tensorflow(S[0] * 40 - 20)) < 1e-6
+    assert ao.rel_l2(audio._denormalize_tensorflow(S[0] * 1.2 - 0.1), tfo._denormalize_tensorflow(S[0] * 1.2 - 0.1, ohp)) < 1e-6

@@ -69,6 +69,11 @@ def test_ragged_batch_and_tiles(emu):
     pc.check_ragged_batch_and_tiles()
 
 
+@pytest.mark.parametrize("over", pc.CONFIGS[:2])
+def test_tf_twin_vs_oracle(emu, over):
+    pc.check_tf_twin_vs_oracle(over)
+
+
 def test_errors_and_edge_cases(emu):
     pc.check_errors_and_edge_cases()
 

@@ -153,3 +153,24 @@ def test_griffin_lim_fp32_vs_fp64_margin():
     y1 = ao._griffin_lim(S, hp, angles=angles, iters=10)
     y2 = ao._griffin_lim(S.astype(np.float32), hp, angles=angles.astype(np.complex64), iters=10)
     assert ao.snr_db(y2, y1) > 60
+
+
+def test_tf_signal_restatement_vs_torch():
+    """tf.contrib.signal.stft / inverse_stft (TF 1.7) restated in oracle/tf_signal17.py, against torch.stft(center=False)
+    with the window placed on the first win samples of the n_fft frame (tf zero-pads at the END)."""
+    from oracle import tf_signal17 as tfo
+    hp = make_hp()
+    y = speechlike(6100, 3)
+    D = tfo._stft_tensorflow(y, hp)
+    assert D.shape == (1 + (6100 - 1000) // 250, 1025) and D.dtype == np.complex64
+    w = torch.zeros(2048, dtype=torch.float64)
+    w[:1000] = torch.hann_window(1000, periodic=True, dtype=torch.float64)
+    yp = torch.cat([torch.from_numpy(y.astype(np.float64)), torch.zeros(2048 - 1000, dtype=torch.float64)])
+    Dt = torch.stft(yp, 2048, hop_length=250, win_length=2048, window=w, center=False, return_complex=True).numpy().T
+    assert ao.rel_l2(D, Dt[:D.shape[0]]) < 1e-6
+    # inverse: un-normalised windowed overlap-add; with hop = win/4 the Hann^2 sum is 1.5 in the interior
+    x = tfo._istft_tensorflow(D, hp)
+    assert x.shape == (1000 + 250 * (D.shape[0] - 1),) and x.dtype == np.float32
+    assert ao.rel_l2(x[750:-750], 1.5 * y[750:x.size - 750]) < 1e-5
+    # zero phase start + est/max(1e-8,|est|): an all-zero spectrogram stays silent
+    assert np.all(tfo._griffin_lim_tensorflow(np.zeros((4, 1025), np.float32), hp, iters=2) == 0)
