@@ -89,7 +89,7 @@ class ClockSampler(object):
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.windows = index, None, [], []
 
     def start(self):
         try:
@@ -103,7 +103,16 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def wait_first(self, timeout=5.0):
+        """nvidia-smi needs a few hundred ms to print its first line: do not start a short timed region before it"""
+        t0 = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        self.windows.append(time.perf_counter())
 
     def stop(self):
         if not self.proc:
@@ -115,7 +124,10 @@ class ClockSampler(object):
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        # keep the samples taken inside the marked (start, end) windows = the timed regions
+        wins = list(zip(self.windows[0::2], self.windows[1::2]))
+        inside = [ln for t, ln in self.lines if any(a <= t <= b + 0.1 for a, b in wins)] if wins else []
+        for ln in (inside or [ln for _, ln in self.lines]):
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -250,6 +262,8 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.wait_first()
+    sampler.mark()
     l0 = h.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -271,7 +285,7 @@ def main():
     h.griffin_lim_iterate(n_it, st)
     k1.record()
     torch.cuda.synchronize()
-    clocks = sampler.stop()
+    sampler.mark()
     ms_iter = k0.elapsed_time(k1) / n_it
     frames = N_UTT * N_FRAMES
     peaks, peak_kind = measured_peaks()
@@ -282,11 +296,14 @@ def main():
     for i in range(max(1, args.warmup // 2)):
         step_host(i)
     barrier()
+    sampler.mark()
     t0 = time.perf_counter()
     for i in range(args.steps):
         step_host(200 + i)
     torch.cuda.synchronize()
     ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    sampler.mark()
+    clocks = sampler.stop()
     barrier()
     assert np.isfinite(pin_out.array[:1000]).all()
 
