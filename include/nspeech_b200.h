@@ -154,7 +154,9 @@ int nsb_free_pinned(void* p);
 /* tuning / accounting hooks (not in the reference) */
 int nsb_set_tile_hops(nsb_handle_t h, int32_t tile_hops);       /* 0 = automatic */
 int nsb_set_host_chunks(nsb_handle_t h, int32_t n);             /* NSB_HOST Griffin-Lim pipelining: 0 = automatic (4 chunks above 8 MB), n = force n chunks */
-int nsb_set_generic_iteration(nsb_handle_t h, int32_t on);     /* A/B hook: iterate with the generic k_synth<SRC_Y> kernel instead of k_gl_iter */
+int nsb_set_generic_iteration(nsb_handle_t h, int32_t on);     /* A/B hook: Griffin-Lim iterations with 0 = k_gl_stream (production), 1 = the generic k_synth<SRC_Y>, 2 = the tile kernel k_gl_iter */
+int nsb_set_stream_grid(nsb_handle_t h, int32_t ctas);          /* k_gl_stream grid: 0 = automatic, n = force n CTAs (tests: long pieces, many rounds of the ring) */
+int nsb_stream_trace(nsb_handle_t h, int32_t enable, uint64_t* out, int32_t max_ctas);   /* profiling: per-CTA (SM id, start ns, end ns) of the last k_gl_stream launch -> number of CTAs written */
 uint64_t nsb_kernel_launches(nsb_handle_t h);                    /* kernels launched through this handle so far */
 /* the Griffin-Lim iteration kernel alone on device-resident state, for roofline timing: runs `iters`
  * iterations on the state left by the last nsb_griffin_lim(NSB_DEVICE) call */

@@ -65,7 +65,9 @@ SIGNATURES = {
     "nsb_check_status": (ctypes.c_int, [_vp, _vp]),
     "nsb_set_tile_hops": (ctypes.c_int, [_vp, _i32]),
     "nsb_set_generic_iteration": (ctypes.c_int, [_vp, _i32]),
+    "nsb_set_stream_grid": (ctypes.c_int, [_vp, _i32]),
     "nsb_set_host_chunks": (ctypes.c_int, [_vp, _i32]),
+    "nsb_stream_trace": (ctypes.c_int, [_vp, _i32, _vp, _i32]),
     "nsb_kernel_launches": (_u64, [_vp]),
     "nsb_griffin_lim_iterate": (ctypes.c_int, [_vp, _i32, _vp]),
     "nsb_alloc_pinned": (ctypes.c_int, [_u64, ctypes.POINTER(_vp)]),
@@ -265,6 +267,18 @@ class Handle(object):
 
     def set_generic_iteration(self, on):
         self._call("nsb_set_generic_iteration", int(on))
+
+    def set_stream_grid(self, n):
+        self._call("nsb_set_stream_grid", int(n))
+
+    def stream_trace(self, enable=True, max_ctas=4096):
+        """profiling hook: enable tracing / fetch (sm_id, start_ns, end_ns) per CTA of the last k_gl_stream launch"""
+        import numpy as np
+        buf = np.zeros((max_ctas, 3), dtype=np.uint64)
+        n = self.lib.dll.nsb_stream_trace(self._h, int(bool(enable)), buf.ctypes.data_as(ctypes.c_void_p), max_ctas)
+        if n < 0:
+            raise RuntimeError("nsb_stream_trace failed")
+        return buf[:n]
 
     def kernel_launches(self):
         return int(self.lib.dll.nsb_kernel_launches(self._h))

@@ -62,6 +62,18 @@ __device__ __forceinline__ void spin_pause() { __nanosleep(32); }
 __device__ __forceinline__ bool warp_any(bool p) { return __any_sync(0xffffffffu, p); }
 #endif
 
+// 1/sqrt(x) as ONE MUFU.RSQ: plain rsqrtf() wraps the instruction in a subnormal-input rescue (FSETP + two predicated
+// FMULs per call, 96 instructions per frame); the callers below never pass a subnormal that matters
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+#ifdef NSB_EMULATE
+    return 1.0f / sqrtf(x);
+#else
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
+
 struct GlParams {
     Plan plan;
     Batch batch;
@@ -77,7 +89,7 @@ struct GlParams {
 // TF twin: angles = est / max(1e-8, |est|) -> z * S * min(1/|z|, 1/thr); |z| = 0 gives 0 (not S)
 __device__ __forceinline__ void renorm_tf(c2& z, float S, float inv_thr) {
     float m2 = fmaf(z.x, z.x, z.y * z.y);
-    z = cscale(z, fminf(rsqrtf(m2), inv_thr) * S);
+    z = cscale(z, fminf(rsqrt_ftz(m2), inv_thr) * S);
 }
 
 constexpr int kMagBytes = 4096 + 16;                 // slots + the float4 that carries the Nyquist magnitude
@@ -87,7 +99,7 @@ constexpr int kXchOffsetF2 = (kMagBytes + 112) / 8;  // exchange area starts at 
 __device__ __forceinline__ void renorm_fast(c2& z, float S, bool& zero) {
     float m2 = fmaf(z.x, z.x, z.y * z.y);
     zero |= (m2 == 0.f);
-    z = cscale(z, rsqrtf(fmaxf(m2, 1e-36f)) * S);
+    z = cscale(z, rsqrt_ftz(fmaxf(m2, 1e-36f)) * S);
 }
 
 // normalise the finished tile by the summed squared window and store it (all threads of the CTA)

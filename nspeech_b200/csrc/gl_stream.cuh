@@ -1,0 +1,509 @@
+// k_gl_stream: ONE Griffin-Lim iteration (audio.py:85-86: angles = exp(1j*angle(_stft(y))); y = _istft(S*angles))
+// as a persistent STREAMING kernel.  Successor of k_gl_iter (gl_iter.cuh), same per-frame arithmetic, different
+// walk over the batch:
+//
+//   * the batch is ONE stream of GROUPS (C = ceil(win/hop) consecutive hops): utterance b contributes its G_b groups
+//     plus one END-HALO group (the frames past its last full group, they only reach back), so the stream needs no
+//     special case at utterance boundaries.  CTA n owns the contiguous range [V0, V1) = [n*NV/grid, (n+1)*NV/grid) of
+//     it and also transforms the group V1 as its own halo (the C-1 frames of it that reach back into V1-1): a range
+//     of 54 groups wastes 1.4 % of its FFTs, the old tile kernel recomputed C-1 frames per 8 groups (32 frames
+//     for 28 hops, 12.5 %).  Every CTA gets the same number of positions whatever the utterance lengths are;
+//   * the range is walked from its RIGHT end: position i = 0 is the halo group V1, i = V1 - V0 the group V0;
+//     position i belongs to warp i mod 8 (round i div 8).  A frame of colour s (= its place in the group) overlaps
+//     the right-hand group's frames of colour < s and the left-hand group's frames of colour > s, so adding in colour
+//     order needs ONE dependency: (group j, colour s) waits for (j+1, < s) - and j+1 is either the neighbour warp in
+//     the same round or a group of the previous round.  Walking leftwards keeps every dependency pointing at work
+//     that is in step or long done: the warps stay in lockstep (a first version walked rightwards, needed warp 0 a
+//     whole round ahead of warp 7, desynchronised the warps and lost 23 % of the issue slots to instruction-cache
+//     misses, profiles/r1/ncu_full_k_gl_stream_ascending.txt).  The left-hand neighbour is waited for as well,
+//     purely to pace the warps (one colour of drift at most).  Counters: per-warp events in shared memory
+//     (st.release / ld.acquire);
+//   * the overlap-add goes into a shared-memory RING of 8 groups + the hops a group reaches back.  When a group's
+//     last colour is in, its own C hops are final: the SAME warp normalises them by the window sum, stores them to
+//     HBM and zeroes them.  There is no CTA barrier inside a piece and no epilogue phase;
+//   * ring reuse: the group at position i writes where positions i-8 (the same warp) and i-9 (the right-hand warp,
+//     one round ago) stored - (i, colour 0) waits for that store, which is a round old by then;
+//   * while a group is stored, the first frame of the warp's next group (8 positions to the left, possibly another
+//     utterance) is already on its way into the scratch tile (cp.async) and its magnitude row towards L2.
+//
+// The summation order of every output sample is the colour order 0..C-1 with colour = (k - k_first0) mod C, a
+// property of the frame index alone: pieces, grids and batches never change a bit of the result.
+#pragma once
+#include "gl_iter.cuh"
+
+namespace nsb {
+
+struct GlStreamParams {
+    Plan plan;
+    Batch batch;             // group_off / group_base describe the concatenated group space
+    const float* y_in;
+    float* y_out;
+    const float* mag;        // permuted, pre-scaled magnitudes [frames][kMagPitch]
+    int colours;             // C
+    int total_groups;        // groups in this (sub-)batch (without the end-halo groups)
+    int sync_mode;           // CTA barriers that re-align the warps (instruction-cache locality): 0 none, 1 per round, 2 per frame
+    float inv_thr;           // TF twin clamp, see GlParams
+    int* status;
+    unsigned long long* trace;   // optional [grid][3]: SM id, start and end time (globaltimer ns) of every CTA
+};
+
+__device__ __forceinline__ unsigned long long global_ns() {
+#ifdef NSB_EMULATE
+    return 0;
+#else
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+#endif
+}
+__device__ __forceinline__ unsigned sm_id() {
+#ifdef NSB_EMULATE
+    return 0;
+#else
+    unsigned v;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
+    return v;
+#endif
+}
+
+__device__ __forceinline__ void wait_events(const int* flag, int target, int lane) {
+    if (lane == 0) while (flag_load(flag) < target) spin_pause();
+    __syncwarp();
+}
+
+// normalise the warp's finished group by the summed squared window, store it and clear the ring slot.
+// rinv[j] (global memory, Plan::rinv) holds 1 / (n_fft * window-sum) of the interior (all covering frames exist);
+// win_t[n] is the window.
+// The group's samples sit at ring[(r0 + i) mod RS].
+__device__ __noinline__ void gl_store_group(float* ring, int r0, int RS, float* yo, int n_store, int h_a, int T, const float* win_t,
+                                            const float* __restrict__ rinv_s, int hop, int win, int lo, int a, int norm_wss, int lane, bool& bad) {
+    const int ncov = (win + hop - 1) / hop;
+    const int h_b = h_a + (n_store - 1) / hop;
+    // interior group: every sample is covered by all of its frames -> no per-sample frame tests
+    const bool interior = !norm_wss || ((h_a + a / hop - (ncov - 1) >= 0) && (h_b + (hop - 1 + a) / hop <= T - 1));
+    float chk = 0.f;                                  // NaN/Inf detector: v*0 accumulates to NaN iff some v is not finite
+    if (interior && ((hop | n_store | r0 | RS) & 1) == 0 && (reinterpret_cast<uintptr_t>(yo) & 7) == 0) {
+        float2* s2 = reinterpret_cast<float2*>(ring);          // the ring is 16-byte aligned
+        const int r02 = r0 >> 1, RS2 = RS >> 1;
+        const float2* r2 = reinterpret_cast<const float2*>(rinv_s);
+        float2* yo2 = reinterpret_cast<float2*>(yo);
+        const int hop2 = hop >> 1;
+        c2 chk2 = mk2(0.f, 0.f);
+        int jj = lane % hop2;
+        const int step = 32 % hop2;
+        for (int i = lane; i < (n_store >> 1); i += 32) {
+            int ri = r02 + i;
+            if (ri >= RS2) ri -= RS2;
+            c2 v = p_mul(s2[ri], __ldg(r2 + jj));
+            chk2 = p_fma(v, mk2(0.f, 0.f), chk2);
+            yo2[i] = v;
+            s2[ri] = mk2(0.f, 0.f);
+            jj += step;
+            if (jj >= hop2) jj -= hop2;
+        }
+        chk = chk2.x + chk2.y;
+    } else {
+        for (int i = lane; i < n_store; i += 32) {
+            const int hh = i / hop, j = i - hh * hop, h = h_a + hh;
+            const int dj = (j + a) / hop, rj = (j + a) - dj * hop;
+            int ncover = 0;
+            for (int idx = rj; idx < win; idx += hop) ++ncover;
+            const int k_hi = h + dj, k_lo = k_hi - (ncover - 1);
+            int ri = r0 + i;
+            if (ri >= RS) ri -= RS;
+            float v = ring[ri];
+            if (!norm_wss || (k_lo >= 0 && k_hi <= T - 1)) {
+                v *= __ldg(rinv_s + j);
+            } else {
+                v *= (1.0f / (float)kNfft);
+                float sm = 0.f;
+                int kk = k_hi;
+                for (int idx = rj; idx < win; idx += hop, --kk)
+                    if (kk >= 0 && kk <= T - 1) { float w = win_t[lo + idx]; sm = fmaf(w, w, sm); }
+                if (sm > 1.17549435e-38f) v /= sm;
+            }
+            chk = fmaf(v, 0.f, chk);
+            yo[i] = v;
+            ring[ri] = 0.f;
+        }
+    }
+    bad |= (chk != 0.f);
+}
+
+template <int PRUNE> struct WinTable {          // the part of the n_fft-long window the kernel can touch
+    static constexpr int n0 = PRUNE == 1 ? 512 : 0;
+    static constexpr int len = PRUNE == 0 ? kNfft : 1024;
+};
+
+// where a group of the stream lives: utterance, utterance-local group index and the utterance's geometry
+struct GroupLoc {
+    int b;                   // utterance (index into the (sub-)batch), -1: past the end of the stream
+    int g, Gb;               // group index inside the utterance, number of (real) groups of the utterance; g == Gb: end-halo
+    int f_off, T, L;
+    long long s_off;
+};
+
+// stream coordinate of utterance b's first group: its groups before it + one end-halo per earlier utterance
+__device__ __forceinline__ int stream_off(const Batch& B, int b) { return __ldg(B.group_off + b) - B.group_base + b; }
+
+__device__ __forceinline__ void fill_loc(const Batch& B, int V, int b, GroupLoc& o) {
+    o.b = b;
+    o.g = V - stream_off(B, b);
+    o.Gb = __ldg(B.group_off + b + 1) - __ldg(B.group_off + b);
+    o.f_off = __ldg(B.frame_off + b);
+    o.T = __ldg(B.frame_off + b + 1) - o.f_off;
+    o.s_off = __ldg(B.samp_off + b);
+    o.L = (int)(__ldg(B.samp_off + b + 1) - o.s_off);          // hop*(T-1) (librosa) or hop*(T-1)+win (tf)
+}
+// binary search
+__device__ __forceinline__ void locate(const Batch& B, int NV, int V, GroupLoc& o) {
+    if (V >= NV) { o.b = -1; o.g = 0; o.Gb = 0; o.f_off = 0; o.T = 0; o.L = 0; o.s_off = 0; return; }
+    int lo = 0, hi = B.batch;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (stream_off(B, mid) <= V) lo = mid; else hi = mid;
+    }
+    fill_loc(B, V, lo, o);
+}
+// walking leftwards from a known place: the utterance is the hint's or a few before it
+__device__ __forceinline__ void locate_left(const Batch& B, int V, int b_hint, GroupLoc& o) {
+    int b = b_hint;
+    while (b > 0 && stream_off(B, b) > V) --b;
+    fill_loc(B, V, b, o);
+}
+
+template <int PRUNE, bool DEFCFG, bool TFM>
+__global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
+    NSB_DYN_SMEM(smem_raw);
+    const int hop = DEFCFG ? 250 : P.plan.hop;
+    const int win = DEFCFG ? 1000 : P.plan.win_len;
+    const int lo = DEFCFG ? 524 : P.plan.lo;
+    const int C = DEFCFG ? 4 : P.colours;
+    const int origin = DEFCFG ? kNfft / 2 : P.plan.origin;
+    const int a = origin - lo;                       // frame k's window support starts at sample k*hop - a
+    // hop h is touched by the frames h + kfirst0 .. h + klast0
+    const int kfirst0 = (a - win >= 0) ? (a - win) / hop + 1 : -((win - a - 1) / hop + 1) + 1;
+    const int klast0 = (hop - 1 + a) / hop;
+    const int back = min(klast0 - kfirst0, C);       // hops a group reaches back = colours of group j+1 that group j's hops need
+    const int GH = C * hop;                          // samples per group
+    const int RS = (kWarpsPerCta * C + back) * hop;  // ring size: 8 groups + the hops the leftmost one reaches back
+    constexpr int t0 = PruneRange<PRUNE>::t0, t1 = PruneRange<PRUNE>::t1;
+
+    float2* tw_s = reinterpret_cast<float2*>(smem_raw);
+    float* win_tab = reinterpret_cast<float*>(tw_s + kTwF2);
+    const float* win_s = win_tab - WinTable<PRUNE>::n0;      // win_s[n] for n inside the table
+    float* ring = win_tab + WinTable<PRUNE>::len;            // 16-byte aligned
+    int* progress = reinterpret_cast<int*>(ring + ((RS + 3) & ~3));    // [kWarpsPerCta] (+ pad to 16 ints)
+    float2* scratch_all = reinterpret_cast<float2*>(progress + 16);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2* scratch = scratch_all + warp * kScratchF2;
+    float* stage = reinterpret_cast<float*>(scratch);
+    if (P.trace && threadIdx.x == 0) { P.trace[3 * blockIdx.x] = sm_id(); P.trace[3 * blockIdx.x + 1] = global_ns(); }
+
+    for (int i = threadIdx.x; i < kTwF2; i += kThreads) tw_s[i] = P.plan.tw[i];
+    for (int i = threadIdx.x; i < WinTable<PRUNE>::len; i += kThreads) win_tab[i] = P.plan.win[WinTable<PRUNE>::n0 + i];
+    {
+        float4* r4 = reinterpret_cast<float4*>(ring);
+        for (int i = threadIdx.x; i < (RS + 3) / 4; i += kThreads) r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (threadIdx.x < 16) progress[threadIdx.x] = 0;
+    __syncthreads();
+    bool bad = false;
+    const int E = C + 1;                              // events per round: C adds + 1 store
+
+    // ---- this CTA's range of the stream ----
+    const int NV = P.total_groups + P.batch.batch;
+    const int V0 = (int)((long long)NV * blockIdx.x / gridDim.x), V1 = (int)((long long)NV * (blockIdx.x + 1) / gridDim.x);
+    const int n_pos = V1 - V0 + 1;                    // positions: i = 0 is the halo group V1, i = n_pos - 1 the group V0
+    // samples left of the range's first group belong to the CTA on the left: frames of V0 must not add there
+    int b_low, x_low;
+    {
+        GroupLoc l0;
+        locate(P.batch, NV, V0, l0);
+        b_low = l0.b; x_low = l0.g * GH;
+    }
+
+    bool staged = false;                         // this frame's samples were cp.async'ed into the scratch tile already
+    GroupLoc cur;
+    const int n_pad = (n_pos + kWarpsPerCta - 1) & ~(kWarpsPerCta - 1);   // phantom positions fill the last round (barriers are CTA-wide)
+    locate(P.batch, NV, warp < n_pos ? V1 - warp : NV, cur);
+    for (int i = warp; i < n_pad; i += kWarpsPerCta) {      // position i counts groups from the range's right end
+        const int u = n_pos - 1 - i;                        // stream coordinate of the group relative to V0
+        const int r = i >> 3;
+        const bool has_right = (i >= 1);                    // group V+1: neighbour warp, this round or (warp 0) the previous one
+        const int wr = (warp + 7) & 7, r_r = (i - 1) >> 3;
+        const bool has_left = (warp < kWarpsPerCta - 1) && (i + 1 < n_pos);   // group V-1 in the same round: pacing only
+        const int kbase = C * cur.g + kfirst0;
+        // frames of this group that exist and that this range needs (the halo group V1: only those that reach back, and
+        // none at all if V1 starts an utterance)
+        int k_hi = cur.T - 1;
+        if (i == 0) k_hi = (cur.g == 0) ? -1 : min(k_hi, kbase + back - 1);
+        if (cur.b < 0) k_hi = -1;
+        const int T = cur.T, L = cur.L;
+        const float* yin = P.y_in + cur.s_off;
+        const float* mag0 = P.mag + (size_t)cur.f_off * kMagPitch;
+        const int xmin = (cur.b == b_low) ? x_low : 0;      // lowest utterance sample this CTA accumulates
+        const int ubase = (u - cur.g) * GH;                 // utterance sample x sits at ring[(ubase + x) mod RS]
+        for (int s = 0; s < C; ++s) {
+            const int k = kbase + s;
+            const bool active = (k >= 0 && k <= k_hi);        // warp-uniform
+            const bool next_active = (s + 1 < C) && (k + 1 >= 0 && k + 1 <= k_hi);   // the group's next frame
+            c2 z[32];
+            if (active) {
+                // pull the NEXT frame's magnitude row towards L2 (it streams from HBM) while this frame computes
+                if (next_active) {
+                    const char* nm = reinterpret_cast<const char*>(mag0 + (size_t)(k + 1) * kMagPitch);
+                    prefetch_l2(nm + lane * 128);
+                    if (lane == 0) prefetch_l2(nm + 4096);
+                }
+                const float* magrow = mag0 + (size_t)k * kMagPitch;
+                if (staged) {
+                    // samples were staged by the previous frame of this warp (see below): window them from shared memory
+                    cp_async_wait_all();
+                    __syncwarp();
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) {
+                        if (t >= t0 && t < t1) z[t] = p_mul(mk2(stage[64 * t + lane], stage[64 * t + 32 + lane]), mk2(win_s[64 * t + lane], win_s[64 * t + 32 + lane]));
+                        else z[t] = mk2(0.f, 0.f);
+                    }
+                    __syncwarp();
+                } else {
+                    load_frame<false, PRUNE>(z, yin, (long long)L, (long long)k * hop - origin, win_s, lane, 0.f, stage);
+                }
+                fwd_phase1(z, lane, scratch, tw_s);
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < 32; ++t) z[t] = scratch[lane * kRowStride + t];
+                __syncwarp();                        // every lane has its row: the scratch tile is free
+                {
+                    const char* src = reinterpret_cast<const char*>(magrow);
+                    char* dst = reinterpret_cast<char*>(scratch);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) cp_async16(dst + (q * 32 + lane) * 16, src + (q * 32 + lane) * 16);
+                    if (lane == 0) cp_async16(dst + 4096, src + 4096);
+                }
+                fft32<-1>(z);
+                float2* xch = scratch + kXchOffsetF2;
+                if (lane == 0) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) xch[q] = z[q];
+                }
+                cp_async_wait_all();
+                __syncwarp();
+                const float4* mrow = reinterpret_cast<const float4*>(scratch);
+                const float* mflt = reinterpret_cast<const float*>(scratch);
+                bool zero = false;
+                // (a) every lane renormalises its 32 slots (lane 0's registers hold the packed-row FFT, not bins:
+                //     replaced below)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float4 S = mrow[q * 32 + lane];
+                    if (TFM) {
+                        renorm_tf(z[4 * q], S.x, P.inv_thr); renorm_tf(z[4 * q + 1], S.y, P.inv_thr);
+                        renorm_tf(z[4 * q + 2], S.z, P.inv_thr); renorm_tf(z[4 * q + 3], S.w, P.inv_thr);
+                    } else {
+                        renorm_fast(z[4 * q], S.x, zero);
+                        renorm_fast(z[4 * q + 1], S.y, zero);
+                        renorm_fast(z[4 * q + 2], S.z, zero);
+                        renorm_fast(z[4 * q + 3], S.w, zero);
+                    }
+                }
+                if (lane == 0) zero = false;
+                if (!TFM && warp_any(zero)) {                // rare: some bin of y's STFT is exactly 0 -> phase 0 (np.angle(0))
+                    if (lane != 0) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float4 S = mrow[q * 32 + lane];
+                            const float Ss[4] = {S.x, S.y, S.z, S.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (z[4 * q + e].x == 0.f && z[4 * q + e].y == 0.f) z[4 * q + e].x = Ss[e];
+                        }
+                    }
+                }
+                // (b) bins k = 32 j (rows 0/32): lane j in 1..16 does pair (j, 32-j); lane 0 the real DC/Nyquist pair
+                if (lane <= 16) {
+                    if (lane == 0) {
+                        float2 g0 = xch[0];
+                        float x0 = g0.x + g0.y, xn = g0.x - g0.y;          // (X[0], X[1024]) up to the factor 2
+                        float S0 = mflt[0], Sn = mflt[1024];
+                        if (TFM) {                                          // x / max(1e-8, |x|); x0, xn carry g * est (no factor 2)
+                            x0 = x0 * fminf(1.0f / fabsf(x0), 2.0f * P.inv_thr) * S0;
+                            xn = xn * fminf(1.0f / fabsf(xn), 2.0f * P.inv_thr) * Sn;
+                            if (!(fabsf(x0) <= S0)) x0 = 0.f;               // 0 * inf
+                            if (!(fabsf(xn) <= Sn)) xn = 0.f;
+                        } else {
+                            x0 = (x0 < 0.f) ? -S0 : S0;                     // phase of a real number is its sign
+                            xn = (xn < 0.f) ? -Sn : Sn;
+                        }
+                        xch[0] = make_float2(x0 + xn, x0 - xn);
+                    } else {
+                        const int jq = lane, jj = 32 - lane;
+                        // u = -i * w64^j with w64^j = w2048^(16 * 2j) from the twiddle table (j = 16: w = -i)
+                        const float2 wj = (jq <= 15) ? tw_s[15 * 32 + 2 * jq] : make_float2(0.f, -1.f);
+                        const c2 u = mk2(wj.y, -wj.x);
+                        const c2 Aj = xch[jq], Bj = xch[jj];
+                        const c2 S1 = cadd_conj(Aj, Bj), D1 = csub_conj(Aj, Bj);
+                        const c2 T1 = cmul(D1, u);
+                        c2 c1 = cadd(S1, T1);                               // 2*X[32 j]
+                        c2 c2v = cconj(csub(S1, T1));                       // 2*X[32 (32-j)]
+                        bool z2 = false;
+                        if (TFM) {
+                            renorm_tf(c1, mflt[(jq >> 2) * 128 + (jq & 3)], P.inv_thr);
+                            renorm_tf(c2v, mflt[(jj >> 2) * 128 + (jj & 3)], P.inv_thr);
+                        } else {
+                            renorm_fast(c1, mflt[(jq >> 2) * 128 + (jq & 3)], z2);
+                            renorm_fast(c2v, mflt[(jj >> 2) * 128 + (jj & 3)], z2);
+                        }
+                        if (z2) {
+                            if (c1.x == 0.f && c1.y == 0.f) c1.x = mflt[(jq >> 2) * 128 + (jq & 3)];
+                            if (c2v.x == 0.f && c2v.y == 0.f) c2v.x = mflt[(jj >> 2) * 128 + (jj & 3)];
+                        }
+                        // inverse split: S' = V[j] + conj V[32-j], D' = V[j] - conj V[32-j], P = D' * conj(u)
+                        const c2 S2 = cadd_conj(c1, c2v), D2 = csub_conj(c1, c2v);
+                        const c2 Pv = cmul_conj(D2, u);
+                        // lane j reads and writes only xch[j] and xch[32-j]: no cross-lane hazard inside this block
+                        xch[jq] = cadd(S2, Pv);
+                        if (jq != 16) xch[jj] = cconj(csub(S2, Pv));
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) z[q] = xch[q];
+                }
+                __syncwarp();                        // magnitude row and exchange area fully consumed
+                // inverse pass 1 (the lane-0 pre-split already happened above)
+                fft32<+1>(z);
+                scratch[lane * kRowStride] = z[0];
+#pragma unroll
+                for (int q = 1; q < 32; ++q) scratch[lane * kRowStride + q] = cmul_conj(z[q], tw_s[(q - 1) * 32 + lane]);
+                __syncwarp();
+                inv_phase2(z, lane, scratch);
+                __syncwarp();                        // the scratch tile may be rewritten by this warp's next frame
+            }
+            // The scratch tile now idles through the overlap-add: stage the group's NEXT frame into it with cp.async so
+            // that its load latency hides behind the neighbour wait and the accumulate.  Only frames that need no
+            // reflect padding and (8-byte copies) start at an even sample.
+            staged = false;
+            if (PRUNE != 0 && next_active) {
+                const long long nstart = (long long)(k + 1) * hop - origin;
+                if (nstart + 64 * t0 >= 0 && nstart + 64 * t1 <= L && ((cur.s_off + nstart) & 1) == 0) {
+                    const float* src = yin + nstart + 64 * t0 + 2 * lane;
+                    float* dst = stage + 64 * t0 + 2 * lane;
+#pragma unroll
+                    for (int q = 0; q < t1 - t0; ++q) cp_async8(dst + 64 * q, src + 64 * q);
+                    staged = true;
+                }
+            }
+            // ---- overlap-add ordering ----
+            if (s == 0) {
+                // ring reuse: this group writes where positions i-8 (this warp) and i-9 (the right-hand warp) stored
+                if (i >= 9) wait_events(progress + wr, E * (((i - 9) >> 3) + 1), lane);
+            } else {
+                // my colour-s frame overlaps the right-hand group's frames of colour < s: they go first
+                if (has_right) wait_events(progress + wr, E * r_r + s, lane);
+                // pacing: stay within one colour of the left-hand neighbour (keeps the CTA's warps in the same code)
+                if (has_left) wait_events(progress + warp + 1, E * r + s, lane);
+            }
+            if (active) {
+                const int base = k * hop - origin;                            // utterance sample of n = 0
+                int q0 = (ubase + base + lo) % RS;                            // ring index of the first support sample
+                if (q0 < 0) q0 += RS;
+                const bool inside = (base + lo >= xmin) && (base + lo + win <= L);
+                if (DEFCFG && inside && q0 + win <= RS) {
+                    // default hparams: the support n in [524, 1524) is known at compile time; (acc[n], acc[n+32]) and the
+                    // two window values ride in register pairs so the accumulate is one FFMA2
+                    float* ap = ring + (q0 - lo) + lane;
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) {
+                        if (t >= t0 && t < t1) {
+                            if (t == 8) {
+                                if (lane >= 12) ap[64 * t] = fmaf(z[t].x, win_s[64 * t + lane], ap[64 * t]);
+                                ap[64 * t + 32] = fmaf(z[t].y, win_s[64 * t + 32 + lane], ap[64 * t + 32]);
+                            } else if (t == 23) {
+                                ap[64 * t] = fmaf(z[t].x, win_s[64 * t + lane], ap[64 * t]);
+                                if (lane < 20) ap[64 * t + 32] = fmaf(z[t].y, win_s[64 * t + 32 + lane], ap[64 * t + 32]);
+                            } else {
+                                c2 rr = p_fma(z[t], mk2(win_s[64 * t + lane], win_s[64 * t + 32 + lane]), mk2(ap[64 * t], ap[64 * t + 32]));
+                                ap[64 * t] = rr.x;
+                                ap[64 * t + 32] = rr.y;
+                            }
+                        }
+                    }
+                } else {
+                    // window support [lo, lo+win) clipped to the piece -> per-lane bitmasks of the valid t
+                    // (n = 64 t + lane [+32]); indices wrap around the ring.  Touching nothing outside the support
+                    // makes the plain read-modify-write race-free.
+                    const int nlo = max(lo, xmin - base), nhi = min(lo + win, L - base);
+                    const int a0 = min(max((nlo - lane + 63) >> 6, 0), 32), a1 = min(max((nhi - lane + 63) >> 6, 0), 32);
+                    const int b0 = min(max((nlo - lane - 32 + 63) >> 6, 0), 32), b1 = min(max((nhi - lane - 32 + 63) >> 6, 0), 32);
+                    const unsigned mre = (a1 > a0) ? ((0xffffffffu >> (32 - (a1 - a0))) << a0) : 0u;
+                    const unsigned mim = (b1 > b0) ? ((0xffffffffu >> (32 - (b1 - b0))) << b0) : 0u;
+                    const int qb = q0 - lo + lane;
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) {
+                        if (t >= t0 && t < t1) {
+                            int i0 = qb + 64 * t, i1 = i0 + 32;
+                            if (i0 >= RS) i0 -= RS;
+                            if (i1 >= RS) i1 -= RS;
+                            if ((mre >> t) & 1u) ring[i0] = fmaf(z[t].x, win_s[64 * t + lane], ring[i0]);
+                            if ((mim >> t) & 1u) ring[i1] = fmaf(z[t].y, win_s[64 * t + 32 + lane], ring[i1]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) flag_store(progress + warp, E * r + s + 1);
+            if (P.sync_mode == 2) __syncthreads();
+        }
+        // ---- the group is complete (z is dead from here on) ----
+        // the warp's next group sits 8 positions to the left: find it, send its first frame on its way
+        GroupLoc nxt;
+        const bool more = (i + kWarpsPerCta < n_pos);
+        if (!more) locate(P.batch, NV, NV, nxt);              // phantom
+        if (more) {
+            locate_left(P.batch, V1 - i - kWarpsPerCta, cur.b < 0 ? P.batch.batch - 1 : cur.b, nxt);
+            const int kn = C * nxt.g + kfirst0;               // its colour-0 frame (does not exist at an utterance's start)
+            if (PRUNE != 0 && kn >= 0 && kn <= nxt.T - 1) {
+                const char* nm = reinterpret_cast<const char*>(P.mag + ((size_t)nxt.f_off + kn) * kMagPitch);
+                prefetch_l2(nm + lane * 128);
+                if (lane == 0) prefetch_l2(nm + 4096);
+                const long long nstart = (long long)kn * hop - origin;
+                if (nstart + 64 * t0 >= 0 && nstart + 64 * t1 <= nxt.L && ((nxt.s_off + nstart) & 1) == 0) {
+                    const float* src = P.y_in + nxt.s_off + nstart + 64 * t0 + 2 * lane;
+                    float* dst = stage + 64 * t0 + 2 * lane;
+#pragma unroll
+                    for (int q = 0; q < t1 - t0; ++q) cp_async8(dst + 64 * q, src + 64 * q);
+                    staged = true;
+                }
+            }
+        }
+        if (i >= 1 && cur.b >= 0 && cur.g < cur.Gb) {
+            // my hops also need the right-hand group's first `back` colours; the colour C-1 wait covered back <= C-1
+            if (back > C - 1) wait_events(progress + wr, E * r_r + back, lane);
+            const int x0 = cur.g * GH;                               // utterance sample of the group's first hop
+            const int n_store = min(GH, L - x0);
+            if (n_store > 0)
+                gl_store_group(ring, (u * GH) % RS, RS, P.y_out + cur.s_off + x0, n_store, C * cur.g, T, win_s, P.plan.rinv, hop, win, lo, a,
+                               P.plan.norm_wss, lane, bad);
+            __syncwarp();
+        } else if (i == 0 && k_hi >= 0) {
+            // the halo group's own hops belong to the CTA on the right: nothing to store, but positions 8 and 9 reuse the space
+            const int r0 = (u * GH) % RS;
+            for (int q = lane; q < GH; q += 32) { int ri = r0 + q; if (ri >= RS) ri -= RS; ring[ri] = 0.f; }
+            __syncwarp();
+        }
+        if (lane == 0) flag_store(progress + warp, E * (r + 1));
+        cur = nxt;
+        if (P.sync_mode == 1) __syncthreads();
+    }
+    if (bad) atomicOr(P.status, 1);
+    if (P.trace) {
+        __syncthreads();
+        if (threadIdx.x == 0) P.trace[3 * blockIdx.x + 2] = global_ns();
+    }
+}
+
+}  // namespace nsb

@@ -35,6 +35,8 @@ struct Batch {
     const long long* samp_off;   // [batch+1]
     const int* tile_off;         // [batch+1] (synthesis tiles), may be null for analysis
     const int* tile_utt;         // [total tiles] GLOBAL tile index -> GLOBAL utterance index
+    const int* group_off;        // [batch+1] groups of C = ceil(win/hop) hops per utterance, GLOBAL prefix sums (k_gl_stream)
+    int group_base;              // global index of this (sub-)batch's first group
     int batch;
     int utt_base;                // global index of this (sub-)batch's first utterance (pointers above are offset by it)
     int frame_base, tile_base;   // global index of this (sub-)batch's first frame / tile: the arrays hold GLOBAL prefix
@@ -44,6 +46,7 @@ struct Batch {
 struct Plan {                    // device tables owned by the handle
     const float2* tw;            // [31*32]
     const float* win;            // [2048] window padded centrally to n_fft (unscaled)
+    const float* rinv;           // [hop] 1 / (n_fft * summed squared window) of the interior, 1/n_fft without normalisation (k_gl_stream)
     const float* mel_w;          // mel weights, rows concatenated
     const int* mel_lo;           // [num_mels] first bin of row
     const int* mel_n;            // [num_mels] row length

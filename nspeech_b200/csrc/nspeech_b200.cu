@@ -9,7 +9,7 @@
 
 #include "../../include/nspeech_b200.h"
 #include "kernels.cuh"
-#include "gl_iter.cuh"
+#include "gl_stream.cuh"
 
 using namespace nsb;
 
@@ -64,13 +64,17 @@ struct nsb_handle_s {
     nsb_hparams hp{};
     int n_fft = 0, hop = 0, win = 0, lo = 0, colours = 0, prune = 0, defcfg = 0, num_mels = 0;
     int num_sms = 0;
-    int user_tile_hops = 0;
+    int user_tile_hops = 0, user_stream_grid = 0;
     cudaStream_t own_stream = nullptr, copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t desc_done = nullptr;
     // tables
     float2* d_tw = nullptr;
     float* d_win = nullptr;          // periodic Hann padded centrally to n_fft (librosa geometry)
     float* d_win_tf = nullptr;       // the same window at n in [0, win) (tf.contrib.signal geometry)
+    float *d_rinv = nullptr, *d_rinv_tf = nullptr;   // [hop] reciprocal interior window sums of the two geometries
+    int stream_sync_mode = 0;
+    DevBuf d_trace; int trace_on = 0, trace_grid = 0;
+    int stream_ctas_per_sm = 1;      // resident k_gl_stream CTAs per SM (occupancy query at creation)
     int prune_tf = 0, colours_tf = 0;
     float* d_mel_w = nullptr;
     int *d_mel_lo = nullptr, *d_mel_n = nullptr, *d_mel_ptr = nullptr;
@@ -83,8 +87,8 @@ struct nsb_handle_s {
     // workspaces
     DevBuf ws_mag, ws_y0, ws_y1, ws_in, ws_in2, ws_out, ws_out2;
     // state of the last device-resident Griffin-Lim (for nsb_griffin_lim_iterate)
-    struct { bool valid = false; Batch batch{}; int total_frames = 0; int tile_hops = 0; int total_tiles = 0; int cur = 0; bool tf = false; float inv_thr = 0.f; } gl;
-    std::vector<int> h_frame_off, h_tile_off;       // host copies of the last descriptors (chunking)
+    struct { bool valid = false; Batch batch{}; int total_frames = 0; int tile_hops = 0; int total_tiles = 0; int total_groups = 0; int cur = 0; bool tf = false; float inv_thr = 0.f; } gl;
+    std::vector<int> h_frame_off, h_tile_off, h_group_off;       // host copies of the last descriptors (chunking)
     std::vector<long long> h_samp_off;
     int host_chunks = 0;             // 0 = automatic chunking of NSB_HOST Griffin-Lim calls, n > 0 = force n chunks
     int use_generic_iter = 0;        // debugging / A-B hook: run the iterations with k_synth<SRC_Y> instead of k_gl_iter
@@ -96,8 +100,8 @@ static Plan make_plan(nsb_handle_s* h, bool tf = false) {
     Plan p;
     p.tw = h->d_tw; p.mel_w = h->d_mel_w; p.mel_lo = h->d_mel_lo; p.mel_n = h->d_mel_n; p.mel_ptr = h->d_mel_ptr;
     p.n_fft = h->n_fft; p.hop = h->hop; p.win_len = h->win; p.num_mels = h->num_mels;
-    if (tf) { p.win = h->d_win_tf; p.lo = 0; p.origin = 0; p.norm_wss = 0; p.prune = h->prune_tf; }
-    else { p.win = h->d_win; p.lo = h->lo; p.origin = h->n_fft / 2; p.norm_wss = 1; p.prune = h->prune; }
+    if (tf) { p.win = h->d_win_tf; p.rinv = h->d_rinv_tf; p.lo = 0; p.origin = 0; p.norm_wss = 0; p.prune = h->prune_tf; }
+    else { p.win = h->d_win; p.rinv = h->d_rinv; p.lo = h->lo; p.origin = h->n_fft / 2; p.norm_wss = 1; p.prune = h->prune; }
     return p;
 }
 
@@ -141,6 +145,13 @@ static size_t synth_smem(int hop, int H) {
     return fl * sizeof(float) + sizeof(float2) * kScratchF2 * kWarpsPerCta;
 }
 static size_t gl_smem(int hop, int H) { return synth_smem(hop, H) + 64 + 16; }   // + neighbour progress flags + rinv padding   // + neighbour progress flags
+// k_gl_stream: twiddles | window table (the part the pruned transform touches) | rinv | ring of 8 groups | counters | scratch
+static size_t stream_smem(int hop, int win, int a, int colours, int prune) {
+    const int kfirst0 = (a - win >= 0) ? (a - win) / hop + 1 : -((win - a - 1) / hop + 1) + 1, klast0 = (hop - 1 + a) / hop;
+    const int back = klast0 - kfirst0 < colours ? klast0 - kfirst0 : colours;
+    size_t fl = 2 * kTwF2 + (prune == 0 ? kNfft : 1024) + (((size_t)(kWarpsPerCta * colours + back) * hop + 3) & ~(size_t)3) + 16;
+    return fl * sizeof(float) + sizeof(float2) * kScratchF2 * kWarpsPerCta;
+}
 static const size_t kSmemPerCtaTwoResident = (227 * 1024) / 2 - 1024;   // two CTAs per SM, 1 KB reserved each
 
 static int max_tile_hops(const nsb_handle_s* h, bool tf = false) {
@@ -188,10 +199,10 @@ extern "C" int nsb_destroy(nsb_handle_t h) {
     if (h->copy_in) cudaStreamDestroy(h->copy_in);
     if (h->copy_out) cudaStreamDestroy(h->copy_out);
     if (h->desc_done) cudaEventDestroy(h->desc_done);
-    cudaFree(h->d_tw); cudaFree(h->d_win); cudaFree(h->d_win_tf); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo); cudaFree(h->d_mel_n); cudaFree(h->d_mel_ptr);
+    cudaFree(h->d_tw); cudaFree(h->d_win); cudaFree(h->d_win_tf); cudaFree(h->d_rinv); cudaFree(h->d_rinv_tf); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo); cudaFree(h->d_mel_n); cudaFree(h->d_mel_ptr);
     cudaFree(h->d_status);
     if (h->h_desc) cudaFreeHost(h->h_desc);
-    h->d_desc.release(); h->ws_mag.release(); h->ws_y0.release(); h->ws_y1.release();
+    h->d_desc.release(); h->d_trace.release(); h->ws_mag.release(); h->ws_y0.release(); h->ws_y1.release();
     h->ws_in.release(); h->ws_in2.release(); h->ws_out.release(); h->ws_out2.release();
     delete h;
     return NSB_OK;
@@ -256,6 +267,22 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
         CUB(cudaMemcpy(h->d_win_tf, wt.data(), sizeof(float) * kNfft, cudaMemcpyHostToDevice));
         h->prune_tf = (win <= 1024) ? 2 : 0;
         h->colours_tf = h->colours;
+        // reciprocal of the interior window sum per offset inside a hop, in the arithmetic the kernels use
+        // (float fmaf chain over the covering frames, IEEE division), times 1/n_fft of the unnormalised inverse FFT
+        std::vector<float> ri(hop), rt(hop);
+        for (int geo = 0; geo < 2; ++geo) {
+            const int lo_g = geo ? 0 : h->lo, a = geo ? 0 : kNfft / 2 - h->lo;
+            const std::vector<float>& wg = geo ? wt : w;
+            for (int j = 0; j < hop; ++j) {
+                float sum = 0.f;
+                for (int idx = (j + a) % hop; idx < win; idx += hop) sum = std::fmaf(wg[lo_g + idx], wg[lo_g + idx], sum);
+                (geo ? rt : ri)[j] = ((geo == 0 && sum > 1.17549435e-38f) ? 1.0f / sum : 1.0f) * (1.0f / (float)kNfft);
+            }
+        }
+        CUB(cudaMalloc(&h->d_rinv, sizeof(float) * hop));
+        CUB(cudaMemcpy(h->d_rinv, ri.data(), sizeof(float) * hop, cudaMemcpyHostToDevice));
+        CUB(cudaMalloc(&h->d_rinv_tf, sizeof(float) * hop));
+        CUB(cudaMemcpy(h->d_rinv_tf, rt.data(), sizeof(float) * hop, cudaMemcpyHostToDevice));
     }
     // sparse mel rows
     {
@@ -296,6 +323,18 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
     SET((k_synth<SRC_MAGZERO, 0>), ss);  SET((k_synth<SRC_MAGZERO, 2>), ss);
     SET((k_gl_iter<1, true, false>), gs); SET((k_gl_iter<1, false, false>), gs); SET((k_gl_iter<0, false, false>), gs);
     SET((k_gl_iter<2, false, true>), gs); SET((k_gl_iter<0, false, true>), gs);
+    SET((k_gl_stream<1, true, false>), gs); SET((k_gl_stream<1, false, false>), gs); SET((k_gl_stream<0, false, false>), gs);
+    SET((k_gl_stream<2, false, true>), gs); SET((k_gl_stream<0, false, true>), gs);
+    {
+        // two CTAs per SM is what the shared-memory layout of k_gl_stream is sized for; ask the runtime instead of trusting the sum
+        int nb = 0;
+        const size_t sm = stream_smem(hop, win, kNfft / 2 - h->lo, h->colours, h->prune);
+        cudaError_t oe = h->defcfg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gl_stream<1, true, false>, kThreads, sm)
+                       : h->prune == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gl_stream<1, false, false>, kThreads, sm)
+                                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gl_stream<0, false, false>, kThreads, sm);
+        if (oe != cudaSuccess) { cudaGetLastError(); nb = 1; }
+        h->stream_ctas_per_sm = nb < 1 ? 1 : (nb > 2 ? 2 : nb);
+    }
 #undef SET
 #undef CUB
     *out = h;
@@ -321,6 +360,25 @@ extern "C" int nsb_set_host_chunks(nsb_handle_t h, int32_t n) {
 extern "C" int nsb_set_generic_iteration(nsb_handle_t h, int32_t on) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");
     h->use_generic_iter = on;
+    return NSB_OK;
+}
+// profiling hook: per-CTA (SM id, start ns, end ns) of the LAST k_gl_stream launch; returns the number of CTAs written
+extern "C" int nsb_stream_trace(nsb_handle_t h, int32_t enable, uint64_t* out, int32_t max_ctas) {
+    if (!h) return -1;
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaSetDevice(h->device);
+    h->trace_on = enable;
+    if (!out || !h->d_trace.p || h->trace_grid <= 0) return 0;
+    const int n = h->trace_grid < max_ctas ? h->trace_grid : max_ctas;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpy(out, h->d_trace.p, sizeof(uint64_t) * 3 * n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return n;
+}
+extern "C" int nsb_set_stream_grid(nsb_handle_t h, int32_t n) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    if (n <= -100) { h->stream_sync_mode = -n - 100; return NSB_OK; }     // experiment hook: -100 / -101 / -102 = barrier mode 0 / 1 / 2
+    if (n < 0) return fail(NSB_ERR_INVALID, "stream grid %d < 0", n);
+    h->user_stream_grid = n;
     return NSB_OK;
 }
 extern "C" int nsb_set_tile_hops(nsb_handle_t h, int32_t t) {
@@ -376,6 +434,7 @@ struct Desc {
     long long total_samples = 0;
     int total_frames = 0;
     int total_tiles = 0;
+    int total_groups = 0;
 };
 
 static int upload_desc(nsb_handle_s* h, cudaStream_t st, const std::vector<int>& frames, const std::vector<long long>& samples,
@@ -387,7 +446,8 @@ static int upload_desc(nsb_handle_s* h, cudaStream_t st, const std::vector<int>&
     const size_t n_int = 2 * (size_t)(B + 1);
     const size_t off_samp = (n_int * sizeof(int) + 7) & ~(size_t)7;
     const size_t off_tutt = off_samp + (size_t)(B + 1) * sizeof(long long);
-    const size_t bytes = off_tutt + (size_t)(n_tiles > 0 ? n_tiles : 1) * sizeof(int);
+    const size_t off_goff = off_tutt + (size_t)(n_tiles > 0 ? n_tiles : 1) * sizeof(int);
+    const size_t bytes = off_goff + (size_t)(B + 1) * sizeof(int);
     if (bytes > h->h_desc_cap) {
         if (h->h_desc) { CU(cudaEventSynchronize(h->desc_done)); cudaFreeHost(h->h_desc); h->h_desc = nullptr; h->h_desc_cap = 0; }
         CU(cudaHostAlloc(&h->h_desc, bytes * 2, cudaHostAllocDefault));
@@ -402,7 +462,8 @@ static int upload_desc(nsb_handle_s* h, cudaStream_t st, const std::vector<int>&
     int* to = fo + (B + 1);
     long long* so = reinterpret_cast<long long*>(hb + off_samp);
     int* tu = reinterpret_cast<int*>(hb + off_tutt);
-    fo[0] = 0; to[0] = 0; so[0] = 0;
+    int* go = reinterpret_cast<int*>(hb + off_goff);
+    fo[0] = 0; to[0] = 0; so[0] = 0; go[0] = 0;
     for (int b = 0; b < B; ++b) {
         long long nf = (long long)fo[b] + frames[b];
         if (nf > 2000000000LL) return fail(NSB_ERR_INVALID, "batch too large: more than 2e9 frames");
@@ -412,8 +473,11 @@ static int upload_desc(nsb_handle_s* h, cudaStream_t st, const std::vector<int>&
         to[b + 1] = to[b] + tiles;
         for (int t = to[b]; t < to[b + 1]; ++t) tu[t] = b;       // tile -> utterance (saves a binary search per tile on the GPU)
         so[b + 1] = so[b] + samples[b];
+        const long long hops_b = (samples[b] + h->hop - 1) / h->hop;
+        go[b + 1] = go[b] + (int)((hops_b + h->colours - 1) / h->colours);    // <= frames: cannot overflow after the check above
     }
     h->h_frame_off.assign(fo, fo + B + 1); h->h_tile_off.assign(to, to + B + 1); h->h_samp_off.assign(so, so + B + 1);
+    h->h_group_off.assign(go, go + B + 1);
     CU(cudaMemcpyAsync(h->d_desc.p, h->h_desc, bytes, cudaMemcpyHostToDevice, st));
     CU(cudaEventRecord(h->desc_done, st));
     const char* db = reinterpret_cast<const char*>(h->d_desc.p);
@@ -421,8 +485,10 @@ static int upload_desc(nsb_handle_s* h, cudaStream_t st, const std::vector<int>&
     d->dev.tile_off = d->dev.frame_off + (B + 1);
     d->dev.samp_off = reinterpret_cast<const long long*>(db + off_samp);
     d->dev.tile_utt = reinterpret_cast<const int*>(db + off_tutt);
+    d->dev.group_off = reinterpret_cast<const int*>(db + off_goff);
     d->dev.batch = B;
-    d->dev.frame_base = 0; d->dev.tile_base = 0; d->dev.utt_base = 0;
+    d->dev.frame_base = 0; d->dev.tile_base = 0; d->dev.utt_base = 0; d->dev.group_base = 0;
+    d->total_groups = go[B];
     d->total_frames = fo[B];
     d->total_tiles = to[B];
     d->total_samples = so[B];
@@ -625,10 +691,48 @@ extern "C" int nsb_istft_tf(nsb_handle_t h, const float* spec, int32_t layout, c
 }
 
 // `iters` Griffin-Lim iterations on the (sub-)batch B; y ping-pongs between ws_y0 / ws_y1, `cur` says which holds y
-static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int H, int& cur, int iters, cudaStream_t st,
+static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int total_groups, int H, int& cur, int iters, cudaStream_t st,
                          bool tf = false, float inv_thr = 0.f) {
     float* y[2] = {reinterpret_cast<float*>(h->ws_y0.p), reinterpret_cast<float*>(h->ws_y1.p)};
     if (total_tiles <= 0) return NSB_OK;
+    if (h->use_generic_iter == 0) {
+        // the production path: streaming kernel, CTA i owns the contiguous group range [i*N/n, (i+1)*N/n)
+        GlStreamParams S{};
+        S.plan = make_plan(h, tf); S.batch = B; S.mag = reinterpret_cast<const float*>(h->ws_mag.p);
+        S.colours = h->colours; S.total_groups = total_groups; S.status = h->d_status; S.inv_thr = inv_thr;
+        S.sync_mode = h->stream_sync_mode;
+        S.trace = nullptr;
+        const size_t smem = stream_smem(h->hop, h->win, S.plan.origin - S.plan.lo, h->colours, S.plan.prune);
+        const int ctas = h->stream_ctas_per_sm * h->num_sms;
+        // the stream: every utterance's groups + one end-halo group each; CTA n takes [n*NV/grid, (n+1)*NV/grid) + its halo.
+        // Short batches: at most 7 groups per CTA, so a range and its halo are one round of the 8 warps.
+        const long long NV = (long long)total_groups + B.batch;
+        long long want = (NV + 6) / 7;
+        if (h->user_tile_hops > 0) want = (NV + h->user_tile_hops / h->colours - 1) / (h->user_tile_hops / h->colours);   // tests: ranges of that many groups
+        if (h->user_stream_grid > 0) want = h->user_stream_grid;
+        if (want > NV) want = NV;
+        if (want < 1) want = 1;
+        const int grid = (int)((h->user_tile_hops > 0 || h->user_stream_grid > 0 || want < ctas) ? want : ctas);
+        if (h->trace_on) {
+            int rc = h->d_trace.reserve(sizeof(unsigned long long) * 3 * (size_t)grid);
+            if (rc) return rc;
+            S.trace = reinterpret_cast<unsigned long long*>(h->d_trace.p);
+            h->trace_grid = grid;
+        }
+        for (int it = 0; it < iters; ++it) {
+            S.y_in = y[cur]; S.y_out = y[cur ^ 1];
+            if (tf) {
+                if (S.plan.prune == 2) NSB_LAUNCH((k_gl_stream<2, false, true>), grid, kThreads, smem, st, S);
+                else NSB_LAUNCH((k_gl_stream<0, false, true>), grid, kThreads, smem, st, S);
+            } else if (h->defcfg) NSB_LAUNCH((k_gl_stream<1, true, false>), grid, kThreads, smem, st, S);
+            else if (h->prune == 1) NSB_LAUNCH((k_gl_stream<1, false, false>), grid, kThreads, smem, st, S);
+            else NSB_LAUNCH((k_gl_stream<0, false, false>), grid, kThreads, smem, st, S);
+            int rc = check_launch(h, "k_gl_stream");
+            if (rc) return rc;
+            cur ^= 1;
+        }
+        return NSB_OK;
+    }
     if (h->use_generic_iter == 1 && !tf) {
         SynthParams P{};
         P.plan = make_plan(h); P.batch = B; P.mag = reinterpret_cast<const float*>(h->ws_mag.p);
@@ -668,7 +772,7 @@ extern "C" int nsb_griffin_lim_iterate(nsb_handle_t h, int32_t iters, void* stre
     std::lock_guard<std::mutex> lk(h->mu);
     if (!h->gl.valid) return fail(NSB_ERR_INVALID, "no device-resident Griffin-Lim state (call nsb_griffin_lim with NSB_DEVICE first)");
     CU(cudaSetDevice(h->device));
-    return gl_iterations(h, h->gl.batch, h->gl.total_tiles, h->gl.tile_hops, h->gl.cur, iters, pick_stream(h, stream), h->gl.tf, h->gl.inv_thr);
+    return gl_iterations(h, h->gl.batch, h->gl.total_tiles, h->gl.total_groups, h->gl.tile_hops, h->gl.cur, iters, pick_stream(h, stream), h->gl.tf, h->gl.inv_thr);
 }
 
 extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout, const int32_t* n_frames, int32_t batch,
@@ -766,6 +870,8 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
         Batch B = d.dev;
         B.frame_off += b0; B.tile_off += b0; B.samp_off += b0; B.batch = b1 - b0;
         B.frame_base = h->h_frame_off[b0]; B.tile_base = h->h_tile_off[b0]; B.utt_base = b0;
+        B.group_off += b0; B.group_base = h->h_group_off[b0];
+        const int n_groups_c = h->h_group_off[b1] - h->h_group_off[b0];
         const int n_frames_c = h->h_frame_off[b1] - h->h_frame_off[b0];
         const int n_tiles_c = h->h_tile_off[b1] - h->h_tile_off[b0];
         if (space == NSB_HOST) CUE(cudaStreamWaitEvent(st, ev_in[c], 0));
@@ -795,7 +901,7 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
 
         cur = 0;
         const float inv_thr = (float)(1.0 / (2.0e-8 * gscale));      // est / max(1e-8, |est|) on slots that hold 2*g*est
-        if ((rc = gl_iterations(h, B, n_tiles_c, H, cur, iters, st, tf, inv_thr))) { cleanup(); return rc; }
+        if ((rc = gl_iterations(h, B, n_tiles_c, n_groups_c, H, cur, iters, st, tf, inv_thr))) { cleanup(); return rc; }
         const float* y_fin = reinterpret_cast<const float*>(cur ? h->ws_y1.p : h->ws_y0.p);
 
         const long long s_base = h->h_samp_off[b0], s_cnt = h->h_samp_off[b1] - s_base;
@@ -817,7 +923,7 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
     }
     // device-resident state for nsb_griffin_lim_iterate: the whole batch
     h->gl.valid = true; h->gl.batch = d.dev; h->gl.total_frames = d.total_frames; h->gl.tile_hops = H;
-    h->gl.total_tiles = d.total_tiles; h->gl.cur = cur; h->gl.tf = tf; h->gl.inv_thr = (float)(1.0 / (2.0e-8 * gscale));
+    h->gl.total_tiles = d.total_tiles; h->gl.total_groups = d.total_groups; h->gl.cur = cur; h->gl.tf = tf; h->gl.inv_thr = (float)(1.0 / (2.0e-8 * gscale));
     if (space == NSB_HOST) {
         CUE(cudaStreamSynchronize(h->copy_out));
         cleanup();

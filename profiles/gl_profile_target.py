@@ -13,6 +13,8 @@ batch = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 T = 1000
 hparams.load()
 h = audio._handle()
+if os.environ.get('NSB_SYNC_MODE'):
+    h.set_stream_grid(-100 - int(os.environ['NSB_SYNC_MODE']))
 spec = torch.rand((batch, T, 1025), device="cuda")
 out = torch.empty(batch * h.num_samples(T), dtype=torch.float64, device="cuda")
 st = torch.cuda.current_stream().cuda_stream

@@ -11,26 +11,29 @@ hparams.load()
 h = audio._handle()
 T = 1000
 st = torch.cuda.current_stream().cuda_stream
-cases = [(64, 0, 0), (64, 0, 1), (64, 21, 0), (8, 0, 0), (1, 0, 0), (256, 0, 0)]
+cases = [(64, 0, 0), (64, 0, 2), (64, 0, 1), (8, 0, 0), (8, 0, 2), (1, 0, 0), (1, 0, 2), (256, 0, 0), (256, 0, 2)]
 if len(sys.argv) > 1:
     cases = [tuple(int(v) for v in c.split(",")) for c in sys.argv[1:]]
 for batch, tile, generic in cases:
-    spec = torch.rand((batch, T, 1025), device="cuda")
-    out = torch.empty(batch * h.num_samples(T), dtype=torch.float64, device="cuda")
-    h.set_tile_hops(tile)
-    h.set_generic_iteration(generic)
-    h.griffin_lim(spec, _lib.FRAME_MAJOR, [T] * batch, out, seed=1, iters=2, flags=3, out_dtype=_lib.F64, space=_lib.DEVICE, stream=st)
-    h.griffin_lim_iterate(20, st)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 100
-    e0.record()
-    h.griffin_lim_iterate(n, st)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
-    print("batch %4d tile %2d %s: %.4f ms/iter  %.2f ns/frame-iter  -> %.0f audio-s/s at 61 passes" % (
-        batch, tile, {0: "k_gl_iter ", 1: "k_synth<Y>"}[generic], ms, ms * 1e6 / (batch * T), batch * T * 0.0125 / (ms * 1e-3 * 61)), flush=True)
-    del spec, out
+  for sm in ((0, 1, 2) if generic == 0 else (0,)):
+      h.set_stream_grid(-100 - sm)
+      spec = torch.rand((batch, T, 1025), device="cuda")
+      out = torch.empty(batch * h.num_samples(T), dtype=torch.float64, device="cuda")
+      h.set_tile_hops(tile)
+      h.set_generic_iteration(generic)
+      h.griffin_lim(spec, _lib.FRAME_MAJOR, [T] * batch, out, seed=1, iters=2, flags=3, out_dtype=_lib.F64, space=_lib.DEVICE, stream=st)
+      h.griffin_lim_iterate(20, st)
+      torch.cuda.synchronize()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      n = 100
+      e0.record()
+      h.griffin_lim_iterate(n, st)
+      e1.record()
+      torch.cuda.synchronize()
+      ms = e0.elapsed_time(e1) / n
+      print("sync %d batch %4d tile %2d %s: %.4f ms/iter  %.2f ns/frame-iter  -> %.0f audio-s/s at 61 passes" % (
+          sm, batch, tile, {0: "k_gl_stream", 1: "k_synth<Y> ", 2: "k_gl_iter  "}[generic], ms, ms * 1e6 / (batch * T), batch * T * 0.0125 / (ms * 1e-3 * 61)), flush=True)
+      del spec, out
 h.set_tile_hops(0)
 h.set_generic_iteration(0)
+h.set_stream_grid(-100)

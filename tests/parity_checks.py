@@ -220,3 +220,49 @@ def check_tf_twin_vs_oracle(over):
         audio.inv_spectrogram_tensorflow(np.zeros((4, 513), np.float32))
     assert ao.rel_l2(audio._db_to_amp_tensorflow(S[0] * 40 - 20), tfo._db_to_amp_tensorflow(S[0] * 40 - 20)) < 1e-6
     assert ao.rel_l2(audio._denormalize_tensorflow(S[0] * 1.2 - 0.1), tfo._denormalize_tensorflow(S[0] * 1.2 - 0.1, ohp)) < 1e-6
+
+
+def check_streaming_rounds(T=150, iters=2, tf=False):
+    """k_gl_stream on long pieces: one CTA walks many rounds of its 8-group ring (slot reuse, wrap-around of the
+    accumulate, the warp-7 -> warp-0 dependency across rounds), against the oracle and bit-for-bit against every
+    other partition of the same batch and against the older kernels."""
+    ohp = _load(min_level_db=-100)
+    h = audio._handle()
+    rs = np.random.RandomState(11)
+    Ts = [T, 2, 37, T // 2 + 3]
+    specs = [rs.rand(t, 1025).astype(np.float32) for t in Ts]
+    packed = np.concatenate(specs)
+    flags = _lib.GL_DENORMALIZE | (_lib.GL_TF_TWIN if tf else _lib.GL_DEEMPHASIS)
+    nsamp = [h.num_samples_tf(t) if tf else h.num_samples(t) for t in Ts]
+    phases = None if tf else np.concatenate([np.exp(2j * np.pi * rs.rand(t, 1025)).astype(np.complex64) for t in Ts])
+
+    def run():
+        out = np.empty(sum(nsamp), dtype=np.float32 if tf else np.float64)
+        h.griffin_lim(packed, _lib.FRAME_MAJOR, Ts, out, init_phase=phases, iters=iters, flags=flags,
+                      out_dtype=_lib.F32 if tf else _lib.F64)
+        return out
+    outs = {}
+    try:
+        for grid in (1, 2, 3, 0):
+            h.set_stream_grid(grid)
+            outs["grid%d" % grid] = run()
+        h.set_stream_grid(1)
+        h.set_tile_hops(12)
+        outs["piece3"] = run()
+        h.set_tile_hops(0)
+        h.set_generic_iteration(2)           # the tile kernel adds in the same colour order: identical bits
+        outs["tile"] = run()
+    finally:
+        h.set_stream_grid(0); h.set_tile_hops(0); h.set_generic_iteration(0)
+    ref = outs.pop("grid1")
+    for name, o in outs.items():
+        np.testing.assert_array_equal(o, ref, err_msg=name)
+    off = 0
+    for i, (t, n) in enumerate(zip(Ts, nsamp)):
+        if tf:
+            want = tfo.inv_spectrogram_tensorflow(specs[i], ohp, iters=iters)
+        else:
+            ph = phases[sum(Ts[:i]):sum(Ts[:i + 1])]
+            want = ao.inv_spectrogram(specs[i].T, ohp, angles=ph.T, iters=iters)
+        assert ao.snr_db(ref[off:off + n], want) > 60, (i, t)
+        off += n

@@ -15,7 +15,7 @@ from oracle import audio_oracle as ao
 
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
 EMU_SO = os.path.join(EMU_DIR, "_build", "libnspeech_b200_emu.so")
-SOURCES = [os.path.join(ROOT, "nspeech_b200", "csrc", f) for f in ("nspeech_b200.cu", "kernels.cuh", "frame_fft.cuh", "fft_core.cuh")] + \
+SOURCES = [os.path.join(ROOT, "nspeech_b200", "csrc", f) for f in ("nspeech_b200.cu", "kernels.cuh", "frame_fft.cuh", "fft_core.cuh", "gl_iter.cuh", "gl_stream.cuh")] + \
           [os.path.join(EMU_DIR, f) for f in ("cuda_emu.h", "emu_runtime.cpp")]
 
 
@@ -72,6 +72,11 @@ def test_ragged_batch_and_tiles(emu):
 @pytest.mark.parametrize("over", pc.CONFIGS[:2])
 def test_tf_twin_vs_oracle(emu, over):
     pc.check_tf_twin_vs_oracle(over)
+
+
+@pytest.mark.parametrize("tf", [False, True])
+def test_streaming_rounds(emu, tf):
+    pc.check_streaming_rounds(T=110, iters=2, tf=tf)
 
 
 def test_errors_and_edge_cases(emu):

@@ -45,6 +45,11 @@ def test_tf_twin_vs_oracle(over):
     pc.check_tf_twin_vs_oracle(over)
 
 
+@pytest.mark.parametrize("tf", [False, True])
+def test_streaming_rounds(tf):
+    pc.check_streaming_rounds(T=700, iters=6, tf=tf)
+
+
 def test_errors_and_edge_cases():
     pc.check_errors_and_edge_cases()
 
