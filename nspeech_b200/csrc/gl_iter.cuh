@@ -29,6 +29,8 @@ __device__ __forceinline__ void cp_async_wait_all() {}
 __device__ __forceinline__ int flag_load(const int* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 __device__ __forceinline__ void flag_store(int* p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 __device__ __forceinline__ void spin_pause() { std::this_thread::yield(); }
+__device__ __forceinline__ int gflag_load(const int* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ void gflag_store(int* p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 __device__ __forceinline__ bool warp_any(bool p) {
     auto* c = nsb_emu::g_ctx;
     const int w = threadIdx.x >> 5;
@@ -59,6 +61,12 @@ __device__ __forceinline__ void flag_store(int* p, int v) {
     asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
 __device__ __forceinline__ void spin_pause() { __nanosleep(32); }
+__device__ __forceinline__ int gflag_load(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void gflag_store(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ bool warp_any(bool p) { return __any_sync(0xffffffffu, p); }
 #endif
 
@@ -81,6 +89,14 @@ struct GlParams {
     float* y_out;
     const float* mag;        // permuted, pre-scaled magnitudes [frames][kMagPitch]
     int tile_hops, colours, total_tiles;
+    // One launch runs `iters` Griffin-Lim iterations: the work items (iteration n, tile t), n-major, are handed out by a
+    // global counter; item (n, t) may start once the tiles t-1, t, t+1 of iteration n-1 are stored (per-tile counters
+    // `done`, release/acquire at GPU scope).  y ping-pongs between ybuf[0] and ybuf[1]: iteration n reads
+    // ybuf[(cur0 + n) & 1] and writes the other one (y_in / y_out above are unused by this kernel).
+    float* ybuf[2];
+    int cur0, iters;
+    int* item_counter;       // [1], zeroed by the host before the launch
+    int* done;               // [total_tiles], zeroed by the host before the launch: iterations finished by each tile
     float inv_thr;           // TF twin: the clamp of est / max(1e-8, |est|) (audio.py:101) for register slots, which hold
                              // 2 * g * est (g = magnitude pre-scale): 1 / (2 * g * 1e-8)
     int* status;
@@ -105,7 +121,7 @@ __device__ __forceinline__ void renorm_fast(c2& z, float S, bool& zero) {
 // normalise the finished tile by the summed squared window and store it (all threads of the CTA)
 // rinv_s[j] already contains 1 / (n_fft * window-sum) for the interior (all covering frames exist).
 template <bool DEFCFG>
-__device__ __noinline__ void gl_store_tile(const GlParams& P, int tile_g, const float* acc, const float* win_s, const float* rinv_s,
+__device__ __noinline__ void gl_store_tile(const GlParams& P, float* y_out, int tile_g, const float* acc, const float* win_s, const float* rinv_s,
                                            int hop, int win, int lo, int H, bool& bad) {
     const int a = P.plan.origin - lo;
     const int b = __ldg(P.batch.tile_utt + tile_g) - P.batch.utt_base;
@@ -116,7 +132,7 @@ __device__ __noinline__ void gl_store_tile(const GlParams& P, int tile_g, const 
     const int n_hops = (int)((L + hop - 1) / hop);
     const int h0 = tile * H, h1 = min(h0 + H, n_hops);
     const long long o0 = s_off + (long long)h0 * hop;
-    float* yo = P.y_out + o0;
+    float* yo = y_out + o0;
     const int n_out = (int)(min((long long)h1 * hop, L) - (long long)h0 * hop);
     // interior tile: every sample is covered by all of its ceil(win/hop) frames -> no per-sample frame tests
     // (without window-sum normalisation every tile is "interior": rinv_s is the constant 1/n_fft)
@@ -202,7 +218,30 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
     }
     bool bad = false;
 
-    for (int tile_g = P.batch.tile_base + blockIdx.x; tile_g < P.batch.tile_base + P.total_tiles; tile_g += gridDim.x) {
+    // Dynamic scheduling of (iteration, tile) items from one global counter.  SMs do not all run at the same speed and
+    // the older of an SM's two CTAs gets the issue slots first (per-CTA timelines: profiles/r1/trace_*.txt): a static
+    // round-robin left SMs idle at the end of EVERY iteration's launch.  Here a CTA that runs out of tiles of iteration
+    // n simply starts on iteration n+1 - only the last iteration has a tail, and there is no launch gap and no table
+    // reload between iterations.
+    const long long total_items = (long long)P.iters * P.total_tiles;
+    int item_it = 0;
+    if (threadIdx.x == 0) progress[8] = atomicAdd(P.item_counter, 1);
+    __syncthreads();
+    for (long long item = progress[8]; item < total_items; item = progress[8 + (++item_it & 1)]) {
+        const int n_it = (int)(item / P.total_tiles);
+        const int tile_l = (int)(item - (long long)n_it * P.total_tiles);
+        const int tile_g = P.batch.tile_base + tile_l;
+        const float* y_in = P.ybuf[(P.cur0 + n_it) & 1];
+        float* y_out = P.ybuf[(P.cur0 + n_it + 1) & 1];
+        if (threadIdx.x == 0) {
+            progress[8 + ((item_it + 1) & 1)] = atomicAdd(P.item_counter, 1);     // the next item, read after this tile's barriers
+            if (n_it > 0) {
+                // my frames read hops of the tiles t-1, t, t+1 as iteration n-1 left them; my store overwrites what those
+                // tiles READ in iteration n-1 - both hazards are covered by waiting for their iteration n-1 to be stored
+                const int ta = tile_l > 0 ? tile_l - 1 : 0, tb = tile_l + 1 < P.total_tiles ? tile_l + 1 : tile_l;
+                for (int t = ta; t <= tb; ++t) while (gflag_load(P.done + t) < n_it) spin_pause();
+            }
+        }
         const int b = __ldg(P.batch.tile_utt + tile_g) - P.batch.utt_base;
         const int tile = tile_g - __ldg(P.batch.tile_off + b);
         const int f_off = __ldg(P.batch.frame_off + b);
@@ -226,10 +265,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
             float4* a4 = reinterpret_cast<float4*>(acc);            // the tile buffer is 16-byte aligned and a multiple of 4 long (+pad)
             for (int i = threadIdx.x; i < (n_out + 3) / 4; i += kThreads) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (threadIdx.x < 16) progress[threadIdx.x] = 0;
+        if (threadIdx.x < kWarpsPerCta) progress[threadIdx.x] = 0;
         __syncthreads();
 
         bool staged = false;                         // this frame's samples were cp.async'ed into the scratch tile already
+        int stage_off = 0;                           // ... shifted by this many floats (16-byte alignment of the copies)
         for (int s = 0; s < C; ++s) {
             const int k = kg + s;
             const bool active = (k >= 0 && k <= k_max);        // warp-uniform
@@ -246,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                     // samples were staged by the previous frame of this warp (see below): window them from shared memory
                     cp_async_wait_all();
                     __syncwarp();
-                    const float* stage = reinterpret_cast<const float*>(scratch);
+                    const float* stage = reinterpret_cast<const float*>(scratch) + stage_off;
 #pragma unroll
                     for (int t = 0; t < 32; ++t) {
                         if (t >= 8 && t < 24) z[t] = p_mul(mk2(stage[64 * t + lane], stage[64 * t + 32 + lane]), mk2(win_s[64 * t + lane], win_s[64 * t + 32 + lane]));
@@ -254,8 +294,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                     }
                     __syncwarp();
                 } else {
-                    load_frame<false, PRUNE>(z, P.y_in + s_off, L, (long long)k * hop - origin, win_s, lane, 0.f,
-                                             reinterpret_cast<float*>(scratch));
+                    load_frame<false, PRUNE, true>(z, y_in + s_off, L, (long long)k * hop - origin, win_s, lane, 0.f,
+                                                   reinterpret_cast<float*>(scratch));
                 }
                 fwd_phase1(z, lane, scratch, tw_s);
                 __syncwarp();
@@ -375,10 +415,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                 if (PRUNE == 1 && s + 1 < C && k + 1 <= k_max) {
                     const long long nstart = (long long)(k + 1) * hop - origin;
                     if (nstart + 512 >= 0 && nstart + 1536 <= L && ((s_off + nstart) & 1) == 0) {
-                        const float* src = P.y_in + s_off + nstart + 512 + 2 * lane;
-                        float* dst = reinterpret_cast<float*>(scratch) + 512 + 2 * lane;
+                        // 16-byte L2-only copies (y is rewritten by other SMs inside this launch: nothing of it may sit in L1);
+                        // the frame starts on an 8-byte boundary, so copy from the 16-byte boundary at or below it
+                        const float* src0 = y_in + s_off + nstart + 512;
+                        stage_off = (int)((reinterpret_cast<uintptr_t>(src0) >> 2) & 3);        // 0 or 2
+                        const float* src = src0 - stage_off + 4 * lane;
+                        float* dst = reinterpret_cast<float*>(scratch) + 512 + 4 * lane;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) cp_async8(dst + 64 * j, src + 64 * j);
+                        for (int j = 0; j < 8; ++j) cp_async16(dst + 128 * j, src + 128 * j);
+                        if (lane == 0) cp_async16(dst + 1024, src + 1024);
                         staged = true;
                     }
                 }
@@ -440,8 +485,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
             if (lane == 0) flag_store(progress + warp, s + 1);
         }
         __syncthreads();
-        gl_store_tile<DEFCFG>(P, tile_g, acc, win_s, rinv_s, hop, win, lo, H, bad);
-        __syncthreads();                             // acc and progress are reused by the next tile
+        gl_store_tile<DEFCFG>(P, y_out, tile_g, acc, win_s, rinv_s, hop, win, lo, H, bad);
+        __syncthreads();                             // acc and progress are reused by the next tile; every thread's stores are issued
+        if (threadIdx.x == 0) { __threadfence(); gflag_store(P.done + tile_l, n_it + 1); }
     }
     if (bad) atomicOr(P.status, 1);
 }

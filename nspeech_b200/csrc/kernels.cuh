@@ -84,18 +84,23 @@ __device__ __forceinline__ int reflect_index(int i, int L) {
 
 // ---- frame load: windowed samples of frame k into the lane registers -----------------------
 // re[t] = w[n] * s(start + n), n = 64 t + lane ; im[t] likewise with n + 32.   s = (pre-emphasised) signal
-template <bool PREEMPH>
+// COHERENT: the signal is rewritten by other SMs inside the same launch (iteration-fused Griffin-Lim): read it from L2
+// (ld.global.cg), never through the non-coherent L1 path
+template <bool COHERENT>
+__device__ __forceinline__ float ld_sig(const float* p) { return COHERENT ? __ldcg(p) : __ldg(p); }
+
+template <bool PREEMPH, bool COHERENT = false>
 __device__ __forceinline__ float sample_at(const float* __restrict__ x, int L, int i, float p) {
     int m = reflect_index(i, L);
-    float v = __ldg(x + m);
-    if (PREEMPH) { if (m > 0) v = fmaf(-p, __ldg(x + m - 1), v); }
+    float v = ld_sig<COHERENT>(x + m);
+    if (PREEMPH) { if (m > 0) v = fmaf(-p, ld_sig<COHERENT>(x + m - 1), v); }
     return v;
 }
 
 // `stage` is the warp's scratch tile (>= 2048 floats): frames that touch the utterance's ends (reflect padding)
 // are gathered through it by a rolled loop, so the rare path costs a few dozen instructions of code instead of
 // an unrolled copy of the index arithmetic per register
-template <bool PREEMPH, int PRUNE>
+template <bool PREEMPH, int PRUNE, bool COHERENT = false>
 __device__ __forceinline__ void load_frame(c2 (&z)[32], const float* __restrict__ x, long long L, long long start,
                                            const float* __restrict__ win_s, int lane, float p, float* stage) {
     constexpr int t0 = PruneRange<PRUNE>::t0, t1 = PruneRange<PRUNE>::t1;
@@ -106,17 +111,17 @@ __device__ __forceinline__ void load_frame(c2 (&z)[32], const float* __restrict_
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
             if (t >= t0 && t < t1) {
-                float a = __ldg(xs + 64 * t), b = __ldg(xs + 64 * t + 32);
+                float a = ld_sig<COHERENT>(xs + 64 * t), b = ld_sig<COHERENT>(xs + 64 * t + 32);
                 if (PREEMPH) {
-                    a = fmaf(-p, __ldg(xs + 64 * t - 1), a);
-                    b = fmaf(-p, __ldg(xs + 64 * t + 31), b);
+                    a = fmaf(-p, ld_sig<COHERENT>(xs + 64 * t - 1), a);
+                    b = fmaf(-p, ld_sig<COHERENT>(xs + 64 * t + 31), b);
                 }
                 z[t] = p_mul(mk2(a, b), mk2(win_s[64 * t + lane], win_s[64 * t + 32 + lane]));
             } else { z[t] = mk2(0.f, 0.f); }
         }
     } else {
 #pragma unroll 1
-        for (int n = 64 * t0 + lane; n < 64 * t1; n += 32) stage[n] = sample_at<PREEMPH>(x, (int)L, (int)start + n, p);
+        for (int n = 64 * t0 + lane; n < 64 * t1; n += 32) stage[n] = sample_at<PREEMPH, COHERENT>(x, (int)L, (int)start + n, p);
         __syncwarp();
 #pragma unroll
         for (int t = 0; t < 32; ++t) {

@@ -74,6 +74,8 @@ struct nsb_handle_s {
     float *d_rinv = nullptr, *d_rinv_tf = nullptr;   // [hop] reciprocal interior window sums of the two geometries
     int stream_sync_mode = 0;
     DevBuf d_trace; int trace_on = 0, trace_grid = 0;
+    DevBuf d_done;                   // k_gl_iter: item counter + per-tile completion counters
+    int fuse_iterations = 1;         // all Griffin-Lim iterations of a call in ONE launch (0: one launch per iteration, A/B hook)
     int stream_ctas_per_sm = 1;      // resident k_gl_stream CTAs per SM (occupancy query at creation)
     int prune_tf = 0, colours_tf = 0;
     float* d_mel_w = nullptr;
@@ -91,7 +93,7 @@ struct nsb_handle_s {
     std::vector<int> h_frame_off, h_tile_off, h_group_off;       // host copies of the last descriptors (chunking)
     std::vector<long long> h_samp_off;
     int host_chunks = 0;             // 0 = automatic chunking of NSB_HOST Griffin-Lim calls, n > 0 = force n chunks
-    int use_generic_iter = 0;        // debugging / A-B hook: run the iterations with k_synth<SRC_Y> instead of k_gl_iter
+    int use_generic_iter = 2;        // 0 = k_gl_stream, 1 = generic k_synth<SRC_Y>, 2 = tile kernel k_gl_iter; A-B hook: run the iterations with k_synth<SRC_Y> instead of k_gl_iter
     unsigned long long launches = 0;
     std::mutex mu;
 };
@@ -202,7 +204,7 @@ extern "C" int nsb_destroy(nsb_handle_t h) {
     cudaFree(h->d_tw); cudaFree(h->d_win); cudaFree(h->d_win_tf); cudaFree(h->d_rinv); cudaFree(h->d_rinv_tf); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo); cudaFree(h->d_mel_n); cudaFree(h->d_mel_ptr);
     cudaFree(h->d_status);
     if (h->h_desc) cudaFreeHost(h->h_desc);
-    h->d_desc.release(); h->d_trace.release(); h->ws_mag.release(); h->ws_y0.release(); h->ws_y1.release();
+    h->d_desc.release(); h->d_trace.release(); h->d_done.release(); h->ws_mag.release(); h->ws_y0.release(); h->ws_y1.release();
     h->ws_in.release(); h->ws_in2.release(); h->ws_out.release(); h->ws_out2.release();
     delete h;
     return NSB_OK;
@@ -359,7 +361,7 @@ extern "C" int nsb_set_host_chunks(nsb_handle_t h, int32_t n) {
 }
 extern "C" int nsb_set_generic_iteration(nsb_handle_t h, int32_t on) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");
-    h->use_generic_iter = on;
+    h->use_generic_iter = on < 0 ? 2 : on;      // < 0: the library's default
     return NSB_OK;
 }
 // profiling hook: per-CTA (SM id, start ns, end ns) of the LAST k_gl_stream launch; returns the number of CTAs written
@@ -376,6 +378,7 @@ extern "C" int nsb_stream_trace(nsb_handle_t h, int32_t enable, uint64_t* out, i
 }
 extern "C" int nsb_set_stream_grid(nsb_handle_t h, int32_t n) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    if (n <= -200) { h->fuse_iterations = (n == -201); return NSB_OK; }    // experiment hook: -200 / -201 = one launch per iteration / fused
     if (n <= -100) { h->stream_sync_mode = -n - 100; return NSB_OK; }     // experiment hook: -100 / -101 / -102 = barrier mode 0 / 1 / 2
     if (n < 0) return fail(NSB_ERR_INVALID, "stream grid %d < 0", n);
     h->user_stream_grid = n;
@@ -751,18 +754,27 @@ static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int t
     G.plan = make_plan(h, tf); G.batch = B; G.mag = reinterpret_cast<const float*>(h->ws_mag.p);
     G.tile_hops = H; G.colours = h->colours; G.total_tiles = total_tiles; G.status = h->d_status; G.inv_thr = inv_thr;
     const size_t smem = gl_smem(h->hop, H);
-    const int grid = total_tiles < 2 * h->num_sms ? total_tiles : 2 * h->num_sms;   // persistent: 2 CTAs per SM
-    for (int it = 0; it < iters; ++it) {
-        G.y_in = y[cur]; G.y_out = y[cur ^ 1];
+    // one launch runs all the iterations: (iteration, tile) items from a global counter, per-tile completion counters
+    int rc = h->d_done.reserve(sizeof(int) * ((size_t)total_tiles + 1));
+    if (rc) return rc;
+    G.item_counter = reinterpret_cast<int*>(h->d_done.p);
+    G.done = G.item_counter + 1;
+    G.ybuf[0] = y[0]; G.ybuf[1] = y[1];
+    const int per_launch = h->fuse_iterations ? iters : 1;
+    for (int it = 0; it < iters; it += per_launch) {
+        const int n = iters - it < per_launch ? iters - it : per_launch;
+        CU(cudaMemsetAsync(h->d_done.p, 0, sizeof(int) * ((size_t)total_tiles + 1), st));
+        G.cur0 = cur; G.iters = n;
+        const long long items = (long long)n * total_tiles;
+        const int grid = items < 2LL * h->num_sms ? (int)items : 2 * h->num_sms;   // persistent: 2 CTAs per SM
         if (tf) {
             if (G.plan.prune == 2) NSB_LAUNCH((k_gl_iter<2, false, true>), grid, kThreads, smem, st, G);
             else NSB_LAUNCH((k_gl_iter<0, false, true>), grid, kThreads, smem, st, G);
         } else if (h->defcfg) NSB_LAUNCH((k_gl_iter<1, true, false>), grid, kThreads, smem, st, G);
         else if (h->prune == 1) NSB_LAUNCH((k_gl_iter<1, false, false>), grid, kThreads, smem, st, G);
         else NSB_LAUNCH((k_gl_iter<0, false, false>), grid, kThreads, smem, st, G);
-        int rc = check_launch(h, "k_gl_iter");
-        if (rc) return rc;
-        cur ^= 1;
+        if ((rc = check_launch(h, "k_gl_iter"))) return rc;
+        cur ^= (n & 1);
     }
     return NSB_OK;
 }

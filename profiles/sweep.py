@@ -35,5 +35,5 @@ for batch, tile, generic in cases:
           sm, batch, tile, {0: "k_gl_stream", 1: "k_synth<Y> ", 2: "k_gl_iter  "}[generic], ms, ms * 1e6 / (batch * T), batch * T * 0.0125 / (ms * 1e-3 * 61)), flush=True)
       del spec, out
 h.set_tile_hops(0)
-h.set_generic_iteration(0)
+h.set_generic_iteration(-1)
 h.set_stream_grid(-100)

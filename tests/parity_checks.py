@@ -243,6 +243,7 @@ def check_streaming_rounds(T=150, iters=2, tf=False):
         return out
     outs = {}
     try:
+        h.set_generic_iteration(0)           # k_gl_stream
         for grid in (1, 2, 3, 0):
             h.set_stream_grid(grid)
             outs["grid%d" % grid] = run()
@@ -253,7 +254,7 @@ def check_streaming_rounds(T=150, iters=2, tf=False):
         h.set_generic_iteration(2)           # the tile kernel adds in the same colour order: identical bits
         outs["tile"] = run()
     finally:
-        h.set_stream_grid(0); h.set_tile_hops(0); h.set_generic_iteration(0)
+        h.set_stream_grid(0); h.set_tile_hops(0); h.set_generic_iteration(-1)
     ref = outs.pop("grid1")
     for name, o in outs.items():
         np.testing.assert_array_equal(o, ref, err_msg=name)
