@@ -12,8 +12,8 @@ no collective on the data path; weak scaling) and the value is the whole-job agg
   value : device-resident inputs/outputs, CUDA events on the launching stream, max over ranks
   e2e   : the public Python API (nspeech_b200.batch.inv_spectrogram_batch) on pinned HOST buffers, H2D and
           D2H inside the timed region
-  roofline : the Griffin-Lim iteration kernel (k_gl_iter) timed alone with CUDA events; algorithmic bytes
-          = 6,100 B per frame per launch (SURVEY.md section 8d) against MEASURED_PEAKS.json's HBM copy bandwidth;
+  roofline : the Griffin-Lim iteration kernel (k_gl_iter; one launch runs all 60 iterations) timed alone with CUDA events;
+          algorithmic bytes = 6,100 B per frame per iteration (SURVEY.md section 8d) against MEASURED_PEAKS.json's HBM copy bandwidth;
           the FP32-side numbers are reported beside it because the fused iteration is FP32-bound
   cpu_baseline : the numpy oracle (a port of the reference's librosa path; the reference itself cannot be
           imported here) on this box's host cores, on a bounded sample of the same workload
@@ -42,7 +42,9 @@ BYTES_PER_FRAME_ITER = 4 * N_BINS + 8 * HOP            # magnitude read + y writ
 FLOPS_PER_FRAME_ITER = 2 * 56320 + 12 * N_BINS         # 2 real 2048-FFTs (2.5 N log2 N) + per-bin work
 BYTES_PER_FRAME_FULL = (ITERS + 1) * 4 * N_BINS + (2 * ITERS + 1) * 4 * HOP + 8 * HOP + 4 * N_BINS
 FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 335.3e6 + 61.2e6        # from the committed ncu --set full capture of k_gl_iter
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_gl_iter launch, from the committed ncu --set full capture
+NCU_TRAFFIC_BYTES_PER_LAUNCH = ITERS * (335.3e6 + 61.2e6)
+NCU_TRAFFIC_SOURCE = "60 x the one-iteration launch of profiles/r1/ncu_full_k_gl_iter_final.txt (dram__bytes_read.sum + dram__bytes_write.sum)"
 
 
 def oracle_hp():
@@ -66,7 +68,7 @@ def _cpu_one(args):
     return time.perf_counter() - t0, len(y)
 
 
-def cpu_baseline_sample(n_frames=201, iters=ITERS, cores=None):
+def cpu_baseline_sample(n_frames=N_FRAMES, iters=ITERS, cores=None):
     """All host cores, one utterance per process; returns (audio-s/s, cores, description)."""
     from concurrent.futures import ProcessPoolExecutor
     cores = cores or os.cpu_count() or 1
@@ -164,7 +166,7 @@ def run_reference_arm(args, rank, world):
         if i >= args.warmup:
             vals.append(v)
     value = statistics.mean(vals)
-    audio_per_step = cores * HOP * (201 - 1) / SR
+    audio_per_step = cores * HOP * (N_FRAMES - 1) / SR
     line = {
         "impl": "reference", "metric": "griffin_lim_audio_sec_per_sec", "value": value, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * audio_per_step / value,
@@ -276,17 +278,19 @@ def main():
     barrier()
     h.check_status(st)
 
-    # ---- the dominant kernel alone: one launch = one Griffin-Lim iteration over the batch ----
-    n_it = 3 * ITERS
+    # ---- the dominant kernel alone: one launch of k_gl_iter = all ITERS Griffin-Lim iterations over the batch ----
+    n_launch = 3
     h.griffin_lim_iterate(ITERS, st)
     torch.cuda.synchronize()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record()
-    h.griffin_lim_iterate(n_it, st)
+    for _ in range(n_launch):
+        h.griffin_lim_iterate(ITERS, st)
     k1.record()
     torch.cuda.synchronize()
     sampler.mark()
-    ms_iter = k0.elapsed_time(k1) / n_it
+    ms_launch = k0.elapsed_time(k1) / n_launch
+    ms_iter = ms_launch / ITERS
     frames = N_UTT * N_FRAMES
     peaks, peak_kind = measured_peaks()
     achieved_gbs = frames * BYTES_PER_FRAME_ITER / (ms_iter * 1e-3) / 1e9
@@ -351,11 +355,11 @@ def main():
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(pin_in.array.nbytes),
                 "d2h_bytes_per_step": int(pin_out.array.nbytes), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_gl_iter (one Griffin-Lim iteration over the batch)",
+        "roofline": {"bound": "hbm", "kernel": "k_gl_iter (one launch = all %d Griffin-Lim iterations over the batch)" % ITERS,
                      "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"],
-                     "peak_source": peak_kind, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_source": "profiles/r1/ncu_full_k_gl_iter_final.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
-                     "ms_per_launch": ms_iter,
-                     "algorithmic_bytes_per_launch": frames * BYTES_PER_FRAME_ITER,
+                     "peak_source": peak_kind, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_source": NCU_TRAFFIC_SOURCE,
+                     "ms_per_launch": ms_launch, "iterations_per_launch": ITERS, "ms_per_iteration": ms_iter,
+                     "algorithmic_bytes_per_launch": frames * BYTES_PER_FRAME_ITER * ITERS,
                      "fp32": {"achieved_tflops_conventional_count": achieved_tflops, "peak_tflops_nominal": FP32_PEAK_TFLOPS_NOMINAL,
                               "frac": achieved_tflops / FP32_PEAK_TFLOPS_NOMINAL},
                      "whole_path_hbm_frac": frames * BYTES_PER_FRAME_FULL / (ms_dev / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"]},

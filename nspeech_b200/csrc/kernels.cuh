@@ -493,6 +493,7 @@ struct PrepParams {
     int bin_major;            // 0: [T][F] frame-major, 1: [F][T] bin-major (per utterance)
     int denorm;               // 1: apply _denormalize + ref, _db_to_amp, **power ; 0: |S| as is
     double min_level_db, ref_level_db, power;
+    double e_slope, e_offset; // S * scale = 2 ** (clip(v,0,1) * e_slope + e_offset)  (host: the dB chain times log2(10), + log2(scale))
     float* mag;               // [frames][kMagPitch]
     float scale;              // power-of-two pre-scale of the magnitudes (undone on output; Griffin-Lim is linear in S)
     int total_frames;
@@ -510,12 +511,15 @@ __device__ __forceinline__ int slot_index(int bin) {
     return ((p >> 2) * 32 + lane) * 4 + (p & 3);
 }
 
-// S = (10 ** ((clip(v,0,1) * -min + min + ref) * 0.05)) ** power, evaluated as one double exp10 and rounded once
+// S = (10 ** ((clip(v,0,1) * -min + min + ref) * 0.05)) ** power: the exponent is formed in double (one FMA) and split
+// into integer + fraction, 2 ** fraction is a float exp2 (|fraction| <= 0.5, ~1e-7 relative), the integer part an exact
+// ldexp.  (A double exp10 per element made this kernel 5 % of a Griffin-Lim call.)
 __device__ __forceinline__ float prep_magnitude(const PrepParams& P, float v) {
     if (!P.denorm) return fabsf(v) * P.scale;
-    double c = fmin(fmax((double)v, 0.0), 1.0);
-    double db = c * (-P.min_level_db) + P.min_level_db + P.ref_level_db;
-    return (float)(exp10(db * 0.05 * P.power) * (double)P.scale);
+    const double c = fmin(fmax((double)v, 0.0), 1.0);
+    const double e = fma(c, P.e_slope, P.e_offset);
+    const double n = rint(e);
+    return ldexpf(exp2f((float)(e - n)), (int)n);
 }
 
 // frame-major input: one warp per frame, row staged in shared memory in slot order, written back as float4
@@ -523,16 +527,19 @@ __global__ void __launch_bounds__(kThreads) k_prepare_mag_rows(PrepParams P) {
     __align__(16) __shared__ float row[kWarpsPerCta][kMagPitch];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     bool bad = false;
-    int b = 0;
+    for (int i = 1025 + lane; i < kMagPitch; i += 32) row[warp][i] = 0.f;      // the pad of the row never changes
     for (int f = P.batch.frame_base + blockIdx.x * kWarpsPerCta + warp; f < P.batch.frame_base + P.total_frames; f += gridDim.x * kWarpsPerCta) {
-        if (!(f >= __ldg(P.batch.frame_off + b) && f < __ldg(P.batch.frame_off + b + 1)))
-            b = find_segment(P.batch.frame_off, P.batch.batch, f);
         const float* in = P.in + (size_t)f * kBins;            // frame-major blocks are packed: global frame index addresses the row
-        for (int i = 1025 + lane; i < kMagPitch; i += 32) row[warp][i] = 0.f;
-        for (int kb = lane; kb < kBins; kb += 32) {
-            float v = __ldg(in + kb);
-            bad |= !isfinite(v);
-            row[warp][slot_index(kb)] = prep_magnitude(P, v);
+        float v[33];
+#pragma unroll
+        for (int q = 0; q < 33; ++q) { const int kb = lane + 32 * q; v[q] = kb < kBins ? __ldg(in + kb) : 0.f; }   // all loads in flight at once
+#pragma unroll
+        for (int q = 0; q < 33; ++q) {
+            const int kb = lane + 32 * q;
+            if (kb < kBins) {
+                bad |= !isfinite(v[q]);
+                row[warp][slot_index(kb)] = prep_magnitude(P, v[q]);
+            }
         }
         __syncwarp();
         float4* out = reinterpret_cast<float4*>(P.mag + (size_t)f * kMagPitch);

@@ -841,14 +841,14 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
     std::vector<int> cuts;           // utterance index where each chunk starts, plus the end
     cuts.push_back(0);
     if (space == NSB_HOST && batch > 1 && (h->host_chunks > 0 || n_spec * sizeof(float) > (8u << 20))) {
-        const int want_cfg = h->host_chunks > 0 ? h->host_chunks : 4;
+        // automatic mode: up to 4 equal chunks of at least ~16k frames each.  Smaller chunks are not worth it: below about
+        // one tile per resident CTA and iteration the fused iteration kernel is latency-bound (measured: 8 chunks of 8
+        // utterances x 1000 frames run 40 % slower than 4 of 16, profiles/r1/e2e_chunks.txt)
+        int want_cfg = h->host_chunks;
+        if (want_cfg <= 0) { want_cfg = d.total_frames / 16000; if (want_cfg > 4) want_cfg = 4; if (want_cfg < 1) want_cfg = 1; }
         const int want = batch < want_cfg ? batch : want_cfg;
-        // automatic mode: small first and last chunks (1:3:3:1) - only the first copy-in and the last copy-out are
-        // exposed, everything in between hides behind the compute of a neighbouring chunk
-        const bool taper = (h->host_chunks == 0 && want == 4 && batch >= 8);
-        const int weight[4] = {1, 4, 7, 8};
         for (int c = 1; c < want; ++c) {
-            const long long target = taper ? (long long)d.total_frames * weight[c - 1] / 8 : (long long)d.total_frames * c / want;
+            const long long target = (long long)d.total_frames * c / want;
             int b = cuts.back() + 1;
             while (b < batch && h->h_frame_off[b] < target) ++b;
             if (b < batch && b > cuts.back()) cuts.push_back(b);
@@ -892,6 +892,11 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
         PrepParams Q{};
         Q.batch = B; Q.in = d_spec; Q.bin_major = (layout == NSB_BIN_MAJOR); Q.denorm = (flags & NSB_GL_DENORMALIZE) ? 1 : 0;
         Q.min_level_db = h->hp.min_level_db; Q.ref_level_db = h->hp.ref_level_db; Q.power = h->hp.power;
+        {
+            const double l2_10 = 3.321928094887362347870319429489390175864831;     // log2(10)
+            Q.e_slope = -h->hp.min_level_db * 0.05 * h->hp.power * l2_10;
+            Q.e_offset = (h->hp.min_level_db + h->hp.ref_level_db) * 0.05 * h->hp.power * l2_10 + std::log2(gscale);
+        }
         Q.mag = reinterpret_cast<float*>(h->ws_mag.p); Q.total_frames = n_frames_c; Q.status = h->d_status; Q.scale = (float)gscale;
         if (Q.bin_major) {
             CUE(cudaMemsetAsync(Q.mag + (size_t)B.frame_base * kMagPitch, 0, sizeof(float) * kMagPitch * (size_t)n_frames_c, st));
