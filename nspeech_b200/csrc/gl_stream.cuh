@@ -36,8 +36,14 @@ namespace nsb {
 struct GlStreamParams {
     Plan plan;
     Batch batch;             // group_off / group_base describe the concatenated group space
-    const float* y_in;
-    float* y_out;
+    // One launch runs `iters` iterations: items (iteration n, chunk c) - chunk c = groups [c*CH, (c+1)*CH) of the stream -
+    // come from a global counter, n-major; (n, c) starts when the chunks c-1, c, c+1 of iteration n-1 are stored.
+    // Iteration n reads ybuf[(cur0 + n) & 1] and writes the other buffer.
+    float* ybuf[2];
+    int cur0, iters;
+    int chunk_groups;        // CH
+    int* item_counter;       // [1], zeroed by the host before the launch
+    int* done;               // [chunks], zeroed by the host: iterations finished by each chunk
     const float* mag;        // permuted, pre-scaled magnitudes [frames][kMagPitch]
     int colours;             // C
     int total_groups;        // groups in this (sub-)batch (without the end-halo groups)
@@ -63,6 +69,14 @@ __device__ __forceinline__ unsigned sm_id() {
     unsigned v;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
     return v;
+#endif
+}
+
+// barrier among the 4 warps of one half of the CTA (warps 0-3: barrier 1, warps 4-7: barrier 2); an experiment in how many
+// instruction streams per SM the kernel should run (the counters keep the overlap-add ordered whatever the barriers do)
+__device__ __forceinline__ void half_cta_barrier(int warp) {
+#ifndef NSB_EMULATE
+    if (warp < 4) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
 #endif
 }
 
@@ -172,6 +186,20 @@ __device__ __forceinline__ void locate_left(const Batch& B, int V, int b_hint, G
     fill_loc(B, V, b, o);
 }
 
+// cp.async the samples n in [64*T0, 64*T1) of a frame into the warp's scratch tile.  16-byte L2-only copies: the waveform
+// is rewritten by other SMs inside the same launch, nothing of it may sit in L1.  `src` (the frame's sample 64*T0) is
+// 8-byte aligned; the copy starts at the 16-byte boundary at or below it and `off` (0 or 2 floats) tells the reader
+// where sample n landed: stage[n + off].
+template <int T0, int T1>
+__device__ __forceinline__ void stage_frame(float* stage, const float* src0, int lane, int& off) {
+    off = (int)((reinterpret_cast<uintptr_t>(src0) >> 2) & 3);
+    const float* src = src0 - off + 4 * lane;
+    float* dst = stage + 64 * T0 + 4 * lane;
+#pragma unroll
+    for (int q = 0; q < (T1 - T0) / 2; ++q) cp_async16(dst + 128 * q, src + 128 * q);
+    if (lane == 0) cp_async16(dst + 64 * (T1 - T0), src + 64 * (T1 - T0));
+}
+
 template <int PRUNE, bool DEFCFG, bool TFM>
 __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
     NSB_DYN_SMEM(smem_raw);
@@ -212,9 +240,31 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
     bool bad = false;
     const int E = C + 1;                              // events per round: C adds + 1 store
 
-    // ---- this CTA's range of the stream ----
+    // ---- (iteration, chunk) items from one global counter (see k_gl_iter for why) ----
     const int NV = P.total_groups + P.batch.batch;
-    const int V0 = (int)((long long)NV * blockIdx.x / gridDim.x), V1 = (int)((long long)NV * (blockIdx.x + 1) / gridDim.x);
+    const int CH = P.chunk_groups;
+    const int n_chunks = (NV + CH - 1) / CH;
+    const long long total_items = (long long)P.iters * n_chunks;
+    int item_it = 0;
+    if (threadIdx.x == 0) progress[8] = atomicAdd(P.item_counter, 1);
+    __syncthreads();
+    for (long long item = progress[8]; item < total_items; item = progress[8 + (++item_it & 1)]) {
+    const int n_it = (int)(item / n_chunks);
+    const int chunk = (int)(item - (long long)n_it * n_chunks);
+    const float* y_in = P.ybuf[(P.cur0 + n_it) & 1];
+    float* y_out = P.ybuf[(P.cur0 + n_it + 1) & 1];
+    if (threadIdx.x == 0) {
+        progress[8 + ((item_it + 1) & 1)] = atomicAdd(P.item_counter, 1);     // the next item, read after this chunk's barriers
+        if (n_it > 0) {
+            // my frames read hops of the chunks c-1, c, c+1 as iteration n-1 left them, and my stores overwrite what those
+            // chunks READ in iteration n-1: both hazards end when their iteration n-1 is stored
+            const int ca = chunk > 0 ? chunk - 1 : 0, cb = chunk + 1 < n_chunks ? chunk + 1 : chunk;
+            for (int c = ca; c <= cb; ++c) while (gflag_load(P.done + c) < n_it) spin_pause();
+        }
+    }
+    if (threadIdx.x < kWarpsPerCta) progress[threadIdx.x] = 0;     // the ring is all zero again after every chunk
+    __syncthreads();
+    const int V0 = chunk * CH, V1 = min(NV, V0 + CH);
     const int n_pos = V1 - V0 + 1;                    // positions: i = 0 is the halo group V1, i = n_pos - 1 the group V0
     // samples left of the range's first group belong to the CTA on the left: frames of V0 must not add there
     int b_low, x_low;
@@ -225,6 +275,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
     }
 
     bool staged = false;                         // this frame's samples were cp.async'ed into the scratch tile already
+    int stage_off = 0;                           // ... shifted by this many floats (16-byte alignment of the copies)
     GroupLoc cur;
     const int n_pad = (n_pos + kWarpsPerCta - 1) & ~(kWarpsPerCta - 1);   // phantom positions fill the last round (barriers are CTA-wide)
     locate(P.batch, NV, warp < n_pos ? V1 - warp : NV, cur);
@@ -241,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
         if (i == 0) k_hi = (cur.g == 0) ? -1 : min(k_hi, kbase + back - 1);
         if (cur.b < 0) k_hi = -1;
         const int T = cur.T, L = cur.L;
-        const float* yin = P.y_in + cur.s_off;
+        const float* yin = y_in + cur.s_off;
         const float* mag0 = P.mag + (size_t)cur.f_off * kMagPitch;
         const int xmin = (cur.b == b_low) ? x_low : 0;      // lowest utterance sample this CTA accumulates
         const int ubase = (u - cur.g) * GH;                 // utterance sample x sits at ring[(ubase + x) mod RS]
@@ -263,13 +314,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
                     cp_async_wait_all();
                     __syncwarp();
 #pragma unroll
+                    const float* sg = stage + stage_off;
                     for (int t = 0; t < 32; ++t) {
-                        if (t >= t0 && t < t1) z[t] = p_mul(mk2(stage[64 * t + lane], stage[64 * t + 32 + lane]), mk2(win_s[64 * t + lane], win_s[64 * t + 32 + lane]));
+                        if (t >= t0 && t < t1) z[t] = p_mul(mk2(sg[64 * t + lane], sg[64 * t + 32 + lane]), mk2(win_s[64 * t + lane], win_s[64 * t + 32 + lane]));
                         else z[t] = mk2(0.f, 0.f);
                     }
                     __syncwarp();
                 } else {
-                    load_frame<false, PRUNE>(z, yin, (long long)L, (long long)k * hop - origin, win_s, lane, 0.f, stage);
+                    load_frame<false, PRUNE, true>(z, yin, (long long)L, (long long)k * hop - origin, win_s, lane, 0.f, stage);
                 }
                 fwd_phase1(z, lane, scratch, tw_s);
                 __syncwarp();
@@ -390,10 +442,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
             if (PRUNE != 0 && next_active) {
                 const long long nstart = (long long)(k + 1) * hop - origin;
                 if (nstart + 64 * t0 >= 0 && nstart + 64 * t1 <= L && ((cur.s_off + nstart) & 1) == 0) {
-                    const float* src = yin + nstart + 64 * t0 + 2 * lane;
-                    float* dst = stage + 64 * t0 + 2 * lane;
-#pragma unroll
-                    for (int q = 0; q < t1 - t0; ++q) cp_async8(dst + 64 * q, src + 64 * q);
+                    stage_frame<t0, t1>(stage, yin + nstart + 64 * t0, lane, stage_off);
                     staged = true;
                 }
             }
@@ -405,7 +454,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
                 // my colour-s frame overlaps the right-hand group's frames of colour < s: they go first
                 if (has_right) wait_events(progress + wr, E * r_r + s, lane);
                 // pacing: stay within one colour of the left-hand neighbour (keeps the CTA's warps in the same code)
-                if (has_left) wait_events(progress + warp + 1, E * r + s, lane);
+                if (has_left && !(P.sync_mode & 4)) wait_events(progress + warp + 1, E * r + s, lane);
             }
             if (active) {
                 const int base = k * hop - origin;                            // utterance sample of n = 0
@@ -456,7 +505,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
             }
             __syncwarp();
             if (lane == 0) flag_store(progress + warp, E * r + s + 1);
-            if (P.sync_mode == 2) __syncthreads();
+            if ((P.sync_mode & 3) == 2) __syncthreads();
+            if ((P.sync_mode & 3) == 3) half_cta_barrier(warp);
         }
         // ---- the group is complete (z is dead from here on) ----
         // the warp's next group sits 8 positions to the left: find it, send its first frame on its way
@@ -472,10 +522,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
                 if (lane == 0) prefetch_l2(nm + 4096);
                 const long long nstart = (long long)kn * hop - origin;
                 if (nstart + 64 * t0 >= 0 && nstart + 64 * t1 <= nxt.L && ((nxt.s_off + nstart) & 1) == 0) {
-                    const float* src = P.y_in + nxt.s_off + nstart + 64 * t0 + 2 * lane;
-                    float* dst = stage + 64 * t0 + 2 * lane;
-#pragma unroll
-                    for (int q = 0; q < t1 - t0; ++q) cp_async8(dst + 64 * q, src + 64 * q);
+                    stage_frame<t0, t1>(stage, y_in + nxt.s_off + nstart + 64 * t0, lane, stage_off);
                     staged = true;
                 }
             }
@@ -486,7 +533,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
             const int x0 = cur.g * GH;                               // utterance sample of the group's first hop
             const int n_store = min(GH, L - x0);
             if (n_store > 0)
-                gl_store_group(ring, (u * GH) % RS, RS, P.y_out + cur.s_off + x0, n_store, C * cur.g, T, win_s, P.plan.rinv, hop, win, lo, a,
+                gl_store_group(ring, (u * GH) % RS, RS, y_out + cur.s_off + x0, n_store, C * cur.g, T, win_s, P.plan.rinv, hop, win, lo, a,
                                P.plan.norm_wss, lane, bad);
             __syncwarp();
         } else if (i == 0 && k_hi >= 0) {
@@ -497,8 +544,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
         }
         if (lane == 0) flag_store(progress + warp, E * (r + 1));
         cur = nxt;
-        if (P.sync_mode == 1) __syncthreads();
+        if ((P.sync_mode & 3) == 1) __syncthreads();
     }
+    __syncthreads();                                 // every thread's stores of this chunk are issued
+    if (threadIdx.x == 0) { __threadfence(); gflag_store(P.done + chunk, n_it + 1); }
+    }   // items
     if (bad) atomicOr(P.status, 1);
     if (P.trace) {
         __syncthreads();

@@ -72,7 +72,7 @@ struct nsb_handle_s {
     float* d_win = nullptr;          // periodic Hann padded centrally to n_fft (librosa geometry)
     float* d_win_tf = nullptr;       // the same window at n in [0, win) (tf.contrib.signal geometry)
     float *d_rinv = nullptr, *d_rinv_tf = nullptr;   // [hop] reciprocal interior window sums of the two geometries
-    int stream_sync_mode = 0;
+    int stream_sync_mode = 1;        // CTA barrier per round of k_gl_stream (keeps the warps in the same code: instruction cache)
     DevBuf d_trace; int trace_on = 0, trace_grid = 0;
     DevBuf d_done;                   // k_gl_iter: item counter + per-tile completion counters
     int fuse_iterations = 1;         // all Griffin-Lim iterations of a call in ONE launch (0: one launch per iteration, A/B hook)
@@ -707,32 +707,42 @@ static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int t
         S.trace = nullptr;
         const size_t smem = stream_smem(h->hop, h->win, S.plan.origin - S.plan.lo, h->colours, S.plan.prune);
         const int ctas = h->stream_ctas_per_sm * h->num_sms;
-        // the stream: every utterance's groups + one end-halo group each; CTA n takes [n*NV/grid, (n+1)*NV/grid) + its halo.
-        // Short batches: at most 7 groups per CTA, so a range and its halo are one round of the 8 warps.
+        // the stream: every utterance's groups + one end-halo group each, cut into chunks of CH groups; a chunk and its
+        // halo group fill whole rounds of the 8 warps when CH + 1 is a multiple of 8.  Long chunks waste fewer halo frames
+        // (3 of 4*CH+3) but the launch needs a few chunks per CTA and iteration to keep every SM busy.
         const long long NV = (long long)total_groups + B.batch;
-        long long want = (NV + 6) / 7;
-        if (h->user_tile_hops > 0) want = (NV + h->user_tile_hops / h->colours - 1) / (h->user_tile_hops / h->colours);   // tests: ranges of that many groups
-        if (h->user_stream_grid > 0) want = h->user_stream_grid;
-        if (want > NV) want = NV;
-        if (want < 1) want = 1;
-        const int grid = (int)((h->user_tile_hops > 0 || h->user_stream_grid > 0 || want < ctas) ? want : ctas);
-        if (h->trace_on) {
-            int rc = h->d_trace.reserve(sizeof(unsigned long long) * 3 * (size_t)grid);
-            if (rc) return rc;
-            S.trace = reinterpret_cast<unsigned long long*>(h->d_trace.p);
-            h->trace_grid = grid;
-        }
-        for (int it = 0; it < iters; ++it) {
-            S.y_in = y[cur]; S.y_out = y[cur ^ 1];
+        int CH = 7;
+        for (int c = 31; c > 7; c -= 8) if ((NV + c - 1) / c >= 2LL * ctas) { CH = c; break; }
+        if (h->user_tile_hops > 0) CH = h->user_tile_hops / h->colours;                       // tests: chunks of that many groups
+        if (h->user_stream_grid > 0) CH = (int)((NV + h->user_stream_grid - 1) / h->user_stream_grid);   // tests: that many chunks
+        if (CH < 1) CH = 1;
+        const long long n_chunks = (NV + CH - 1) / CH;
+        int rc = h->d_done.reserve(sizeof(int) * ((size_t)n_chunks + 1));
+        if (rc) return rc;
+        S.item_counter = reinterpret_cast<int*>(h->d_done.p);
+        S.done = S.item_counter + 1;
+        S.ybuf[0] = y[0]; S.ybuf[1] = y[1];
+        S.chunk_groups = CH;
+        const int per_launch = h->fuse_iterations ? iters : 1;
+        for (int it = 0; it < iters; it += per_launch) {
+            const int n = iters - it < per_launch ? iters - it : per_launch;
+            CU(cudaMemsetAsync(h->d_done.p, 0, sizeof(int) * ((size_t)n_chunks + 1), st));
+            S.cur0 = cur; S.iters = n;
+            const long long items = (long long)n * n_chunks;
+            const int grid = items < ctas ? (int)items : ctas;
+            if (h->trace_on) {
+                if ((rc = h->d_trace.reserve(sizeof(unsigned long long) * 3 * (size_t)grid))) return rc;
+                S.trace = reinterpret_cast<unsigned long long*>(h->d_trace.p);
+                h->trace_grid = grid;
+            }
             if (tf) {
                 if (S.plan.prune == 2) NSB_LAUNCH((k_gl_stream<2, false, true>), grid, kThreads, smem, st, S);
                 else NSB_LAUNCH((k_gl_stream<0, false, true>), grid, kThreads, smem, st, S);
             } else if (h->defcfg) NSB_LAUNCH((k_gl_stream<1, true, false>), grid, kThreads, smem, st, S);
             else if (h->prune == 1) NSB_LAUNCH((k_gl_stream<1, false, false>), grid, kThreads, smem, st, S);
             else NSB_LAUNCH((k_gl_stream<0, false, false>), grid, kThreads, smem, st, S);
-            int rc = check_launch(h, "k_gl_stream");
-            if (rc) return rc;
-            cur ^= 1;
+            if ((rc = check_launch(h, "k_gl_stream"))) return rc;
+            cur ^= (n & 1);
         }
         return NSB_OK;
     }

@@ -180,25 +180,30 @@ def test_threads_share_nothing():
 
 
 def test_fused_iterations_match_one_launch_per_iteration():
-    """All Griffin-Lim iterations of a call run in ONE launch of k_gl_iter: (iteration, tile) items from a global counter,
-    tile (n, t) starts when tiles t-1, t, t+1 of iteration n-1 are stored.  The result must not differ by a bit from one
-    launch per iteration - at config-3 size, where 296 CTAs race through 2304 tiles per iteration."""
+    """All Griffin-Lim iterations of a call run in ONE launch: (iteration, tile | chunk) items from a global counter, an
+    item starts when its three neighbours of the previous iteration are stored.  The result must not differ by a bit
+    from one launch per iteration, nor between the tile kernel (k_gl_iter) and the streaming kernel (k_gl_stream) - at
+    config-3 size, where 296 CTAs race through the batch."""
     torch = pytest.importorskip("torch")
     pc._load()
     h = audio._handle()
     st = torch.cuda.current_stream().cuda_stream
-    for Ts, iters in (([1000] * 64, 60), ([2, 3, 700, 41, 1500, 29, 5] * 9, 25)):
-        g = torch.Generator(device="cuda").manual_seed(5)
-        spec = torch.rand((sum(Ts), 1025), device="cuda", generator=g)
-        outs = []
-        for mode in (-201, -200, -201):            # fused, one launch per iteration, fused again
-            h.set_stream_grid(mode)
-            out = torch.empty(sum(h.num_samples(t) for t in Ts), dtype=torch.float64, device="cuda")
-            h.griffin_lim(spec, _lib.FRAME_MAJOR, Ts, out, seed=3, iters=iters, flags=_lib.GL_DENORMALIZE | _lib.GL_DEEMPHASIS,
-                          out_dtype=_lib.F64, space=_lib.DEVICE, stream=st)
-            h.check_status(st)
-            outs.append(out.cpu().numpy())
+    try:
+        for Ts, iters in (([1000] * 64, 60), ([2, 3, 700, 41, 1500, 29, 5] * 9, 25)):
+            g = torch.Generator(device="cuda").manual_seed(5)
+            spec = torch.rand((sum(Ts), 1025), device="cuda", generator=g)
+            outs = []
+            for kernel, mode in ((2, -201), (2, -200), (0, -201), (0, -200), (0, -201)):   # -201 fused, -200 one launch per iteration
+                h.set_generic_iteration(kernel)
+                h.set_stream_grid(mode)
+                out = torch.empty(sum(h.num_samples(t) for t in Ts), dtype=torch.float64, device="cuda")
+                h.griffin_lim(spec, _lib.FRAME_MAJOR, Ts, out, seed=3, iters=iters, flags=_lib.GL_DENORMALIZE | _lib.GL_DEEMPHASIS,
+                              out_dtype=_lib.F64, space=_lib.DEVICE, stream=st)
+                h.check_status(st)
+                outs.append(out.cpu().numpy())
+            assert np.isfinite(outs[0]).all()
+            for o in outs[1:]:
+                np.testing.assert_array_equal(outs[0], o)
+    finally:
         h.set_stream_grid(-201)
-        assert np.isfinite(outs[0]).all()
-        np.testing.assert_array_equal(outs[0], outs[1])
-        np.testing.assert_array_equal(outs[0], outs[2])
+        h.set_generic_iteration(-1)
