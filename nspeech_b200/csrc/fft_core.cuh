@@ -124,14 +124,19 @@ NSB_HD c2 ctw(c2 z) {
 // ---------------------------------------------------------------------------------------------
 // out-of-place radix-4 decimation-in-time FFT on register arrays: y[k] = sum_j x[IS*j] exp(DIR*2*pi*i*j*k/N)
 // ---------------------------------------------------------------------------------------------
-template <int N, int DIR, int IS>
+// NZ0, NZ1: only the inputs x[t] with NZ0 <= t < NZ1 (t = absolute index, OFF = index of this sub-transform's x[0]) are
+// non-zero - the frame's window support covers half of the 2048 samples, so the first radix-2 layer of the forward
+// transform adds zeros: its butterflies degenerate to copies (32 packed adds and 32 zero-initialising moves per frame)
+template <int N, int DIR, int IS, int OFF = 0, int NZ0 = 0, int NZ1 = 1 << 30>
 struct FftC {
     static NSB_HD void run(const c2* x, c2* y) {
         static_assert(N % 4 == 0, "radix-4 step");
         constexpr int Q = N / 4;
         c2 f[4][Q];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) FftC<Q, DIR, IS * 4>::run(x + IS * j, f[j]);
+        FftC<Q, DIR, IS * 4, OFF, NZ0, NZ1>::run(x, f[0]);
+        FftC<Q, DIR, IS * 4, OFF + IS, NZ0, NZ1>::run(x + IS, f[1]);
+        FftC<Q, DIR, IS * 4, OFF + 2 * IS, NZ0, NZ1>::run(x + 2 * IS, f[2]);
+        FftC<Q, DIR, IS * 4, OFF + 3 * IS, NZ0, NZ1>::run(x + 3 * IS, f[3]);
         combine<0>(f, y);
     }
     template <int K>
@@ -148,13 +153,19 @@ struct FftC {
         }
     }
 };
-template <int DIR, int IS>
-struct FftC<1, DIR, IS> {
+template <int DIR, int IS, int OFF, int NZ0, int NZ1>
+struct FftC<1, DIR, IS, OFF, NZ0, NZ1> {
     static NSB_HD void run(const c2* x, c2* y) { y[0] = x[0]; }
 };
-template <int DIR, int IS>
-struct FftC<2, DIR, IS> {
-    static NSB_HD void run(const c2* x, c2* y) { c2 a = x[0], b = x[IS]; y[0] = cadd(a, b); y[1] = csub(a, b); }
+template <int DIR, int IS, int OFF, int NZ0, int NZ1>
+struct FftC<2, DIR, IS, OFF, NZ0, NZ1> {
+    static NSB_HD void run(const c2* x, c2* y) {
+        constexpr bool a_nz = (OFF >= NZ0 && OFF < NZ1), b_nz = (OFF + IS >= NZ0 && OFF + IS < NZ1);
+        if constexpr (a_nz && b_nz) { c2 a = x[0], b = x[IS]; y[0] = cadd(a, b); y[1] = csub(a, b); }
+        else if constexpr (a_nz) { y[0] = x[0]; y[1] = x[0]; }
+        else if constexpr (b_nz) { y[0] = x[IS]; y[1] = mk2(-x[IS].x, -x[IS].y); }
+        else { y[0] = mk2(0.f, 0.f); y[1] = mk2(0.f, 0.f); }
+    }
 };
 
 // in-place convenience wrapper: 32-point complex FFT (DIR = -1 forward, +1 inverse, unnormalised)
@@ -162,6 +173,14 @@ template <int DIR>
 NSB_HD void fft32(c2 (&z)[32]) {
     c2 y[32];
     FftC<32, DIR, 1>::run(z, y);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) z[k] = y[k];
+}
+// the same for an input whose entries outside [NZ0, NZ1) are zero (they are never read)
+template <int DIR, int NZ0, int NZ1>
+NSB_HD void fft32_sparse(c2 (&z)[32]) {
+    c2 y[32];
+    FftC<32, DIR, 1, 0, NZ0, NZ1>::run(z, y);
 #pragma unroll
     for (int k = 0; k < 32; ++k) z[k] = y[k];
 }

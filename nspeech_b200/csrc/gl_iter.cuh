@@ -112,10 +112,11 @@ constexpr int kMagBytes = 4096 + 16;                 // slots + the float4 that 
 constexpr int kXchOffsetF2 = (kMagBytes + 112) / 8;  // exchange area starts at byte 4224 of the scratch tile (8-byte units)
 
 // renormalise one slot, branch-free; `zero` collects exact zeros for the rare fix-up
+// (the 1e-36 rides in the second FMA instead of costing an FMNMX per slot: |z|^2 + 1e-36 never reaches rsqrt as 0)
 __device__ __forceinline__ void renorm_fast(c2& z, float S, bool& zero) {
-    float m2 = fmaf(z.x, z.x, z.y * z.y);
-    zero |= (m2 == 0.f);
-    z = cscale(z, rsqrt_ftz(fmaxf(m2, 1e-36f)) * S);
+    float m2 = fmaf(z.x, z.x, fmaf(z.y, z.y, 1e-36f));
+    zero |= (m2 <= 1e-36f);
+    z = cscale(z, rsqrt_ftz(m2) * S);
 }
 
 // normalise the finished tile by the summed squared window and store it (all threads of the CTA)

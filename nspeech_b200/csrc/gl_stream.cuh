@@ -85,37 +85,37 @@ __device__ __forceinline__ void wait_events(const int* flag, int target, int lan
     __syncwarp();
 }
 
+// window value of sample n from the paired table wp[(t - t0) * 32 + lane] = (w[64 t + lane], w[64 t + 32 + lane])
+__device__ __forceinline__ float win_at(const float* wtab, int t0, int n) {
+    return wtab[(((n >> 6) - t0) * 32 + (n & 31)) * 2 + ((n >> 5) & 1)];
+}
+
 // normalise the warp's finished group by the summed squared window, store it and clear the ring slot.
 // rinv[j] (global memory, Plan::rinv) holds 1 / (n_fft * window-sum) of the interior (all covering frames exist);
-// win_t[n] is the window.
+// wtab is the paired window table (win_at).
 // The group's samples sit at ring[(r0 + i) mod RS].
-__device__ __noinline__ void gl_store_group(float* ring, int r0, int RS, float* yo, int n_store, int h_a, int T, const float* win_t,
-                                            const float* __restrict__ rinv_s, int hop, int win, int lo, int a, int norm_wss, int lane, bool& bad) {
+__device__ __noinline__ void gl_store_group(float* ring, int r0, int RS, float* yo, int n_store, int h_a, int T, const float* wtab, int wt0,
+                                            const float* __restrict__ rinv_s, int hop, int win, int lo, int a, int norm_wss, int lane) {
     const int ncov = (win + hop - 1) / hop;
     const int h_b = h_a + (n_store - 1) / hop;
     // interior group: every sample is covered by all of its frames -> no per-sample frame tests
     const bool interior = !norm_wss || ((h_a + a / hop - (ncov - 1) >= 0) && (h_b + (hop - 1 + a) / hop <= T - 1));
-    float chk = 0.f;                                  // NaN/Inf detector: v*0 accumulates to NaN iff some v is not finite
+    // (no NaN/Inf test here: the inputs are tested by k_prepare_mag / k_synth, the result by k_deemphasis)
     if (interior && ((hop | n_store | r0 | RS) & 1) == 0 && (reinterpret_cast<uintptr_t>(yo) & 7) == 0) {
         float2* s2 = reinterpret_cast<float2*>(ring);          // the ring is 16-byte aligned
-        const int r02 = r0 >> 1, RS2 = RS >> 1;
-        const float2* r2 = reinterpret_cast<const float2*>(rinv_s);
+        const float2* r2 = reinterpret_cast<const float2*>(rinv_s);   // indexed by the sample inside the group
         float2* yo2 = reinterpret_cast<float2*>(yo);
-        const int hop2 = hop >> 1;
-        c2 chk2 = mk2(0.f, 0.f);
-        int jj = lane % hop2;
-        const int step = 32 % hop2;
-        for (int i = lane; i < (n_store >> 1); i += 32) {
-            int ri = r02 + i;
-            if (ri >= RS2) ri -= RS2;
-            c2 v = p_mul(s2[ri], __ldg(r2 + jj));
-            chk2 = p_fma(v, mk2(0.f, 0.f), chk2);
-            yo2[i] = v;
-            s2[ri] = mk2(0.f, 0.f);
-            jj += step;
-            if (jj >= hop2) jj -= hop2;
+        const int n2 = n_store >> 1, RS2 = RS >> 1;
+        const int n_a = min(n2, RS2 - (r0 >> 1));              // pairs before the ring wraps
+        const float2* src = s2 + (r0 >> 1);
+        for (int i = lane; i < n_a; i += 32) {
+            yo2[i] = p_mul(src[i], __ldg(r2 + i));
+            const_cast<float2*>(src)[i] = mk2(0.f, 0.f);
         }
-        chk = chk2.x + chk2.y;
+        for (int i = n_a + lane; i < n2; i += 32) {            // the part that wrapped to the ring's start
+            yo2[i] = p_mul(s2[i - n_a], __ldg(r2 + i));
+            s2[i - n_a] = mk2(0.f, 0.f);
+        }
     } else {
         for (int i = lane; i < n_store; i += 32) {
             const int hh = i / hop, j = i - hh * hop, h = h_a + hh;
@@ -133,15 +133,13 @@ __device__ __noinline__ void gl_store_group(float* ring, int r0, int RS, float* 
                 float sm = 0.f;
                 int kk = k_hi;
                 for (int idx = rj; idx < win; idx += hop, --kk)
-                    if (kk >= 0 && kk <= T - 1) { float w = win_t[lo + idx]; sm = fmaf(w, w, sm); }
+                    if (kk >= 0 && kk <= T - 1) { float w = win_at(wtab, wt0, lo + idx); sm = fmaf(w, w, sm); }
                 if (sm > 1.17549435e-38f) v /= sm;
             }
-            chk = fmaf(v, 0.f, chk);
             yo[i] = v;
             ring[ri] = 0.f;
         }
     }
-    bad |= (chk != 0.f);
 }
 
 template <int PRUNE> struct WinTable {          // the part of the n_fft-long window the kernel can touch
@@ -186,6 +184,48 @@ __device__ __forceinline__ void locate_left(const Batch& B, int V, int b_hint, G
     fill_loc(B, V, b, o);
 }
 
+// forward pass 1 with the paired twiddle table (see the kernel's shared-memory layout)
+template <int PRUNE>
+__device__ __forceinline__ void fwd_phase1_tw4(c2 (&z)[32], int lane, f2* scratch, const float4* tw4, const float2* tw31) {
+    fft32_sparse<-1, PruneRange<PRUNE>::t0, PruneRange<PRUNE>::t1>(z);      // z[t] outside the window support is zero and never read
+    real64_post(z);
+    float* row0 = reinterpret_cast<float*>(scratch);
+    row0[lane] = z[0].x;
+    row0[lane + 32] = z[0].y;
+#pragma unroll
+    for (int p = 0; p < 15; ++p) {
+        const float4 w = tw4[p * 32 + lane];
+        scratch[(2 * p + 1) * kRowStride + lane] = cmul(z[2 * p + 1], mk2(w.x, w.y));
+        scratch[(2 * p + 2) * kRowStride + lane] = cmul(z[2 * p + 2], mk2(w.z, w.w));
+    }
+    scratch[31 * kRowStride + lane] = cmul(z[31], tw31[lane]);
+}
+
+// frame load (kernels.cuh load_frame) for the paired window table, reading the waveform from L2 (it is rewritten by
+// other SMs inside the launch)
+template <int PRUNE>
+__device__ __forceinline__ void load_frame_wp(c2 (&z)[32], const float* x, int L, int start, const float2* wp, int lane, float* stage) {
+    constexpr int t0 = PruneRange<PRUNE>::t0, t1 = PruneRange<PRUNE>::t1;
+    if (start + 64 * t0 >= 0 && start + 64 * t1 <= L) {
+        const float* xs = x + start + lane;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+            if (t >= t0 && t < t1) z[t] = p_mul(mk2(__ldcg(xs + 64 * t), __ldcg(xs + 64 * t + 32)), wp[t * 32 + lane]);
+            else z[t] = mk2(0.f, 0.f);
+        }
+    } else {
+#pragma unroll 1
+        for (int n = 64 * t0 + lane; n < 64 * t1; n += 32) stage[n] = sample_at<false, true>(x, L, start + n, 0.f);
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+            if (t >= t0 && t < t1) z[t] = p_mul(mk2(stage[64 * t + lane], stage[64 * t + 32 + lane]), wp[t * 32 + lane]);
+            else z[t] = mk2(0.f, 0.f);
+        }
+        __syncwarp();
+    }
+}
+
 // cp.async the samples n in [64*T0, 64*T1) of a frame into the warp's scratch tile.  16-byte L2-only copies: the waveform
 // is rewritten by other SMs inside the same launch, nothing of it may sit in L1.  `src` (the frame's sample 64*T0) is
 // 8-byte aligned; the copy starts at the 16-byte boundary at or below it and `off` (0 or 2 floats) tells the reader
@@ -217,10 +257,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
     const int RS = (kWarpsPerCta * C + back) * hop;  // ring size: 8 groups + the hops the leftmost one reaches back
     constexpr int t0 = PruneRange<PRUNE>::t0, t1 = PruneRange<PRUNE>::t1;
 
+    // twiddles w2048^(q*l) in PAIRS of rows: tw4[p*32 + l] = (w^((2p+1) l), w^((2p+2) l)), p = 0..14, row 31 after them -
+    // one LDS.128 serves two twiddle multiplications (every instruction less counts: the kernel is bound by instruction
+    // supply, profiles/r1/microbench_icache.txt).  The window likewise in the pairs the registers want:
+    // wp[(t - t0)*32 + lane] = (w[64 t + lane], w[64 t + 32 + lane]).
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
-    float* win_tab = reinterpret_cast<float*>(tw_s + kTwF2);
-    const float* win_s = win_tab - WinTable<PRUNE>::n0;      // win_s[n] for n inside the table
-    float* ring = win_tab + WinTable<PRUNE>::len;            // 16-byte aligned
+    const float4* tw4 = reinterpret_cast<const float4*>(tw_s);
+    const float2* tw31 = tw_s + 15 * 64;
+    float2* wp_tab = tw_s + kTwF2;
+    const float2* wp = wp_tab - t0 * 32;                     // wp[t*32 + lane] for t in [t0, t1)
+    float* ring = reinterpret_cast<float*>(wp_tab + (t1 - t0) * 32);   // 16-byte aligned
     int* progress = reinterpret_cast<int*>(ring + ((RS + 3) & ~3));    // [kWarpsPerCta] (+ pad to 16 ints)
     float2* scratch_all = reinterpret_cast<float2*>(progress + 16);
 
@@ -229,8 +275,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
     float* stage = reinterpret_cast<float*>(scratch);
     if (P.trace && threadIdx.x == 0) { P.trace[3 * blockIdx.x] = sm_id(); P.trace[3 * blockIdx.x + 1] = global_ns(); }
 
-    for (int i = threadIdx.x; i < kTwF2; i += kThreads) tw_s[i] = P.plan.tw[i];
-    for (int i = threadIdx.x; i < WinTable<PRUNE>::len; i += kThreads) win_tab[i] = P.plan.win[WinTable<PRUNE>::n0 + i];
+    for (int i = threadIdx.x; i < kTwF2; i += kThreads) {
+        const int q = i / 32 + 1, l = i % 32;                 // global table: tw[(q-1)*32 + l]
+        tw_s[q < 31 ? (((q - 1) >> 1) * 32 + l) * 2 + ((q - 1) & 1) : 15 * 64 + l] = P.plan.tw[i];
+    }
+    for (int i = threadIdx.x; i < (t1 - t0) * 32; i += kThreads) {
+        const int n = 64 * (t0 + i / 32) + (i & 31);
+        wp_tab[i] = make_float2(P.plan.win[n], P.plan.win[n + 32]);
+    }
     {
         float4* r4 = reinterpret_cast<float4*>(ring);
         for (int i = threadIdx.x; i < (RS + 3) / 4; i += kThreads) r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -239,6 +291,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
     __syncthreads();
     bool bad = false;
     const int E = C + 1;                              // events per round: C adds + 1 store
+    const bool frame_barrier = (P.sync_mode & 3) == 2 && back <= C - 1;   // back == C: a group's hops need ALL colours of the next one
 
     // ---- (iteration, chunk) items from one global counter (see k_gl_iter for why) ----
     const int NV = P.total_groups + P.batch.batch;
@@ -316,14 +369,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
 #pragma unroll
                     const float* sg = stage + stage_off;
                     for (int t = 0; t < 32; ++t) {
-                        if (t >= t0 && t < t1) z[t] = p_mul(mk2(sg[64 * t + lane], sg[64 * t + 32 + lane]), mk2(win_s[64 * t + lane], win_s[64 * t + 32 + lane]));
+                        if (t >= t0 && t < t1) z[t] = p_mul(mk2(sg[64 * t + lane], sg[64 * t + 32 + lane]), wp[t * 32 + lane]);
                         else z[t] = mk2(0.f, 0.f);
                     }
                     __syncwarp();
                 } else {
-                    load_frame<false, PRUNE, true>(z, yin, (long long)L, (long long)k * hop - origin, win_s, lane, 0.f, stage);
+                    load_frame_wp<PRUNE>(z, yin, L, k * hop - origin, wp, lane, stage);
                 }
-                fwd_phase1(z, lane, scratch, tw_s);
+                fwd_phase1_tw4<PRUNE>(z, lane, scratch, tw4, tw31);
                 __syncwarp();
 #pragma unroll
                 for (int t = 0; t < 32; ++t) z[t] = scratch[lane * kRowStride + t];
@@ -338,8 +391,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
                 fft32<-1>(z);
                 float2* xch = scratch + kXchOffsetF2;
                 if (lane == 0) {
+                    float4* x4 = reinterpret_cast<float4*>(xch);               // 16-byte aligned: 16 stores instead of 32
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) xch[q] = z[q];
+                    for (int q = 0; q < 16; ++q) x4[q] = make_float4(z[2 * q].x, z[2 * q].y, z[2 * q + 1].x, z[2 * q + 1].y);
                 }
                 cp_async_wait_all();
                 __syncwarp();
@@ -393,7 +447,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
                     } else {
                         const int jq = lane, jj = 32 - lane;
                         // u = -i * w64^j with w64^j = w2048^(16 * 2j) from the twiddle table (j = 16: w = -i)
-                        const float2 wj = (jq <= 15) ? tw_s[15 * 32 + 2 * jq] : make_float2(0.f, -1.f);
+                        const float2 wj = (jq <= 15) ? tw_s[(7 * 32 + 2 * jq) * 2 + 1] : make_float2(0.f, -1.f);   // row 16 of the table
                         const c2 u = mk2(wj.y, -wj.x);
                         const c2 Aj = xch[jq], Bj = xch[jj];
                         const c2 S1 = cadd_conj(Aj, Bj), D1 = csub_conj(Aj, Bj);
@@ -422,15 +476,21 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
                 }
                 __syncwarp();
                 if (lane == 0) {
+                    const float4* x4 = reinterpret_cast<const float4*>(xch);
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) z[q] = xch[q];
+                    for (int q = 0; q < 16; ++q) { const float4 v = x4[q]; z[2 * q] = mk2(v.x, v.y); z[2 * q + 1] = mk2(v.z, v.w); }
                 }
                 __syncwarp();                        // magnitude row and exchange area fully consumed
                 // inverse pass 1 (the lane-0 pre-split already happened above)
                 fft32<+1>(z);
                 scratch[lane * kRowStride] = z[0];
 #pragma unroll
-                for (int q = 1; q < 32; ++q) scratch[lane * kRowStride + q] = cmul_conj(z[q], tw_s[(q - 1) * 32 + lane]);
+                for (int p = 0; p < 15; ++p) {
+                    const float4 w = tw4[p * 32 + lane];
+                    scratch[lane * kRowStride + 2 * p + 1] = cmul_conj(z[2 * p + 1], mk2(w.x, w.y));
+                    scratch[lane * kRowStride + 2 * p + 2] = cmul_conj(z[2 * p + 2], mk2(w.z, w.w));
+                }
+                scratch[lane * kRowStride + 31] = cmul_conj(z[31], tw31[lane]);
                 __syncwarp();
                 inv_phase2(z, lane, scratch);
                 __syncwarp();                        // the scratch tile may be rewritten by this warp's next frame
@@ -450,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
             if (s == 0) {
                 // ring reuse: this group writes where positions i-8 (this warp) and i-9 (the right-hand warp) stored
                 if (i >= 9) wait_events(progress + wr, E * (((i - 9) >> 3) + 1), lane);
-            } else {
+            } else if (!frame_barrier) {
                 // my colour-s frame overlaps the right-hand group's frames of colour < s: they go first
                 if (has_right) wait_events(progress + wr, E * r_r + s, lane);
                 // pacing: stay within one colour of the left-hand neighbour (keeps the CTA's warps in the same code)
@@ -468,14 +528,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
 #pragma unroll
                     for (int t = 0; t < 32; ++t) {
                         if (t >= t0 && t < t1) {
+                            const c2 w = wp[t * 32 + lane];
                             if (t == 8) {
-                                if (lane >= 12) ap[64 * t] = fmaf(z[t].x, win_s[64 * t + lane], ap[64 * t]);
-                                ap[64 * t + 32] = fmaf(z[t].y, win_s[64 * t + 32 + lane], ap[64 * t + 32]);
+                                if (lane >= 12) ap[64 * t] = fmaf(z[t].x, w.x, ap[64 * t]);
+                                ap[64 * t + 32] = fmaf(z[t].y, w.y, ap[64 * t + 32]);
                             } else if (t == 23) {
-                                ap[64 * t] = fmaf(z[t].x, win_s[64 * t + lane], ap[64 * t]);
-                                if (lane < 20) ap[64 * t + 32] = fmaf(z[t].y, win_s[64 * t + 32 + lane], ap[64 * t + 32]);
+                                ap[64 * t] = fmaf(z[t].x, w.x, ap[64 * t]);
+                                if (lane < 20) ap[64 * t + 32] = fmaf(z[t].y, w.y, ap[64 * t + 32]);
                             } else {
-                                c2 rr = p_fma(z[t], mk2(win_s[64 * t + lane], win_s[64 * t + 32 + lane]), mk2(ap[64 * t], ap[64 * t + 32]));
+                                c2 rr = p_fma(z[t], w, mk2(ap[64 * t], ap[64 * t + 32]));
                                 ap[64 * t] = rr.x;
                                 ap[64 * t + 32] = rr.y;
                             }
@@ -497,15 +558,22 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
                             int i0 = qb + 64 * t, i1 = i0 + 32;
                             if (i0 >= RS) i0 -= RS;
                             if (i1 >= RS) i1 -= RS;
-                            if ((mre >> t) & 1u) ring[i0] = fmaf(z[t].x, win_s[64 * t + lane], ring[i0]);
-                            if ((mim >> t) & 1u) ring[i1] = fmaf(z[t].y, win_s[64 * t + 32 + lane], ring[i1]);
+                            const c2 w = wp[t * 32 + lane];
+                            if ((mre >> t) & 1u) ring[i0] = fmaf(z[t].x, w.x, ring[i0]);
+                            if ((mim >> t) & 1u) ring[i1] = fmaf(z[t].y, w.y, ring[i1]);
                         }
                     }
                 }
             }
-            __syncwarp();
-            if (lane == 0) flag_store(progress + warp, E * r + s + 1);
-            if ((P.sync_mode & 3) == 2) __syncthreads();
+            // With a CTA barrier after every colour (the production mode: it keeps the 8 warps in the same stretch of code,
+            // which is what the instruction caches need) the barrier itself orders the adds: colour s starts when every
+            // warp has added its colours < s.  Without it the per-warp event counters do.
+            if (frame_barrier) {
+                __syncthreads();
+            } else {
+                __syncwarp();
+                if (lane == 0) flag_store(progress + warp, E * r + s + 1);
+            }
             if ((P.sync_mode & 3) == 3) half_cta_barrier(warp);
         }
         // ---- the group is complete (z is dead from here on) ----
@@ -529,12 +597,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
         }
         if (i >= 1 && cur.b >= 0 && cur.g < cur.Gb) {
             // my hops also need the right-hand group's first `back` colours; the colour C-1 wait covered back <= C-1
-            if (back > C - 1) wait_events(progress + wr, E * r_r + back, lane);
+            if (back > C - 1 && !frame_barrier) wait_events(progress + wr, E * r_r + back, lane);
             const int x0 = cur.g * GH;                               // utterance sample of the group's first hop
             const int n_store = min(GH, L - x0);
             if (n_store > 0)
-                gl_store_group(ring, (u * GH) % RS, RS, y_out + cur.s_off + x0, n_store, C * cur.g, T, win_s, P.plan.rinv, hop, win, lo, a,
-                               P.plan.norm_wss, lane, bad);
+                gl_store_group(ring, (u * GH) % RS, RS, y_out + cur.s_off + x0, n_store, C * cur.g, T, reinterpret_cast<const float*>(wp_tab), t0, P.plan.rinv, hop, win, lo, a,
+                               P.plan.norm_wss, lane);
             __syncwarp();
         } else if (i == 0 && k_hi >= 0) {
             // the halo group's own hops belong to the CTA on the right: nothing to store, but positions 8 and 9 reuse the space

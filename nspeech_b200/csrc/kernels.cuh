@@ -46,7 +46,8 @@ struct Batch {
 struct Plan {                    // device tables owned by the handle
     const float2* tw;            // [31*32]
     const float* win;            // [2048] window padded centrally to n_fft (unscaled)
-    const float* rinv;           // [hop] 1 / (n_fft * summed squared window) of the interior, 1/n_fft without normalisation (k_gl_stream)
+    const float* rinv;           // [C*hop] (one hop's table repeated over a group) 1 / (n_fft * summed squared window) of the interior,
+                                 // 1/n_fft without normalisation (k_gl_stream)
     const float* mel_w;          // mel weights, rows concatenated
     const int* mel_lo;           // [num_mels] first bin of row
     const int* mel_n;            // [num_mels] row length
@@ -596,6 +597,7 @@ struct EmphParams {
     float* out32;
     double p;
     double scale;         // output multiplier (undoes the magnitude pre-scale); 0 is treated as 1
+    int* status;          // optional device flag: bit0 = non-finite sample (the Griffin-Lim result passes through here)
 };
 
 // y[n] = x[n] + p*y[n-1] per utterance (scipy.signal.lfilter([1],[1,-p]), zero initial state), in double.
@@ -626,6 +628,7 @@ __global__ void __launch_bounds__(kDeemphThreads) k_deemphasis(EmphParams P) {
     for (int d = 1; d < 6; ++d) pw[d] = pw[d - 1] * pw[d - 1];
     if (tid == 0) carry_s = 0.0;
     __syncthreads();
+    bool bad = false;
     const long long chunk = (long long)kDeemphThreads * kPerThread;
     for (long long c0 = 0; c0 < L; c0 += chunk) {
         const long long i0 = c0 + (long long)tid * kPerThread;
@@ -633,7 +636,9 @@ __global__ void __launch_bounds__(kDeemphThreads) k_deemphasis(EmphParams P) {
         double s = 0.0;
 #pragma unroll
         for (int i = 0; i < kPerThread; ++i) {
-            double v = (i0 + i < L) ? (double)__ldg(x + i0 + i) * oscale : 0.0;
+            const float xv = (i0 + i < L) ? __ldg(x + i0 + i) : 0.f;
+            bad |= !isfinite(xv);
+            double v = (double)xv * oscale;
             s = fma(p, s, v);
             loc[i] = s;
         }
@@ -671,6 +676,7 @@ __global__ void __launch_bounds__(kDeemphThreads) k_deemphasis(EmphParams P) {
         if (tid == kDeemphThreads - 1) carry_s = fma(ppow[kPerThread], cin, loc[kPerThread - 1]);
         __syncthreads();
     }
+    if (bad && P.status) atomicOr(P.status, 1);
 }
 
 // y[n] = x[n] - p*x[n-1] (lfilter([1,-p],[1])), double arithmetic like scipy

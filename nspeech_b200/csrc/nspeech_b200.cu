@@ -93,7 +93,7 @@ struct nsb_handle_s {
     std::vector<int> h_frame_off, h_tile_off, h_group_off;       // host copies of the last descriptors (chunking)
     std::vector<long long> h_samp_off;
     int host_chunks = 0;             // 0 = automatic chunking of NSB_HOST Griffin-Lim calls, n > 0 = force n chunks
-    int use_generic_iter = 2;        // 0 = k_gl_stream, 1 = generic k_synth<SRC_Y>, 2 = tile kernel k_gl_iter; A-B hook: run the iterations with k_synth<SRC_Y> instead of k_gl_iter
+    int use_generic_iter = -1;       // -1 = automatic (k_gl_stream for long batches, k_gl_iter otherwise), 0 = k_gl_stream, 1 = generic k_synth<SRC_Y>, 2 = tile kernel k_gl_iter; A-B hook: run the iterations with k_synth<SRC_Y> instead of k_gl_iter
     unsigned long long launches = 0;
     std::mutex mu;
 };
@@ -271,20 +271,22 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
         h->colours_tf = h->colours;
         // reciprocal of the interior window sum per offset inside a hop, in the arithmetic the kernels use
         // (float fmaf chain over the covering frames, IEEE division), times 1/n_fft of the unnormalised inverse FFT
-        std::vector<float> ri(hop), rt(hop);
+        const int GHs = h->colours * hop;                    // k_gl_stream indexes the table by the sample inside a group of C hops
+        std::vector<float> ri(GHs), rt(GHs);
         for (int geo = 0; geo < 2; ++geo) {
             const int lo_g = geo ? 0 : h->lo, a = geo ? 0 : kNfft / 2 - h->lo;
             const std::vector<float>& wg = geo ? wt : w;
             for (int j = 0; j < hop; ++j) {
                 float sum = 0.f;
                 for (int idx = (j + a) % hop; idx < win; idx += hop) sum = std::fmaf(wg[lo_g + idx], wg[lo_g + idx], sum);
-                (geo ? rt : ri)[j] = ((geo == 0 && sum > 1.17549435e-38f) ? 1.0f / sum : 1.0f) * (1.0f / (float)kNfft);
+                const float v = ((geo == 0 && sum > 1.17549435e-38f) ? 1.0f / sum : 1.0f) * (1.0f / (float)kNfft);
+                for (int c = 0; c < h->colours; ++c) (geo ? rt : ri)[c * hop + j] = v;
             }
         }
-        CUB(cudaMalloc(&h->d_rinv, sizeof(float) * hop));
-        CUB(cudaMemcpy(h->d_rinv, ri.data(), sizeof(float) * hop, cudaMemcpyHostToDevice));
-        CUB(cudaMalloc(&h->d_rinv_tf, sizeof(float) * hop));
-        CUB(cudaMemcpy(h->d_rinv_tf, rt.data(), sizeof(float) * hop, cudaMemcpyHostToDevice));
+        CUB(cudaMalloc(&h->d_rinv, sizeof(float) * GHs));
+        CUB(cudaMemcpy(h->d_rinv, ri.data(), sizeof(float) * GHs, cudaMemcpyHostToDevice));
+        CUB(cudaMalloc(&h->d_rinv_tf, sizeof(float) * GHs));
+        CUB(cudaMemcpy(h->d_rinv_tf, rt.data(), sizeof(float) * GHs, cudaMemcpyHostToDevice));
     }
     // sparse mel rows
     {
@@ -361,7 +363,7 @@ extern "C" int nsb_set_host_chunks(nsb_handle_t h, int32_t n) {
 }
 extern "C" int nsb_set_generic_iteration(nsb_handle_t h, int32_t on) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");
-    h->use_generic_iter = on < 0 ? 2 : on;      // < 0: the library's default
+    h->use_generic_iter = on < 0 ? -1 : on;     // < 0: the library's choice
     return NSB_OK;
 }
 // profiling hook: per-CTA (SM id, start ns, end ns) of the LAST k_gl_stream launch; returns the number of CTAs written
@@ -698,8 +700,12 @@ static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int t
                          bool tf = false, float inv_thr = 0.f) {
     float* y[2] = {reinterpret_cast<float*>(h->ws_y0.p), reinterpret_cast<float*>(h->ws_y1.p)};
     if (total_tiles <= 0) return NSB_OK;
-    if (h->use_generic_iter == 0) {
-        // the production path: streaming kernel, CTA i owns the contiguous group range [i*N/n, (i+1)*N/n)
+    // automatic choice: the streaming kernel needs chunks of >= 15 groups (two rounds of its 8 warps) and two chunks per
+    // resident CTA and iteration to beat the tile kernel (measured: profiles/r1/sweep_kernels.txt)
+    int which = h->use_generic_iter;
+    if (which < 0) which = ((long long)total_groups + B.batch >= 2LL * h->stream_ctas_per_sm * h->num_sms * 15 && h->stream_ctas_per_sm >= 2) ? 0 : 2;
+    if (which == 0) {
+        // the production path for long batches: streaming kernel, CTA i owns the contiguous group range [i*N/n, (i+1)*N/n)
         GlStreamParams S{};
         S.plan = make_plan(h, tf); S.batch = B; S.mag = reinterpret_cast<const float*>(h->ws_mag.p);
         S.colours = h->colours; S.total_groups = total_groups; S.status = h->d_status; S.inv_thr = inv_thr;
@@ -746,7 +752,7 @@ static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int t
         }
         return NSB_OK;
     }
-    if (h->use_generic_iter == 1 && !tf) {
+    if (which == 1 && !tf) {
         SynthParams P{};
         P.plan = make_plan(h); P.batch = B; P.mag = reinterpret_cast<const float*>(h->ws_mag.p);
         P.tile_hops = H; P.colours = h->colours; P.status = h->d_status;
@@ -935,6 +941,7 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
         if ((flags & NSB_GL_DEEMPHASIS) || gscale != 1.0) {
             EmphParams E{};
             E.batch = B; E.in = y_fin; E.p = (flags & NSB_GL_DEEMPHASIS) ? h->hp.preemphasis : 0.0; E.scale = 1.0 / gscale;
+            E.status = h->d_status;
             if (out_dtype == NSB_F64) E.out64 = reinterpret_cast<double*>(d_out); else E.out32 = reinterpret_cast<float*>(d_out);
             NSB_LAUNCH(k_deemphasis, b1 - b0, kDeemphThreads, 0, st, E);
             if ((rc = check_launch(h, "k_deemphasis"))) { cleanup(); return rc; }
