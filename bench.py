@@ -12,7 +12,7 @@ no collective on the data path; weak scaling) and the value is the whole-job agg
   value : device-resident inputs/outputs, CUDA events on the launching stream, max over ranks
   e2e   : the public Python API (nspeech_b200.batch.inv_spectrogram_batch) on pinned HOST buffers, H2D and
           D2H inside the timed region
-  roofline : the Griffin-Lim iteration kernel (k_gl_iter; one launch runs all 60 iterations) timed alone with CUDA events;
+  roofline : the Griffin-Lim iteration kernel (k_gl_stream; one launch runs all 60 iterations) timed alone with CUDA events;
           algorithmic bytes = 6,100 B per frame per iteration (SURVEY.md section 8d) against MEASURED_PEAKS.json's HBM copy bandwidth;
           the FP32-side numbers are reported beside it because the fused iteration is FP32-bound
   cpu_baseline : the numpy oracle (a port of the reference's librosa path; the reference itself cannot be
@@ -43,8 +43,8 @@ FLOPS_PER_FRAME_ITER = 2 * 56320 + 12 * N_BINS         # 2 real 2048-FFTs (2.5 N
 BYTES_PER_FRAME_FULL = (ITERS + 1) * 4 * N_BINS + (2 * ITERS + 1) * 4 * HOP + 8 * HOP + 4 * N_BINS
 FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_gl_iter launch, from the committed ncu --set full capture
-NCU_TRAFFIC_BYTES_PER_LAUNCH = ITERS * (335.3e6 + 61.2e6)
-NCU_TRAFFIC_SOURCE = "60 x the one-iteration launch of profiles/r1/ncu_full_k_gl_iter_final.txt (dram__bytes_read.sum + dram__bytes_write.sum)"
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 20.684e9 + 3.850e9
+NCU_TRAFFIC_SOURCE = "profiles/r1/ncu_full_k_gl_stream_fused60.txt (dram__bytes_read.sum + dram__bytes_write.sum of one 60-iteration launch)"
 
 
 def oracle_hp():
@@ -355,7 +355,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(pin_in.array.nbytes),
                 "d2h_bytes_per_step": int(pin_out.array.nbytes), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_gl_iter (one launch = all %d Griffin-Lim iterations over the batch)" % ITERS,
+        "roofline": {"bound": "hbm", "kernel": "k_gl_stream (one launch = all %d Griffin-Lim iterations over the batch)" % ITERS,
                      "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"],
                      "peak_source": peak_kind, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_source": NCU_TRAFFIC_SOURCE,
                      "ms_per_launch": ms_launch, "iterations_per_launch": ITERS, "ms_per_iteration": ms_iter,

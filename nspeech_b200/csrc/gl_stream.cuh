@@ -192,13 +192,17 @@ __device__ __forceinline__ void fwd_phase1_tw4(c2 (&z)[32], int lane, f2* scratc
     float* row0 = reinterpret_cast<float*>(scratch);
     row0[lane] = z[0].x;
     row0[lane + 32] = z[0].y;
+    // multiply in place, store afterwards: a product that lives in its own z register is not copied before its store
+    // (ptxas moves a store's source aside when the register is about to be reused - two MOVs per twiddle otherwise)
 #pragma unroll
     for (int p = 0; p < 15; ++p) {
         const float4 w = tw4[p * 32 + lane];
-        scratch[(2 * p + 1) * kRowStride + lane] = cmul(z[2 * p + 1], mk2(w.x, w.y));
-        scratch[(2 * p + 2) * kRowStride + lane] = cmul(z[2 * p + 2], mk2(w.z, w.w));
+        z[2 * p + 1] = cmul(z[2 * p + 1], mk2(w.x, w.y));
+        z[2 * p + 2] = cmul(z[2 * p + 2], mk2(w.z, w.w));
     }
-    scratch[31 * kRowStride + lane] = cmul(z[31], tw31[lane]);
+    z[31] = cmul(z[31], tw31[lane]);
+#pragma unroll
+    for (int q = 1; q < 32; ++q) scratch[q * kRowStride + lane] = z[q];
 }
 
 // frame load (kernels.cuh load_frame) for the paired window table, reading the waveform from L2 (it is rewritten by
@@ -390,10 +394,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
                 }
                 fft32<-1>(z);
                 float2* xch = scratch + kXchOffsetF2;
-                if (lane == 0) {
-                    float4* x4 = reinterpret_cast<float4*>(xch);               // 16-byte aligned: 16 stores instead of 32
+                if (lane == 0) {       // (128-bit stores would need the two pairs in four consecutive registers: four MOVs each)
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) x4[q] = make_float4(z[2 * q].x, z[2 * q].y, z[2 * q + 1].x, z[2 * q + 1].y);
+                    for (int q = 0; q < 32; ++q) xch[q] = z[q];
                 }
                 cp_async_wait_all();
                 __syncwarp();
@@ -476,9 +479,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
                 }
                 __syncwarp();
                 if (lane == 0) {
-                    const float4* x4 = reinterpret_cast<const float4*>(xch);
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) { const float4 v = x4[q]; z[2 * q] = mk2(v.x, v.y); z[2 * q + 1] = mk2(v.z, v.w); }
+                    for (int q = 0; q < 32; ++q) z[q] = xch[q];
                 }
                 __syncwarp();                        // magnitude row and exchange area fully consumed
                 // inverse pass 1 (the lane-0 pre-split already happened above)
@@ -487,10 +489,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
 #pragma unroll
                 for (int p = 0; p < 15; ++p) {
                     const float4 w = tw4[p * 32 + lane];
-                    scratch[lane * kRowStride + 2 * p + 1] = cmul_conj(z[2 * p + 1], mk2(w.x, w.y));
-                    scratch[lane * kRowStride + 2 * p + 2] = cmul_conj(z[2 * p + 2], mk2(w.z, w.w));
+                    z[2 * p + 1] = cmul_conj(z[2 * p + 1], mk2(w.x, w.y));
+                    z[2 * p + 2] = cmul_conj(z[2 * p + 2], mk2(w.z, w.w));
                 }
-                scratch[lane * kRowStride + 31] = cmul_conj(z[31], tw31[lane]);
+                z[31] = cmul_conj(z[31], tw31[lane]);
+#pragma unroll
+                for (int q = 1; q < 32; ++q) scratch[lane * kRowStride + q] = z[q];
                 __syncwarp();
                 inv_phase2(z, lane, scratch);
                 __syncwarp();                        // the scratch tile may be rewritten by this warp's next frame

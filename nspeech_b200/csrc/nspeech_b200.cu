@@ -857,14 +857,22 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
     std::vector<int> cuts;           // utterance index where each chunk starts, plus the end
     cuts.push_back(0);
     if (space == NSB_HOST && batch > 1 && (h->host_chunks > 0 || n_spec * sizeof(float) > (8u << 20))) {
-        // automatic mode: up to 4 equal chunks of at least ~16k frames each.  Smaller chunks are not worth it: below about
-        // one tile per resident CTA and iteration the fused iteration kernel is latency-bound (measured: 8 chunks of 8
-        // utterances x 1000 frames run 40 % slower than 4 of 16, profiles/r1/e2e_chunks.txt)
-        int want_cfg = h->host_chunks;
-        if (want_cfg <= 0) { want_cfg = d.total_frames / 16000; if (want_cfg > 4) want_cfg = 4; if (want_cfg < 1) want_cfg = 1; }
-        const int want = batch < want_cfg ? batch : want_cfg;
-        for (int c = 1; c < want; ++c) {
-            const long long target = (long long)d.total_frames * c / want;
+        // Only the first chunk's copy-in and the last chunk's copy-out are exposed, so those two chunks should be small -
+        // but below ~16k frames the iteration kernels are latency-bound, and the streaming kernel (the fastest) needs
+        // ~35k frames.  Automatic mode: long batches (>= 60k frames) are cut 16k | rest | 12k frames, shorter ones into up
+        // to 4 equal chunks of >= 16k frames (measured: profiles/r1/e2e_chunks.txt).
+        std::vector<long long> targets;
+        if (h->host_chunks > 0) {
+            for (int c = 1; c < h->host_chunks; ++c) targets.push_back((long long)d.total_frames * c / h->host_chunks);
+        } else if (d.total_frames >= 60000) {
+            targets.push_back(16000);
+            targets.push_back((long long)d.total_frames - 12000);
+        } else {
+            int want = d.total_frames / 16000;
+            if (want > 4) want = 4;
+            for (int c = 1; c < want; ++c) targets.push_back((long long)d.total_frames * c / want);
+        }
+        for (long long target : targets) {
             int b = cuts.back() + 1;
             while (b < batch && h->h_frame_off[b] < target) ++b;
             if (b < batch && b > cuts.back()) cuts.push_back(b);

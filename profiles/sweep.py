@@ -19,7 +19,10 @@ for batch, tile, generic in cases:
       h.set_stream_grid(-100 - sm)
       spec = torch.rand((batch, T, 1025), device="cuda")
       out = torch.empty(batch * h.num_samples(T), dtype=torch.float64, device="cuda")
-      h.set_tile_hops(tile)
+      if tile > 28:      # k_gl_stream chunks of tile/4 groups
+          h.set_tile_hops(0); h.set_stream_grid(-(-(batch * (T // 4 + 1)) // (tile // 4)))
+      else:
+          h.set_tile_hops(tile); h.set_stream_grid(0)
       h.set_generic_iteration(generic)
       h.griffin_lim(spec, _lib.FRAME_MAJOR, [T] * batch, out, seed=1, iters=2, flags=3, out_dtype=_lib.F64, space=_lib.DEVICE, stream=st)
       h.griffin_lim_iterate(20, st)
@@ -36,4 +39,5 @@ for batch, tile, generic in cases:
       del spec, out
 h.set_tile_hops(0)
 h.set_generic_iteration(-1)
-h.set_stream_grid(-100)
+h.set_stream_grid(0)
+h.set_stream_grid(-102)
