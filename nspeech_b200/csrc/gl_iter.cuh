@@ -181,6 +181,37 @@ __device__ __noinline__ void gl_store_tile(const GlParams& P, float* y_out, int 
     bad |= (chk != 0.f);
 }
 
+// Twiddles w2048^(q*l) in shared memory in PAIRS of rows: tw4[p*32 + l] = (w^((2p+1) l), w^((2p+2) l)), p = 0..14, row 31 after
+// them (tw31 = tw_s + 15*64) - one LDS.128 serves two twiddle multiplications (every instruction less counts: the kernels are
+// bound by instruction supply, profiles/r1/microbench_icache.txt).  `src` is the handle's table tw[(q-1)*32 + l].
+__device__ __forceinline__ void load_twiddle_pairs(float2* tw_s, const float2* src) {
+    for (int i = threadIdx.x; i < kTwF2; i += kThreads) {
+        const int q = i / 32 + 1, l = i % 32;
+        tw_s[q < 31 ? (((q - 1) >> 1) * 32 + l) * 2 + ((q - 1) & 1) : 15 * 64 + l] = src[i];
+    }
+}
+
+// forward pass 1 with the paired twiddle table
+template <int PRUNE>
+__device__ __forceinline__ void fwd_phase1_tw4(c2 (&z)[32], int lane, f2* scratch, const float4* tw4, const float2* tw31) {
+    fft32_sparse<-1, PruneRange<PRUNE>::t0, PruneRange<PRUNE>::t1>(z);      // z[t] outside the window support is zero and never read
+    real64_post(z);
+    float* row0 = reinterpret_cast<float*>(scratch);
+    row0[lane] = z[0].x;
+    row0[lane + 32] = z[0].y;
+    // multiply in place, store afterwards: a product that lives in its own z register is not copied before its store
+    // (ptxas moves a store's source aside when the register is about to be reused - two MOVs per twiddle otherwise)
+#pragma unroll
+    for (int p = 0; p < 15; ++p) {
+        const float4 w = tw4[p * 32 + lane];
+        z[2 * p + 1] = cmul(z[2 * p + 1], mk2(w.x, w.y));
+        z[2 * p + 2] = cmul(z[2 * p + 2], mk2(w.z, w.w));
+    }
+    z[31] = cmul(z[31], tw31[lane]);
+#pragma unroll
+    for (int q = 1; q < 32; ++q) scratch[q * kRowStride + lane] = z[q];
+}
+
 // Rejected variants (measured on B200, batch 64 x 1000 frames, see profiles/README.md): one shared FFT32 copy for
 // the four passes through a rolled pass loop (i-cache stalls 23% -> 6% but +12% instructions from loop-carried
 // register shuffling: no gain); software-pipelined tile hand-over (4% slower); global-colour order that rotates
@@ -209,7 +240,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
     // first frame (possibly negative = does not exist) whose window support can reach hop h is h + kfirst0
     const int kfirst0 = (a - win >= 0) ? (a - win) / hop + 1 : -((win - a - 1) / hop + 1) + 1;
 
-    for (int i = threadIdx.x; i < kTwF2; i += kThreads) tw_s[i] = P.plan.tw[i];
+    load_twiddle_pairs(tw_s, P.plan.tw);
+    const float4* tw4 = reinterpret_cast<const float4*>(tw_s);
+    const float2* tw31 = tw_s + 15 * 64;
     for (int i = threadIdx.x; i < kNfft; i += kThreads) win_s[i] = P.plan.win[i];
     __syncthreads();
     for (int j = threadIdx.x; j < hop; j += kThreads) {
@@ -298,7 +331,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                     load_frame<false, PRUNE, true>(z, y_in + s_off, L, (long long)k * hop - origin, win_s, lane, 0.f,
                                                    reinterpret_cast<float*>(scratch));
                 }
-                fwd_phase1(z, lane, scratch, tw_s);
+                fwd_phase1_tw4<PRUNE>(z, lane, scratch, tw4, tw31);
                 __syncwarp();
 #pragma unroll
                 for (int t = 0; t < 32; ++t) z[t] = scratch[lane * kRowStride + t];
@@ -368,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                     } else {
                         const int j = lane, jj = 32 - lane;
                         // u = -i * w64^j with w64^j = w2048^(16 * 2j) from the twiddle table (j = 16: w = -i)
-                        const float2 wj = (j <= 15) ? tw_s[15 * 32 + 2 * j] : make_float2(0.f, -1.f);
+                        const float2 wj = (j <= 15) ? tw_s[(7 * 32 + 2 * j) * 2 + 1] : make_float2(0.f, -1.f);   // row 16 of the paired table
                         const c2 u = mk2(wj.y, -wj.x);
                         const c2 Aj = xch[j], Bj = xch[jj];
                         const c2 S1 = cadd_conj(Aj, Bj), D1 = csub_conj(Aj, Bj);
@@ -405,7 +438,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                 fft32<+1>(z);
                 scratch[lane * kRowStride] = z[0];
 #pragma unroll
-                for (int r = 1; r < 32; ++r) scratch[lane * kRowStride + r] = cmul_conj(z[r], tw_s[(r - 1) * 32 + lane]);
+                for (int p = 0; p < 15; ++p) {             // multiply in place, store afterwards (see fwd_phase1_tw4)
+                    const float4 w = tw4[p * 32 + lane];
+                    z[2 * p + 1] = cmul_conj(z[2 * p + 1], mk2(w.x, w.y));
+                    z[2 * p + 2] = cmul_conj(z[2 * p + 2], mk2(w.z, w.w));
+                }
+                z[31] = cmul_conj(z[31], tw31[lane]);
+#pragma unroll
+                for (int r = 1; r < 32; ++r) scratch[lane * kRowStride + r] = z[r];
                 __syncwarp();
                 inv_phase2(z, lane, scratch);
                 __syncwarp();                        // the scratch tile may be rewritten by this warp's next frame

@@ -184,27 +184,6 @@ __device__ __forceinline__ void locate_left(const Batch& B, int V, int b_hint, G
     fill_loc(B, V, b, o);
 }
 
-// forward pass 1 with the paired twiddle table (see the kernel's shared-memory layout)
-template <int PRUNE>
-__device__ __forceinline__ void fwd_phase1_tw4(c2 (&z)[32], int lane, f2* scratch, const float4* tw4, const float2* tw31) {
-    fft32_sparse<-1, PruneRange<PRUNE>::t0, PruneRange<PRUNE>::t1>(z);      // z[t] outside the window support is zero and never read
-    real64_post(z);
-    float* row0 = reinterpret_cast<float*>(scratch);
-    row0[lane] = z[0].x;
-    row0[lane + 32] = z[0].y;
-    // multiply in place, store afterwards: a product that lives in its own z register is not copied before its store
-    // (ptxas moves a store's source aside when the register is about to be reused - two MOVs per twiddle otherwise)
-#pragma unroll
-    for (int p = 0; p < 15; ++p) {
-        const float4 w = tw4[p * 32 + lane];
-        z[2 * p + 1] = cmul(z[2 * p + 1], mk2(w.x, w.y));
-        z[2 * p + 2] = cmul(z[2 * p + 2], mk2(w.z, w.w));
-    }
-    z[31] = cmul(z[31], tw31[lane]);
-#pragma unroll
-    for (int q = 1; q < 32; ++q) scratch[q * kRowStride + lane] = z[q];
-}
-
 // frame load (kernels.cuh load_frame) for the paired window table, reading the waveform from L2 (it is rewritten by
 // other SMs inside the launch)
 template <int PRUNE>
@@ -279,10 +258,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
     float* stage = reinterpret_cast<float*>(scratch);
     if (P.trace && threadIdx.x == 0) { P.trace[3 * blockIdx.x] = sm_id(); P.trace[3 * blockIdx.x + 1] = global_ns(); }
 
-    for (int i = threadIdx.x; i < kTwF2; i += kThreads) {
-        const int q = i / 32 + 1, l = i % 32;                 // global table: tw[(q-1)*32 + l]
-        tw_s[q < 31 ? (((q - 1) >> 1) * 32 + l) * 2 + ((q - 1) & 1) : 15 * 64 + l] = P.plan.tw[i];
-    }
+    load_twiddle_pairs(tw_s, P.plan.tw);
     for (int i = threadIdx.x; i < (t1 - t0) * 32; i += kThreads) {
         const int n = 64 * (t0 + i / 32) + (i & 31);
         wp_tab[i] = make_float2(P.plan.win[n], P.plan.win[n + 32]);

@@ -598,10 +598,16 @@ struct EmphParams {
     double p;
     double scale;         // output multiplier (undoes the magnitude pre-scale); 0 is treated as 1
     int* status;          // optional device flag: bit0 = non-finite sample (the Griffin-Lim result passes through here)
+    int n_seg;            // CTAs per utterance (blockIdx.x = utterance * n_seg + segment), >= 1
+    long long seg_len;    // samples per CTA (a multiple of the chunk); 0: one CTA per utterance
+    long long warmup;     // samples a segment's CTA runs through before its first output: p^warmup is below double rounding, so
+                          // the dropped history cannot be seen in the result (host: smallest chunk multiple with p^w < 1e-24)
 };
 
 // y[n] = x[n] + p*y[n-1] per utterance (scipy.signal.lfilter([1],[1,-p]), zero initial state), in double.
-// One CTA walks one utterance chunk by chunk; inside a chunk each thread owns kPerThread consecutive
+// An utterance is cut into segments of seg_len samples, one CTA each: the filter's memory decays like p^n, so
+// a CTA that starts `warmup` samples early from a zero state reproduces the sequential result to below double rounding.
+// One CTA walks its segment chunk by chunk; inside a chunk each thread owns kPerThread consecutive
 // samples and the carries are combined with a warp/CTA scan of the constant-ratio recurrence.
 constexpr int kDeemphThreads = 256;
 constexpr int kPerThread = 8;
@@ -609,7 +615,8 @@ constexpr int kPerThread = 8;
 __global__ void __launch_bounds__(kDeemphThreads) k_deemphasis(EmphParams P) {
     __shared__ double warp_tot[kDeemphThreads / 32];
     __shared__ double carry_s;
-    const int b = blockIdx.x;
+    const int nseg = P.n_seg > 0 ? P.n_seg : 1;
+    const int b = blockIdx.x / nseg, seg = blockIdx.x - b * nseg;
     const long long s_off = __ldg(P.batch.samp_off + b);
     const long long L = __ldg(P.batch.samp_off + b + 1) - s_off;
     const float* x = P.in + s_off;
@@ -630,7 +637,10 @@ __global__ void __launch_bounds__(kDeemphThreads) k_deemphasis(EmphParams P) {
     __syncthreads();
     bool bad = false;
     const long long chunk = (long long)kDeemphThreads * kPerThread;
-    for (long long c0 = 0; c0 < L; c0 += chunk) {
+    const long long seg0 = P.seg_len > 0 ? (long long)seg * P.seg_len : 0;      // first sample this CTA writes
+    const long long seg1 = P.seg_len > 0 ? min(L, seg0 + P.seg_len) : L;
+    if (seg0 >= L) return;
+    for (long long c0 = max(0LL, seg0 - P.warmup); c0 < seg1; c0 += chunk) {
         const long long i0 = c0 + (long long)tid * kPerThread;
         double loc[kPerThread];
         double s = 0.0;
@@ -667,7 +677,7 @@ __global__ void __launch_bounds__(kDeemphThreads) k_deemphasis(EmphParams P) {
         const double cin = fma(dec, enter, prev);
 #pragma unroll
         for (int i = 0; i < kPerThread; ++i) {
-            if (i0 + i < L) {
+            if (i0 + i < seg1 && i0 + i >= seg0) {
                 double v = fma(ppow[i + 1], cin, loc[i]);
                 if (P.out64) P.out64[s_off + i0 + i] = v; else P.out32[s_off + i0 + i] = (float)v;
             }

@@ -695,6 +695,23 @@ extern "C" int nsb_istft_tf(nsb_handle_t h, const float* spec, int32_t layout, c
     return run_istft(h, spec, layout, n_frames, batch, wav_out, space, stream, true);
 }
 
+// k_deemphasis launch geometry: segments of 16 chunks (32768 samples) per CTA once the filter's memory is short enough
+static int deemph_grid(double p, long long max_len, EmphParams& E, int batch) {
+    const long long chunk = (long long)kDeemphThreads * kPerThread;
+    E.seg_len = 0; E.warmup = 0; E.n_seg = 1;
+    const double ap = std::fabs(p);
+    if (ap > 0.0 && ap < 1.0) {
+        const long long w = (long long)std::ceil(std::log(1e-24) / std::log(ap));
+        const long long wc = (w + chunk - 1) / chunk * chunk;
+        const long long seg = 16 * chunk;
+        if (wc <= seg / 4 && max_len > seg) { E.seg_len = seg; E.warmup = wc; E.n_seg = (int)((max_len + seg - 1) / seg); }
+    } else if (ap == 0.0) {
+        const long long seg = 16 * chunk;
+        if (max_len > seg) { E.seg_len = seg; E.warmup = 0; E.n_seg = (int)((max_len + seg - 1) / seg); }
+    }
+    return batch * E.n_seg;
+}
+
 // `iters` Griffin-Lim iterations on the (sub-)batch B; y ping-pongs between ws_y0 / ws_y1, `cur` says which holds y
 static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int total_groups, int H, int& cur, int iters, cudaStream_t st,
                          bool tf = false, float inv_thr = 0.f) {
@@ -951,7 +968,10 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
             E.batch = B; E.in = y_fin; E.p = (flags & NSB_GL_DEEMPHASIS) ? h->hp.preemphasis : 0.0; E.scale = 1.0 / gscale;
             E.status = h->d_status;
             if (out_dtype == NSB_F64) E.out64 = reinterpret_cast<double*>(d_out); else E.out32 = reinterpret_cast<float*>(d_out);
-            NSB_LAUNCH(k_deemphasis, b1 - b0, kDeemphThreads, 0, st, E);
+            long long max_len = 0;
+            for (int b = b0; b < b1; ++b) max_len = std::max(max_len, (long long)(h->h_samp_off[b + 1] - h->h_samp_off[b]));
+            const int dgrid = deemph_grid(E.p, max_len, E, b1 - b0);
+            NSB_LAUNCH(k_deemphasis, dgrid, kDeemphThreads, 0, st, E);
             if ((rc = check_launch(h, "k_deemphasis"))) { cleanup(); return rc; }
         } else {
             CUE(cudaMemcpyAsync(d_out + s_base * sizeof(float), y_fin + s_base, sizeof(float) * s_cnt, cudaMemcpyDeviceToDevice, st));
@@ -1007,7 +1027,12 @@ static int run_emph(nsb_handle_s* h, bool inverse, const float* x, const int64_t
     EmphParams E{};
     E.batch = d.dev; E.in = d_x; E.p = h->hp.preemphasis;
     if (out_dtype == NSB_F64) E.out64 = reinterpret_cast<double*>(d_out); else E.out32 = reinterpret_cast<float*>(d_out);
-    if (inverse) NSB_LAUNCH(k_deemphasis, batch, kDeemphThreads, 0, st, E);
+    if (inverse) {
+        long long max_len = 0;
+        for (int b = 0; b < batch; ++b) max_len = std::max(max_len, (long long)n_samples[b]);
+        const int dgrid = deemph_grid(E.p, max_len, E, batch);
+        NSB_LAUNCH(k_deemphasis, dgrid, kDeemphThreads, 0, st, E);
+    }
     else NSB_LAUNCH(k_preemphasis, grid_1d(d.total_samples, 256, 4 * h->num_sms), 256, 0, st, E, d.total_samples);
     if ((rc = check_launch(h, inverse ? "k_deemphasis" : "k_preemphasis"))) return rc;
     if (space == NSB_HOST) {

@@ -46,6 +46,9 @@ def check_single_ops_vs_oracle(over):
     assert pe.dtype == np.float64 and de.dtype == np.float64
     assert ao.rel_l2(pe, ao.preemphasis(x, ohp)) < 1e-12
     assert ao.rel_l2(de, ao.inv_preemphasis(x, ohp)) < 1e-12
+    # long signal: k_deemphasis cuts it into segments of 32768 samples, one CTA each, with a warm-up instead of a carry
+    xl = speechlike(90001, 4)
+    assert ao.rel_l2(audio.inv_preemphasis(xl), ao.inv_preemphasis(xl, ohp)) < 1e-12
     v = (np.random.RandomState(5).randn(777) * 50).astype(np.float32)
     assert ao.rel_l2(audio._amp_to_db(np.abs(v)), ao._amp_to_db(np.abs(v))) < 1e-6
     assert ao.rel_l2(audio._db_to_amp(v), ao._db_to_amp(v)) < 1e-6
