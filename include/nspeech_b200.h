@@ -146,6 +146,18 @@ int nsb_elementwise(nsb_handle_t h, int32_t op, const float* in, int64_t n, floa
 /* deferred device-side error flag of NSB_DEVICE calls (bit 0: non-finite data seen); synchronises; clears it */
 int nsb_check_status(nsb_handle_t h, void* stream);
 
+/* find_endpoint(wav, threshold_db=-40, min_silence_sec=0.8) (utils/audio.py:67-74), batched: wav packed per utterance,
+ * wav_dtype NSB_F32 / NSB_F64; endpoints[b] = the sample count to keep (x + hop of the first silent window, else the length). */
+int nsb_find_endpoint(nsb_handle_t h, const void* wav, int32_t wav_dtype, const int64_t* n_samples, int32_t batch,
+                      double threshold_db, double min_silence_sec, int64_t* endpoints, int32_t space, void* stream);
+
+/* The spectrogram -> waveform stage of Synthesizer.synthesize (synthesizer.py:30, 51-53) for a batch, in one pipeline:
+ * inv_spectrogram_tensorflow (NSB_GL_TF_TWIN semantics) -> inv_preemphasis -> find_endpoint.  spec: normalised linear
+ * spectrograms, frame-major [sum T][num_freq]; wav_out float64, win + hop*(T-1) samples per utterance (the caller keeps the
+ * first endpoints[b] of them, synthesizer.py:53). */
+int nsb_synthesize(nsb_handle_t h, const float* spec, const int32_t* n_frames, int32_t batch, int32_t iters,
+                   double threshold_db, double min_silence_sec, double* wav_out, int64_t* endpoints, int32_t space, void* stream);
+
 /* page-locked host buffers for the NSB_HOST entry points (plain cudaHostAlloc / cudaFreeHost): copies from
  * pageable numpy memory are staged by the driver and reach only a fraction of PCIe bandwidth */
 int nsb_alloc_pinned(uint64_t bytes, void** out);

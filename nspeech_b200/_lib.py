@@ -69,6 +69,8 @@ SIGNATURES = {
     "nsb_set_host_chunks": (ctypes.c_int, [_vp, _i32]),
     "nsb_stream_trace": (ctypes.c_int, [_vp, _i32, _vp, _i32]),
     "nsb_kernel_launches": (_u64, [_vp]),
+    "nsb_find_endpoint": (ctypes.c_int, [_vp, _vp, _i32, _pi64, _i32, ctypes.c_double, ctypes.c_double, _vp, _i32, _vp]),
+    "nsb_synthesize": (ctypes.c_int, [_vp, _vp, _pi32, _i32, _i32, ctypes.c_double, ctypes.c_double, _vp, _vp, _i32, _vp]),
     "nsb_griffin_lim_iterate": (ctypes.c_int, [_vp, _i32, _vp]),
     "nsb_alloc_pinned": (ctypes.c_int, [_u64, ctypes.POINTER(_vp)]),
     "nsb_free_pinned": (ctypes.c_int, [_vp]),
@@ -219,6 +221,14 @@ class Handle(object):
 
     def num_samples_tf(self, T):
         return self.hop * (int(T) - 1) + self.win
+
+    def find_endpoint(self, wav, n_samples, endpoints, dtype=F64, threshold_db=-40.0, min_silence_sec=0.8, space=HOST, stream=None):
+        self._call("nsb_find_endpoint", _ptr(wav), dtype, self._lens(n_samples, ctypes.c_int64), len(n_samples), float(threshold_db),
+                   float(min_silence_sec), _ptr(endpoints), space, _ptr(stream))
+
+    def synthesize(self, spec, n_frames, wav_out, endpoints, iters=-1, threshold_db=-40.0, min_silence_sec=0.8, space=HOST, stream=None):
+        self._call("nsb_synthesize", _ptr(spec), self._lens(n_frames, ctypes.c_int32), len(n_frames), int(iters), float(threshold_db),
+                   float(min_silence_sec), _ptr(wav_out), _ptr(endpoints), space, _ptr(stream))
 
     def features(self, wav, n_samples, lin_out, mel_out, space=HOST, stream=None):
         self._call("nsb_features", _ptr(wav), self._lens(n_samples, ctypes.c_int64), len(n_samples), _ptr(lin_out),

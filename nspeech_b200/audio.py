@@ -309,3 +309,40 @@ def _db_to_amp_tensorflow(x):
 def _denormalize_tensorflow(S):
     # reference audio.py:170-171
     return _denormalize(S)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The steps after the vocoder in Synthesizer.synthesize (reference synthesizer.py:51-53)
+# ---------------------------------------------------------------------------------------------------------------
+
+def find_endpoint(wav, threshold_db=-40, min_silence_sec=0.8):
+    # reference audio.py:67-74 (np.max of the window, not max |.|; returns len(wav) when no silent window is found)
+    w = np.asarray(wav)
+    if w.ndim != 1:
+        raise ValueError("expected a 1-D waveform, got shape %r" % (w.shape,))
+    if w.size == 0:
+        return 0
+    dt = _lib.F64 if w.dtype == np.float64 else _lib.F32
+    w = np.ascontiguousarray(w, dtype=np.float64 if dt == _lib.F64 else np.float32)
+    out = np.zeros(1, dtype=np.int64)
+    _handle().find_endpoint(w, [w.size], out, dtype=dt, threshold_db=threshold_db, min_silence_sec=min_silence_sec)
+    return int(out[0])
+
+
+def synthesize_waveforms(linear_outputs, iters=None, threshold_db=-40, min_silence_sec=0.8):
+    """The spectrogram -> waveform stage of ``Synthesizer.synthesize`` (synthesizer.py:30, 51-53) for ``[T, F]`` or a
+    batch ``[N, T, F]`` of normalised linear spectrograms, in one device pipeline:
+    ``wav = inv_spectrogram_tensorflow(lin); wav = inv_preemphasis(wav); wav = wav[:find_endpoint(wav)]``.
+    Returns a float64 waveform (or a list of N)."""
+    S, batched = _tf_batch(linear_outputs, np.float32)
+    h = _handle()
+    if S.shape[-1] != h.num_freq:
+        raise ValueError("expected %d frequency bins on the last axis, got %d" % (h.num_freq, S.shape[-1]))
+    N = S.shape[0] if batched else 1
+    T = S.shape[-2]
+    n = h.num_samples_tf(T)
+    wav = np.empty((N, n), dtype=np.float64)
+    ends = np.zeros(N, dtype=np.int64)
+    h.synthesize(S, [T] * N, wav, ends, iters=-1 if iters is None else iters, threshold_db=threshold_db, min_silence_sec=min_silence_sec)
+    outs = [wav[i, :int(ends[i])] for i in range(N)]
+    return outs if batched else outs[0]

@@ -753,4 +753,59 @@ __global__ void __launch_bounds__(kThreads) k_linear_to_mel(MelParams P) {
     }
 }
 
+// =============================================================================================
+// find_endpoint (utils/audio.py:67-74): the first x = hop, 2*hop, ... < len - window with max(wav[x : x + window]) < threshold
+// gives x + hop, else len.  window = int(sample_rate * min_silence_sec), hop = int(window / 4); note np.max, not max |.|.
+// One CTA per utterance: maxima of the hop-long blocks (shared memory), then every candidate window is the maximum of its
+// window/hop whole blocks and the window % hop samples after them; the smallest hit wins (64-bit atomicMin in shared memory).
+// =============================================================================================
+struct EndpointParams {
+    Batch batch;
+    const float* in32;        // packed samples: one of the two inputs is non-null
+    const double* in64;
+    long long* out;           // [batch] endpoints (sample counts)
+    long long window, hop;
+    double threshold;         // amplitude (the caller applies _db_to_amp)
+};
+constexpr int kEndpointBlocks = 4096;     // hop-long blocks held in shared memory per pass (4096 * 4000 samples = 13 min at 20 kHz)
+
+__global__ void __launch_bounds__(256) k_find_endpoint(EndpointParams P) {
+    __shared__ double bmax[kEndpointBlocks];
+    __shared__ unsigned long long best;
+    const int b = blockIdx.x;
+    const long long s_off = __ldg(P.batch.samp_off + b);
+    const long long L = __ldg(P.batch.samp_off + b + 1) - s_off;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto at = [&](long long i) -> double { return P.in64 ? __ldg(P.in64 + s_off + i) : (double)__ldg(P.in32 + s_off + i); };
+    if (threadIdx.x == 0) best = (unsigned long long)L;
+    const long long nb = (L + P.hop - 1) / P.hop;                 // blocks of the utterance
+    const long long q = P.window / P.hop;                         // whole blocks per window (the rest is read directly)
+    // candidates x = j * hop, j >= 1, x < L - window; processed in passes of kEndpointBlocks - q blocks
+    for (long long j0 = 1; j0 * P.hop < L - P.window; j0 += kEndpointBlocks - q) {
+        __syncthreads();
+        if (best < (unsigned long long)L) break;                  // an earlier pass found the endpoint (uniform: read after the barrier)
+        const long long nblk = min((long long)kEndpointBlocks, nb - j0);
+        for (long long k = warp; k < nblk; k += 8) {              // one warp per block
+            const long long a0 = (j0 + k) * P.hop, a1 = min(L, a0 + P.hop);
+            double m = -INFINITY;
+            bool nan = false;
+            for (long long i = a0 + lane; i < a1; i += 32) { const double v = at(i); nan |= (v != v); m = fmax(m, v); }
+            for (int d = 16; d > 0; d >>= 1) { m = fmax(m, __shfl_xor_sync(0xffffffffu, m, d)); nan |= (__shfl_xor_sync(0xffffffffu, (int)nan, d) != 0); }
+            if (lane == 0) bmax[k] = nan ? NAN : m;               // np.max propagates NaN: such a window never compares below
+        }
+        __syncthreads();
+        for (long long k = threadIdx.x; k + q <= nblk; k += blockDim.x) {
+            const long long x = (j0 + k) * P.hop;
+            if (x >= L - P.window) break;
+            double m = -INFINITY;
+            bool nan = false;
+            for (long long t = 0; t < q; ++t) { const double v = bmax[k + t]; nan |= (v != v); m = fmax(m, v); }
+            for (long long i = x + q * P.hop; i < x + P.window; ++i) { const double v = at(i); nan |= (v != v); m = fmax(m, v); }
+            if (!nan && m < P.threshold) atomicMin(&best, (unsigned long long)(x + P.hop));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) P.out[b] = (long long)best;
+}
+
 }  // namespace nsb

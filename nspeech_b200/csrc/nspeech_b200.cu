@@ -87,7 +87,7 @@ struct nsb_handle_s {
     void* h_desc = nullptr;          // pinned
     size_t h_desc_cap = 0;
     // workspaces
-    DevBuf ws_mag, ws_y0, ws_y1, ws_in, ws_in2, ws_out, ws_out2;
+    DevBuf ws_mag, ws_y0, ws_y1, ws_in, ws_in2, ws_out, ws_out2, ws_ep;
     // state of the last device-resident Griffin-Lim (for nsb_griffin_lim_iterate)
     struct { bool valid = false; Batch batch{}; int total_frames = 0; int tile_hops = 0; int total_tiles = 0; int total_groups = 0; int cur = 0; bool tf = false; float inv_thr = 0.f; } gl;
     std::vector<int> h_frame_off, h_tile_off, h_group_off;       // host copies of the last descriptors (chunking)
@@ -205,7 +205,7 @@ extern "C" int nsb_destroy(nsb_handle_t h) {
     cudaFree(h->d_status);
     if (h->h_desc) cudaFreeHost(h->h_desc);
     h->d_desc.release(); h->d_trace.release(); h->d_done.release(); h->ws_mag.release(); h->ws_y0.release(); h->ws_y1.release();
-    h->ws_in.release(); h->ws_in2.release(); h->ws_out.release(); h->ws_out2.release();
+    h->ws_in.release(); h->ws_in2.release(); h->ws_out.release(); h->ws_out2.release(); h->ws_ep.release();
     delete h;
     return NSB_OK;
 }
@@ -820,9 +820,18 @@ extern "C" int nsb_griffin_lim_iterate(nsb_handle_t h, int32_t iters, void* stre
     return gl_iterations(h, h->gl.batch, h->gl.total_tiles, h->gl.total_groups, h->gl.tile_hops, h->gl.cur, iters, pick_stream(h, stream), h->gl.tf, h->gl.inv_thr);
 }
 
-extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout, const int32_t* n_frames, int32_t batch,
-                               const float* init_phase, uint64_t seed, int32_t iters, int32_t flags,
-                               void* wav_out, int32_t out_dtype, int32_t space, void* stream) {
+// endpoint search fused into the Griffin-Lim pipeline (nsb_synthesize): per chunk, on the device result
+struct EndpointReq { int64_t* out = nullptr; double threshold_db = -40.0, min_silence_sec = 0.8; };
+static void endpoint_params(const nsb_handle_s* h, double threshold_db, double min_silence_sec, EndpointParams& E) {
+    E.window = (long long)(h->hp.sample_rate * min_silence_sec);            // int(sample_rate * min_silence_sec), audio.py:68
+    E.hop = E.window / 4;                                                    // int(window_length / 4), audio.py:69
+    if (E.hop < 1) E.hop = 1;
+    E.threshold = std::pow(10.0, threshold_db * 0.05);                       // _db_to_amp, audio.py:154-155
+}
+
+static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, const int32_t* n_frames, int32_t batch,
+                            const float* init_phase, uint64_t seed, int32_t iters, int32_t flags,
+                            void* wav_out, int32_t out_dtype, int32_t space, void* stream, const EndpointReq* ep) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");
     if (!spec || !n_frames || !wav_out || batch < 1) return fail(NSB_ERR_INVALID, "null/empty argument");
     if (out_dtype != NSB_F32 && out_dtype != NSB_F64) return fail(NSB_ERR_INVALID, "bad out_dtype");
@@ -976,6 +985,16 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
         } else {
             CUE(cudaMemcpyAsync(d_out + s_base * sizeof(float), y_fin + s_base, sizeof(float) * s_cnt, cudaMemcpyDeviceToDevice, st));
         }
+        if (ep) {
+            if ((rc = h->ws_ep.reserve(sizeof(long long) * (size_t)batch))) { cleanup(); return rc; }
+            EndpointParams EP{};
+            EP.batch = B;
+            if (out_dtype == NSB_F64) EP.in64 = reinterpret_cast<const double*>(d_out); else EP.in32 = reinterpret_cast<const float*>(d_out);
+            EP.out = reinterpret_cast<long long*>(h->ws_ep.p) + b0;
+            endpoint_params(h, ep->threshold_db, ep->min_silence_sec, EP);
+            NSB_LAUNCH(k_find_endpoint, b1 - b0, 256, 0, st, EP);
+            if ((rc = check_launch(h, "k_find_endpoint"))) { cleanup(); return rc; }
+        }
         if (space == NSB_HOST) {
             CUE(cudaEventRecord(ev_done[c], st));
             CUE(cudaStreamWaitEvent(h->copy_out, ev_done[c], 0));
@@ -986,6 +1005,8 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
     // device-resident state for nsb_griffin_lim_iterate: the whole batch
     h->gl.valid = true; h->gl.batch = d.dev; h->gl.total_frames = d.total_frames; h->gl.tile_hops = H;
     h->gl.total_tiles = d.total_tiles; h->gl.total_groups = d.total_groups; h->gl.cur = cur; h->gl.tf = tf; h->gl.inv_thr = (float)(1.0 / (2.0e-8 * gscale));
+    if (ep) CUE(cudaMemcpyAsync(ep->out, h->ws_ep.p, sizeof(long long) * (size_t)batch,
+                                space == NSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
     if (space == NSB_HOST) {
         CUE(cudaStreamSynchronize(h->copy_out));
         cleanup();
@@ -993,6 +1014,60 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
     }
 #undef CUE
     cleanup();
+    return NSB_OK;
+}
+
+extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout, const int32_t* n_frames, int32_t batch,
+                               const float* init_phase, uint64_t seed, int32_t iters, int32_t flags,
+                               void* wav_out, int32_t out_dtype, int32_t space, void* stream) {
+    return griffin_lim_impl(h, spec, layout, n_frames, batch, init_phase, seed, iters, flags, wav_out, out_dtype, space, stream, nullptr);
+}
+
+extern "C" int nsb_synthesize(nsb_handle_t h, const float* spec, const int32_t* n_frames, int32_t batch, int32_t iters,
+                              double threshold_db, double min_silence_sec, double* wav_out, int64_t* endpoints, int32_t space, void* stream) {
+    if (!endpoints) return fail(NSB_ERR_INVALID, "null endpoints");
+    if (!(min_silence_sec > 0.0)) return fail(NSB_ERR_INVALID, "min_silence_sec must be positive");
+    EndpointReq ep;
+    ep.out = endpoints; ep.threshold_db = threshold_db; ep.min_silence_sec = min_silence_sec;
+    return griffin_lim_impl(h, spec, NSB_FRAME_MAJOR, n_frames, batch, nullptr, 0, iters,
+                            NSB_GL_TF_TWIN | NSB_GL_DENORMALIZE | NSB_GL_DEEMPHASIS, wav_out, NSB_F64, space, stream, &ep);
+}
+
+extern "C" int nsb_find_endpoint(nsb_handle_t h, const void* wav, int32_t wav_dtype, const int64_t* n_samples, int32_t batch,
+                                 double threshold_db, double min_silence_sec, int64_t* endpoints, int32_t space, void* stream) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    if (!wav || !n_samples || !endpoints || batch < 1) return fail(NSB_ERR_INVALID, "null/empty argument");
+    if (wav_dtype != NSB_F32 && wav_dtype != NSB_F64) return fail(NSB_ERR_INVALID, "bad wav_dtype");
+    if (!(min_silence_sec > 0.0)) return fail(NSB_ERR_INVALID, "min_silence_sec must be positive");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = pick_stream(h, stream, space);
+    std::vector<int> frames(batch, 0); std::vector<long long> samples(batch);
+    for (int b = 0; b < batch; ++b) {
+        if (n_samples[b] < 0) return fail(NSB_ERR_INVALID, "utterance %d has a negative length", b);
+        samples[b] = n_samples[b];
+    }
+    Desc d;
+    int rc = upload_desc(h, st, frames, samples, 0, &d);
+    if (rc) return rc;
+    const size_t elt = wav_dtype == NSB_F64 ? sizeof(double) : sizeof(float);
+    const void* d_wav = wav;
+    if (space == NSB_HOST) {
+        if ((rc = h->ws_in.reserve(elt * (size_t)d.total_samples + 16))) return rc;
+        CU(cudaMemcpyAsync(h->ws_in.p, wav, elt * (size_t)d.total_samples, cudaMemcpyHostToDevice, st));
+        d_wav = h->ws_in.p;
+    }
+    if ((rc = h->ws_ep.reserve(sizeof(long long) * (size_t)batch))) return rc;
+    EndpointParams EP{};
+    EP.batch = d.dev;
+    if (wav_dtype == NSB_F64) EP.in64 = reinterpret_cast<const double*>(d_wav); else EP.in32 = reinterpret_cast<const float*>(d_wav);
+    EP.out = reinterpret_cast<long long*>(h->ws_ep.p);
+    endpoint_params(h, threshold_db, min_silence_sec, EP);
+    NSB_LAUNCH(k_find_endpoint, batch, 256, 0, st, EP);
+    if ((rc = check_launch(h, "k_find_endpoint"))) return rc;
+    CU(cudaMemcpyAsync(endpoints, h->ws_ep.p, sizeof(long long) * (size_t)batch,
+                       space == NSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+    if (space == NSB_HOST) CU(cudaStreamSynchronize(st));
     return NSB_OK;
 }
 

@@ -71,6 +71,21 @@ static inline T __shfl_up_sync(unsigned, T v, int delta) {
     c->warp_bar[w]->arrive_and_wait();
     return r;
 }
+template <typename T>
+static inline T __shfl_xor_sync(unsigned, T v, int mask) {
+    auto* c = nsb_emu::g_ctx;
+    int w = nsb_emu::g_tid.x >> 5, l = nsb_emu::g_tid.x & 31;
+    c->xchg[w][l] = (double)v;
+    c->warp_bar[w]->arrive_and_wait();
+    T r = (T)c->xchg[w][l ^ mask];
+    c->warp_bar[w]->arrive_and_wait();
+    return r;
+}
+static inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) {
+    unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 template <typename T> static inline T __ldcg(const T* p) { return *p; }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }

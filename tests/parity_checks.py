@@ -270,3 +270,45 @@ def check_streaming_rounds(T=150, iters=2, tf=False):
             want = ao.inv_spectrogram(specs[i].T, ohp, angles=ph.T, iters=iters)
         assert ao.snr_db(ref[off:off + n], want) > 60, (i, t)
         off += n
+
+
+def check_find_endpoint_and_synthesis_stage(golden):
+    """find_endpoint (reference audio.py:67-74) and the fused spectrogram -> waveform stage of Synthesizer.synthesize
+    (synthesizer.py:30, 51-53: inv_spectrogram_tensorflow -> inv_preemphasis -> find_endpoint)."""
+    ohp = _load(min_level_db=-100)
+    # the reference's own find_endpoint on this input (tests/golden/make_golden.py)
+    ep_in = np.concatenate([speechlike(30000, 3), np.zeros(30000, np.float32)])
+    assert len(ep_in) == int(golden["endpoint_in_len"])
+    assert audio.find_endpoint(ep_in) == int(golden["endpoint"]) == ao.find_endpoint(ep_in, ohp)
+    rs = np.random.RandomState(4)
+    cases = []
+    w = speechlike(70000, 5).astype(np.float64)
+    w[21000:52000] *= 1e-4                                   # a silent stretch in the middle
+    cases.append((w, {}))
+    cases.append((w.astype(np.float32), {}))
+    cases.append((speechlike(50000, 6), {}))                 # never silent -> len(wav)
+    cases.append((speechlike(9000, 7), {}))                  # shorter than one window -> len(wav)
+    cases.append((np.zeros(40000, np.float32), {}))          # silent from the start -> 2 * hop
+    cases.append((w, {"threshold_db": -25, "min_silence_sec": 0.35}))
+    cases.append((w, {"min_silence_sec": 0.80005}))          # window % 4 != 0: the window is 4 hops + 1 sample
+    neg = -np.abs(speechlike(60000, 8)).astype(np.float64)   # np.max, not max|.|: an all-negative loud signal counts as silent
+    cases.append((neg, {}))
+    cases.append((rs.randn(33000) * 0.004, {}))              # noise whose peaks straddle the threshold
+    for wav, kw in cases:
+        assert audio.find_endpoint(wav, **kw) == ao.find_endpoint(wav, ohp, **kw), (wav.dtype, len(wav), kw)
+    with pytest.raises(ValueError):
+        audio.find_endpoint(np.zeros((2, 10)))
+    # the fused stage: loud frames followed by frames at the floor (normalised 0 -> 1e-6 amplitude), batched and single
+    T = 140
+    specs = rs.rand(2, T, 1025).astype(np.float32)
+    specs[0, 50:] = 0.0
+    outs = audio.synthesize_waveforms(specs, iters=3)
+    assert len(outs) == 2
+    for i in range(2):
+        ref = ao.inv_preemphasis(tfo.inv_spectrogram_tensorflow(specs[i], ohp, iters=3), ohp)
+        end = ao.find_endpoint(ref, ohp)
+        assert outs[i].dtype == np.float64 and outs[i].shape == (end,), (i, outs[i].shape, end)
+        assert ao.snr_db(outs[i], ref[:end]) > 60
+    assert outs[0].size < outs[1].size == audio._handle().num_samples_tf(T)
+    single = audio.synthesize_waveforms(specs[0], iters=3)
+    np.testing.assert_array_equal(single, outs[0])

@@ -79,6 +79,10 @@ def test_streaming_rounds(emu, tf):
     pc.check_streaming_rounds(T=110, iters=2, tf=tf)
 
 
+def test_find_endpoint_and_synthesis_stage(emu, golden):
+    pc.check_find_endpoint_and_synthesis_stage(golden)
+
+
 def test_errors_and_edge_cases(emu):
     pc.check_errors_and_edge_cases()
 

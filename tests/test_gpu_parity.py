@@ -50,6 +50,10 @@ def test_streaming_rounds(tf):
     pc.check_streaming_rounds(T=700, iters=6, tf=tf)
 
 
+def test_find_endpoint_and_synthesis_stage(golden):
+    pc.check_find_endpoint_and_synthesis_stage(golden)
+
+
 def test_errors_and_edge_cases():
     pc.check_errors_and_edge_cases()
 
