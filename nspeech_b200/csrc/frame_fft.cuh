@@ -87,4 +87,38 @@ NSB_HD void inv_phase2(c2 (&z)[32], int lane, const f2* scratch) {
     fft32<+1>(z);
 }
 
+#if defined(__CUDACC__) || defined(NSB_EMULATE)
+// Twiddles w2048^(q*l) in shared memory in PAIRS of rows: tw4[p*32 + l] = (w^((2p+1) l), w^((2p+2) l)), p = 0..14, row 31 after
+// them (tw31 = tw_s + 15*64) - one LDS.128 serves two twiddle multiplications (every instruction less counts: the kernels are
+// bound by instruction supply, profiles/r1/microbench_icache.txt).  `src` is the handle's table tw[(q-1)*32 + l].
+__device__ __forceinline__ void load_twiddle_pairs(float2* tw_s, const float2* src) {
+    for (int i = threadIdx.x; i < kTwF2; i += blockDim.x) {
+        const int q = i / 32 + 1, l = i % 32;
+        tw_s[q < 31 ? (((q - 1) >> 1) * 32 + l) * 2 + ((q - 1) & 1) : 15 * 64 + l] = src[i];
+    }
+}
+
+// forward pass 1 with the paired twiddle table
+template <int NZ0, int NZ1>
+__device__ __forceinline__ void fwd_phase1_tw4(c2 (&z)[32], int lane, f2* scratch, const float4* tw4, const float2* tw31) {
+    fft32_sparse<-1, NZ0, NZ1>(z);      // z[t] outside the window support is zero and never read
+    real64_post(z);
+    float* row0 = reinterpret_cast<float*>(scratch);
+    row0[lane] = z[0].x;
+    row0[lane + 32] = z[0].y;
+    // multiply in place, store afterwards: a product that lives in its own z register is not copied before its store
+    // (ptxas moves a store's source aside when the register is about to be reused - two MOVs per twiddle otherwise)
+#pragma unroll
+    for (int p = 0; p < 15; ++p) {
+        const float4 w = tw4[p * 32 + lane];
+        z[2 * p + 1] = cmul(z[2 * p + 1], mk2(w.x, w.y));
+        z[2 * p + 2] = cmul(z[2 * p + 2], mk2(w.z, w.w));
+    }
+    z[31] = cmul(z[31], tw31[lane]);
+#pragma unroll
+    for (int q = 1; q < 32; ++q) scratch[q * kRowStride + lane] = z[q];
+}
+
+#endif
+
 }  // namespace nsb

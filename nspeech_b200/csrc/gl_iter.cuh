@@ -181,37 +181,6 @@ __device__ __noinline__ void gl_store_tile(const GlParams& P, float* y_out, int 
     bad |= (chk != 0.f);
 }
 
-// Twiddles w2048^(q*l) in shared memory in PAIRS of rows: tw4[p*32 + l] = (w^((2p+1) l), w^((2p+2) l)), p = 0..14, row 31 after
-// them (tw31 = tw_s + 15*64) - one LDS.128 serves two twiddle multiplications (every instruction less counts: the kernels are
-// bound by instruction supply, profiles/r1/microbench_icache.txt).  `src` is the handle's table tw[(q-1)*32 + l].
-__device__ __forceinline__ void load_twiddle_pairs(float2* tw_s, const float2* src) {
-    for (int i = threadIdx.x; i < kTwF2; i += kThreads) {
-        const int q = i / 32 + 1, l = i % 32;
-        tw_s[q < 31 ? (((q - 1) >> 1) * 32 + l) * 2 + ((q - 1) & 1) : 15 * 64 + l] = src[i];
-    }
-}
-
-// forward pass 1 with the paired twiddle table
-template <int PRUNE>
-__device__ __forceinline__ void fwd_phase1_tw4(c2 (&z)[32], int lane, f2* scratch, const float4* tw4, const float2* tw31) {
-    fft32_sparse<-1, PruneRange<PRUNE>::t0, PruneRange<PRUNE>::t1>(z);      // z[t] outside the window support is zero and never read
-    real64_post(z);
-    float* row0 = reinterpret_cast<float*>(scratch);
-    row0[lane] = z[0].x;
-    row0[lane + 32] = z[0].y;
-    // multiply in place, store afterwards: a product that lives in its own z register is not copied before its store
-    // (ptxas moves a store's source aside when the register is about to be reused - two MOVs per twiddle otherwise)
-#pragma unroll
-    for (int p = 0; p < 15; ++p) {
-        const float4 w = tw4[p * 32 + lane];
-        z[2 * p + 1] = cmul(z[2 * p + 1], mk2(w.x, w.y));
-        z[2 * p + 2] = cmul(z[2 * p + 2], mk2(w.z, w.w));
-    }
-    z[31] = cmul(z[31], tw31[lane]);
-#pragma unroll
-    for (int q = 1; q < 32; ++q) scratch[q * kRowStride + lane] = z[q];
-}
-
 // Rejected variants (measured on B200, batch 64 x 1000 frames, see profiles/README.md): one shared FFT32 copy for
 // the four passes through a rolled pass loop (i-cache stalls 23% -> 6% but +12% instructions from loop-carried
 // register shuffling: no gain); software-pipelined tile hand-over (4% slower); global-colour order that rotates
@@ -331,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                     load_frame<false, PRUNE, true>(z, y_in + s_off, L, (long long)k * hop - origin, win_s, lane, 0.f,
                                                    reinterpret_cast<float*>(scratch));
                 }
-                fwd_phase1_tw4<PRUNE>(z, lane, scratch, tw4, tw31);
+                fwd_phase1_tw4<PruneRange<PRUNE>::t0, PruneRange<PRUNE>::t1>(z, lane, scratch, tw4, tw31);
                 __syncwarp();
 #pragma unroll
                 for (int t = 0; t < 32; ++t) z[t] = scratch[lane * kRowStride + t];

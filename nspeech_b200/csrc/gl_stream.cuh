@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
                 } else {
                     load_frame_wp<PRUNE>(z, yin, L, k * hop - origin, wp, lane, stage);
                 }
-                fwd_phase1_tw4<PRUNE>(z, lane, scratch, tw4, tw31);
+                fwd_phase1_tw4<PruneRange<PRUNE>::t0, PruneRange<PRUNE>::t1>(z, lane, scratch, tw4, tw31);
                 __syncwarp();
 #pragma unroll
                 for (int t = 0; t < 32; ++t) z[t] = scratch[lane * kRowStride + t];

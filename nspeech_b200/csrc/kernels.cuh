@@ -165,7 +165,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
     float* win_s = reinterpret_cast<float*>(tw_s + kTwF2);
     float2* scratch_all = reinterpret_cast<float2*>(win_s + kNfft);
-    for (int i = threadIdx.x; i < kTwF2; i += kThreads) tw_s[i] = P.plan.tw[i];
+    load_twiddle_pairs(tw_s, P.plan.tw);
+    const float4* tw4 = reinterpret_cast<const float4*>(tw_s);
+    const float2* tw31 = tw_s + 15 * 64;
     // 0.5 folds the forward transform's factor 2 (frame_fft.cuh) so the registers hold rfft exactly
     for (int i = threadIdx.x; i < kNfft; i += kThreads) win_s[i] = 0.5f * P.plan.win[i];
     __syncthreads();
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
         c2 z[32];
         load_frame<PREEMPH, PRUNE>(z, P.wav + s_off, L, (long long)k * hop - P.plan.origin, win_s, lane, P.preemph,
                                    reinterpret_cast<float*>(scratch));
-        fwd_phase1(z, lane, scratch, tw_s);
+        fwd_phase1_tw4<PruneRange<PRUNE>::t0, PruneRange<PRUNE>::t1>(z, lane, scratch, tw4, tw31);
         __syncwarp();
         fwd_phase2(z, lane, scratch);
         __syncwarp();
