@@ -149,8 +149,40 @@ struct AnalysisParams {
     int total_frames;
     float preemph;         // coefficient (only read when PREEMPH)
     float ref_level_db, min_level_db;
+    // _normalize(_amp_to_db(amp) - ref) = clip(log2(max(1e-5, amp)) * db_scale + db_offset, 0, 1) with
+    // db_scale = 20 log10(2) / (-min_level_db), db_offset = (-ref - min_level_db) / (-min_level_db) (host, from double)
+    float db_scale, db_offset_lin, db_offset_mel;
     int* status;           // device flag: bit0 = non-finite input
 };
+
+// MUFU approximations for the feature epilogue (1025 logarithms and square roots per frame; log10f + sqrtf were a third of
+// the kernel's 4,000 instructions per frame): lg2.approx has an absolute error below 2^-22, i.e. < 2e-6 dB, sqrt.approx
+// about one ulp - far inside the 1e-5 relative-L2 bar of the features.  131 -> 173 M frames/s.
+// (Tried and rejected, both slower: the mel non-zeros cut into equal lane shares with partial sums in shared memory
+// (114 M/s), whole rows dealt to the lanes by non-zero count (165 M/s) - the row-per-lane loop is bound by the latency of
+// its dependent loads, not by its ~190 steps.)
+__device__ __forceinline__ float lg2_approx(float x) {
+#ifdef NSB_EMULATE
+    return log2f(x);
+#else
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+#ifdef NSB_EMULATE
+    return sqrtf(x);
+#else
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
+__device__ __forceinline__ float amp_to_db_norm_fast(float amp, float scale, float offset) {
+    const float v = fmaf(lg2_approx(fmaxf(1e-5f, amp)), scale, offset);
+    return fminf(fmaxf(v, 0.f), 1.f);
+}
 
 __device__ __forceinline__ float amp_to_db_norm(float amp, float ref_db, float min_db) {
     // _normalize(_amp_to_db(amp) - ref): 20*log10(max(1e-5, amp)), (S - min)/(-min), clip [0,1]
@@ -212,13 +244,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
                     magrow[0] = fabsf(z[0].x);
                     magrow[1024] = fabsf(z[0].y);
                 } else {
-                    magrow[bin_of(lane, p)] = sqrtf(fmaf(z[p].x, z[p].x, z[p].y * z[p].y));
+                    magrow[bin_of(lane, p)] = sqrt_approx(fmaf(z[p].x, z[p].x, z[p].y * z[p].y));
                 }
             }
             __syncwarp();
             if (P.out_lin) {
                 float* o = P.out_lin + (size_t)f * kBins;
-                for (int kb = lane; kb < kBins; kb += 32) o[kb] = amp_to_db_norm(magrow[kb], P.ref_level_db, P.min_level_db);
+#pragma unroll 11
+                for (int kb = lane; kb < kBins; kb += 32) o[kb] = amp_to_db_norm_fast(magrow[kb], P.db_scale, P.db_offset_lin);
             }
             if (P.out_mel) {
                 float* o = P.out_mel + (size_t)f * P.plan.num_mels;
@@ -227,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
                     const float* w = P.plan.mel_w + __ldg(P.plan.mel_ptr + m);
                     float acc = 0.f;
                     for (int i = 0; i < n; ++i) acc = fmaf(__ldg(w + i), magrow[lo + i], acc);
-                    o[m] = amp_to_db_norm(acc, 0.f, P.min_level_db);   // melspectrogram subtracts no ref_level_db (audio.py:63)
+                    o[m] = amp_to_db_norm_fast(acc, P.db_scale, P.db_offset_mel);   // melspectrogram subtracts no ref_level_db (audio.py:63)
                 }
             }
             __syncwarp();

@@ -557,6 +557,12 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
     P.plan = make_plan(h, tf); P.batch = d.dev; P.wav = d_wav; P.out_complex = d_c; P.out_lin = d_lin; P.out_mel = d_mel;
     P.total_frames = d.total_frames; P.preemph = (float)h->hp.preemphasis;
     P.ref_level_db = (float)h->hp.ref_level_db; P.min_level_db = (float)h->hp.min_level_db; P.status = h->d_status;
+    {
+        const double inv = 1.0 / (-h->hp.min_level_db);
+        P.db_scale = (float)(20.0 * 0.30102999566398119521 * inv);      // 20 log10(2) / (-min_level_db)
+        P.db_offset_lin = (float)((-h->hp.ref_level_db - h->hp.min_level_db) * inv);
+        P.db_offset_mel = (float)((-h->hp.min_level_db) * inv);
+    }
     const int grid = grid_1d(d.total_frames, kWarpsPerCta, 2 * h->num_sms);
     const size_t smem = analysis_smem();
     const int prune = tf ? h->prune_tf : h->prune;
