@@ -223,7 +223,12 @@ __device__ __forceinline__ void stage_frame(float* stage, const float* src0, int
     if (lane == 0) cp_async16(dst + 64 * (T1 - T0), src + 64 * (T1 - T0));
 }
 
-template <int PRUNE, bool DEFCFG, bool TFM>
+// FB: one CTA barrier after every colour step (the production mode).  It keeps the 8 warps in the same stretch of code, which
+// is what the instruction caches need, and it orders the overlap-add by itself: colour s starts when every warp has added
+// its colours < s, and a group is stored before the barrier of its last colour, so ring space is never reused before it is
+// free.  Without FB the per-warp event counters do both (kept for window/hop ratios where a group's hops need ALL colours of
+// the next group, and for the barrier experiments of profiles/r1/sweep_kernels.txt).
+template <int PRUNE, bool DEFCFG, bool TFM, bool FB>
 __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
     NSB_DYN_SMEM(smem_raw);
     const int hop = DEFCFG ? 250 : P.plan.hop;
@@ -271,7 +276,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
     __syncthreads();
     bool bad = false;
     const int E = C + 1;                              // events per round: C adds + 1 store
-    const bool frame_barrier = (P.sync_mode & 3) == 2 && back <= C - 1;   // back == C: a group's hops need ALL colours of the next one
 
     // ---- (iteration, chunk) items from one global counter (see k_gl_iter for why) ----
     const int NV = P.total_groups + P.batch.batch;
@@ -329,6 +333,20 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
         const float* mag0 = P.mag + (size_t)cur.f_off * kMagPitch;
         const int xmin = (cur.b == b_low) ? x_low : 0;      // lowest utterance sample this CTA accumulates
         const int ubase = (u - cur.g) * GH;                 // utterance sample x sits at ring[(ubase + x) mod RS]
+        // the group's own C hops are final once its last colour is in: normalise, store, clear the ring
+        auto store_group = [&]() {
+            if (i >= 1 && cur.b >= 0 && cur.g < cur.Gb) {
+                const int x0 = cur.g * GH;                               // utterance sample of the group's first hop
+                const int n_store = min(GH, L - x0);
+                if (n_store > 0)
+                    gl_store_group(ring, (u * GH) % RS, RS, y_out + cur.s_off + x0, n_store, C * cur.g, T, reinterpret_cast<const float*>(wp_tab), t0,
+                                   P.plan.rinv, hop, win, lo, a, P.plan.norm_wss, lane);
+            } else if (i == 0 && k_hi >= 0) {
+                // the halo group's own hops belong to the chunk on the right: nothing to store, but positions 8 and 9 reuse the space
+                const int r0 = (u * GH) % RS;
+                for (int q = lane; q < GH; q += 32) { int ri = r0 + q; if (ri >= RS) ri -= RS; ring[ri] = 0.f; }
+            }
+        };
         for (int s = 0; s < C; ++s) {
             const int k = kbase + s;
             const bool active = (k >= 0 && k <= k_hi);        // warp-uniform
@@ -487,10 +505,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
                 }
             }
             // ---- overlap-add ordering ----
-            if (s == 0) {
+            if (FB) {
+                // nothing to wait for: the barriers order everything
+            } else if (s == 0) {
                 // ring reuse: this group writes where positions i-8 (this warp) and i-9 (the right-hand warp) stored
                 if (i >= 9) wait_events(progress + wr, E * (((i - 9) >> 3) + 1), lane);
-            } else if (!frame_barrier) {
+            } else {
                 // my colour-s frame overlaps the right-hand group's frames of colour < s: they go first
                 if (has_right) wait_events(progress + wr, E * r_r + s, lane);
                 // pacing: stay within one colour of the left-hand neighbour (keeps the CTA's warps in the same code)
@@ -545,16 +565,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
                     }
                 }
             }
-            // With a CTA barrier after every colour (the production mode: it keeps the 8 warps in the same stretch of code,
-            // which is what the instruction caches need) the barrier itself orders the adds: colour s starts when every
-            // warp has added its colours < s.  Without it the per-warp event counters do.
-            if (frame_barrier) {
+            if (FB) {
+                if (s == C - 1) { __syncwarp(); store_group(); }      // the lanes read each other's accumulates
                 __syncthreads();
             } else {
                 __syncwarp();
                 if (lane == 0) flag_store(progress + warp, E * r + s + 1);
+                if ((P.sync_mode & 3) == 3) half_cta_barrier(warp);
             }
-            if ((P.sync_mode & 3) == 3) half_cta_barrier(warp);
         }
         // ---- the group is complete (z is dead from here on) ----
         // the warp's next group sits 8 positions to the left: find it, send its first frame on its way
@@ -575,24 +593,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
                 }
             }
         }
-        if (i >= 1 && cur.b >= 0 && cur.g < cur.Gb) {
+        if (!FB) {
             // my hops also need the right-hand group's first `back` colours; the colour C-1 wait covered back <= C-1
-            if (back > C - 1 && !frame_barrier) wait_events(progress + wr, E * r_r + back, lane);
-            const int x0 = cur.g * GH;                               // utterance sample of the group's first hop
-            const int n_store = min(GH, L - x0);
-            if (n_store > 0)
-                gl_store_group(ring, (u * GH) % RS, RS, y_out + cur.s_off + x0, n_store, C * cur.g, T, reinterpret_cast<const float*>(wp_tab), t0, P.plan.rinv, hop, win, lo, a,
-                               P.plan.norm_wss, lane);
+            if (back > C - 1 && i >= 1) wait_events(progress + wr, E * r_r + back, lane);
+            store_group();
             __syncwarp();
-        } else if (i == 0 && k_hi >= 0) {
-            // the halo group's own hops belong to the CTA on the right: nothing to store, but positions 8 and 9 reuse the space
-            const int r0 = (u * GH) % RS;
-            for (int q = lane; q < GH; q += 32) { int ri = r0 + q; if (ri >= RS) ri -= RS; ring[ri] = 0.f; }
-            __syncwarp();
+            if (lane == 0) flag_store(progress + warp, E * (r + 1));
         }
-        if (lane == 0) flag_store(progress + warp, E * (r + 1));
         cur = nxt;
-        if ((P.sync_mode & 3) == 1) __syncthreads();
+        if (!FB && (P.sync_mode & 3) == 1) __syncthreads();
     }
     __syncthreads();                                 // every thread's stores of this chunk are issued
     if (threadIdx.x == 0) { __threadfence(); gflag_store(P.done + chunk, n_it + 1); }

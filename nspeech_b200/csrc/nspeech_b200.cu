@@ -72,7 +72,7 @@ struct nsb_handle_s {
     float* d_win = nullptr;          // periodic Hann padded centrally to n_fft (librosa geometry)
     float* d_win_tf = nullptr;       // the same window at n in [0, win) (tf.contrib.signal geometry)
     float *d_rinv = nullptr, *d_rinv_tf = nullptr;   // [hop] reciprocal interior window sums of the two geometries
-    int stream_sync_mode = 1;        // CTA barrier per round of k_gl_stream (keeps the warps in the same code: instruction cache)
+    int stream_sync_mode = 2;        // 2: CTA barrier per colour step of k_gl_stream (production); 0, 1, 3, +4: the event-counter variants (experiments)
     DevBuf d_trace; int trace_on = 0, trace_grid = 0;
     DevBuf d_done;                   // k_gl_iter: item counter + per-tile completion counters
     int fuse_iterations = 1;         // all Griffin-Lim iterations of a call in ONE launch (0: one launch per iteration, A/B hook)
@@ -327,15 +327,17 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
     SET((k_synth<SRC_MAGZERO, 0>), ss);  SET((k_synth<SRC_MAGZERO, 2>), ss);
     SET((k_gl_iter<1, true, false>), gs); SET((k_gl_iter<1, false, false>), gs); SET((k_gl_iter<0, false, false>), gs);
     SET((k_gl_iter<2, false, true>), gs); SET((k_gl_iter<0, false, true>), gs);
-    SET((k_gl_stream<1, true, false>), gs); SET((k_gl_stream<1, false, false>), gs); SET((k_gl_stream<0, false, false>), gs);
-    SET((k_gl_stream<2, false, true>), gs); SET((k_gl_stream<0, false, true>), gs);
+    SET((k_gl_stream<1, true, false, true>), gs); SET((k_gl_stream<1, false, false, true>), gs); SET((k_gl_stream<0, false, false, true>), gs);
+    SET((k_gl_stream<2, false, true, true>), gs); SET((k_gl_stream<0, false, true, true>), gs);
+    SET((k_gl_stream<1, false, false, false>), gs); SET((k_gl_stream<0, false, false, false>), gs);
+    SET((k_gl_stream<2, false, true, false>), gs); SET((k_gl_stream<0, false, true, false>), gs);
     {
         // two CTAs per SM is what the shared-memory layout of k_gl_stream is sized for; ask the runtime instead of trusting the sum
         int nb = 0;
         const size_t sm = stream_smem(hop, win, kNfft / 2 - h->lo, h->colours, h->prune);
-        cudaError_t oe = h->defcfg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gl_stream<1, true, false>, kThreads, sm)
-                       : h->prune == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gl_stream<1, false, false>, kThreads, sm)
-                                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gl_stream<0, false, false>, kThreads, sm);
+        cudaError_t oe = h->defcfg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gl_stream<1, true, false, true>, kThreads, sm)
+                       : h->prune == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gl_stream<1, false, false, true>, kThreads, sm)
+                                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gl_stream<0, false, false, true>, kThreads, sm);
         if (oe != cudaSuccess) { cudaGetLastError(); nb = 1; }
         h->stream_ctas_per_sm = nb < 1 ? 1 : (nb > 2 ? 2 : nb);
     }
@@ -752,6 +754,12 @@ static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int t
         S.done = S.item_counter + 1;
         S.ybuf[0] = y[0]; S.ybuf[1] = y[1];
         S.chunk_groups = CH;
+        bool fb;
+        {
+            const int a = S.plan.origin - S.plan.lo, hop = h->hop, win = h->win;
+            const int kfirst0 = (a - win >= 0) ? (a - win) / hop + 1 : -((win - a - 1) / hop + 1) + 1, klast0 = (hop - 1 + a) / hop;
+            fb = (klast0 - kfirst0 <= h->colours - 1) && h->stream_sync_mode == 2;
+        }
         const int per_launch = h->fuse_iterations ? iters : 1;
         for (int it = 0; it < iters; it += per_launch) {
             const int n = iters - it < per_launch ? iters - it : per_launch;
@@ -764,12 +772,22 @@ static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int t
                 S.trace = reinterpret_cast<unsigned long long*>(h->d_trace.p);
                 h->trace_grid = grid;
             }
-            if (tf) {
-                if (S.plan.prune == 2) NSB_LAUNCH((k_gl_stream<2, false, true>), grid, kThreads, smem, st, S);
-                else NSB_LAUNCH((k_gl_stream<0, false, true>), grid, kThreads, smem, st, S);
-            } else if (h->defcfg) NSB_LAUNCH((k_gl_stream<1, true, false>), grid, kThreads, smem, st, S);
-            else if (h->prune == 1) NSB_LAUNCH((k_gl_stream<1, false, false>), grid, kThreads, smem, st, S);
-            else NSB_LAUNCH((k_gl_stream<0, false, false>), grid, kThreads, smem, st, S);
+            // the per-frame barrier variant whenever a group's hops need at most C-1 colours of the next group (always at the
+            // default hparams) and no barrier experiment is selected
+            if (fb) {
+                if (tf) {
+                    if (S.plan.prune == 2) NSB_LAUNCH((k_gl_stream<2, false, true, true>), grid, kThreads, smem, st, S);
+                    else NSB_LAUNCH((k_gl_stream<0, false, true, true>), grid, kThreads, smem, st, S);
+                } else if (h->defcfg) NSB_LAUNCH((k_gl_stream<1, true, false, true>), grid, kThreads, smem, st, S);
+                else if (h->prune == 1) NSB_LAUNCH((k_gl_stream<1, false, false, true>), grid, kThreads, smem, st, S);
+                else NSB_LAUNCH((k_gl_stream<0, false, false, true>), grid, kThreads, smem, st, S);
+            } else {
+                if (tf) {
+                    if (S.plan.prune == 2) NSB_LAUNCH((k_gl_stream<2, false, true, false>), grid, kThreads, smem, st, S);
+                    else NSB_LAUNCH((k_gl_stream<0, false, true, false>), grid, kThreads, smem, st, S);
+                } else if (h->prune == 1) NSB_LAUNCH((k_gl_stream<1, false, false, false>), grid, kThreads, smem, st, S);
+                else NSB_LAUNCH((k_gl_stream<0, false, false, false>), grid, kThreads, smem, st, S);
+            }
             if ((rc = check_launch(h, "k_gl_stream"))) return rc;
             cur ^= (n & 1);
         }
