@@ -364,8 +364,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
                     // samples were staged by the previous frame of this warp (see below): window them from shared memory
                     cp_async_wait_all();
                     __syncwarp();
-#pragma unroll
                     const float* sg = stage + stage_off;
+#pragma unroll
                     for (int t = 0; t < 32; ++t) {
                         if (t >= t0 && t < t1) z[t] = p_mul(mk2(sg[64 * t + lane], sg[64 * t + 32 + lane]), wp[t * 32 + lane]);
                         else z[t] = mk2(0.f, 0.f);
