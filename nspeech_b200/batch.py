@@ -34,8 +34,9 @@ def features_batch(wavs, device=None, want_linear=True, want_mel=True):
     ns = [w.size for w in wavs]
     Ts = [h.num_frames(n) for n in ns]
     packed = np.concatenate(wavs) if len(wavs) > 1 else wavs[0]
-    lin = np.empty((sum(Ts), h.num_freq), np.float32) if want_linear else None
-    mel = np.empty((sum(Ts), h.num_mels), np.float32) if want_mel else None
+    pool = h.lib.pinned_pool()             # results in pooled page-locked memory: the copy out runs at PCIe speed
+    lin = pool.empty((sum(Ts), h.num_freq), np.float32) if want_linear else None
+    mel = pool.empty((sum(Ts), h.num_mels), np.float32) if want_mel else None
     h.features(packed, ns, lin, mel)
     out, off = [], 0
     for T in Ts:
@@ -76,7 +77,9 @@ def inv_spectrogram_batch(specs, init_phase=None, seed=0, iters=None, device=Non
     ns = [h.num_samples(T) for T in Ts]
     dt = np.float64 if deemphasis else np.float32
     if out is None:
-        out = np.empty(sum(ns), dtype=dt)
+        # results land in pooled page-locked memory (PinnedPool): the copy out runs at PCIe speed
+        nbytes = sum(ns) * np.dtype(dt).itemsize
+        out = h.lib.pinned_pool().empty((sum(ns),), dt) if nbytes >= (1 << 20) else np.empty(sum(ns), dtype=dt)
     flags = (_lib.GL_DENORMALIZE if denormalize else 0) | (_lib.GL_DEEMPHASIS if deemphasis else 0)
     h.griffin_lim(packed, _lib.FRAME_MAJOR, Ts, out, init_phase=init_phase, seed=seed, iters=-1 if iters is None else iters,
                   flags=flags, out_dtype=_lib.F64 if deemphasis else _lib.F32)

@@ -89,3 +89,28 @@ def test_errors_and_edge_cases(emu):
 
 def test_device_random_phase_is_deterministic_per_seed(emu):
     pc.check_device_random_phase_is_deterministic_per_seed()
+
+
+def test_pinned_result_pool_lifecycle(emu):
+    """batch.* hand out arrays backed by pooled page-locked blocks: a block goes back to the pool when the LAST view of it
+    dies, and the next call reuses it."""
+    import gc
+    from nspeech_b200 import batch
+    hparams.load()
+    specs = np.random.RandomState(0).rand(3, 400, 1025).astype(np.float32)
+    pool = audio._handle().lib.pinned_pool()
+    gc.collect()
+    kept0 = pool.kept
+    outs = batch.inv_spectrogram_batch(specs, seed=1, iters=1)
+    want = outs[2].copy()
+    keep = outs[2]
+    del outs
+    gc.collect()
+    assert pool.kept == kept0                      # one view is still alive
+    np.testing.assert_array_equal(keep, want)
+    del keep
+    gc.collect()
+    assert pool.kept > kept0                       # the block came back
+    again = batch.inv_spectrogram_batch(specs, seed=1, iters=1)
+    assert pool.kept == kept0                      # ... and was reused
+    np.testing.assert_array_equal(again[2], want)
