@@ -236,14 +236,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
         const int tile_g = P.batch.tile_base + tile_l;
         const float* y_in = P.ybuf[(P.cur0 + n_it) & 1];
         float* y_out = P.ybuf[(P.cur0 + n_it + 1) & 1];
-        if (threadIdx.x == 0) {
-            progress[8 + ((item_it + 1) & 1)] = atomicAdd(P.item_counter, 1);     // the next item, read after this tile's barriers
-            if (n_it > 0) {
-                // my frames read hops of the tiles t-1, t, t+1 as iteration n-1 left them; my store overwrites what those
-                // tiles READ in iteration n-1 - both hazards are covered by waiting for their iteration n-1 to be stored
-                const int ta = tile_l > 0 ? tile_l - 1 : 0, tb = tile_l + 1 < P.total_tiles ? tile_l + 1 : tile_l;
-                for (int t = ta; t <= tb; ++t) while (gflag_load(P.done + t) < n_it) spin_pause();
-            }
+        // four lanes of warp 0, four round trips to L2 side by side: the next item, and the three tiles whose iteration n-1 this
+        // tile reads (t-1, t, t+1; my store also overwrites what THEY read in iteration n-1 - one wait covers both hazards)
+        if (threadIdx.x == 0) progress[8 + ((item_it + 1) & 1)] = atomicAdd(P.item_counter, 1);     // read after this tile's barriers
+        if (n_it > 0 && threadIdx.x >= 1 && threadIdx.x <= 3) {
+            int t = tile_l + (int)threadIdx.x - 2;
+            t = t < 0 ? 0 : (t >= P.total_tiles ? P.total_tiles - 1 : t);
+            while (gflag_load(P.done + t) < n_it) spin_pause();
         }
         const int b = __ldg(P.batch.tile_utt + tile_g) - P.batch.utt_base;
         const int tile = tile_g - __ldg(P.batch.tile_off + b);

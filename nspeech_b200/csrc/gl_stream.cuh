@@ -290,14 +290,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
     const int chunk = (int)(item - (long long)n_it * n_chunks);
     const float* y_in = P.ybuf[(P.cur0 + n_it) & 1];
     float* y_out = P.ybuf[(P.cur0 + n_it + 1) & 1];
-    if (threadIdx.x == 0) {
-        progress[8 + ((item_it + 1) & 1)] = atomicAdd(P.item_counter, 1);     // the next item, read after this chunk's barriers
-        if (n_it > 0) {
-            // my frames read hops of the chunks c-1, c, c+1 as iteration n-1 left them, and my stores overwrite what those
-            // chunks READ in iteration n-1: both hazards end when their iteration n-1 is stored
-            const int ca = chunk > 0 ? chunk - 1 : 0, cb = chunk + 1 < n_chunks ? chunk + 1 : chunk;
-            for (int c = ca; c <= cb; ++c) while (gflag_load(P.done + c) < n_it) spin_pause();
-        }
+    // four lanes, four round trips to L2 side by side: the next item, and the three chunks whose iteration n-1 this chunk reads
+    // (c-1, c, c+1; my stores also overwrite what THEY read in iteration n-1 - one wait covers both hazards)
+    if (threadIdx.x == 0) progress[8 + ((item_it + 1) & 1)] = atomicAdd(P.item_counter, 1);     // read after this chunk's barriers
+    if (n_it > 0 && threadIdx.x >= 1 && threadIdx.x <= 3) {
+        int c = chunk + (int)threadIdx.x - 2;
+        c = c < 0 ? 0 : (c >= n_chunks ? n_chunks - 1 : c);
+        while (gflag_load(P.done + c) < n_it) spin_pause();
     }
     if (threadIdx.x < kWarpsPerCta) progress[threadIdx.x] = 0;     // the ring is all zero again after every chunk
     __syncthreads();

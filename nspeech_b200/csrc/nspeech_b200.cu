@@ -915,8 +915,9 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
         if (h->host_chunks > 0) {
             for (int c = 1; c < h->host_chunks; ++c) targets.push_back((long long)d.total_frames * c / h->host_chunks);
         } else if (d.total_frames >= 60000) {
-            targets.push_back(16000);
-            targets.push_back((long long)d.total_frames - 12000);
+            const char* ef = std::getenv("NSB_CHUNK_FIRST"); const char* el = std::getenv("NSB_CHUNK_LAST");     // tuning hooks
+            targets.push_back(ef ? std::atoll(ef) : 16000);
+            targets.push_back((long long)d.total_frames - (el ? std::atoll(el) : 12000));
         } else {
             int want = d.total_frames / 16000;
             if (want > 4) want = 4;
