@@ -89,6 +89,9 @@ struct GlParams {
     float* y_out;
     const float* mag;        // permuted, pre-scaled magnitudes [frames][kMagPitch]
     int tile_hops, colours, total_tiles;
+    int wide;                // 1: small batches - frame j of a tile goes to warp j mod 8 (one frame per warp and step instead of C
+                             // consecutive ones): a tile of C hops is 1 frame-time long instead of C, and there are H/C times more tiles
+                             // to spread over the SMs.  The overlap-add is then ordered by C CTA barriers per step (colour = j mod C).
     // One launch runs `iters` Griffin-Lim iterations: the work items (iteration n, tile t), n-major, are handed out by a
     // global counter; item (n, t) may start once the tiles t-1, t, t+1 of iteration n-1 are stored (per-tile counters
     // `done`, release/acquire at GPU scope).  y ping-pongs between ybuf[0] and ybuf[1]: iteration n reads
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
         const int k_first = h0 + kfirst0;
         int k_max = (s0 + n_out + a + hop - 1) / hop - 1;      // last frame with k*hop - a < s1
         if (k_max > T - 1) k_max = T - 1;
-        if (k_max - k_first + 1 > kWarpsPerCta * C) bad = true;   // host sizes tiles so this cannot happen; never drop frames silently
+        if (!P.wide && k_max - k_first + 1 > kWarpsPerCta * C) bad = true;   // host sizes tiles so this cannot happen; never drop frames silently
         const int kg = k_first + C * warp;
         {
             float4* a4 = reinterpret_cast<float4*>(acc);            // the tile buffer is 16-byte aligned and a multiple of 4 long (+pad)
@@ -272,14 +275,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
 
         bool staged = false;                         // this frame's samples were cp.async'ed into the scratch tile already
         int stage_off = 0;                           // ... shifted by this many floats (16-byte alignment of the copies)
-        for (int s = 0; s < C; ++s) {
-            const int k = kg + s;
+        const bool wide = P.wide != 0;
+        const int n_steps = wide ? max(0, k_max - k_first + kWarpsPerCta) / kWarpsPerCta : C;
+        for (int s = 0; s < n_steps; ++s) {
+            const int k = wide ? k_first + warp + kWarpsPerCta * s : kg + s;
             const bool active = (k >= 0 && k <= k_max);        // warp-uniform
             c2 z[32];
             if (active) {
                 const int fg = f_off + k;
                 // pull the NEXT frame's magnitude row towards L2 (it streams from HBM) while this frame computes
-                if (k + 1 <= k_max) {
+                if (!wide && k + 1 <= k_max) {
                     const char* nm = reinterpret_cast<const char*>(P.mag + (size_t)(fg + 1) * kMagPitch);
                     prefetch_l2(nm + lane * 128);
                     if (lane == 0) prefetch_l2(nm + 4096);
@@ -421,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                 // cp.async so that its load latency hides behind the neighbour wait and the accumulate.  Only for
                 // frames that need no reflect padding and (8-byte copies) an even sample offset.
                 staged = false;
-                if (PRUNE == 1 && s + 1 < C && k + 1 <= k_max) {
+                if (PRUNE == 1 && !wide && s + 1 < C && k + 1 <= k_max) {
                     const long long nstart = (long long)(k + 1) * hop - origin;
                     if (nstart + 512 >= 0 && nstart + 1536 <= L && ((s_off + nstart) & 1) == 0) {
                         // 16-byte L2-only copies (y is rewritten by other SMs inside this launch: nothing of it may sit in L1);
@@ -440,7 +445,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                 staged = false;
             }
             // ---- overlap-add ordering ----
-            if (s > 0) {
+            const int colour = (k - k_first) % C;              // wide mode: every warp passes C barriers per step, `colour` of them first
+            if (wide) {
+                for (int c = 0; c < colour; ++c) __syncthreads();
+            } else if (s > 0) {
                 // my colour-s frame overlaps only frames of the two neighbour warps; those of colour < s must be in
                 if (lane == 0) {
                     if (warp > 0) while (flag_load(progress + warp - 1) < s) spin_pause();
@@ -490,8 +498,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                     }
                 }
             }
-            __syncwarp();
-            if (lane == 0) flag_store(progress + warp, s + 1);
+            if (wide) {
+                for (int c = colour; c < C; ++c) __syncthreads();
+            } else {
+                __syncwarp();
+                if (lane == 0) flag_store(progress + warp, s + 1);
+            }
         }
         __syncthreads();
         gl_store_tile<DEFCFG>(P, y_out, tile_g, acc, win_s, rinv_s, hop, win, lo, H, bad);

@@ -75,6 +75,7 @@ struct nsb_handle_s {
     int stream_sync_mode = 2;        // 2: CTA barrier per colour step of k_gl_stream (production); 0, 1, 3, +4: the event-counter variants (experiments)
     DevBuf d_trace; int trace_on = 0, trace_grid = 0;
     DevBuf d_done;                   // k_gl_iter: item counter + per-tile completion counters
+    int wide_mode = -1;              // k_gl_iter wide mode: -1 automatic (small batches), 0 off, 1 forced (tests)
     int fuse_iterations = 1;         // all Griffin-Lim iterations of a call in ONE launch (0: one launch per iteration, A/B hook)
     int stream_ctas_per_sm = 1;      // resident k_gl_stream CTAs per SM (occupancy query at creation)
     int prune_tf = 0, colours_tf = 0;
@@ -382,6 +383,7 @@ extern "C" int nsb_stream_trace(nsb_handle_t h, int32_t enable, uint64_t* out, i
 }
 extern "C" int nsb_set_stream_grid(nsb_handle_t h, int32_t n) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    if (n <= -300) { h->wide_mode = (n == -301) ? -1 : (n == -302 ? 1 : 0); return NSB_OK; }   // hook: -300 wide mode off, -301 automatic, -302 forced
     if (n <= -200) { h->fuse_iterations = (n == -201); return NSB_OK; }    // experiment hook: -200 / -201 = one launch per iteration / fused
     if (n <= -100) { h->stream_sync_mode = -n - 100; return NSB_OK; }     // experiment hook: -100 / -101 / -102 = barrier mode 0 / 1 / 2
     if (n < 0) return fail(NSB_ERR_INVALID, "stream grid %d < 0", n);
@@ -608,8 +610,19 @@ extern "C" int nsb_features(nsb_handle_t h, const float* wav, const int64_t* n_s
 // ---------------------------------------------------------------------------------------------
 // synthesis entry points
 // ---------------------------------------------------------------------------------------------
+// small batches: tiles of C hops with one frame per warp (k_gl_iter's wide mode) when that still gives at most two tiles per
+// resident CTA - a tile is then one frame-time long instead of C, which is what a single utterance needs (demo_server.py)
+static bool choose_wide(nsb_handle_s* h, const std::vector<long long>& samples) {
+    if (h->wide_mode == 0 || h->user_tile_hops > 0) return false;
+    if (h->wide_mode == 1) return true;
+    long long tiles = 0;
+    for (size_t b = 0; b < samples.size(); ++b) { long long hops = (samples[b] + h->hop - 1) / h->hop; tiles += (hops + h->colours - 1) / h->colours; }
+    return tiles <= 4LL * h->num_sms;
+}
+
 static int choose_tile_hops(nsb_handle_s* h, const std::vector<long long>& samples, bool tf = false) {
     const int Hmax = max_tile_hops(h, tf), C = h->colours;
+    if (choose_wide(h, samples)) return C;
     if (h->user_tile_hops > 0) {
         int H = h->user_tile_hops < Hmax ? h->user_tile_hops : Hmax;
         H -= H % C;                  // multiples of C only (tiling-independent summation order, see max_tile_hops)
@@ -810,6 +823,7 @@ static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int t
     GlParams G{};
     G.plan = make_plan(h, tf); G.batch = B; G.mag = reinterpret_cast<const float*>(h->ws_mag.p);
     G.tile_hops = H; G.colours = h->colours; G.total_tiles = total_tiles; G.status = h->d_status; G.inv_thr = inv_thr;
+    G.wide = (h->wide_mode != 0 && h->user_tile_hops == 0 && H == h->colours && (h->wide_mode == 1 || total_tiles <= 4 * h->num_sms)) ? 1 : 0;
     const size_t smem = gl_smem(h->hop, H);
     // one launch runs all the iterations: (iteration, tile) items from a global counter, per-tile completion counters
     int rc = h->d_done.reserve(sizeof(int) * ((size_t)total_tiles + 1));
