@@ -738,10 +738,10 @@ static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int t
                          bool tf = false, float inv_thr = 0.f) {
     float* y[2] = {reinterpret_cast<float*>(h->ws_y0.p), reinterpret_cast<float*>(h->ws_y1.p)};
     if (total_tiles <= 0) return NSB_OK;
-    // automatic choice: the streaming kernel needs chunks of >= 15 groups (two rounds of its 8 warps) and two chunks per
-    // resident CTA and iteration to beat the tile kernel (measured: profiles/r1/sweep_kernels.txt)
+    // automatic choice: the streaming kernel wins from about 7,000 groups (28k frames) per launch on; below that the tile
+    // kernel, which has less to set up per work item (measured: profiles/r1/sweep_kernels.txt)
     int which = h->use_generic_iter;
-    if (which < 0) which = ((long long)total_groups + B.batch >= 2LL * h->stream_ctas_per_sm * h->num_sms * 15 && h->stream_ctas_per_sm >= 2) ? 0 : 2;
+    if (which < 0) which = (2 * ((long long)total_groups + B.batch) >= 49LL * h->stream_ctas_per_sm * h->num_sms && h->stream_ctas_per_sm >= 2) ? 0 : 2;   // >= 3.5 chunks of 7 groups per CTA
     if (which == 0) {
         // the production path for long batches: streaming kernel, CTA i owns the contiguous group range [i*N/n, (i+1)*N/n)
         GlStreamParams S{};
