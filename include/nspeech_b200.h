@@ -151,6 +151,12 @@ int nsb_check_status(nsb_handle_t h, void* stream);
 int nsb_find_endpoint(nsb_handle_t h, const void* wav, int32_t wav_dtype, const int64_t* n_samples, int32_t batch,
                       double threshold_db, double min_silence_sec, int64_t* endpoints, int32_t space, void* stream);
 
+/* mean(|x|^2) of every centred frame = librosa.feature.rmse(y, frame_length, hop_length) ** 2 (reflect padding), the
+ * reduction behind trim_wav / trim_silence (datasets/process.py:39-54).  out: float64, 1 + n // hop_length values per
+ * utterance, packed. */
+int nsb_frame_energy(nsb_handle_t h, const float* wav, const int64_t* n_samples, int32_t batch, int32_t frame_length,
+                     int32_t hop_length, double* out, int32_t space, void* stream);
+
 /* The spectrogram -> waveform stage of Synthesizer.synthesize (synthesizer.py:30, 51-53) for a batch, in one pipeline:
  * inv_spectrogram_tensorflow (NSB_GL_TF_TWIN semantics) -> inv_preemphasis -> find_endpoint.  spec: normalised linear
  * spectrograms, frame-major [sum T][num_freq]; wav_out float64, win + hop*(T-1) samples per utterance (the caller keeps the

@@ -69,6 +69,7 @@ SIGNATURES = {
     "nsb_set_host_chunks": (ctypes.c_int, [_vp, _i32]),
     "nsb_stream_trace": (ctypes.c_int, [_vp, _i32, _vp, _i32]),
     "nsb_kernel_launches": (_u64, [_vp]),
+    "nsb_frame_energy": (ctypes.c_int, [_vp, _vp, _pi64, _i32, _i32, _i32, _vp, _i32, _vp]),
     "nsb_find_endpoint": (ctypes.c_int, [_vp, _vp, _i32, _pi64, _i32, ctypes.c_double, ctypes.c_double, _vp, _i32, _vp]),
     "nsb_synthesize": (ctypes.c_int, [_vp, _vp, _pi32, _i32, _i32, ctypes.c_double, ctypes.c_double, _vp, _vp, _i32, _vp]),
     "nsb_griffin_lim_iterate": (ctypes.c_int, [_vp, _i32, _vp]),
@@ -266,6 +267,10 @@ class Handle(object):
 
     def num_samples_tf(self, T):
         return self.hop * (int(T) - 1) + self.win
+
+    def frame_energy(self, wav, n_samples, frame_length, hop_length, out, space=HOST, stream=None):
+        self._call("nsb_frame_energy", _ptr(wav), self._lens(n_samples, ctypes.c_int64), len(n_samples), int(frame_length),
+                   int(hop_length), _ptr(out), space, _ptr(stream))
 
     def find_endpoint(self, wav, n_samples, endpoints, dtype=F64, threshold_db=-40.0, min_silence_sec=0.8, space=HOST, stream=None):
         self._call("nsb_find_endpoint", _ptr(wav), dtype, self._lens(n_samples, ctypes.c_int64), len(n_samples), float(threshold_db),

@@ -843,4 +843,39 @@ __global__ void __launch_bounds__(256) k_find_endpoint(EndpointParams P) {
     if (threadIdx.x == 0) P.out[b] = (long long)best;
 }
 
+
+// =============================================================================================
+// frame energy: mean(|x|^2) of every centred frame (librosa.feature.rmse(y, frame_length, hop_length, center=True,
+// pad_mode='reflect') ** 2), the reduction behind trim_wav (librosa.effects.split) and trim_silence
+// (datasets/process.py:39-54).  One warp per frame, double accumulation.  frames per utterance = 1 + n // hop.
+// =============================================================================================
+struct EnergyParams {
+    Batch batch;              // frame_off counts THESE frames
+    const float* wav;         // packed samples
+    double* out;              // [frames] mean square
+    int frame_length, hop_length, total_frames;
+};
+
+__global__ void __launch_bounds__(256) k_frame_energy(EnergyParams P) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int b = 0;
+    for (int f = P.batch.frame_base + blockIdx.x * 8 + warp; f < P.batch.frame_base + P.total_frames; f += gridDim.x * 8) {
+        if (!(f >= __ldg(P.batch.frame_off + b) && f < __ldg(P.batch.frame_off + b + 1)))
+            b = find_segment(P.batch.frame_off, P.batch.batch, f);
+        const int k = f - __ldg(P.batch.frame_off + b);
+        const long long s_off = __ldg(P.batch.samp_off + b);
+        const int L = (int)(__ldg(P.batch.samp_off + b + 1) - s_off);
+        const float* x = P.wav + s_off;
+        const int start = k * P.hop_length - P.frame_length / 2;
+        double acc = 0.0;
+        if (start >= 0 && start + P.frame_length <= L) {
+            for (int i = lane; i < P.frame_length; i += 32) { const double v = __ldg(x + start + i); acc = fma(v, v, acc); }
+        } else {
+            for (int i = lane; i < P.frame_length; i += 32) { const double v = __ldg(x + reflect_index(start + i, L)); acc = fma(v, v, acc); }
+        }
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0) P.out[f] = acc / (double)P.frame_length;
+    }
+}
+
 }  // namespace nsb

@@ -1072,6 +1072,43 @@ extern "C" int nsb_synthesize(nsb_handle_t h, const float* spec, const int32_t* 
                             NSB_GL_TF_TWIN | NSB_GL_DENORMALIZE | NSB_GL_DEEMPHASIS, wav_out, NSB_F64, space, stream, &ep);
 }
 
+extern "C" int nsb_frame_energy(nsb_handle_t h, const float* wav, const int64_t* n_samples, int32_t batch, int32_t frame_length,
+                                int32_t hop_length, double* out, int32_t space, void* stream) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    if (!wav || !n_samples || !out || batch < 1) return fail(NSB_ERR_INVALID, "null/empty argument");
+    if (frame_length < 1 || hop_length < 1) return fail(NSB_ERR_INVALID, "frame_length and hop_length must be positive");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = pick_stream(h, stream, space);
+    std::vector<int> frames(batch); std::vector<long long> samples(batch);
+    for (int b = 0; b < batch; ++b) {
+        if (n_samples[b] < 1) return fail(NSB_ERR_INVALID, "utterance %d is empty", b);
+        samples[b] = n_samples[b];
+        frames[b] = (int)(1 + n_samples[b] / hop_length);
+    }
+    Desc d;
+    int rc = upload_desc(h, st, frames, samples, 0, &d);
+    if (rc) return rc;
+    const float* d_wav = wav;
+    double* d_out = out;
+    if (space == NSB_HOST) {
+        if ((rc = h->ws_in.reserve(sizeof(float) * (size_t)d.total_samples))) return rc;
+        if ((rc = h->ws_out.reserve(sizeof(double) * (size_t)d.total_frames))) return rc;
+        CU(cudaMemcpyAsync(h->ws_in.p, wav, sizeof(float) * (size_t)d.total_samples, cudaMemcpyHostToDevice, st));
+        d_wav = reinterpret_cast<const float*>(h->ws_in.p);
+        d_out = reinterpret_cast<double*>(h->ws_out.p);
+    }
+    EnergyParams E{};
+    E.batch = d.dev; E.wav = d_wav; E.out = d_out; E.frame_length = frame_length; E.hop_length = hop_length; E.total_frames = d.total_frames;
+    NSB_LAUNCH(k_frame_energy, grid_1d(d.total_frames, 8, 8 * h->num_sms), 256, 0, st, E);
+    if ((rc = check_launch(h, "k_frame_energy"))) return rc;
+    if (space == NSB_HOST) {
+        CU(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)d.total_frames, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return NSB_OK;
+}
+
 extern "C" int nsb_find_endpoint(nsb_handle_t h, const void* wav, int32_t wav_dtype, const int64_t* n_samples, int32_t batch,
                                  double threshold_db, double min_silence_sec, int64_t* endpoints, int32_t space, void* stream) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");

@@ -40,3 +40,20 @@ def speechlike(n, seed, sr=20000):
 def golden():
     path = os.path.join(ROOT, "tests", "golden", "reference_audio.npz")
     return dict(np.load(path))
+
+
+def trim_signals():
+    """the clips of tests/golden/make_golden_process.py (same seeds, same code)"""
+    out = {}
+    out["quiet_ends"] = np.concatenate([0.002 * speechlike(9000, 1), speechlike(30000, 2), 0.001 * speechlike(12000, 3)]).astype(np.float32)
+    out["pauses"] = np.concatenate([np.zeros(5000, np.float32), speechlike(15000, 4), np.zeros(7000, np.float32), speechlike(800, 5),
+                                    np.zeros(6000, np.float32), speechlike(14000, 6), np.zeros(3000, np.float32)]).astype(np.float32)
+    out["loud"] = speechlike(20000, 7)
+    out["short"] = speechlike(1500, 8)
+    out["silence"] = np.zeros(8000, np.float32)
+    return out
+
+
+@pytest.fixture(scope="session")
+def golden_process():
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "reference_process.npz")))

@@ -4,7 +4,7 @@ binds whichever native library the caller selected - and compares with the oracl
 import numpy as np
 import pytest
 
-from conftest import make_hp, speechlike
+from conftest import make_hp, speechlike, trim_signals
 from nspeech_b200 import _lib, audio, hparams
 from oracle import audio_oracle as ao
 from oracle import tf_signal17 as tfo
@@ -315,3 +315,30 @@ def check_find_endpoint_and_synthesis_stage(golden):
     assert outs[0].size < outs[1].size == audio._handle().num_samples_tf(T)
     single = audio.synthesize_waveforms(specs[0], iters=3)
     np.testing.assert_array_equal(single, outs[0])
+
+
+def _span(sub, wav):
+    if sub.size == 0:
+        return (0, 0)
+    return ((sub.__array_interface__["data"][0] - wav.__array_interface__["data"][0]) // wav.itemsize, sub.size)
+
+
+def check_trimming(golden_process):
+    """trim_wav / trim_silence (reference datasets/process.py:39-54): frame energies from the GPU, the reference's interval
+    logic on the host; sample indices must equal the oracle's and the fixtures made by the reference's own process.py."""
+    from nspeech_b200 import process
+    from oracle import process_oracle as po
+    _load(min_level_db=-100)
+    for name, wav in trim_signals().items():
+        for fl, hop in ((1024, 512), (2048, 512)):
+            if wav.size >= fl:
+                assert ao.rel_l2(process.frame_energy(wav, fl, hop), (po.rmse(wav.astype(np.float64), fl, hop) ** 2)[0]) < 1e-12
+        t = process.trim_wav(wav)
+        assert _span(t, wav) == _span(po.trim_wav(wav), wav) == tuple(golden_process[name + "_trim_wav"]), name
+        for thr in (0.01, 0.1):
+            s = process.trim_silence(wav, thr)
+            assert _span(s, wav) == _span(po.trim_silence(wav, thr), wav) == tuple(golden_process["%s_trim_silence_%g" % (name, thr)]), (name, thr)
+    wav = trim_signals()["quiet_ends"]
+    w2, lin_t, mel_t, n_frames = process.process_utterance_arrays(wav)
+    assert _span(w2, wav) == tuple(golden_process["quiet_ends_trim_wav"])
+    assert lin_t.shape == (n_frames, 1025) and mel_t.shape == (n_frames, 80) and n_frames == 1 + w2.size // 250

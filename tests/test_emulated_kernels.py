@@ -83,6 +83,10 @@ def test_find_endpoint_and_synthesis_stage(emu, golden):
     pc.check_find_endpoint_and_synthesis_stage(golden)
 
 
+def test_trimming(emu, golden_process):
+    pc.check_trimming(golden_process)
+
+
 def test_errors_and_edge_cases(emu):
     pc.check_errors_and_edge_cases()
 

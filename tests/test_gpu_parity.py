@@ -54,6 +54,10 @@ def test_find_endpoint_and_synthesis_stage(golden):
     pc.check_find_endpoint_and_synthesis_stage(golden)
 
 
+def test_trimming(golden_process):
+    pc.check_trimming(golden_process)
+
+
 def test_errors_and_edge_cases():
     pc.check_errors_and_edge_cases()
 

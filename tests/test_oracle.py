@@ -174,3 +174,23 @@ def test_tf_signal_restatement_vs_torch():
     assert ao.rel_l2(x[750:-750], 1.5 * y[750:x.size - 750]) < 1e-5
     # zero phase start + est/max(1e-8,|est|): an all-zero spectrogram stays silent
     assert np.all(tfo._griffin_lim_tensorflow(np.zeros((4, 1025), np.float32), hp, iters=2) == 0)
+
+
+def test_trimming_oracle_matches_reference_process(golden_process):
+    """oracle/process_oracle.py against the fixtures written by the reference's own datasets/process.py
+    (tests/golden/make_golden_process.py)."""
+    from conftest import trim_signals
+    from oracle import process_oracle as po
+    for name, wav in trim_signals().items():
+        t = po.trim_wav(wav)
+        start = (t.__array_interface__["data"][0] - wav.__array_interface__["data"][0]) // wav.itemsize if t.size else 0
+        assert (start, t.size) == tuple(golden_process[name + "_trim_wav"])
+        for thr in (0.01, 0.1):
+            s_ = po.trim_silence(wav, thr)
+            start = (s_.__array_interface__["data"][0] - wav.__array_interface__["data"][0]) // wav.itemsize if s_.size else 0
+            assert (start, s_.size) == tuple(golden_process["%s_trim_silence_%g" % (name, thr)])
+    # rmse against a direct definition
+    y = trim_signals()["loud"].astype(np.float64)
+    e = po.rmse(y, 1024, 512)[0]
+    yp = np.pad(y, 512, mode="reflect")
+    assert abs(e[3] - np.sqrt(np.mean(yp[3 * 512:3 * 512 + 1024] ** 2))) < 1e-12
