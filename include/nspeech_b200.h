@@ -151,6 +151,13 @@ int nsb_check_status(nsb_handle_t h, void* stream);
 int nsb_find_endpoint(nsb_handle_t h, const void* wav, int32_t wav_dtype, const int64_t* n_samples, int32_t batch,
                       double threshold_db, double min_silence_sec, int64_t* endpoints, int32_t space, void* stream);
 
+/* The feeder's target tensors in one pass (datasets/datafeeder.py:190-220, _prepare_targets): spectrogram(y).T and
+ * melspectrogram(y).T of every utterance written time-major into zero-padded batch tensors
+ * lin_out [batch][rows_per_utt][num_freq], mel_out [batch][rows_per_utt][num_mels] (either may be NULL);
+ * rows_per_utt >= every utterance's frame count (the feeder uses round_up(max frames + 1, outputs_per_step)). */
+int nsb_features_padded(nsb_handle_t h, const float* wav, const int64_t* n_samples, int32_t batch, int32_t rows_per_utt,
+                        float* lin_out, float* mel_out, int32_t space, void* stream);
+
 /* mean(|x|^2) of every centred frame = librosa.feature.rmse(y, frame_length, hop_length) ** 2 (reflect padding), the
  * reduction behind trim_wav / trim_silence (datasets/process.py:39-54).  out: float64, 1 + n // hop_length values per
  * utterance, packed. */

@@ -69,6 +69,7 @@ SIGNATURES = {
     "nsb_set_host_chunks": (ctypes.c_int, [_vp, _i32]),
     "nsb_stream_trace": (ctypes.c_int, [_vp, _i32, _vp, _i32]),
     "nsb_kernel_launches": (_u64, [_vp]),
+    "nsb_features_padded": (ctypes.c_int, [_vp, _vp, _pi64, _i32, _i32, _vp, _vp, _i32, _vp]),
     "nsb_frame_energy": (ctypes.c_int, [_vp, _vp, _pi64, _i32, _i32, _i32, _vp, _i32, _vp]),
     "nsb_find_endpoint": (ctypes.c_int, [_vp, _vp, _i32, _pi64, _i32, ctypes.c_double, ctypes.c_double, _vp, _i32, _vp]),
     "nsb_synthesize": (ctypes.c_int, [_vp, _vp, _pi32, _i32, _i32, ctypes.c_double, ctypes.c_double, _vp, _vp, _i32, _vp]),
@@ -267,6 +268,10 @@ class Handle(object):
 
     def num_samples_tf(self, T):
         return self.hop * (int(T) - 1) + self.win
+
+    def features_padded(self, wav, n_samples, rows_per_utt, lin_out, mel_out, space=HOST, stream=None):
+        self._call("nsb_features_padded", _ptr(wav), self._lens(n_samples, ctypes.c_int64), len(n_samples), int(rows_per_utt),
+                   _ptr(lin_out), _ptr(mel_out), space, _ptr(stream))
 
     def frame_energy(self, wav, n_samples, frame_length, hop_length, out, space=HOST, stream=None):
         self._call("nsb_frame_energy", _ptr(wav), self._lens(n_samples, ctypes.c_int64), len(n_samples), int(frame_length),

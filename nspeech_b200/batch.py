@@ -45,6 +45,30 @@ def features_batch(wavs, device=None, want_linear=True, want_mel=True):
     return out
 
 
+def _round_up(x, multiple):
+    # reference datasets/datafeeder.py:219-221
+    remainder = x % multiple
+    return x if remainder == 0 else x + multiple - remainder
+
+
+def feeder_targets(wavs, outputs_per_step, device=None):
+    """The feeder's target tensors straight from the waveforms (reference datasets/datafeeder.py:190-216): what
+    ``_prepare_targets([spectrogram(w).T ...], r)`` and ``_prepare_targets([melspectrogram(w).T ...], r)`` build with one
+    numpy pad per utterance - time-major, zero-padded to ``round_up(max frames + 1, outputs_per_step)`` rows, stacked.
+    Returns (mel_targets [N, Tpad, num_mels], linear_targets [N, Tpad, num_freq], n_frames list)."""
+    h = audio._handle(device)
+    wavs = [audio._as_wav(w) for w in wavs]
+    ns = [w.size for w in wavs]
+    Ts = [h.num_frames(n) for n in ns]
+    rows = _round_up(max(Ts) + 1, outputs_per_step)
+    packed = np.concatenate(wavs) if len(wavs) > 1 else wavs[0]
+    pool = h.lib.pinned_pool()
+    lin = pool.empty((len(wavs), rows, h.num_freq), np.float32)
+    mel = pool.empty((len(wavs), rows, h.num_mels), np.float32)
+    h.features_padded(packed, ns, rows, lin, mel)
+    return mel, lin, Ts
+
+
 def inv_spectrogram_batch(specs, init_phase=None, seed=0, iters=None, device=None, denormalize=True, deemphasis=True,
                           out=None):
     """Griffin-Lim inversion of a batch.

@@ -147,6 +147,8 @@ struct AnalysisParams {
     float* out_lin;        // [frames][1025] or null
     float* out_mel;        // [frames][num_mels] or null
     int total_frames;
+    int rows_per_utt;      // > 0: feature row of frame k of utterance b is (utt_base + b) * rows_per_utt + k (padded batch layout of the
+                           // feeder, datasets/datafeeder.py:205-220) instead of the packed global frame index
     float preemph;         // coefficient (only read when PREEMPH)
     float ref_level_db, min_level_db;
     // _normalize(_amp_to_db(amp) - ref) = clip(log2(max(1e-5, amp)) * db_scale + db_offset, 0, 1) with
@@ -235,6 +237,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
                 }
             }
         } else {
+            const long long orow = P.rows_per_utt > 0 ? (long long)(P.batch.utt_base + b) * P.rows_per_utt + k : (long long)f;
             // magnitudes -> scratch (as floats, 1025 <= 2112), then linear dB and sparse mel
             float* magrow = reinterpret_cast<float*>(scratch);
 #pragma unroll
@@ -249,12 +252,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
             }
             __syncwarp();
             if (P.out_lin) {
-                float* o = P.out_lin + (size_t)f * kBins;
+                float* o = P.out_lin + (size_t)orow * kBins;
 #pragma unroll 11
                 for (int kb = lane; kb < kBins; kb += 32) o[kb] = amp_to_db_norm_fast(magrow[kb], P.db_scale, P.db_offset_lin);
             }
             if (P.out_mel) {
-                float* o = P.out_mel + (size_t)f * P.plan.num_mels;
+                float* o = P.out_mel + (size_t)orow * P.plan.num_mels;
                 for (int m = lane; m < P.plan.num_mels; m += 32) {
                     const int lo = __ldg(P.plan.mel_lo + m), n = __ldg(P.plan.mel_n + m);
                     const float* w = P.plan.mel_w + __ldg(P.plan.mel_ptr + m);

@@ -522,7 +522,7 @@ static int grid_1d(long long n, int threads, int max_blocks) {
 // analysis entry points
 // ---------------------------------------------------------------------------------------------
 static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wav, const int64_t* n_samples, int batch,
-                        float* out_complex, float* lin_out, float* mel_out, int space, void* stream, bool tf = false) {
+                        float* out_complex, float* lin_out, float* mel_out, int space, void* stream, bool tf = false, int rows_per_utt = 0) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");
     if (!wav || !n_samples || batch < 1) return fail(NSB_ERR_INVALID, "null/empty input");
     if (mode == ANALYSIS_COMPLEX && !out_complex) return fail(NSB_ERR_INVALID, "out_complex is null");
@@ -537,11 +537,13 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
         if (tf && n_samples[b] < h->win) return fail(NSB_ERR_INVALID, "utterance %d is shorter than one frame (%d samples)", b, h->win);
         samples[b] = n_samples[b];
         frames[b] = tf ? (int)(1 + (n_samples[b] - h->win) / h->hop) : (int)(1 + n_samples[b] / h->hop);
+        if (rows_per_utt > 0 && frames[b] > rows_per_utt) return fail(NSB_ERR_INVALID, "utterance %d has %d frames, more than rows_per_utt = %d", b, frames[b], rows_per_utt);
     }
     Desc d;
     int rc = upload_desc(h, st, frames, samples, 0, &d);
     if (rc) return rc;
     const size_t F = kBins, M = h->num_mels;
+    const size_t out_rows = rows_per_utt > 0 ? (size_t)rows_per_utt * batch : (size_t)d.total_frames;     // padded or packed
     const float* d_wav = wav;
     float2* d_c = reinterpret_cast<float2*>(out_complex);
     float *d_lin = lin_out, *d_mel = mel_out;
@@ -553,13 +555,17 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
             if ((rc = h->ws_out.reserve(sizeof(float2) * F * d.total_frames))) return rc;
             d_c = reinterpret_cast<float2*>(h->ws_out.p);
         } else {
-            if (lin_out) { if ((rc = h->ws_out.reserve(sizeof(float) * F * d.total_frames))) return rc; d_lin = reinterpret_cast<float*>(h->ws_out.p); }
-            if (mel_out) { if ((rc = h->ws_out2.reserve(sizeof(float) * M * d.total_frames))) return rc; d_mel = reinterpret_cast<float*>(h->ws_out2.p); }
+            if (lin_out) { if ((rc = h->ws_out.reserve(sizeof(float) * F * out_rows))) return rc; d_lin = reinterpret_cast<float*>(h->ws_out.p); }
+            if (mel_out) { if ((rc = h->ws_out2.reserve(sizeof(float) * M * out_rows))) return rc; d_mel = reinterpret_cast<float*>(h->ws_out2.p); }
         }
     }
     AnalysisParams P;
     P.plan = make_plan(h, tf); P.batch = d.dev; P.wav = d_wav; P.out_complex = d_c; P.out_lin = d_lin; P.out_mel = d_mel;
-    P.total_frames = d.total_frames; P.preemph = (float)h->hp.preemphasis;
+    P.total_frames = d.total_frames; P.preemph = (float)h->hp.preemphasis; P.rows_per_utt = rows_per_utt;
+    if (rows_per_utt > 0) {             // the padding rows are zeros (_pad = 0, datafeeder.py:216)
+        if (d_lin) CU(cudaMemsetAsync(d_lin, 0, sizeof(float) * F * out_rows, st));
+        if (d_mel) CU(cudaMemsetAsync(d_mel, 0, sizeof(float) * M * out_rows, st));
+    }
     P.ref_level_db = (float)h->hp.ref_level_db; P.min_level_db = (float)h->hp.min_level_db; P.status = h->d_status;
     {
         const double inv = 1.0 / (-h->hp.min_level_db);
@@ -587,8 +593,8 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
     if (space == NSB_HOST) {
         if (mode == ANALYSIS_COMPLEX) CU(cudaMemcpyAsync(out_complex, d_c, sizeof(float2) * F * d.total_frames, cudaMemcpyDeviceToHost, st));
         else {
-            if (lin_out) CU(cudaMemcpyAsync(lin_out, d_lin, sizeof(float) * F * d.total_frames, cudaMemcpyDeviceToHost, st));
-            if (mel_out) CU(cudaMemcpyAsync(mel_out, d_mel, sizeof(float) * M * d.total_frames, cudaMemcpyDeviceToHost, st));
+            if (lin_out) CU(cudaMemcpyAsync(lin_out, d_lin, sizeof(float) * F * out_rows, cudaMemcpyDeviceToHost, st));
+            if (mel_out) CU(cudaMemcpyAsync(mel_out, d_mel, sizeof(float) * M * out_rows, cudaMemcpyDeviceToHost, st));
         }
         return read_status(h, st);
     }
@@ -1070,6 +1076,12 @@ extern "C" int nsb_synthesize(nsb_handle_t h, const float* spec, const int32_t* 
     ep.out = endpoints; ep.threshold_db = threshold_db; ep.min_silence_sec = min_silence_sec;
     return griffin_lim_impl(h, spec, NSB_FRAME_MAJOR, n_frames, batch, nullptr, 0, iters,
                             NSB_GL_TF_TWIN | NSB_GL_DENORMALIZE | NSB_GL_DEEMPHASIS, wav_out, NSB_F64, space, stream, &ep);
+}
+
+extern "C" int nsb_features_padded(nsb_handle_t h, const float* wav, const int64_t* n_samples, int32_t batch, int32_t rows_per_utt,
+                                   float* lin_out, float* mel_out, int32_t space, void* stream) {
+    if (rows_per_utt < 1) return fail(NSB_ERR_INVALID, "rows_per_utt must be positive");
+    return run_analysis(h, ANALYSIS_FEATURES, true, wav, n_samples, batch, nullptr, lin_out, mel_out, space, stream, false, rows_per_utt);
 }
 
 extern "C" int nsb_frame_energy(nsb_handle_t h, const float* wav, const int64_t* n_samples, int32_t batch, int32_t frame_length,

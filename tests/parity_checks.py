@@ -342,3 +342,21 @@ def check_trimming(golden_process):
     w2, lin_t, mel_t, n_frames = process.process_utterance_arrays(wav)
     assert _span(w2, wav) == tuple(golden_process["quiet_ends_trim_wav"])
     assert lin_t.shape == (n_frames, 1025) and mel_t.shape == (n_frames, 80) and n_frames == 1 + w2.size // 250
+
+
+def check_feeder_targets():
+    """batch.feeder_targets = the reference feeder's _prepare_targets over spectrogram(w).T / melspectrogram(w).T
+    (datasets/datafeeder.py:190-216): padded, time-major, stacked - written by the feature kernel itself."""
+    from nspeech_b200 import batch
+    ohp = _load(min_level_db=-100)
+    wavs = [speechlike(n, i) for i, n in enumerate((5200, 900, 12345))]
+    r = 5
+    mel, lin, Ts = batch.feeder_targets(wavs, r)
+    max_len = max(Ts) + 1
+    rows = max_len if max_len % r == 0 else max_len + r - max_len % r
+    assert lin.shape == (3, rows, 1025) and mel.shape == (3, rows, 80) and lin.dtype == mel.dtype == np.float32
+    for i, w in enumerate(wavs):
+        assert Ts[i] == 1 + w.size // 250
+        assert ao.rel_l2(lin[i, :Ts[i]], ao.spectrogram(w, ohp).T) < 1e-5
+        assert ao.rel_l2(mel[i, :Ts[i]], ao.melspectrogram(w, ohp).T) < 1e-5
+        assert not lin[i, Ts[i]:].any() and not mel[i, Ts[i]:].any()          # _pad = 0

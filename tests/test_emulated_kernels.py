@@ -87,6 +87,10 @@ def test_trimming(emu, golden_process):
     pc.check_trimming(golden_process)
 
 
+def test_feeder_targets(emu):
+    pc.check_feeder_targets()
+
+
 def test_errors_and_edge_cases(emu):
     pc.check_errors_and_edge_cases()
 

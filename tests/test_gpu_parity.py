@@ -58,6 +58,10 @@ def test_trimming(golden_process):
     pc.check_trimming(golden_process)
 
 
+def test_feeder_targets():
+    pc.check_feeder_targets()
+
+
 def test_errors_and_edge_cases():
     pc.check_errors_and_edge_cases()
 
