@@ -180,6 +180,12 @@ int nsb_free_pinned(void* p);
 int nsb_set_tile_hops(nsb_handle_t h, int32_t tile_hops);       /* 0 = automatic */
 int nsb_set_host_chunks(nsb_handle_t h, int32_t n);             /* NSB_HOST Griffin-Lim pipelining: 0 = automatic (4 chunks above 8 MB), n = force n chunks */
 int nsb_set_generic_iteration(nsb_handle_t h, int32_t on);     /* A/B hook: Griffin-Lim iterations with 0 = k_gl_stream (production), 1 = the generic k_synth<SRC_Y>, 2 = the tile kernel k_gl_iter */
+enum {                          /* nsb_set_option keys: A/B switches of the iteration kernels (defaults are the production settings) */
+    NSB_OPT_STREAM_SYNC_MODE = 1,   /* k_gl_stream: 2 = CTA barrier per colour step (default); 0 none, 1 per round, 3 per half CTA (+4: no pacing) use the event counters */
+    NSB_OPT_FUSE_ITERATIONS = 2,    /* 1 = all iterations of a call in one launch (default), 0 = one launch per iteration */
+    NSB_OPT_WIDE_MODE = 3           /* k_gl_iter one-frame-per-warp tiles: -1 automatic for a few utterances (default), 0 off, 1 forced */
+};
+int nsb_set_option(nsb_handle_t h, int32_t key, int32_t value);
 int nsb_set_stream_grid(nsb_handle_t h, int32_t ctas);          /* k_gl_stream grid: 0 = automatic, n = force n CTAs (tests: long pieces, many rounds of the ring) */
 int nsb_stream_trace(nsb_handle_t h, int32_t enable, uint64_t* out, int32_t max_ctas);   /* profiling: per-CTA (SM id, start ns, end ns) of the last k_gl_stream launch -> number of CTAs written */
 uint64_t nsb_kernel_launches(nsb_handle_t h);                    /* kernels launched through this handle so far */

@@ -20,6 +20,7 @@ FRAME_MAJOR, BIN_MAJOR = 0, 1
 F32, F64 = 0, 1
 EW_AMP_TO_DB, EW_DB_TO_AMP, EW_NORMALIZE, EW_DENORMALIZE = range(4)
 GL_DENORMALIZE, GL_DEEMPHASIS, GL_TF_TWIN = 1, 2, 4
+OPT_STREAM_SYNC_MODE, OPT_FUSE_ITERATIONS, OPT_WIDE_MODE = 1, 2, 3
 
 
 class ParameterError(ValueError):
@@ -66,6 +67,7 @@ SIGNATURES = {
     "nsb_set_tile_hops": (ctypes.c_int, [_vp, _i32]),
     "nsb_set_generic_iteration": (ctypes.c_int, [_vp, _i32]),
     "nsb_set_stream_grid": (ctypes.c_int, [_vp, _i32]),
+    "nsb_set_option": (ctypes.c_int, [_vp, _i32, _i32]),
     "nsb_set_host_chunks": (ctypes.c_int, [_vp, _i32]),
     "nsb_stream_trace": (ctypes.c_int, [_vp, _i32, _vp, _i32]),
     "nsb_kernel_launches": (_u64, [_vp]),
@@ -335,6 +337,9 @@ class Handle(object):
 
     def set_stream_grid(self, n):
         self._call("nsb_set_stream_grid", int(n))
+
+    def set_option(self, key, value):
+        self._call("nsb_set_option", int(key), int(value))
 
     def stream_trace(self, enable=True, max_ctas=4096):
         """profiling hook: enable tracing / fetch (sm_id, start_ns, end_ns) per CTA of the last k_gl_stream launch"""

@@ -383,12 +383,19 @@ extern "C" int nsb_stream_trace(nsb_handle_t h, int32_t enable, uint64_t* out, i
 }
 extern "C" int nsb_set_stream_grid(nsb_handle_t h, int32_t n) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");
-    if (n <= -300) { h->wide_mode = (n == -301) ? -1 : (n == -302 ? 1 : 0); return NSB_OK; }   // hook: -300 wide mode off, -301 automatic, -302 forced
-    if (n <= -200) { h->fuse_iterations = (n == -201); return NSB_OK; }    // experiment hook: -200 / -201 = one launch per iteration / fused
-    if (n <= -100) { h->stream_sync_mode = -n - 100; return NSB_OK; }     // experiment hook: -100 / -101 / -102 = barrier mode 0 / 1 / 2
     if (n < 0) return fail(NSB_ERR_INVALID, "stream grid %d < 0", n);
     h->user_stream_grid = n;
     return NSB_OK;
+}
+// A/B switches of the Griffin-Lim iteration kernels (profiles/sweep.py, tests): see the enum in the header
+extern "C" int nsb_set_option(nsb_handle_t h, int32_t key, int32_t value) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    switch (key) {
+        case NSB_OPT_STREAM_SYNC_MODE: if (value < 0 || value > 7) return fail(NSB_ERR_INVALID, "sync mode %d outside [0,7]", value); h->stream_sync_mode = value; return NSB_OK;
+        case NSB_OPT_FUSE_ITERATIONS: h->fuse_iterations = value != 0; return NSB_OK;
+        case NSB_OPT_WIDE_MODE: if (value < -1 || value > 1) return fail(NSB_ERR_INVALID, "wide mode %d outside [-1,1]", value); h->wide_mode = value; return NSB_OK;
+        default: return fail(NSB_ERR_INVALID, "unknown option %d", key);
+    }
 }
 extern "C" int nsb_set_tile_hops(nsb_handle_t h, int32_t t) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");

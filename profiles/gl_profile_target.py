@@ -14,7 +14,7 @@ T = 1000
 hparams.load()
 h = audio._handle()
 if os.environ.get('NSB_SYNC_MODE'):
-    h.set_stream_grid(-100 - int(os.environ['NSB_SYNC_MODE']))
+    h.set_option(_lib.OPT_STREAM_SYNC_MODE, int(os.environ['NSB_SYNC_MODE']))
 if os.environ.get('NSB_GL_KERNEL'):
     h.set_generic_iteration(int(os.environ['NSB_GL_KERNEL']))      # 0 k_gl_stream, 2 k_gl_iter
 spec = torch.rand((batch, T, 1025), device="cuda")

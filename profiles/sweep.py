@@ -16,7 +16,7 @@ if len(sys.argv) > 1:
     cases = [tuple(int(v) for v in c.split(",")) for c in sys.argv[1:]]
 for batch, tile, generic in cases:
   for sm in (2,):
-      h.set_stream_grid(-100 - sm)
+      h.set_option(_lib.OPT_STREAM_SYNC_MODE, sm)
       spec = torch.rand((batch, T, 1025), device="cuda")
       out = torch.empty(batch * h.num_samples(T), dtype=torch.float64, device="cuda")
       if tile > 28:      # k_gl_stream chunks of tile/4 groups
@@ -40,4 +40,4 @@ for batch, tile, generic in cases:
 h.set_tile_hops(0)
 h.set_generic_iteration(-1)
 h.set_stream_grid(0)
-h.set_stream_grid(-102)
+h.set_option(_lib.OPT_STREAM_SYNC_MODE, 2)

@@ -16,7 +16,7 @@ T = 1000
 st = torch.cuda.current_stream().cuda_stream
 spec = torch.rand((batch, T, 1025), device="cuda")
 out = torch.empty(batch * h.num_samples(T), dtype=torch.float64, device="cuda")
-h.set_stream_grid(-100 - sync)
+h.set_option(_lib.OPT_STREAM_SYNC_MODE, sync)
 h.griffin_lim(spec, _lib.FRAME_MAJOR, [T] * batch, out, seed=1, iters=2, flags=3, out_dtype=_lib.F64, space=_lib.DEVICE, stream=st)
 h.griffin_lim_iterate(10, st)
 h.stream_trace(True)
@@ -47,6 +47,6 @@ x = np.array([max(a[k]) for k in common]); y = np.array([max(per_sm[k]) for k in
 print("correlation of per-SM duration between consecutive launches: %.3f" % np.corrcoef(x, y)[0, 1])
 print("per-SM duration by SM id (us):", " ".join("%d:%.0f" % (k, max(per_sm[k])) for k in sorted(per_sm)))
 h.stream_trace(False)
-h.set_stream_grid(-100)
+h.set_option(_lib.OPT_STREAM_SYNC_MODE, 2)
 sm, dur, end = runs[-1]
 print("duration by blockIdx (us):", " ".join("%d:%.0f/%d" % (i, dur[i], sm[i]) for i in range(len(dur))))

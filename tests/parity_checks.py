@@ -255,12 +255,12 @@ def check_streaming_rounds(T=150, iters=2, tf=False):
         outs["piece3"] = run()
         h.set_tile_hops(0)
         h.set_generic_iteration(2)           # the tile kernel adds in the same colour order: identical bits
-        h.set_stream_grid(-300)              # ... with C consecutive frames per warp
+        h.set_option(_lib.OPT_WIDE_MODE, 0)             # ... with C consecutive frames per warp
         outs["tile"] = run()
-        h.set_stream_grid(-302)              # ... and in its wide (low-latency) mode: one frame per warp and step
+        h.set_option(_lib.OPT_WIDE_MODE, 1)             # ... and in its wide (low-latency) mode: one frame per warp and step
         outs["tile_wide"] = run()
     finally:
-        h.set_stream_grid(0); h.set_tile_hops(0); h.set_generic_iteration(-1); h.set_stream_grid(-301)
+        h.set_stream_grid(0); h.set_tile_hops(0); h.set_generic_iteration(-1); h.set_option(_lib.OPT_WIDE_MODE, -1)
     ref = outs.pop("grid1")
     for name, o in outs.items():
         np.testing.assert_array_equal(o, ref, err_msg=name)

@@ -205,9 +205,9 @@ def test_fused_iterations_match_one_launch_per_iteration():
             g = torch.Generator(device="cuda").manual_seed(5)
             spec = torch.rand((sum(Ts), 1025), device="cuda", generator=g)
             outs = []
-            for kernel, mode in ((2, -201), (2, -200), (0, -201), (0, -200), (0, -201)):   # -201 fused, -200 one launch per iteration
+            for kernel, mode in ((2, 1), (2, 0), (0, 1), (0, 0), (0, 1)):   # 1: all iterations in one launch, 0: one launch per iteration
                 h.set_generic_iteration(kernel)
-                h.set_stream_grid(mode)
+                h.set_option(_lib.OPT_FUSE_ITERATIONS, mode)
                 out = torch.empty(sum(h.num_samples(t) for t in Ts), dtype=torch.float64, device="cuda")
                 h.griffin_lim(spec, _lib.FRAME_MAJOR, Ts, out, seed=3, iters=iters, flags=_lib.GL_DENORMALIZE | _lib.GL_DEEMPHASIS,
                               out_dtype=_lib.F64, space=_lib.DEVICE, stream=st)
@@ -217,5 +217,5 @@ def test_fused_iterations_match_one_launch_per_iteration():
             for o in outs[1:]:
                 np.testing.assert_array_equal(outs[0], o)
     finally:
-        h.set_stream_grid(-201)
+        h.set_option(_lib.OPT_FUSE_ITERATIONS, 1)
         h.set_generic_iteration(-1)
