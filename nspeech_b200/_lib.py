@@ -20,7 +20,7 @@ FRAME_MAJOR, BIN_MAJOR = 0, 1
 F32, F64 = 0, 1
 EW_AMP_TO_DB, EW_DB_TO_AMP, EW_NORMALIZE, EW_DENORMALIZE = range(4)
 GL_DENORMALIZE, GL_DEEMPHASIS, GL_TF_TWIN = 1, 2, 4
-OPT_STREAM_SYNC_MODE, OPT_FUSE_ITERATIONS, OPT_WIDE_MODE = 1, 2, 3
+OPT_STREAM_SYNC_MODE, OPT_FUSE_ITERATIONS, OPT_WIDE_MODE, OPT_OVERLAP_CHUNKS, OPT_WAVE_SCHEDULE = 1, 2, 3, 4, 5
 
 
 class ParameterError(ValueError):

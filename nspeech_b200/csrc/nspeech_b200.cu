@@ -66,7 +66,8 @@ struct nsb_handle_s {
     int num_sms = 0;
     int user_tile_hops = 0, user_stream_grid = 0;
     cudaStream_t own_stream = nullptr, copy_in = nullptr, copy_out = nullptr;
-    cudaEvent_t desc_done = nullptr;
+    cudaStream_t chunk_stream = nullptr;   // odd chunks of a pipelined NSB_HOST Griffin-Lim call (even ones run on the call's stream)
+    cudaEvent_t desc_done = nullptr, chunk_fork = nullptr, chunk_join = nullptr;
     // tables
     float2* d_tw = nullptr;
     float* d_win = nullptr;          // periodic Hann padded centrally to n_fft (librosa geometry)
@@ -75,6 +76,9 @@ struct nsb_handle_s {
     int stream_sync_mode = 2;        // 2: CTA barrier per colour step of k_gl_stream (production); 0, 1, 3, +4: the event-counter variants (experiments)
     DevBuf d_trace; int trace_on = 0, trace_grid = 0;
     DevBuf d_done;                   // k_gl_iter: item counter + per-tile completion counters
+    DevBuf d_done2;                  // the same for launches on chunk_stream (two chunks' iteration launches overlap)
+    int wave_schedule = 1;           // NSB_HOST Griffin-Lim on long batches: wave schedule (griffin_lim_impl), 0 = plain chunk pipeline
+    int overlap_chunks = 1;          // NSB_HOST Griffin-Lim: consecutive chunks on two streams, a chunk's tail overlaps the next chunk's start
     int wide_mode = -1;              // k_gl_iter wide mode: -1 automatic (small batches), 0 off, 1 forced (tests)
     int fuse_iterations = 1;         // all Griffin-Lim iterations of a call in ONE launch (0: one launch per iteration, A/B hook)
     int stream_ctas_per_sm = 1;      // resident k_gl_stream CTAs per SM (occupancy query at creation)
@@ -201,11 +205,14 @@ extern "C" int nsb_destroy(nsb_handle_t h) {
     if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
     if (h->copy_in) cudaStreamDestroy(h->copy_in);
     if (h->copy_out) cudaStreamDestroy(h->copy_out);
+    if (h->chunk_stream) { cudaStreamSynchronize(h->chunk_stream); cudaStreamDestroy(h->chunk_stream); }
     if (h->desc_done) cudaEventDestroy(h->desc_done);
+    if (h->chunk_fork) cudaEventDestroy(h->chunk_fork);
+    if (h->chunk_join) cudaEventDestroy(h->chunk_join);
     cudaFree(h->d_tw); cudaFree(h->d_win); cudaFree(h->d_win_tf); cudaFree(h->d_rinv); cudaFree(h->d_rinv_tf); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo); cudaFree(h->d_mel_n); cudaFree(h->d_mel_ptr);
     cudaFree(h->d_status);
     if (h->h_desc) cudaFreeHost(h->h_desc);
-    h->d_desc.release(); h->d_trace.release(); h->d_done.release(); h->ws_mag.release(); h->ws_y0.release(); h->ws_y1.release();
+    h->d_desc.release(); h->d_trace.release(); h->d_done.release(); h->d_done2.release(); h->ws_mag.release(); h->ws_y0.release(); h->ws_y1.release();
     h->ws_in.release(); h->ws_in2.release(); h->ws_out.release(); h->ws_out2.release(); h->ws_ep.release();
     delete h;
     return NSB_OK;
@@ -245,7 +252,10 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
     CUB(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&h->chunk_stream, cudaStreamNonBlocking));
     CUB(cudaEventCreateWithFlags(&h->desc_done, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&h->chunk_fork, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&h->chunk_join, cudaEventDisableTiming));
     // twiddles w2048^(j*l), j = 1..31, l = 0..31, rounded from double
     {
         std::vector<float2> tw(kTwF2);
@@ -394,6 +404,8 @@ extern "C" int nsb_set_option(nsb_handle_t h, int32_t key, int32_t value) {
         case NSB_OPT_STREAM_SYNC_MODE: if (value < 0 || value > 7) return fail(NSB_ERR_INVALID, "sync mode %d outside [0,7]", value); h->stream_sync_mode = value; return NSB_OK;
         case NSB_OPT_FUSE_ITERATIONS: h->fuse_iterations = value != 0; return NSB_OK;
         case NSB_OPT_WIDE_MODE: if (value < -1 || value > 1) return fail(NSB_ERR_INVALID, "wide mode %d outside [-1,1]", value); h->wide_mode = value; return NSB_OK;
+        case NSB_OPT_OVERLAP_CHUNKS: h->overlap_chunks = value != 0; return NSB_OK;
+        case NSB_OPT_WAVE_SCHEDULE: h->wave_schedule = value != 0; return NSB_OK;
         default: return fail(NSB_ERR_INVALID, "unknown option %d", key);
     }
 }
@@ -748,7 +760,8 @@ static int deemph_grid(double p, long long max_len, EmphParams& E, int batch) {
 
 // `iters` Griffin-Lim iterations on the (sub-)batch B; y ping-pongs between ws_y0 / ws_y1, `cur` says which holds y
 static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int total_groups, int H, int& cur, int iters, cudaStream_t st,
-                         bool tf = false, float inv_thr = 0.f) {
+                         bool tf = false, float inv_thr = 0.f, DevBuf* done_buf = nullptr) {
+    DevBuf& d_done = done_buf ? *done_buf : h->d_done;     // scheduling counters of this stream's launches
     float* y[2] = {reinterpret_cast<float*>(h->ws_y0.p), reinterpret_cast<float*>(h->ws_y1.p)};
     if (total_tiles <= 0) return NSB_OK;
     // automatic choice: the streaming kernel wins from about 7,000 groups (28k frames) per launch on; below that the tile
@@ -774,9 +787,9 @@ static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int t
         if (h->user_stream_grid > 0) CH = (int)((NV + h->user_stream_grid - 1) / h->user_stream_grid);   // tests: that many chunks
         if (CH < 1) CH = 1;
         const long long n_chunks = (NV + CH - 1) / CH;
-        int rc = h->d_done.reserve(sizeof(int) * ((size_t)n_chunks + 1));
+        int rc = d_done.reserve(sizeof(int) * ((size_t)n_chunks + 1));
         if (rc) return rc;
-        S.item_counter = reinterpret_cast<int*>(h->d_done.p);
+        S.item_counter = reinterpret_cast<int*>(d_done.p);
         S.done = S.item_counter + 1;
         S.ybuf[0] = y[0]; S.ybuf[1] = y[1];
         S.chunk_groups = CH;
@@ -789,7 +802,7 @@ static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int t
         const int per_launch = h->fuse_iterations ? iters : 1;
         for (int it = 0; it < iters; it += per_launch) {
             const int n = iters - it < per_launch ? iters - it : per_launch;
-            CU(cudaMemsetAsync(h->d_done.p, 0, sizeof(int) * ((size_t)n_chunks + 1), st));
+            CU(cudaMemsetAsync(d_done.p, 0, sizeof(int) * ((size_t)n_chunks + 1), st));
             S.cur0 = cur; S.iters = n;
             const long long items = (long long)n * n_chunks;
             const int grid = items < ctas ? (int)items : ctas;
@@ -839,15 +852,15 @@ static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int t
     G.wide = (h->wide_mode != 0 && h->user_tile_hops == 0 && H == h->colours && (h->wide_mode == 1 || total_tiles <= 4 * h->num_sms)) ? 1 : 0;
     const size_t smem = gl_smem(h->hop, H);
     // one launch runs all the iterations: (iteration, tile) items from a global counter, per-tile completion counters
-    int rc = h->d_done.reserve(sizeof(int) * ((size_t)total_tiles + 1));
+    int rc = d_done.reserve(sizeof(int) * ((size_t)total_tiles + 1));
     if (rc) return rc;
-    G.item_counter = reinterpret_cast<int*>(h->d_done.p);
+    G.item_counter = reinterpret_cast<int*>(d_done.p);
     G.done = G.item_counter + 1;
     G.ybuf[0] = y[0]; G.ybuf[1] = y[1];
     const int per_launch = h->fuse_iterations ? iters : 1;
     for (int it = 0; it < iters; it += per_launch) {
         const int n = iters - it < per_launch ? iters - it : per_launch;
-        CU(cudaMemsetAsync(h->d_done.p, 0, sizeof(int) * ((size_t)total_tiles + 1), st));
+        CU(cudaMemsetAsync(d_done.p, 0, sizeof(int) * ((size_t)total_tiles + 1), st));
         G.cur0 = cur; G.iters = n;
         const long long items = (long long)n * total_tiles;
         const int grid = items < 2LL * h->num_sms ? (int)items : 2 * h->num_sms;   // persistent: 2 CTAs per SM
@@ -939,7 +952,10 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
         // ~35k frames.  Automatic mode: long batches (>= 60k frames) are cut 16k | rest | 12k frames, shorter ones into up
         // to 4 equal chunks of >= 16k frames (measured: profiles/r1/e2e_chunks.txt).
         std::vector<long long> targets;
-        if (h->host_chunks > 0) {
+        const char* ecuts = std::getenv("NSB_CHUNK_CUTS");        // tuning hook: comma-separated frame positions of the cuts
+        if (ecuts && *ecuts) {
+            for (const char* q = ecuts; *q;) { char* end; long long v = std::strtoll(q, &end, 10); if (end == q) break; targets.push_back(v); q = (*end == ',') ? end + 1 : end; }
+        } else if (h->host_chunks > 0) {
             for (int c = 1; c < h->host_chunks; ++c) targets.push_back((long long)d.total_frames * c / h->host_chunks);
         } else if (d.total_frames >= 60000) {
             const char* ef = std::getenv("NSB_CHUNK_FIRST"); const char* el = std::getenv("NSB_CHUNK_LAST");     // tuning hooks
@@ -955,6 +971,43 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
             while (b < batch && h->h_frame_off[b] < target) ++b;
             if (b < batch && b > cuts.back()) cuts.push_back(b);
         }
+    }
+    // Wave schedule for long NSB_HOST batches.  The input arrives over PCIe ~3.5x faster than Griffin-Lim consumes it, but
+    // a chunk small enough to arrive quickly cannot fill the GPU for 60 iterations on its own.  So the iterations are cut into
+    // `waves` launches of `wave_iters` (even) iterations; chunk g joins at wave g, and every launch runs ALL chunks that have
+    // arrived and are not finished: the launches grow with the data, only the very first ones are small, and a finished chunk's
+    // de-emphasis and copy-out hide behind the later waves.  Chunk g+1 is sized to arrive while wave g runs.
+    int waves = 0, wave_iters = 0;
+    if (space == NSB_HOST && batch > 1 && h->wave_schedule && h->host_chunks == 0 && !h->trace_on && h->fuse_iterations
+        && !(std::getenv("NSB_CHUNK_CUTS") && *std::getenv("NSB_CHUNK_CUTS")) && d.total_frames >= 40000) {
+        const int ie = iters - (iters & 1);
+        const char* ew = std::getenv("NSB_WAVES");                 // tuning hooks
+        const int kmax = ew ? std::atoi(ew) : 6;
+        for (int K = kmax; K >= 3; --K) if (ie % (2 * K) == 0 && ie / K >= 4) { waves = K; wave_iters = ie / K; break; }
+    }
+    if (waves > 0) {
+        const char* ef = std::getenv("NSB_WAVE_FIRST"); const char* eg = std::getenv("NSB_WAVE_GROWTH");
+        const double first = ef ? std::atof(ef) : 4000.0, growth = eg ? std::atof(eg) : 1.0;
+        const double in_ms_per_frame = (init_phase ? 3.0 : 1.0) * kBins * sizeof(float) / 53.0e6;     // ~53 GB/s host to device
+        const double it_ms_per_frame = 4.3e-6, it_ms_floor = 0.045;                                   // measured: profiles/r1/sweep_kernels.txt
+        cuts.assign(1, 0);
+        std::vector<long long> joined;       // frames of the chunks so far
+        double target = first;
+        while (cuts.back() < batch) {
+            int b = cuts.back() + 1;
+            const long long f0 = h->h_frame_off[cuts.back()];
+            while (b < batch && h->h_frame_off[b] - f0 < (long long)target) ++b;
+            if (batch - b < 2 || (long long)d.total_frames - h->h_frame_off[b] < 2000 || (int)cuts.size() >= 12) b = batch;     // no crumbs at the end
+            cuts.push_back(b);
+            joined.push_back(h->h_frame_off[b] - f0);
+            // the wave that starts now runs the last `waves` chunks; the next chunk should arrive while it runs
+            long long active = 0;
+            for (int g = (int)joined.size() - 1; g >= 0 && g > (int)joined.size() - 1 - waves; --g) active += joined[g];
+            const double wave_ms = wave_iters * std::max(it_ms_floor, active * it_ms_per_frame);
+            target = growth * wave_ms / in_ms_per_frame;
+        }
+        cuts.pop_back();                     // re-added below
+        if ((int)cuts.size() < 3) { waves = 0; wave_iters = 0; cuts.assign(1, 0); }      // not worth it: one chunk
     }
     cuts.push_back(batch);
     const int n_chunks = (int)cuts.size() - 1;
@@ -979,80 +1032,141 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
     }
     h->gl.valid = false;
     int cur = 0;
-    for (int c = 0; c < n_chunks; ++c) {
-        const int b0 = cuts[c], b1 = cuts[c + 1];
-        Batch B = d.dev;
-        B.frame_off += b0; B.tile_off += b0; B.samp_off += b0; B.batch = b1 - b0;
-        B.frame_base = h->h_frame_off[b0]; B.tile_base = h->h_tile_off[b0]; B.utt_base = b0;
-        B.group_off += b0; B.group_base = h->h_group_off[b0];
-        const int n_groups_c = h->h_group_off[b1] - h->h_group_off[b0];
-        const int n_frames_c = h->h_frame_off[b1] - h->h_frame_off[b0];
-        const int n_tiles_c = h->h_tile_off[b1] - h->h_tile_off[b0];
-        if (space == NSB_HOST) CUE(cudaStreamWaitEvent(st, ev_in[c], 0));
-
+    const float inv_thr = (float)(1.0 / (2.0e-8 * gscale));      // est / max(1e-8, |est|) on slots that hold 2*g*est
+    if (ep && (rc = h->ws_ep.reserve(sizeof(long long) * (size_t)batch))) { cleanup(); return rc; }
+    // the utterances [b0, b1) as a batch of their own (descriptor pointers shifted, bases remembered)
+    struct Sub { Batch B; int groups, frames, tiles; };
+    auto sub_batch = [&](int b0, int b1) {
+        Sub s;
+        s.B = d.dev;
+        s.B.frame_off += b0; s.B.tile_off += b0; s.B.samp_off += b0; s.B.batch = b1 - b0;
+        s.B.frame_base = h->h_frame_off[b0]; s.B.tile_base = h->h_tile_off[b0]; s.B.utt_base = b0;
+        s.B.group_off += b0; s.B.group_base = h->h_group_off[b0];
+        s.groups = h->h_group_off[b1] - h->h_group_off[b0];
+        s.frames = h->h_frame_off[b1] - h->h_frame_off[b0];
+        s.tiles = h->h_tile_off[b1] - h->h_tile_off[b0];
+        return s;
+    };
+#define CUL(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(NSB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+    // chunk c arrives: magnitudes in the kernels' layout and the initial waveform y0 = _istft(S * angles)
+    auto stage_in = [&](int c, cudaStream_t s_) -> int {
+        const Sub u = sub_batch(cuts[c], cuts[c + 1]);
+        if (space == NSB_HOST) CUL(cudaStreamWaitEvent(s_, ev_in[c], 0));
         // S = _db_to_amp(_denormalize(spec) + ref_level_db) ** power   (or |S| for _griffin_lim), permuted layout
         PrepParams Q{};
-        Q.batch = B; Q.in = d_spec; Q.bin_major = (layout == NSB_BIN_MAJOR); Q.denorm = (flags & NSB_GL_DENORMALIZE) ? 1 : 0;
+        Q.batch = u.B; Q.in = d_spec; Q.bin_major = (layout == NSB_BIN_MAJOR); Q.denorm = (flags & NSB_GL_DENORMALIZE) ? 1 : 0;
         Q.min_level_db = h->hp.min_level_db; Q.ref_level_db = h->hp.ref_level_db; Q.power = h->hp.power;
         {
             const double l2_10 = 3.321928094887362347870319429489390175864831;     // log2(10)
             Q.e_slope = -h->hp.min_level_db * 0.05 * h->hp.power * l2_10;
             Q.e_offset = (h->hp.min_level_db + h->hp.ref_level_db) * 0.05 * h->hp.power * l2_10 + std::log2(gscale);
         }
-        Q.mag = reinterpret_cast<float*>(h->ws_mag.p); Q.total_frames = n_frames_c; Q.status = h->d_status; Q.scale = (float)gscale;
+        Q.mag = reinterpret_cast<float*>(h->ws_mag.p); Q.total_frames = u.frames; Q.status = h->d_status; Q.scale = (float)gscale;
         if (Q.bin_major) {
-            CUE(cudaMemsetAsync(Q.mag + (size_t)B.frame_base * kMagPitch, 0, sizeof(float) * kMagPitch * (size_t)n_frames_c, st));
-            NSB_LAUNCH(k_prepare_mag, (n_frames_c + 31) / 32, 256, 0, st, Q);
+            CUL(cudaMemsetAsync(Q.mag + (size_t)u.B.frame_base * kMagPitch, 0, sizeof(float) * kMagPitch * (size_t)u.frames, s_));
+            NSB_LAUNCH(k_prepare_mag, (u.frames + 31) / 32, 256, 0, s_, Q);
         } else {
-            NSB_LAUNCH(k_prepare_mag_rows, grid_1d(n_frames_c, kWarpsPerCta, 8 * h->num_sms), kThreads, 0, st, Q);
+            NSB_LAUNCH(k_prepare_mag_rows, grid_1d(u.frames, kWarpsPerCta, 8 * h->num_sms), kThreads, 0, s_, Q);
         }
-        if ((rc = check_launch(h, "k_prepare_mag"))) { cleanup(); return rc; }
-
-        // y0 = _istft(S * angles)
+        int r_ = check_launch(h, "k_prepare_mag");
+        if (r_) return r_;
         SynthParams P{};
-        P.plan = make_plan(h, tf); P.batch = B; P.mag = Q.mag; P.spec = d_phase; P.spec_bin_major = (layout == NSB_BIN_MAJOR);
+        P.plan = make_plan(h, tf); P.batch = u.B; P.mag = Q.mag; P.spec = d_phase; P.spec_bin_major = (layout == NSB_BIN_MAJOR);
         P.y_out = reinterpret_cast<float*>(h->ws_y0.p); P.tile_hops = H; P.colours = h->colours; P.seed = seed; P.status = h->d_status;
         const size_t smem = synth_smem(h->hop, H);
-        if (tf) launch_synth_tf(h, SRC_MAGZERO, P, n_tiles_c, smem, st);
-        else if (init_phase) launch_synth<SRC_MAGPHASE>(h, P, n_tiles_c, smem, st);
-        else launch_synth<SRC_MAGRAND>(h, P, n_tiles_c, smem, st);
-        if ((rc = check_launch(h, "k_synth<init>"))) { cleanup(); return rc; }
-
-        cur = 0;
-        const float inv_thr = (float)(1.0 / (2.0e-8 * gscale));      // est / max(1e-8, |est|) on slots that hold 2*g*est
-        if ((rc = gl_iterations(h, B, n_tiles_c, n_groups_c, H, cur, iters, st, tf, inv_thr))) { cleanup(); return rc; }
-        const float* y_fin = reinterpret_cast<const float*>(cur ? h->ws_y1.p : h->ws_y0.p);
-
+        if (tf) launch_synth_tf(h, SRC_MAGZERO, P, u.tiles, smem, s_);
+        else if (init_phase) launch_synth<SRC_MAGPHASE>(h, P, u.tiles, smem, s_);
+        else launch_synth<SRC_MAGRAND>(h, P, u.tiles, smem, s_);
+        return check_launch(h, "k_synth<init>");
+    };
+    // n iterations on the utterances [b0, b1); cur_ says which of the two waveform buffers holds their y
+    auto iterate = [&](int b0, int b1, int n, int& cur_, cudaStream_t s_, DevBuf* done_buf) -> int {
+        const Sub u = sub_batch(b0, b1);
+        return gl_iterations(h, u.B, u.tiles, u.groups, H, cur_, n, s_, tf, inv_thr, done_buf);
+    };
+    // chunk c is finished: de-emphasis (+ endpoint search) and the copy out
+    auto stage_out = [&](int c, int cur_, cudaStream_t s_) -> int {
+        const int b0 = cuts[c], b1 = cuts[c + 1];
+        const Sub u = sub_batch(b0, b1);
+        const float* y_fin = reinterpret_cast<const float*>(cur_ ? h->ws_y1.p : h->ws_y0.p);
         const long long s_base = h->h_samp_off[b0], s_cnt = h->h_samp_off[b1] - s_base;
         if ((flags & NSB_GL_DEEMPHASIS) || gscale != 1.0) {
             EmphParams E{};
-            E.batch = B; E.in = y_fin; E.p = (flags & NSB_GL_DEEMPHASIS) ? h->hp.preemphasis : 0.0; E.scale = 1.0 / gscale;
+            E.batch = u.B; E.in = y_fin; E.p = (flags & NSB_GL_DEEMPHASIS) ? h->hp.preemphasis : 0.0; E.scale = 1.0 / gscale;
             E.status = h->d_status;
             if (out_dtype == NSB_F64) E.out64 = reinterpret_cast<double*>(d_out); else E.out32 = reinterpret_cast<float*>(d_out);
             long long max_len = 0;
             for (int b = b0; b < b1; ++b) max_len = std::max(max_len, (long long)(h->h_samp_off[b + 1] - h->h_samp_off[b]));
             const int dgrid = deemph_grid(E.p, max_len, E, b1 - b0);
-            NSB_LAUNCH(k_deemphasis, dgrid, kDeemphThreads, 0, st, E);
-            if ((rc = check_launch(h, "k_deemphasis"))) { cleanup(); return rc; }
+            NSB_LAUNCH(k_deemphasis, dgrid, kDeemphThreads, 0, s_, E);
+            int r_ = check_launch(h, "k_deemphasis");
+            if (r_) return r_;
         } else {
-            CUE(cudaMemcpyAsync(d_out + s_base * sizeof(float), y_fin + s_base, sizeof(float) * s_cnt, cudaMemcpyDeviceToDevice, st));
+            CUL(cudaMemcpyAsync(d_out + s_base * sizeof(float), y_fin + s_base, sizeof(float) * s_cnt, cudaMemcpyDeviceToDevice, s_));
         }
         if (ep) {
-            if ((rc = h->ws_ep.reserve(sizeof(long long) * (size_t)batch))) { cleanup(); return rc; }
             EndpointParams EP{};
-            EP.batch = B;
+            EP.batch = u.B;
             if (out_dtype == NSB_F64) EP.in64 = reinterpret_cast<const double*>(d_out); else EP.in32 = reinterpret_cast<const float*>(d_out);
             EP.out = reinterpret_cast<long long*>(h->ws_ep.p) + b0;
             endpoint_params(h, ep->threshold_db, ep->min_silence_sec, EP);
-            NSB_LAUNCH(k_find_endpoint, b1 - b0, 256, 0, st, EP);
-            if ((rc = check_launch(h, "k_find_endpoint"))) { cleanup(); return rc; }
+            NSB_LAUNCH(k_find_endpoint, b1 - b0, 256, 0, s_, EP);
+            int r_ = check_launch(h, "k_find_endpoint");
+            if (r_) return r_;
         }
         if (space == NSB_HOST) {
-            CUE(cudaEventRecord(ev_done[c], st));
-            CUE(cudaStreamWaitEvent(h->copy_out, ev_done[c], 0));
-            CUE(cudaMemcpyAsync(reinterpret_cast<char*>(wav_out) + s_base * out_elt, d_out + s_base * out_elt, out_elt * s_cnt,
+            CUL(cudaEventRecord(ev_done[c], s_));
+            CUL(cudaStreamWaitEvent(h->copy_out, ev_done[c], 0));
+            CUL(cudaMemcpyAsync(reinterpret_cast<char*>(wav_out) + s_base * out_elt, d_out + s_base * out_elt, out_elt * s_cnt,
                                 cudaMemcpyDeviceToHost, h->copy_out));
         }
+        return NSB_OK;
+    };
+#undef CUL
+    const cudaStream_t st_call = st;
+    bool overlap = false;
+    if (waves > 0) {
+        // ---- wave schedule (see wave_plan): chunk g joins at wave g and runs `waves` launches of `wave_iters` iterations,
+        // every launch covers the chunks that have arrived and are not finished - a contiguous utterance range ----
+        const int G = n_chunks;
+        cur = iters & 1;                    // an odd iteration count: every chunk does ONE iteration on its own when it arrives,
+                                            // so that all chunks of a launch agree on which buffer holds y
+        for (int w = 0; w < G + waves - 1; ++w) {
+            if (w < G) {
+                if ((rc = stage_in(w, st))) { cleanup(); return rc; }
+                if (iters & 1) { int c1 = 0; if ((rc = iterate(cuts[w], cuts[w + 1], 1, c1, st, nullptr))) { cleanup(); return rc; } }
+            }
+            const int g_lo = w - waves + 1 > 0 ? w - waves + 1 : 0, g_hi = w < G - 1 ? w : G - 1;
+            int cw = cur;
+            if ((rc = iterate(cuts[g_lo], cuts[g_hi + 1], wave_iters, cw, st, nullptr))) { cleanup(); return rc; }   // wave_iters is even: cw == cur
+            if (w - waves + 1 >= 0 && (rc = stage_out(w - waves + 1, cur, st))) { cleanup(); return rc; }
+        }
+    } else {
+    // Two compute streams take the chunks in turn: every chunk's iteration launch is persistent with dynamic work items, so
+    // its CTAs retire one by one in its tail and the NEXT chunk's kernels (other stream) move into the freed SMs - the
+    // tails and ramps of consecutive chunks overlap instead of adding up.  A launch only ever waits for items taken
+    // earlier by CTAs that are already running, so sharing the SMs cannot deadlock.  Chunks touch disjoint ranges of every
+    // workspace; the scheduling counters are per stream (d_done / d_done2).
+    overlap = space == NSB_HOST && n_chunks > 1 && h->overlap_chunks && !h->trace_on;
+    if (overlap) {
+        const size_t cnt = sizeof(int) * ((size_t)d.total_tiles + (size_t)d.total_groups + (size_t)batch + 2);
+        if ((rc = h->d_done.reserve(cnt)) || (rc = h->d_done2.reserve(cnt))) { cleanup(); return rc; }
+        CUE(cudaEventRecord(h->chunk_fork, st));                 // descriptors uploaded, earlier work of this stream done
+        CUE(cudaStreamWaitEvent(h->chunk_stream, h->chunk_fork, 0));
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+        st = (overlap && (c & 1)) ? h->chunk_stream : st_call;
+        DevBuf* done_buf = (overlap && (c & 1)) ? &h->d_done2 : &h->d_done;
+        if ((rc = stage_in(c, st))) { cleanup(); return rc; }
+        cur = 0;
+        if ((rc = iterate(cuts[c], cuts[c + 1], iters, cur, st, done_buf))) { cleanup(); return rc; }
+        if ((rc = stage_out(c, cur, st))) { cleanup(); return rc; }
+    }
+    }
+    st = st_call;
+    if (overlap) {                                               // join: the call's stream continues after both
+        CUE(cudaEventRecord(h->chunk_join, h->chunk_stream));
+        CUE(cudaStreamWaitEvent(st, h->chunk_join, 0));
     }
     // device-resident state for nsb_griffin_lim_iterate: the whole batch
     h->gl.valid = true; h->gl.batch = d.dev; h->gl.total_frames = d.total_frames; h->gl.tile_hops = H;

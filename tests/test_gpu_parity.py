@@ -219,3 +219,32 @@ def test_fused_iterations_match_one_launch_per_iteration():
     finally:
         h.set_option(_lib.OPT_FUSE_ITERATIONS, 1)
         h.set_generic_iteration(-1)
+
+
+def test_host_pipelines_match_one_launch():
+    """NSB_HOST Griffin-Lim never runs the batch as one launch: long batches follow the wave schedule (chunk g joins at wave g,
+    every launch runs all chunks in flight for a few iterations), others a chunk pipeline over two compute streams (a chunk's
+    tail overlaps the next chunk's start, two persistent launches share the SMs).  Whatever the cuts, the waves and the
+    streams, the waveforms must not differ by a bit from the unchunked call - ragged batch, even and odd iteration counts,
+    both iteration kernels in the mix."""
+    pc._load()
+    h = audio._handle()
+    rs = np.random.RandomState(11)
+    Ts = [300, 17, 1000, 2, 640, 1500, 77, 256] * 12              # 45.5k frames: above the wave schedule's threshold
+    specs = [rs.rand(T, 1025).astype(np.float32) for T in Ts]
+    try:
+        for iters in (12, 13):
+            outs = []
+            for chunks, overlap, wave in ((1, 0, 0), (0, 1, 1), (0, 1, 0), (5, 1, 1), (5, 0, 1), (13, 1, 0), (2, 1, 0)):
+                h.set_host_chunks(chunks)
+                h.set_option(_lib.OPT_OVERLAP_CHUNKS, overlap)
+                h.set_option(_lib.OPT_WAVE_SCHEDULE, wave)
+                for rep in range(2):                              # twice: the second call reuses every workspace
+                    outs.append(np.concatenate(batch.inv_spectrogram_batch(specs, seed=7, iters=iters)).copy())
+            assert np.isfinite(outs[0]).all() and np.abs(outs[0]).max() > 0
+            for o in outs[1:]:
+                np.testing.assert_array_equal(outs[0], o)
+    finally:
+        h.set_host_chunks(0)
+        h.set_option(_lib.OPT_OVERLAP_CHUNKS, 1)
+        h.set_option(_lib.OPT_WAVE_SCHEDULE, 1)
