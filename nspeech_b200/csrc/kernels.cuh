@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
                     const int lo = __ldg(P.plan.mel_lo + m), n = __ldg(P.plan.mel_n + m);
                     const float* w = P.plan.mel_w + __ldg(P.plan.mel_ptr + m);
                     float acc = 0.f;
+                    // (#pragma unroll 4 here: 173 -> 160 M frames/s, rejected)
                     for (int i = 0; i < n; ++i) acc = fmaf(__ldg(w + i), magrow[lo + i], acc);
                     o[m] = amp_to_db_norm_fast(acc, P.db_scale, P.db_offset_mel);   // melspectrogram subtracts no ref_level_db (audio.py:63)
                 }

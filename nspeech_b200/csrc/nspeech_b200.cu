@@ -982,12 +982,13 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
         && !(std::getenv("NSB_CHUNK_CUTS") && *std::getenv("NSB_CHUNK_CUTS")) && d.total_frames >= 40000) {
         const int ie = iters - (iters & 1);
         const char* ew = std::getenv("NSB_WAVES");                 // tuning hooks
-        const int kmax = ew ? std::atoi(ew) : 6;
-        for (int K = kmax; K >= 3; --K) if (ie % (2 * K) == 0 && ie / K >= 4) { waves = K; wave_iters = ie / K; break; }
+        // few long waves beat many short ones (every launch has its ramp and tail): 3 waves if the count divides, else 4, 5, 6, 2
+        const int pref[5] = {ew ? std::atoi(ew) : 3, 4, 5, 6, 2};
+        for (int K : pref) if (K >= 2 && ie % (2 * K) == 0 && ie / K >= 4) { waves = K; wave_iters = ie / K; break; }
     }
     if (waves > 0) {
         const char* ef = std::getenv("NSB_WAVE_FIRST"); const char* eg = std::getenv("NSB_WAVE_GROWTH");
-        const double first = ef ? std::atof(ef) : 4000.0, growth = eg ? std::atof(eg) : 1.0;
+        const double first = ef ? std::atof(ef) : 4000.0, growth = eg ? std::atof(eg) : 1.4;     // (measured: profiles/r1/e2e_wave_schedule.txt)
         const double in_ms_per_frame = (init_phase ? 3.0 : 1.0) * kBins * sizeof(float) / 53.0e6;     // ~53 GB/s host to device
         const double it_ms_per_frame = 4.3e-6, it_ms_floor = 0.045;                                   // measured: profiles/r1/sweep_kernels.txt
         cuts.assign(1, 0);
