@@ -184,7 +184,7 @@ enum {                          /* nsb_set_option keys: A/B switches of the iter
     NSB_OPT_STREAM_SYNC_MODE = 1,   /* k_gl_stream: 2 = CTA barrier per colour step (default); 0 none, 1 per round, 3 per half CTA (+4: no pacing) use the event counters */
     NSB_OPT_FUSE_ITERATIONS = 2,    /* 1 = all iterations of a call in one launch (default), 0 = one launch per iteration */
     NSB_OPT_WIDE_MODE = 3,          /* k_gl_iter one-frame-per-warp tiles: -1 automatic for a few utterances (default), 0 off, 1 forced */
-    NSB_OPT_OVERLAP_CHUNKS = 4,     /* NSB_HOST Griffin-Lim: 1 = consecutive chunks on two streams so that tails and ramps overlap (default), 0 = one stream */
+    NSB_OPT_OVERLAP_CHUNKS = 4,     /* NSB_HOST Griffin-Lim chunk pipeline: 1 = consecutive chunks on two streams so that tails and ramps overlap, 0 = one stream (default) */
     NSB_OPT_WAVE_SCHEDULE = 5       /* NSB_HOST Griffin-Lim on long batches: 1 = wave schedule (chunk g joins at wave g, every launch runs all chunks in flight; default), 0 = plain chunk pipeline */
 };
 int nsb_set_option(nsb_handle_t h, int32_t key, int32_t value);

@@ -78,7 +78,7 @@ struct nsb_handle_s {
     DevBuf d_done;                   // k_gl_iter: item counter + per-tile completion counters
     DevBuf d_done2;                  // the same for launches on chunk_stream (two chunks' iteration launches overlap)
     int wave_schedule = 1;           // NSB_HOST Griffin-Lim on long batches: wave schedule (griffin_lim_impl), 0 = plain chunk pipeline
-    int overlap_chunks = 1;          // NSB_HOST Griffin-Lim: consecutive chunks on two streams, a chunk's tail overlaps the next chunk's start
+    int overlap_chunks = 0;          // NSB_HOST chunk pipeline on two streams (a chunk's tail overlaps the next chunk's start); off: the delayed de-emphasis of the earlier chunk costs more than the tails (profiles/r1/e2e_wave_schedule.txt)
     int wide_mode = -1;              // k_gl_iter wide mode: -1 automatic (small batches), 0 off, 1 forced (tests)
     int fuse_iterations = 1;         // all Griffin-Lim iterations of a call in ONE launch (0: one launch per iteration, A/B hook)
     int stream_ctas_per_sm = 1;      // resident k_gl_stream CTAs per SM (occupancy query at creation)

@@ -246,5 +246,5 @@ def test_host_pipelines_match_one_launch():
                 np.testing.assert_array_equal(outs[0], o)
     finally:
         h.set_host_chunks(0)
-        h.set_option(_lib.OPT_OVERLAP_CHUNKS, 1)
+        h.set_option(_lib.OPT_OVERLAP_CHUNKS, 0)
         h.set_option(_lib.OPT_WAVE_SCHEDULE, 1)
