@@ -219,6 +219,8 @@ def main():
     ge.build()
     from nspeech_b200 import _lib, audio, batch, hparams
     audio.DEVICE = local_rank
+    # every rank stages through page-locked memory on its GPU's socket (matters from 4 ranks on: two sockets share 8 GPUs)
+    host_cpus = batch.bind_host_to_gpu(local_rank) if world > 1 else None
     hparams.load()
     h = audio._handle()
     assert (h.n_fft, h.hop, h.win) == (2048, HOP, 1000)
@@ -351,7 +353,8 @@ def main():
     line = {
         "metric": "griffin_lim_audio_sec_per_sec", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(workload_config(), host_binding=("rank 0 pinned to its GPU's %d NUMA-local CPUs" % len(host_cpus)) if host_cpus else "none"),
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(pin_in.array.nbytes),
                 "d2h_bytes_per_step": int(pin_out.array.nbytes), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),

@@ -79,6 +79,8 @@ enum {
 int nsb_abi_version(void);
 const char* nsb_last_error(void);
 int nsb_device_count(int* count);
+/* PCI bus id ("0000:1b:00.0") of a device: lets the host side place its threads and page-locked buffers on the GPU's NUMA node (8-GPU sharding) */
+int nsb_device_pci_bus_id(int device, char* out, int32_t len);
 
 /* handle = hparams + device tables (window, twiddles, sparse mel basis) + grow-only workspaces.
  * Replaces the module-global state of the reference: get_hparams() (hparams/__init__.py:25-26) and the
@@ -185,6 +187,7 @@ enum {                          /* nsb_set_option keys: A/B switches of the iter
     NSB_OPT_FUSE_ITERATIONS = 2,    /* 1 = all iterations of a call in one launch (default), 0 = one launch per iteration */
     NSB_OPT_WIDE_MODE = 3,          /* k_gl_iter one-frame-per-warp tiles: -1 automatic for a few utterances (default), 0 off, 1 forced */
     NSB_OPT_OVERLAP_CHUNKS = 4,     /* NSB_HOST Griffin-Lim chunk pipeline: 1 = consecutive chunks on two streams so that tails and ramps overlap, 0 = one stream (default) */
+    NSB_OPT_MEL_LINES = 6,          /* mel projection: 1 = filters as line segments, two moments per band (default when representable), 0 = sparse rows */
     NSB_OPT_WAVE_SCHEDULE = 5       /* NSB_HOST Griffin-Lim on long batches: 1 = wave schedule (chunk g joins at wave g, every launch runs all chunks in flight; default), 0 = plain chunk pipeline */
 };
 int nsb_set_option(nsb_handle_t h, int32_t key, int32_t value);

@@ -20,7 +20,7 @@ FRAME_MAJOR, BIN_MAJOR = 0, 1
 F32, F64 = 0, 1
 EW_AMP_TO_DB, EW_DB_TO_AMP, EW_NORMALIZE, EW_DENORMALIZE = range(4)
 GL_DENORMALIZE, GL_DEEMPHASIS, GL_TF_TWIN = 1, 2, 4
-OPT_STREAM_SYNC_MODE, OPT_FUSE_ITERATIONS, OPT_WIDE_MODE, OPT_OVERLAP_CHUNKS, OPT_WAVE_SCHEDULE = 1, 2, 3, 4, 5
+OPT_STREAM_SYNC_MODE, OPT_FUSE_ITERATIONS, OPT_WIDE_MODE, OPT_OVERLAP_CHUNKS, OPT_WAVE_SCHEDULE, OPT_MEL_LINES = 1, 2, 3, 4, 5, 6
 
 
 class ParameterError(ValueError):
@@ -46,6 +46,7 @@ SIGNATURES = {
     "nsb_abi_version": (ctypes.c_int, []),
     "nsb_last_error": (ctypes.c_char_p, []),
     "nsb_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "nsb_device_pci_bus_id": (ctypes.c_int, [ctypes.c_int, ctypes.c_char_p, _i32]),
     "nsb_create": (ctypes.c_int, [ctypes.POINTER(HParamsStruct), ctypes.c_int, ctypes.POINTER(_vp)]),
     "nsb_destroy": (ctypes.c_int, [_vp]),
     "nsb_synchronize": (ctypes.c_int, [_vp, _vp]),
@@ -118,6 +119,11 @@ class NativeLib(object):
         n = ctypes.c_int(0)
         rc = self.dll.nsb_device_count(ctypes.byref(n))
         return n.value if rc == NSB_OK else 0
+
+    def device_pci_bus_id(self, device):
+        buf = ctypes.create_string_buffer(32)
+        self.check(self.dll.nsb_device_pci_bus_id(int(device), buf, 32))
+        return buf.value.decode()
 
 
 class PinnedArray(object):

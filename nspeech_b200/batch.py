@@ -114,6 +114,34 @@ def inv_spectrogram_batch(specs, init_phase=None, seed=0, iters=None, device=Non
     return res
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(device=0):
+    """Pin the calling host thread to the CPUs next to ``device`` (its PCIe root's NUMA node, from sysfs), so that the
+    page-locked buffers it allocates afterwards and the copies it drives stay on the GPU's socket.  With 8 GPUs on two sockets
+    every rank / shard thread otherwise stages through node 0.  Returns the CPU list, or None when the topology is unknown
+    (single node, container without sysfs) - then nothing is changed."""
+    import os
+    try:
+        bus = _lib.default_lib().device_pci_bus_id(device).lower()
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bus) as f:
+            cpus = _parse_cpulist(f.read()) & os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except (OSError, ValueError, RuntimeError, AttributeError):
+        return None
+
+
 def shard_by_frames(n_frames, world_size):
     """Greedy longest-first assignment of utterances to ``world_size`` shards, balanced by frame count.
     Deterministic; returns a list (per shard) of utterance indices in ascending order."""
@@ -139,6 +167,8 @@ def run_sharded(fn, items, lengths, devices):
             idx = shards[rank]
             if not idx:
                 return
+            if len(devices) > 1 and isinstance(devices[rank], int):
+                bind_host_to_gpu(devices[rank])        # this thread's staging buffers and copies on the GPU's socket
             outs = fn([items[i] for i in idx], devices[rank])
             for i, o in zip(idx, outs):
                 results[i] = o

@@ -85,6 +85,8 @@ struct nsb_handle_s {
     int prune_tf = 0, colours_tf = 0;
     float* d_mel_w = nullptr;
     int *d_mel_lo = nullptr, *d_mel_n = nullptr, *d_mel_ptr = nullptr;
+    int* d_mel_seg = nullptr; float4* d_mel_coef = nullptr;      // the filters as line segments (null: not representable, sparse rows are used)
+    int mel_lines = 1;               // A/B hook: 0 = sparse mel rows even when the line form exists
     int* d_status = nullptr;
     std::vector<double> mel_dense;   // [num_mels][num_freq]
     // descriptors
@@ -106,6 +108,7 @@ struct nsb_handle_s {
 static Plan make_plan(nsb_handle_s* h, bool tf = false) {
     Plan p;
     p.tw = h->d_tw; p.mel_w = h->d_mel_w; p.mel_lo = h->d_mel_lo; p.mel_n = h->d_mel_n; p.mel_ptr = h->d_mel_ptr;
+    p.mel_seg = h->mel_lines ? h->d_mel_seg : nullptr; p.mel_coef = h->d_mel_coef;
     p.n_fft = h->n_fft; p.hop = h->hop; p.win_len = h->win; p.num_mels = h->num_mels;
     if (tf) { p.win = h->d_win_tf; p.rinv = h->d_rinv_tf; p.lo = 0; p.origin = 0; p.norm_wss = 0; p.prune = h->prune_tf; }
     else { p.win = h->d_win; p.rinv = h->d_rinv; p.lo = h->lo; p.origin = h->n_fft / 2; p.norm_wss = 1; p.prune = h->prune; }
@@ -137,6 +140,41 @@ static void build_mel(int sr, int n_fft, int n_mels, std::vector<double>& dense)
             dense[(size_t)i * F + k] = w * enorm;
         }
     }
+}
+
+// The same filter bank as straight lines: between band edges j and j+1 (segment j, bins [seg[j], seg[j+1])) row j rises and row
+// j-1 falls, both linearly in the bin index.  coef[m] = (value at the first bin of segment m, slope) of the rising side and the
+// same of the falling side on segment m+1.  Returns false when the lines do not reproduce `dense` (then the sparse rows are used).
+static bool build_mel_lines(int sr, int n_fft, int n_mels, const std::vector<double>& dense, std::vector<int>& seg, std::vector<float>& coef) {
+    const int F = 1 + n_fft / 2;
+    std::vector<double> mel_f(n_mels + 2), c(4 * (size_t)n_mels);
+    const double fmax = sr / 2.0, mmin = hz_to_mel(0.0), mmax = hz_to_mel(fmax), df = fmax / (F - 1);
+    for (int i = 0; i < n_mels + 2; ++i) mel_f[i] = mel_to_hz(mmin + (mmax - mmin) * i / (n_mels + 1));
+    seg.assign(n_mels + 2, F);
+    for (int j = 0, k = 0; j <= n_mels; ++j) {                  // first bin at or above edge j; the last segment keeps the Nyquist bin
+        while (k < F && fmax * k / (F - 1) < mel_f[j]) ++k;
+        seg[j] = k;
+    }
+    seg[n_mels + 1] = F;
+    for (int m = 0; m < n_mels; ++m) {
+        const double fd0 = mel_f[m + 1] - mel_f[m], fd1 = mel_f[m + 2] - mel_f[m + 1], enorm = 2.0 / (mel_f[m + 2] - mel_f[m]);
+        if (!(fd0 > 0.0) || !(fd1 > 0.0)) return false;
+        c[4 * m + 0] = enorm * (fmax * seg[m] / (F - 1) - mel_f[m]) / fd0;           c[4 * m + 1] = enorm * df / fd0;
+        c[4 * m + 2] = enorm * (mel_f[m + 2] - fmax * seg[m + 1] / (F - 1)) / fd1;   c[4 * m + 3] = -enorm * df / fd1;
+    }
+    double wmax = 0.0, err = 0.0;
+    for (int m = 0; m < n_mels; ++m)
+        for (int k = 0; k < F; ++k) {
+            double w = 0.0;
+            if (k >= seg[m] && k < seg[m + 1]) w = c[4 * m] + c[4 * m + 1] * (k - seg[m]);
+            else if (k >= seg[m + 1] && k < seg[m + 2]) w = c[4 * m + 2] + c[4 * m + 3] * (k - seg[m + 1]);
+            wmax = std::fmax(wmax, dense[(size_t)m * F + k]);
+            err = std::fmax(err, std::fabs(w - dense[(size_t)m * F + k]));
+        }
+    if (!(err <= 1e-12 * wmax)) return false;
+    coef.resize(c.size());
+    for (size_t i = 0; i < c.size(); ++i) coef[i] = (float)c[i];
+    return true;
 }
 
 template <typename K>
@@ -188,6 +226,18 @@ extern "C" int nsb_device_count(int* count) {
     return NSB_OK;
 }
 
+extern "C" int nsb_device_pci_bus_id(int device, char* out, int32_t len) {
+    if (!out || len < 16) return fail(NSB_ERR_INVALID, "out is null or shorter than 16 bytes");
+    out[0] = 0;
+#ifdef NSB_EMULATE
+    return fail(NSB_ERR_NODEVICE, "no device in the emulated build");
+#else
+    cudaError_t e = cudaDeviceGetPCIBusId(out, len, device);
+    if (e != cudaSuccess) return fail(NSB_ERR_NODEVICE, "cudaDeviceGetPCIBusId(%d): %s", device, cudaGetErrorString(e));
+    return NSB_OK;
+#endif
+}
+
 extern "C" int nsb_alloc_pinned(uint64_t bytes, void** out) {
     if (!out) return fail(NSB_ERR_INVALID, "out is null");
     *out = nullptr;
@@ -209,7 +259,7 @@ extern "C" int nsb_destroy(nsb_handle_t h) {
     if (h->desc_done) cudaEventDestroy(h->desc_done);
     if (h->chunk_fork) cudaEventDestroy(h->chunk_fork);
     if (h->chunk_join) cudaEventDestroy(h->chunk_join);
-    cudaFree(h->d_tw); cudaFree(h->d_win); cudaFree(h->d_win_tf); cudaFree(h->d_rinv); cudaFree(h->d_rinv_tf); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo); cudaFree(h->d_mel_n); cudaFree(h->d_mel_ptr);
+    cudaFree(h->d_tw); cudaFree(h->d_win); cudaFree(h->d_win_tf); cudaFree(h->d_rinv); cudaFree(h->d_rinv_tf); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo); cudaFree(h->d_mel_n); cudaFree(h->d_mel_ptr); cudaFree(h->d_mel_seg); cudaFree(h->d_mel_coef);
     cudaFree(h->d_status);
     if (h->h_desc) cudaFreeHost(h->h_desc);
     h->d_desc.release(); h->d_trace.release(); h->d_done.release(); h->d_done2.release(); h->ws_mag.release(); h->ws_y0.release(); h->ws_y1.release();
@@ -319,6 +369,14 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
         CUB(cudaMemcpy(h->d_mel_n, n.data(), sizeof(int) * n.size(), cudaMemcpyHostToDevice));
         CUB(cudaMalloc(&h->d_mel_ptr, sizeof(int) * ptr.size()));
         CUB(cudaMemcpy(h->d_mel_ptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice));
+        std::vector<int> seg; std::vector<float> coef;
+        // (the two moments per segment live behind the magnitude row in the warp's scratch tile: 1028 + 2 (M + 1) <= 2 kScratchF2 floats)
+        if (1028 + 2 * (hp->num_mels + 1) <= 2 * kScratchF2 && build_mel_lines(hp->sample_rate, n_fft, hp->num_mels, h->mel_dense, seg, coef)) {
+            CUB(cudaMalloc(&h->d_mel_seg, sizeof(int) * seg.size()));
+            CUB(cudaMemcpy(h->d_mel_seg, seg.data(), sizeof(int) * seg.size(), cudaMemcpyHostToDevice));
+            CUB(cudaMalloc(&h->d_mel_coef, sizeof(float) * coef.size()));
+            CUB(cudaMemcpy(h->d_mel_coef, coef.data(), sizeof(float) * coef.size(), cudaMemcpyHostToDevice));
+        }
     }
     CUB(cudaMalloc(&h->d_status, sizeof(int)));
     CUB(cudaMemset(h->d_status, 0, sizeof(int)));
@@ -406,6 +464,7 @@ extern "C" int nsb_set_option(nsb_handle_t h, int32_t key, int32_t value) {
         case NSB_OPT_WIDE_MODE: if (value < -1 || value > 1) return fail(NSB_ERR_INVALID, "wide mode %d outside [-1,1]", value); h->wide_mode = value; return NSB_OK;
         case NSB_OPT_OVERLAP_CHUNKS: h->overlap_chunks = value != 0; return NSB_OK;
         case NSB_OPT_WAVE_SCHEDULE: h->wave_schedule = value != 0; return NSB_OK;
+        case NSB_OPT_MEL_LINES: h->mel_lines = value != 0; return NSB_OK;
         default: return fail(NSB_ERR_INVALID, "unknown option %d", key);
     }
 }
