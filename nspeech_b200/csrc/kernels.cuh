@@ -244,23 +244,35 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
         } else {
             const long long orow = P.rows_per_utt > 0 ? (long long)(P.batch.utt_base + b) * P.rows_per_utt + k : (long long)f;
             // magnitudes -> scratch (as floats, 1025 <= 2112), then linear dB and sparse mel
+            // The linear feature goes out straight from the registers: slot p of lanes 1..31 holds 31 consecutive bins
+            // (bin_of), so the stores coalesce without a trip through shared memory; only the mel projection needs the
+            // magnitudes in bin order.  Non-finite input shows up in every bin of its frames: ONE test per frame on the sum
+            // of the squared magnitudes (squares beyond 3e38, i.e. |D| > 1e19, also count as non-finite).
             float* magrow = reinterpret_cast<float*>(scratch);
+            float* o_lin = P.out_lin ? P.out_lin + (size_t)orow * kBins : nullptr;
+            float chk = 0.f;
 #pragma unroll
             for (int p = 0; p < 32; ++p) {
-                bad |= !(isfinite(z[p].x) && isfinite(z[p].y));
                 if (lane == 0 && p == 0) {
-                    magrow[0] = fabsf(z[0].x);
-                    magrow[1024] = fabsf(z[0].y);
+                    const float m0 = fabsf(z[0].x), m1 = fabsf(z[0].y);
+                    chk += m0 + m1;
+                    magrow[0] = m0;
+                    magrow[1024] = m1;
+                    if (o_lin) {
+                        o_lin[0] = amp_to_db_norm_fast(m0, P.db_scale, P.db_offset_lin);
+                        o_lin[1024] = amp_to_db_norm_fast(m1, P.db_scale, P.db_offset_lin);
+                    }
                 } else {
-                    magrow[bin_of(lane, p)] = sqrt_approx(fmaf(z[p].x, z[p].x, z[p].y * z[p].y));
+                    const float m2 = fmaf(z[p].x, z[p].x, z[p].y * z[p].y);
+                    chk += m2;
+                    const float mg = sqrt_approx(m2);
+                    const int kb = bin_of(lane, p);
+                    magrow[kb] = mg;
+                    if (o_lin) o_lin[kb] = amp_to_db_norm_fast(mg, P.db_scale, P.db_offset_lin);
                 }
             }
+            bad |= !isfinite(chk);
             __syncwarp();
-            if (P.out_lin) {
-                float* o = P.out_lin + (size_t)orow * kBins;
-#pragma unroll 11
-                for (int kb = lane; kb < kBins; kb += 32) o[kb] = amp_to_db_norm_fast(magrow[kb], P.db_scale, P.db_offset_lin);
-            }
             if (P.out_mel && P.plan.mel_seg) {
                 // mel[m] = sum_k W[m,k] |D[k]| with W[m,.] a triangle: per segment j two moments S0 = sum |D|, S1 = sum (k - start) |D|
                 // (every bin read ONCE, no weight loads: 68 dependent steps per lane instead of 135 with two loads each), then
