@@ -1050,6 +1050,7 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
         const double first = ef ? std::atof(ef) : 4000.0, growth = eg ? std::atof(eg) : 1.4;     // (measured: profiles/r1/e2e_wave_schedule.txt)
         const double in_ms_per_frame = (init_phase ? 3.0 : 1.0) * kBins * sizeof(float) / 53.0e6;     // ~53 GB/s host to device
         const double it_ms_per_frame = 4.3e-6, it_ms_floor = 0.045;                                   // measured: profiles/r1/sweep_kernels.txt
+        const std::vector<int> chunk_cuts = cuts;     // the plain chunk pipeline's cuts, should the batch not split into >= 3 chunks
         cuts.assign(1, 0);
         std::vector<long long> joined;       // frames of the chunks so far
         double target = first;
@@ -1067,7 +1068,7 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
             target = growth * wave_ms / in_ms_per_frame;
         }
         cuts.pop_back();                     // re-added below
-        if ((int)cuts.size() < 3) { waves = 0; wave_iters = 0; cuts.assign(1, 0); }      // not worth it: one chunk
+        if ((int)cuts.size() < 3) { waves = 0; wave_iters = 0; cuts = chunk_cuts; }       // a few very long utterances: chunk pipeline
     }
     cuts.push_back(batch);
     const int n_chunks = (int)cuts.size() - 1;

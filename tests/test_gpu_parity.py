@@ -244,6 +244,19 @@ def test_host_pipelines_match_one_launch():
             assert np.isfinite(outs[0]).all() and np.abs(outs[0]).max() > 0
             for o in outs[1:]:
                 np.testing.assert_array_equal(outs[0], o)
+        # the synthesis stage (TF-twin Griffin-Lim + de-emphasis + endpoint search, synthesizer.py:30, 51-53) at eval.py's
+        # batch size rides the same schedules
+        lin = rs.rand(32, 1500, 1025).astype(np.float32)
+        lin[:, 900:, :] = 1.0                                      # quiet tail (the yaml's +100 dB floor inverts the scale): endpoints differ from the length
+        res = []
+        for chunks, wave in ((1, 0), (0, 1), (0, 0), (3, 1)):
+            h.set_host_chunks(chunks)
+            h.set_option(_lib.OPT_WAVE_SCHEDULE, wave)
+            res.append(audio.synthesize_waveforms(lin, iters=20))
+        for r in res[1:]:
+            assert [len(w) for w in r] == [len(w) for w in res[0]]
+            for a, b in zip(res[0], r):
+                np.testing.assert_array_equal(a, b)
     finally:
         h.set_host_chunks(0)
         h.set_option(_lib.OPT_OVERLAP_CHUNKS, 0)
