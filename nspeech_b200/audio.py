@@ -341,7 +341,8 @@ def synthesize_waveforms(linear_outputs, iters=None, threshold_db=-40, min_silen
     N = S.shape[0] if batched else 1
     T = S.shape[-2]
     n = h.num_samples_tf(T)
-    wav = np.empty((N, n), dtype=np.float64)
+    # large results land in pooled page-locked memory (the copy out then runs at PCIe speed, see batch.inv_spectrogram_batch)
+    wav = h.lib.pinned_pool().empty((N, n), np.float64) if N * n * 8 >= (1 << 20) else np.empty((N, n), dtype=np.float64)
     ends = np.zeros(N, dtype=np.int64)
     h.synthesize(S, [T] * N, wav, ends, iters=-1 if iters is None else iters, threshold_db=threshold_db, min_silence_sec=min_silence_sec)
     outs = [wav[i, :int(ends[i])] for i in range(N)]
