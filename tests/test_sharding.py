@@ -109,3 +109,20 @@ def test_two_rank_gloo_shards_equal_single_process():
     assert sorted(merged) == list(range(len(Ts)))
     for i, ref in enumerate(single):
         np.testing.assert_array_equal(merged[i], ref)
+
+
+def test_bind_host_to_gpu_is_harmless_without_topology():
+    """bind_host_to_gpu pins the calling thread to the CPUs next to a GPU (sysfs local_cpulist of its PCI device); with no
+    device or no topology information it must change nothing and return None."""
+    import os
+    assert batch._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert batch._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    try:
+        cpus = batch.bind_host_to_gpu(0)
+        if cpus is None:                              # no GPU (the build container) or no topology: nothing changed
+            assert os.sched_getaffinity(0) == before
+        else:                                         # on a GPU box: a non-empty subset of what was allowed
+            assert cpus and set(cpus) <= before and os.sched_getaffinity(0) == set(cpus)
+    finally:
+        os.sched_setaffinity(0, before)
