@@ -1190,6 +1190,9 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
         // ---- wave schedule (see wave_plan): chunk g joins at wave g and runs `waves` launches of `wave_iters` iterations,
         // every launch covers the chunks that have arrived and are not finished - a contiguous utterance range ----
         const int G = n_chunks;
+        // the launches grow from wave to wave: size the scheduling counters for the largest one now (a reallocation in the
+        // middle of the pipeline would synchronise the device)
+        if ((rc = h->d_done.reserve(sizeof(int) * ((size_t)d.total_tiles + (size_t)d.total_groups + (size_t)batch + 2)))) { cleanup(); return rc; }
         cur = iters & 1;                    // an odd iteration count: every chunk does ONE iteration on its own when it arrives,
                                             // so that all chunks of a launch agree on which buffer holds y
         for (int w = 0; w < G + waves - 1; ++w) {
