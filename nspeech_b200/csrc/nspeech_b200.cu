@@ -627,7 +627,6 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
     float *d_lin = lin_out, *d_mel = mel_out;
     if (space == NSB_HOST) {
         if ((rc = h->ws_in.reserve(sizeof(float) * d.total_samples))) return rc;
-        CU(cudaMemcpyAsync(h->ws_in.p, wav, sizeof(float) * d.total_samples, cudaMemcpyHostToDevice, st));
         d_wav = reinterpret_cast<const float*>(h->ws_in.p);
         if (mode == ANALYSIS_COMPLEX) {
             if ((rc = h->ws_out.reserve(sizeof(float2) * F * d.total_frames))) return rc;
@@ -640,10 +639,6 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
     AnalysisParams P;
     P.plan = make_plan(h, tf); P.batch = d.dev; P.wav = d_wav; P.out_complex = d_c; P.out_lin = d_lin; P.out_mel = d_mel;
     P.total_frames = d.total_frames; P.preemph = (float)h->hp.preemphasis; P.rows_per_utt = rows_per_utt;
-    if (rows_per_utt > 0) {             // the padding rows are zeros (_pad = 0, datafeeder.py:216)
-        if (d_lin) CU(cudaMemsetAsync(d_lin, 0, sizeof(float) * F * out_rows, st));
-        if (d_mel) CU(cudaMemsetAsync(d_mel, 0, sizeof(float) * M * out_rows, st));
-    }
     P.ref_level_db = (float)h->hp.ref_level_db; P.min_level_db = (float)h->hp.min_level_db; P.status = h->d_status;
     {
         const double inv = 1.0 / (-h->hp.min_level_db);
@@ -651,31 +646,87 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
         P.db_offset_lin = (float)((-h->hp.ref_level_db - h->hp.min_level_db) * inv);
         P.db_offset_mel = (float)((-h->hp.min_level_db) * inv);
     }
-    const int grid = grid_1d(d.total_frames, kWarpsPerCta, 2 * h->num_sms);
     const size_t smem = analysis_smem();
     const int prune = tf ? h->prune_tf : h->prune;
-    if (mode == ANALYSIS_COMPLEX) {
-        if (preemph) {
-            if (prune == 1) NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, true, 1>), grid, kThreads, smem, st, P);
-            else NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, true, 0>), grid, kThreads, smem, st, P);
-        } else {
-            if (prune == 1) NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, false, 1>), grid, kThreads, smem, st, P);
-            else if (prune == 2) NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, false, 2>), grid, kThreads, smem, st, P);
-            else NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, false, 0>), grid, kThreads, smem, st, P);
+
+    // Host buffers: the results are 4.4x the input (1025 + 80 floats out per 250 samples in), so the call is bound by the copy
+    // out.  Chunks of whole utterances keep both PCIe directions and the GPU busy at once: chunk c+1 is copied in (copy_in
+    // stream) and transformed while chunk c is copied out (copy_out stream).  Device buffers: one chunk.
+    std::vector<int> cuts(1, 0);
+    if (space == NSB_HOST && batch > 1) {
+        const size_t out_bytes = (mode == ANALYSIS_COMPLEX ? sizeof(float2) * F : sizeof(float) * ((lin_out ? F : 0) + (mel_out ? M : 0))) * (size_t)d.total_frames;
+        int want = h->host_chunks > 0 ? h->host_chunks : (int)(out_bytes / (24u << 20));      // ~24 MB of results per chunk
+        if (want > 32) want = 32;
+        for (int c = 1; c < want; ++c) {
+            const long long target = (long long)d.total_frames * c / want;
+            int bb = cuts.back() + 1;
+            while (bb < batch && h->h_frame_off[bb] < target) ++bb;
+            if (bb < batch) cuts.push_back(bb);
         }
-    } else {
-        if (prune == 1) NSB_LAUNCH((k_analysis<ANALYSIS_FEATURES, true, 1>), grid, kThreads, smem, st, P);
-        else NSB_LAUNCH((k_analysis<ANALYSIS_FEATURES, true, 0>), grid, kThreads, smem, st, P);
     }
-    if ((rc = check_launch(h, "k_analysis"))) return rc;
+    cuts.push_back(batch);
+    const int n_chunks = (int)cuts.size() - 1;
+    std::vector<cudaEvent_t> ev_in(n_chunks, nullptr), ev_done(n_chunks, nullptr);
+    auto cleanup = [&]() { for (auto e : ev_in) if (e) cudaEventDestroy(e); for (auto e : ev_done) if (e) cudaEventDestroy(e); };
+#define CUA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(NSB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
     if (space == NSB_HOST) {
-        if (mode == ANALYSIS_COMPLEX) CU(cudaMemcpyAsync(out_complex, d_c, sizeof(float2) * F * d.total_frames, cudaMemcpyDeviceToHost, st));
-        else {
-            if (lin_out) CU(cudaMemcpyAsync(lin_out, d_lin, sizeof(float) * F * out_rows, cudaMemcpyDeviceToHost, st));
-            if (mel_out) CU(cudaMemcpyAsync(mel_out, d_mel, sizeof(float) * M * out_rows, cudaMemcpyDeviceToHost, st));
+        for (int c = 0; c < n_chunks; ++c) {
+            CUA(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
+            CUA(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
         }
+        for (int c = 0; c < n_chunks; ++c) {                     // all input copies are queued up front, in chunk order
+            const long long s0 = h->h_samp_off[cuts[c]], s1 = h->h_samp_off[cuts[c + 1]];
+            CUA(cudaMemcpyAsync(reinterpret_cast<float*>(h->ws_in.p) + s0, wav + s0, sizeof(float) * (size_t)(s1 - s0), cudaMemcpyHostToDevice, h->copy_in));
+            CUA(cudaEventRecord(ev_in[c], h->copy_in));
+        }
+    }
+    if (rows_per_utt > 0) {             // the padding rows are zeros (_pad = 0, datafeeder.py:216)
+        if (d_lin) CUA(cudaMemsetAsync(d_lin, 0, sizeof(float) * F * out_rows, st));
+        if (d_mel) CUA(cudaMemsetAsync(d_mel, 0, sizeof(float) * M * out_rows, st));
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+        const int b0 = cuts[c], b1 = cuts[c + 1];
+        P.batch = d.dev;
+        P.batch.frame_off += b0; P.batch.samp_off += b0; P.batch.batch = b1 - b0;
+        P.batch.frame_base = h->h_frame_off[b0]; P.batch.utt_base = b0;
+        P.total_frames = h->h_frame_off[b1] - h->h_frame_off[b0];
+        if (space == NSB_HOST) CUA(cudaStreamWaitEvent(st, ev_in[c], 0));
+        const int grid = grid_1d(P.total_frames, kWarpsPerCta, 2 * h->num_sms);
+        if (mode == ANALYSIS_COMPLEX) {
+            if (preemph) {
+                if (prune == 1) NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, true, 1>), grid, kThreads, smem, st, P);
+                else NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, true, 0>), grid, kThreads, smem, st, P);
+            } else {
+                if (prune == 1) NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, false, 1>), grid, kThreads, smem, st, P);
+                else if (prune == 2) NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, false, 2>), grid, kThreads, smem, st, P);
+                else NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, false, 0>), grid, kThreads, smem, st, P);
+            }
+        } else {
+            if (prune == 1) NSB_LAUNCH((k_analysis<ANALYSIS_FEATURES, true, 1>), grid, kThreads, smem, st, P);
+            else NSB_LAUNCH((k_analysis<ANALYSIS_FEATURES, true, 0>), grid, kThreads, smem, st, P);
+        }
+        if ((rc = check_launch(h, "k_analysis"))) { cleanup(); return rc; }
+        if (space == NSB_HOST) {
+            CUA(cudaEventRecord(ev_done[c], st));
+            CUA(cudaStreamWaitEvent(h->copy_out, ev_done[c], 0));
+            // rows of this chunk: packed = its frames, padded = rows_per_utt per utterance
+            const size_t r0 = rows_per_utt > 0 ? (size_t)rows_per_utt * b0 : (size_t)h->h_frame_off[b0];
+            const size_t r1 = rows_per_utt > 0 ? (size_t)rows_per_utt * b1 : (size_t)h->h_frame_off[b1];
+            if (mode == ANALYSIS_COMPLEX)
+                CUA(cudaMemcpyAsync(reinterpret_cast<float2*>(out_complex) + F * r0, d_c + F * r0, sizeof(float2) * F * (r1 - r0), cudaMemcpyDeviceToHost, h->copy_out));
+            else {
+                if (lin_out) CUA(cudaMemcpyAsync(lin_out + F * r0, d_lin + F * r0, sizeof(float) * F * (r1 - r0), cudaMemcpyDeviceToHost, h->copy_out));
+                if (mel_out) CUA(cudaMemcpyAsync(mel_out + M * r0, d_mel + M * r0, sizeof(float) * M * (r1 - r0), cudaMemcpyDeviceToHost, h->copy_out));
+            }
+        }
+    }
+    if (space == NSB_HOST) {
+        CUA(cudaStreamSynchronize(h->copy_out));
+        cleanup();
         return read_status(h, st);
     }
+#undef CUA
+    cleanup();
     return NSB_OK;
 }
 

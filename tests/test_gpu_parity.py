@@ -261,3 +261,31 @@ def test_host_pipelines_match_one_launch():
         h.set_host_chunks(0)
         h.set_option(_lib.OPT_OVERLAP_CHUNKS, 0)
         h.set_option(_lib.OPT_WAVE_SCHEDULE, 1)
+
+
+def test_feature_host_pipeline_matches_one_chunk():
+    """Host-side feature calls are cut into chunks of whole utterances (copy-in, transform and copy-out of consecutive chunks
+    overlap).  Every cut must give the bits of the single-chunk call: packed features, the STFT, and the feeder's padded
+    batch tensors - ragged clip lengths."""
+    pc._load(min_level_db=-100)
+    h = audio._handle()
+    rs = np.random.RandomState(21)
+    lens = [int(n) for n in rs.randint(20000, 200000, size=48)] + [250, 999, 300]
+    wavs = [speechlike(n, 300 + i) for i, n in enumerate(lens)]
+    try:
+        ref = None
+        for chunks in (1, 0, 7, 51):
+            h.set_host_chunks(chunks)
+            feats = batch.features_batch(wavs)
+            mel_t, lin_t, Ts = batch.feeder_targets(wavs, 5)
+            D = audio._stft(np.concatenate(wavs[:6]))
+            cur = ([f[0].copy() for f in feats], [f[1].copy() for f in feats], mel_t.copy(), lin_t.copy(), list(Ts), D.copy())
+            if ref is None:
+                ref = cur
+                assert all(np.isfinite(a).all() for a in ref[0]) and 0 < float(ref[0][0].mean()) < 1
+                continue
+            for a, b in zip(ref[0] + ref[1] + [ref[2], ref[3], ref[5]], cur[0] + cur[1] + [cur[2], cur[3], cur[5]]):
+                np.testing.assert_array_equal(a, b)
+            assert ref[4] == cur[4]
+    finally:
+        h.set_host_chunks(0)
