@@ -745,14 +745,14 @@ extern "C" int nsb_features(nsb_handle_t h, const float* wav, const int64_t* n_s
 // ---------------------------------------------------------------------------------------------
 // synthesis entry points
 // ---------------------------------------------------------------------------------------------
-// small batches: tiles of C hops with one frame per warp (k_gl_iter's wide mode) when that still gives at most two tiles per
+// small batches: tiles of C hops with one frame per warp (k_gl_iter's wide mode) when that still gives at most four tiles per
 // resident CTA - a tile is then one frame-time long instead of C, which is what a single utterance needs (demo_server.py)
 static bool choose_wide(nsb_handle_s* h, const std::vector<long long>& samples) {
     if (h->wide_mode == 0 || h->user_tile_hops > 0) return false;
     if (h->wide_mode == 1) return true;
     long long tiles = 0;
     for (size_t b = 0; b < samples.size(); ++b) { long long hops = (samples[b] + h->hop - 1) / h->hop; tiles += (hops + h->colours - 1) / h->colours; }
-    return tiles <= 4LL * h->num_sms;
+    return tiles <= 8LL * h->num_sms;            // measured crossover ~1,300 tiles (profiles/r1/sweep_wide.txt)
 }
 
 static int choose_tile_hops(nsb_handle_s* h, const std::vector<long long>& samples, bool tf = false) {
@@ -959,7 +959,7 @@ static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int t
     GlParams G{};
     G.plan = make_plan(h, tf); G.batch = B; G.mag = reinterpret_cast<const float*>(h->ws_mag.p);
     G.tile_hops = H; G.colours = h->colours; G.total_tiles = total_tiles; G.status = h->d_status; G.inv_thr = inv_thr;
-    G.wide = (h->wide_mode != 0 && h->user_tile_hops == 0 && H == h->colours && (h->wide_mode == 1 || total_tiles <= 4 * h->num_sms)) ? 1 : 0;
+    G.wide = (h->wide_mode != 0 && h->user_tile_hops == 0 && H == h->colours && (h->wide_mode == 1 || total_tiles <= 8 * h->num_sms)) ? 1 : 0;
     const size_t smem = gl_smem(h->hop, H);
     // one launch runs all the iterations: (iteration, tile) items from a global counter, per-tile completion counters
     int rc = d_done.reserve(sizeof(int) * ((size_t)total_tiles + 1));
