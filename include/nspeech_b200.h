@@ -180,7 +180,7 @@ int nsb_free_pinned(void* p);
 
 /* tuning / accounting hooks (not in the reference) */
 int nsb_set_tile_hops(nsb_handle_t h, int32_t tile_hops);       /* 0 = automatic */
-int nsb_set_host_chunks(nsb_handle_t h, int32_t n);             /* NSB_HOST Griffin-Lim pipelining: 0 = automatic (4 chunks above 8 MB), n = force n chunks */
+int nsb_set_host_chunks(nsb_handle_t h, int32_t n);             /* pipelining of NSB_HOST calls (Griffin-Lim, features, STFT): 0 = automatic (Griffin-Lim: wave schedule on long batches, else a few chunks; analysis: ~24 MB of results per chunk), n = force n equal chunks of whole utterances */
 int nsb_set_generic_iteration(nsb_handle_t h, int32_t on);     /* A/B hook: Griffin-Lim iterations with 0 = k_gl_stream (production), 1 = the generic k_synth<SRC_Y>, 2 = the tile kernel k_gl_iter */
 enum {                          /* nsb_set_option keys: A/B switches of the iteration kernels (defaults are the production settings) */
     NSB_OPT_STREAM_SYNC_MODE = 1,   /* k_gl_stream: 2 = CTA barrier per colour step (default); 0 none, 1 per round, 3 per half CTA (+4: no pacing) use the event counters */
