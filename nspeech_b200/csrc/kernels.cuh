@@ -54,7 +54,7 @@ struct Plan {                    // device tables owned by the handle
     const int* mel_ptr;          // [num_mels] offset into mel_w
     // the same filters as straight lines (librosa's triangles ARE linear in the bin index on either side of the peak):
     // segment j = bins [mel_seg[j], mel_seg[j+1]) between band edges j and j+1; row m rises on segment m as
-    // c.x + c.y (k - mel_seg[m]) and falls on segment m+1 as c.z + c.w (k - mel_seg[m+1]).  Null: use the sparse rows.
+    // c.x + c.y (mel_seg[m+1] - k) and falls on segment m+1 as c.z + c.w (mel_seg[m+2] - k).  Null: use the sparse rows.
     const int* mel_seg;          // [num_mels + 2]
     const float4* mel_coef;      // [num_mels]
     int n_fft, hop, win_len, lo; // window support is n in [lo, lo + win_len) of the n_fft-long frame
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
             bad |= !isfinite(chk);
             __syncwarp();
             if (P.out_mel && P.plan.mel_seg) {
-                // mel[m] = sum_k W[m,k] |D[k]| with W[m,.] a triangle: per segment j two moments S0 = sum |D|, S1 = sum (k - start) |D|
+                // mel[m] = sum_k W[m,k] |D[k]| with W[m,.] a triangle: per segment j two moments S0 = sum |D|, S1 = sum (end - k) |D|
                 // (every bin read ONCE, no weight loads: 68 dependent steps per lane instead of 135 with two loads each), then
                 // every row is four multiply-adds of its two segments' moments
                 float* o = P.out_mel + (size_t)orow * P.plan.num_mels;
@@ -288,8 +288,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
                 const int M = P.plan.num_mels;
                 for (int j = lane; j <= M; j += 32) {
                     const int k0 = __ldg(P.plan.mel_seg + j), k1 = __ldg(P.plan.mel_seg + j + 1);
-                    float a0 = 0.f, a1 = 0.f, fi = 0.f;
-                    for (int kb = k0; kb < k1; ++kb) { const float v = magrow[kb]; a0 += v; a1 = fmaf(fi, v, a1); fi += 1.f; }
+                    // a1 = sum of the running sums = sum (k1 - k) |D[k]|: the first moment counted from the segment's END costs one
+                    // add per bin instead of a multiply-add and an index increment; the host folds the change of origin into c
+                    float a0 = 0.f, a1 = 0.f;
+                    for (int kb = k0; kb < k1; ++kb) { a0 += magrow[kb]; a1 += a0; }
                     mom[2 * j] = a0; mom[2 * j + 1] = a1;
                 }
                 __syncwarp();

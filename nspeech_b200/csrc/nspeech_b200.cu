@@ -143,8 +143,8 @@ static void build_mel(int sr, int n_fft, int n_mels, std::vector<double>& dense)
 }
 
 // The same filter bank as straight lines: between band edges j and j+1 (segment j, bins [seg[j], seg[j+1])) row j rises and row
-// j-1 falls, both linearly in the bin index.  coef[m] = (value at the first bin of segment m, slope) of the rising side and the
-// same of the falling side on segment m+1.  Returns false when the lines do not reproduce `dense` (then the sparse rows are used).
+// j-1 falls, both linearly in the bin index.  coef[m] = (value one bin past the END of segment m, slope per bin counted back from
+// there) of the rising side and the same of the falling side on segment m+1.  Returns false when the lines do not reproduce `dense` (then the sparse rows are used).
 static bool build_mel_lines(int sr, int n_fft, int n_mels, const std::vector<double>& dense, std::vector<int>& seg, std::vector<float>& coef) {
     const int F = 1 + n_fft / 2;
     std::vector<double> mel_f(n_mels + 2), c(4 * (size_t)n_mels);
@@ -172,8 +172,13 @@ static bool build_mel_lines(int sr, int n_fft, int n_mels, const std::vector<dou
             err = std::fmax(err, std::fabs(w - dense[(size_t)m * F + k]));
         }
     if (!(err <= 1e-12 * wmax)) return false;
+    // the kernel measures the first moment from the segment's END (sum of running sums): a + b (k - start) = (a + b len) - b (end - k)
     coef.resize(c.size());
-    for (size_t i = 0; i < c.size(); ++i) coef[i] = (float)c[i];
+    for (int m = 0; m < n_mels; ++m) {
+        const int len0 = seg[m + 1] - seg[m], len1 = seg[m + 2] - seg[m + 1];
+        coef[4 * m + 0] = (float)(c[4 * m + 0] + c[4 * m + 1] * len0); coef[4 * m + 1] = (float)(-c[4 * m + 1]);
+        coef[4 * m + 2] = (float)(c[4 * m + 2] + c[4 * m + 3] * len1); coef[4 * m + 3] = (float)(-c[4 * m + 3]);
+    }
     return true;
 }
 
