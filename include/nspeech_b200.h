@@ -14,7 +14,10 @@
  *    synchronises before returning) or NSB_DEVICE (pointers into the handle's GPU; the call is
  *    stream-ordered on `stream` and returns without synchronising);
  *  - `stream` is a cudaStream_t used as given; NULL means CUDA's default stream for NSB_DEVICE calls and the
- *    handle's private non-blocking stream for the (synchronous) NSB_HOST calls;
+ *    handle's private non-blocking stream for the (synchronous) NSB_HOST calls.  A handle's device state (descriptors,
+ *    scheduling counters, workspaces) is shared by its calls: use ONE stream per handle.  A call that arrives on another
+ *    stream than the previous one first waits (on the device) for the event the previous call recorded when it returned;
+ *  - nsb_*_submit / nsb_wait are the asynchronous form of the NSB_HOST calls (two batches in flight per handle);
  *  - ragged batches: per-utterance lengths are a HOST int array; utterance blocks are packed back to
  *    back in every buffer (a uniform [N,T,F] or [N,n] C-contiguous array is already in that form);
  *  - spectra are float32, 1025 = num_freq bins per frame; layout NSB_FRAME_MAJOR = [T][F] per
@@ -32,7 +35,7 @@
 extern "C" {
 #endif
 
-#define NSB_ABI_VERSION 1
+#define NSB_ABI_VERSION 2
 
 typedef struct nsb_handle_s* nsb_handle_t;
 
@@ -62,7 +65,7 @@ typedef enum nsb_status {
 
 enum { NSB_HOST = 0, NSB_DEVICE = 1 };
 enum { NSB_FRAME_MAJOR = 0, NSB_BIN_MAJOR = 1 };
-enum { NSB_F32 = 0, NSB_F64 = 1 };
+enum { NSB_F32 = 0, NSB_F64 = 1, NSB_I16 = 2 };
 enum { NSB_EW_AMP_TO_DB = 0, NSB_EW_DB_TO_AMP = 1, NSB_EW_NORMALIZE = 2, NSB_EW_DENORMALIZE = 3 };
 
 /* flags of nsb_griffin_lim */
@@ -172,6 +175,50 @@ int nsb_frame_energy(nsb_handle_t h, const float* wav, const int64_t* n_samples,
  * first endpoints[b] of them, synthesizer.py:53). */
 int nsb_synthesize(nsb_handle_t h, const float* spec, const int32_t* n_frames, int32_t batch, int32_t iters,
                    double threshold_db, double min_silence_sec, double* wav_out, int64_t* endpoints, int32_t space, void* stream);
+
+/* The same stage with save_wav's scaling fused in (utils/audio.py:17-19, applied by eval.py:43 / train.py:108 to the trimmed
+ * waveform): flags NSB_SYNTH_PEAK_NORMALIZE multiplies utterance b's first endpoints[b] samples by
+ * 32767 / max(0.01, max |wav[:endpoints[b]]|) (float64, like numpy) and zeroes the rest; out_dtype NSB_F64, or NSB_I16 = the
+ * scaled samples through the C cast numpy's astype(np.int16) performs (needs the flag; a quarter of the bytes to copy out). */
+enum { NSB_SYNTH_PEAK_NORMALIZE = 1 };
+int nsb_synthesize_ex(nsb_handle_t h, const float* spec, const int32_t* n_frames, int32_t batch, int32_t iters,
+                      double threshold_db, double min_silence_sec, int32_t flags, void* wav_out, int32_t out_dtype,
+                      int64_t* endpoints, int32_t space, void* stream);
+/* save_wav's scaling alone (utils/audio.py:17-19): wav (NSB_F32 / NSB_F64, packed per utterance) times
+ * 32767 / max(0.01, max |wav[:limit[b]]|) per utterance (limit NULL: the whole utterance; a DEVICE pointer for NSB_DEVICE);
+ * out NSB_F64 or NSB_I16, samples at and beyond limit[b] are written as 0. */
+int nsb_peak_normalize(nsb_handle_t h, const void* wav, int32_t wav_dtype, const int64_t* n_samples, int32_t batch,
+                       const int64_t* limit, void* out, int32_t out_dtype, int32_t space, void* stream);
+
+/* The feeder's bucketed batches in one pass (datasets/datafeeder.py:130-158: a group of batch_size * batch_group_size
+ * examples is sorted by length, cut into batches, every batch padded on its own): feature row k of utterance b goes to row
+ * row_off[b] + k (HOST int64 array) of lin_out [total_rows][num_freq] / mel_out [total_rows][num_mels]; all other rows are
+ * zeroed (_pad = 0, datafeeder.py:216).  With row_off[b] = b * rows_per_utt this is nsb_features_padded. */
+int nsb_features_rows(nsb_handle_t h, const float* wav, const int64_t* n_samples, int32_t batch, const int64_t* row_off,
+                      int64_t total_rows, float* lin_out, float* mel_out, int32_t space, void* stream);
+
+/* Asynchronous NSB_HOST calls.  submit returns at once with a ticket; the call runs on one of the handle's worker slots
+ * (default 2, nsb_set_async_slots before the first submit), each with private streams and workspaces, so consecutive
+ * batches overlap on the GPU and on PCIe.  Data buffers must stay valid until nsb_wait(ticket), which returns the call's
+ * status (nsb_last_error has its message); lengths arrays are copied at submit.  Tickets may be waited for in any order,
+ * each exactly once.  nsb_destroy runs whatever is still queued.  Caller pattern: the feeder threads of
+ * datasets/datafeeder.py:110-152; eval.py:36-59 synthesising sentence after sentence. */
+int nsb_griffin_lim_submit(nsb_handle_t h, const float* spec, int32_t layout, const int32_t* n_frames, int32_t batch,
+                           const float* init_phase_complex, uint64_t seed, int32_t iters, int32_t flags,
+                           void* wav_out, int32_t out_dtype, uint64_t* ticket);
+int nsb_features_submit(nsb_handle_t h, const float* wav, const int64_t* n_samples, int32_t batch,
+                        float* lin_out, float* mel_out, uint64_t* ticket);
+int nsb_synthesize_submit(nsb_handle_t h, const float* spec, const int32_t* n_frames, int32_t batch, int32_t iters,
+                          double threshold_db, double min_silence_sec, int32_t flags, void* wav_out, int32_t out_dtype,
+                          int64_t* endpoints, uint64_t* ticket);
+int nsb_wait(nsb_handle_t h, uint64_t ticket);
+int nsb_set_async_slots(nsb_handle_t h, int32_t n);
+
+/* device memory owned by the library, for results handed to other frameworks through DLPack / the CUDA array interface
+ * (nspeech_b200/_buffers.py); nsb_device_copy kind: 1 host->device, 2 device->host, 3 device->device, synchronous */
+int nsb_device_alloc(int device, uint64_t bytes, void** out);
+int nsb_device_free(int device, void* p);
+int nsb_device_copy(int device, void* dst, const void* src, uint64_t bytes, int32_t kind);
 
 /* page-locked host buffers for the NSB_HOST entry points (plain cudaHostAlloc / cudaFreeHost): copies from
  * pageable numpy memory are staged by the driver and reach only a fraction of PCIe bandwidth */

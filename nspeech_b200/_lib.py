@@ -17,7 +17,8 @@ DEFAULT_LIB = os.path.join(HERE, "libnspeech_b200.so")
 NSB_OK, NSB_ERR_INVALID, NSB_ERR_CUDA, NSB_ERR_UNSUPPORTED, NSB_ERR_NONFINITE, NSB_ERR_NODEVICE, NSB_ERR_OOM = range(7)
 HOST, DEVICE = 0, 1
 FRAME_MAJOR, BIN_MAJOR = 0, 1
-F32, F64 = 0, 1
+F32, F64, I16 = 0, 1, 2
+SYNTH_PEAK_NORMALIZE = 1
 EW_AMP_TO_DB, EW_DB_TO_AMP, EW_NORMALIZE, EW_DENORMALIZE = range(4)
 GL_DENORMALIZE, GL_DEEMPHASIS, GL_TF_TWIN = 1, 2, 4
 OPT_STREAM_SYNC_MODE, OPT_FUSE_ITERATIONS, OPT_WIDE_MODE, OPT_OVERLAP_CHUNKS, OPT_WAVE_SCHEDULE, OPT_MEL_LINES = 1, 2, 3, 4, 5, 6
@@ -77,6 +78,17 @@ SIGNATURES = {
     "nsb_find_endpoint": (ctypes.c_int, [_vp, _vp, _i32, _pi64, _i32, ctypes.c_double, ctypes.c_double, _vp, _i32, _vp]),
     "nsb_synthesize": (ctypes.c_int, [_vp, _vp, _pi32, _i32, _i32, ctypes.c_double, ctypes.c_double, _vp, _vp, _i32, _vp]),
     "nsb_griffin_lim_iterate": (ctypes.c_int, [_vp, _i32, _vp]),
+    "nsb_synthesize_ex": (ctypes.c_int, [_vp, _vp, _pi32, _i32, _i32, ctypes.c_double, ctypes.c_double, _i32, _vp, _i32, _vp, _i32, _vp]),
+    "nsb_peak_normalize": (ctypes.c_int, [_vp, _vp, _i32, _pi64, _i32, _vp, _vp, _i32, _i32, _vp]),
+    "nsb_features_rows": (ctypes.c_int, [_vp, _vp, _pi64, _i32, _pi64, _i64, _vp, _vp, _i32, _vp]),
+    "nsb_griffin_lim_submit": (ctypes.c_int, [_vp, _vp, _i32, _pi32, _i32, _vp, _u64, _i32, _i32, _vp, _i32, ctypes.POINTER(_u64)]),
+    "nsb_features_submit": (ctypes.c_int, [_vp, _vp, _pi64, _i32, _vp, _vp, ctypes.POINTER(_u64)]),
+    "nsb_synthesize_submit": (ctypes.c_int, [_vp, _vp, _pi32, _i32, _i32, ctypes.c_double, ctypes.c_double, _i32, _vp, _i32, _vp, ctypes.POINTER(_u64)]),
+    "nsb_wait": (ctypes.c_int, [_vp, _u64]),
+    "nsb_set_async_slots": (ctypes.c_int, [_vp, _i32]),
+    "nsb_device_alloc": (ctypes.c_int, [ctypes.c_int, _u64, ctypes.POINTER(_vp)]),
+    "nsb_device_free": (ctypes.c_int, [ctypes.c_int, _vp]),
+    "nsb_device_copy": (ctypes.c_int, [ctypes.c_int, _vp, _vp, _u64, _i32]),
     "nsb_alloc_pinned": (ctypes.c_int, [_u64, ctypes.POINTER(_vp)]),
     "nsb_free_pinned": (ctypes.c_int, [_vp]),
 }
@@ -100,7 +112,7 @@ class NativeLib(object):
             fn = getattr(self.dll, name)       # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if self.dll.nsb_abi_version() != 1:
+        if self.dll.nsb_abi_version() != 2:
             raise NativeError("ABI version mismatch")
 
     def check(self, rc):
@@ -202,17 +214,41 @@ def default_lib():
         return _default
 
 
-def _ptr(a):
-    """void* of a numpy array, a torch tensor, or a raw integer device address."""
+def _ptr(a, need=None, what="buffer"):
+    """void* of a numpy array, a torch tensor, anything with __cuda_array_interface__ / __dlpack__, or a raw integer
+    address.  ``need`` = bytes the native call will touch: arrays that say how large they are must be dense (C- or
+    Fortran-ordered, no gaps) and at least that large - a short or strided buffer would otherwise be read or written
+    past its end by cudaMemcpyAsync and the kernels (raw integer addresses cannot be checked: the caller vouches)."""
     if a is None:
         return None
     if isinstance(a, int):
         return ctypes.c_void_p(a)
     if isinstance(a, np.ndarray):
+        if need is not None:
+            if not (a.flags.c_contiguous or a.flags.f_contiguous):
+                raise ValueError("%s must be contiguous (got strides %r for shape %r)" % (what, a.strides, a.shape))
+            if a.nbytes < need:
+                raise ValueError("%s holds %d bytes, the call needs %d" % (what, a.nbytes, need))
         return ctypes.c_void_p(a.ctypes.data)
     if hasattr(a, "data_ptr"):
+        if need is not None and hasattr(a, "numel"):
+            if not (a.is_contiguous() or a.T.is_contiguous()):
+                raise ValueError("%s must be contiguous" % what)
+            if a.numel() * a.element_size() < need:
+                raise ValueError("%s holds %d bytes, the call needs %d" % (what, a.numel() * a.element_size(), need))
         return ctypes.c_void_p(a.data_ptr())
-    raise TypeError("unsupported buffer type %r" % type(a))
+    from . import _buffers
+    b = _buffers.as_buffer(a)
+    if need is not None:
+        if not (b.c_contiguous or b.f_contiguous):
+            raise ValueError("%s must be contiguous" % what)
+        if b.nbytes < need:
+            raise ValueError("%s holds %d bytes, the call needs %d" % (what, b.nbytes, need))
+    _keep.refs = (getattr(_keep, "refs", ()) + (b,))[-16:]     # DLPack capsules must outlive the native call
+    return ctypes.c_void_p(b.ptr)
+
+
+_keep = threading.local()
 
 
 class Handle(object):
@@ -259,17 +295,24 @@ class Handle(object):
     def _call(self, name, *args):
         self.lib.check(getattr(self.lib.dll, name)(self._h, *args))
 
-    # ---- raw entry points (buffers: numpy arrays for HOST, torch tensors / int addresses for DEVICE) ----
+    # ---- raw entry points (buffers: numpy arrays for HOST; torch tensors, __cuda_array_interface__ / DLPack objects or
+    #      int addresses for DEVICE).  Every buffer that knows its size is checked against what the native call touches. ----
+    def _frames_total(self, n_samples):
+        return sum(self.num_frames(n) for n in n_samples)
+
     def stft(self, wav, n_samples, out, preemphasis=False, space=HOST, stream=None):
-        self._call("nsb_stft", _ptr(wav), self._lens(n_samples, ctypes.c_int64), len(n_samples), int(bool(preemphasis)),
-                   _ptr(out), space, _ptr(stream))
+        F, T = self.num_freq, self._frames_total(n_samples)
+        self._call("nsb_stft", _ptr(wav, 4 * sum(n_samples), "wav"), self._lens(n_samples, ctypes.c_int64), len(n_samples), int(bool(preemphasis)),
+                   _ptr(out, 8 * F * T, "out"), space, _ptr(stream))
 
     def stft_tf(self, wav, n_samples, out, space=HOST, stream=None):
-        self._call("nsb_stft_tf", _ptr(wav), self._lens(n_samples, ctypes.c_int64), len(n_samples), _ptr(out), space, _ptr(stream))
+        T = sum(max(0, self.num_frames_tf(n)) for n in n_samples)
+        self._call("nsb_stft_tf", _ptr(wav, 4 * sum(n_samples), "wav"), self._lens(n_samples, ctypes.c_int64), len(n_samples),
+                   _ptr(out, 8 * self.num_freq * T, "out"), space, _ptr(stream))
 
     def istft_tf(self, spec, layout, n_frames, out, space=HOST, stream=None):
-        self._call("nsb_istft_tf", _ptr(spec), layout, self._lens(n_frames, ctypes.c_int32), len(n_frames), _ptr(out), space,
-                   _ptr(stream))
+        self._call("nsb_istft_tf", _ptr(spec, 8 * self.num_freq * sum(n_frames), "spec"), layout, self._lens(n_frames, ctypes.c_int32), len(n_frames),
+                   _ptr(out, 4 * sum(self.num_samples_tf(t) for t in n_frames), "out"), space, _ptr(stream))
 
     def num_frames_tf(self, n):
         return 1 + (int(n) - self.win) // self.hop
@@ -278,45 +321,94 @@ class Handle(object):
         return self.hop * (int(T) - 1) + self.win
 
     def features_padded(self, wav, n_samples, rows_per_utt, lin_out, mel_out, space=HOST, stream=None):
-        self._call("nsb_features_padded", _ptr(wav), self._lens(n_samples, ctypes.c_int64), len(n_samples), int(rows_per_utt),
-                   _ptr(lin_out), _ptr(mel_out), space, _ptr(stream))
+        rows = int(rows_per_utt) * len(n_samples)
+        self._call("nsb_features_padded", _ptr(wav, 4 * sum(n_samples), "wav"), self._lens(n_samples, ctypes.c_int64), len(n_samples), int(rows_per_utt),
+                   _ptr(lin_out, 4 * self.num_freq * rows, "lin_out"), _ptr(mel_out, 4 * self.num_mels * rows, "mel_out"), space, _ptr(stream))
+
+    def features_rows(self, wav, n_samples, row_off, total_rows, lin_out, mel_out, space=HOST, stream=None):
+        self._call("nsb_features_rows", _ptr(wav, 4 * sum(n_samples), "wav"), self._lens(n_samples, ctypes.c_int64), len(n_samples),
+                   self._lens(row_off, ctypes.c_int64), int(total_rows), _ptr(lin_out, 4 * self.num_freq * int(total_rows), "lin_out"),
+                   _ptr(mel_out, 4 * self.num_mels * int(total_rows), "mel_out"), space, _ptr(stream))
 
     def frame_energy(self, wav, n_samples, frame_length, hop_length, out, space=HOST, stream=None):
-        self._call("nsb_frame_energy", _ptr(wav), self._lens(n_samples, ctypes.c_int64), len(n_samples), int(frame_length),
-                   int(hop_length), _ptr(out), space, _ptr(stream))
+        self._call("nsb_frame_energy", _ptr(wav, 4 * sum(n_samples), "wav"), self._lens(n_samples, ctypes.c_int64), len(n_samples), int(frame_length),
+                   int(hop_length), _ptr(out, 8 * sum(1 + n // int(hop_length) for n in n_samples), "out"), space, _ptr(stream))
 
     def find_endpoint(self, wav, n_samples, endpoints, dtype=F64, threshold_db=-40.0, min_silence_sec=0.8, space=HOST, stream=None):
-        self._call("nsb_find_endpoint", _ptr(wav), dtype, self._lens(n_samples, ctypes.c_int64), len(n_samples), float(threshold_db),
-                   float(min_silence_sec), _ptr(endpoints), space, _ptr(stream))
+        self._call("nsb_find_endpoint", _ptr(wav, (8 if dtype == F64 else 4) * sum(n_samples), "wav"), dtype, self._lens(n_samples, ctypes.c_int64),
+                   len(n_samples), float(threshold_db), float(min_silence_sec), _ptr(endpoints, 8 * len(n_samples), "endpoints"), space, _ptr(stream))
 
-    def synthesize(self, spec, n_frames, wav_out, endpoints, iters=-1, threshold_db=-40.0, min_silence_sec=0.8, space=HOST, stream=None):
-        self._call("nsb_synthesize", _ptr(spec), self._lens(n_frames, ctypes.c_int32), len(n_frames), int(iters), float(threshold_db),
-                   float(min_silence_sec), _ptr(wav_out), _ptr(endpoints), space, _ptr(stream))
+    def synthesize(self, spec, n_frames, wav_out, endpoints, iters=-1, threshold_db=-40.0, min_silence_sec=0.8, space=HOST, stream=None,
+                   flags=0, out_dtype=F64):
+        n = sum(self.num_samples_tf(t) for t in n_frames)
+        self._call("nsb_synthesize_ex", _ptr(spec, 4 * self.num_freq * sum(n_frames), "spec"), self._lens(n_frames, ctypes.c_int32), len(n_frames),
+                   int(iters), float(threshold_db), float(min_silence_sec), int(flags), _ptr(wav_out, (2 if out_dtype == I16 else 8) * n, "wav_out"),
+                   int(out_dtype), _ptr(endpoints, 8 * len(n_frames), "endpoints"), space, _ptr(stream))
+
+    def peak_normalize(self, wav, n_samples, out, wav_dtype=F64, out_dtype=F64, limit=None, space=HOST, stream=None):
+        n = sum(n_samples)
+        lim = None if limit is None else (self._lens(limit, ctypes.c_int64) if space == HOST else _ptr(limit, 8 * len(n_samples), "limit"))
+        self._call("nsb_peak_normalize", _ptr(wav, (8 if wav_dtype == F64 else 4) * n, "wav"), int(wav_dtype), self._lens(n_samples, ctypes.c_int64),
+                   len(n_samples), lim, _ptr(out, (2 if out_dtype == I16 else 8) * n, "out"), int(out_dtype), space, _ptr(stream))
 
     def features(self, wav, n_samples, lin_out, mel_out, space=HOST, stream=None):
-        self._call("nsb_features", _ptr(wav), self._lens(n_samples, ctypes.c_int64), len(n_samples), _ptr(lin_out),
-                   _ptr(mel_out), space, _ptr(stream))
+        T = self._frames_total(n_samples)
+        self._call("nsb_features", _ptr(wav, 4 * sum(n_samples), "wav"), self._lens(n_samples, ctypes.c_int64), len(n_samples),
+                   _ptr(lin_out, 4 * self.num_freq * T, "lin_out"), _ptr(mel_out, 4 * self.num_mels * T, "mel_out"), space, _ptr(stream))
 
     def istft(self, spec, layout, n_frames, out, space=HOST, stream=None):
-        self._call("nsb_istft", _ptr(spec), layout, self._lens(n_frames, ctypes.c_int32), len(n_frames), _ptr(out), space,
-                   _ptr(stream))
+        self._call("nsb_istft", _ptr(spec, 8 * self.num_freq * sum(n_frames), "spec"), layout, self._lens(n_frames, ctypes.c_int32), len(n_frames),
+                   _ptr(out, 4 * sum(self.num_samples(t) for t in n_frames), "out"), space, _ptr(stream))
+
+    def _gl_args(self, spec, layout, n_frames, out, init_phase, seed, iters, flags, out_dtype):
+        FT = self.num_freq * sum(n_frames)
+        n = sum((self.num_samples_tf(t) if flags & GL_TF_TWIN else self.num_samples(t)) for t in n_frames)
+        return (_ptr(spec, 4 * FT, "spec"), layout, self._lens(n_frames, ctypes.c_int32), len(n_frames), _ptr(init_phase, 8 * FT, "init_phase"),
+                ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), int(iters), int(flags), _ptr(out, (8 if out_dtype == F64 else 4) * n, "out"), out_dtype)
 
     def griffin_lim(self, spec, layout, n_frames, out, init_phase=None, seed=0, iters=-1, flags=0, out_dtype=F32,
                     space=HOST, stream=None):
-        self._call("nsb_griffin_lim", _ptr(spec), layout, self._lens(n_frames, ctypes.c_int32), len(n_frames),
-                   _ptr(init_phase), ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), int(iters), int(flags), _ptr(out),
-                   out_dtype, space, _ptr(stream))
+        self._call("nsb_griffin_lim", *(self._gl_args(spec, layout, n_frames, out, init_phase, seed, iters, flags, out_dtype) + (space, _ptr(stream))))
+
+    # ---- asynchronous NSB_HOST calls: submit -> ticket, wait(ticket).  The caller keeps the buffers alive until wait. ----
+    def griffin_lim_submit(self, spec, layout, n_frames, out, init_phase=None, seed=0, iters=-1, flags=0, out_dtype=F32):
+        t = ctypes.c_uint64(0)
+        self._call("nsb_griffin_lim_submit", *(self._gl_args(spec, layout, n_frames, out, init_phase, seed, iters, flags, out_dtype) + (ctypes.byref(t),)))
+        return t.value
+
+    def features_submit(self, wav, n_samples, lin_out, mel_out):
+        T = self._frames_total(n_samples)
+        t = ctypes.c_uint64(0)
+        self._call("nsb_features_submit", _ptr(wav, 4 * sum(n_samples), "wav"), self._lens(n_samples, ctypes.c_int64), len(n_samples),
+                   _ptr(lin_out, 4 * self.num_freq * T, "lin_out"), _ptr(mel_out, 4 * self.num_mels * T, "mel_out"), ctypes.byref(t))
+        return t.value
+
+    def synthesize_submit(self, spec, n_frames, wav_out, endpoints, iters=-1, threshold_db=-40.0, min_silence_sec=0.8, flags=0, out_dtype=F64):
+        n = sum(self.num_samples_tf(t) for t in n_frames)
+        t = ctypes.c_uint64(0)
+        self._call("nsb_synthesize_submit", _ptr(spec, 4 * self.num_freq * sum(n_frames), "spec"), self._lens(n_frames, ctypes.c_int32), len(n_frames),
+                   int(iters), float(threshold_db), float(min_silence_sec), int(flags), _ptr(wav_out, (2 if out_dtype == I16 else 8) * n, "wav_out"),
+                   int(out_dtype), _ptr(endpoints, 8 * len(n_frames), "endpoints"), ctypes.byref(t))
+        return t.value
+
+    def wait(self, ticket):
+        self._call("nsb_wait", ctypes.c_uint64(int(ticket)))
+
+    def set_async_slots(self, n):
+        self._call("nsb_set_async_slots", int(n))
 
     def griffin_lim_iterate(self, iters, stream=None):
         self._call("nsb_griffin_lim_iterate", int(iters), _ptr(stream))
 
     def preemphasis(self, x, n_samples, out, out_dtype=F64, space=HOST, stream=None, inverse=False):
-        self._call("nsb_inv_preemphasis" if inverse else "nsb_preemphasis", _ptr(x), self._lens(n_samples, ctypes.c_int64),
-                   len(n_samples), _ptr(out), out_dtype, space, _ptr(stream))
+        n = sum(n_samples)
+        self._call("nsb_inv_preemphasis" if inverse else "nsb_preemphasis", _ptr(x, 4 * n, "x"), self._lens(n_samples, ctypes.c_int64),
+                   len(n_samples), _ptr(out, (8 if out_dtype == F64 else 4) * n, "out"), out_dtype, space, _ptr(stream))
 
     def linear_to_mel(self, spec, layout, n_frames, out, out_dtype=F64, space=HOST, stream=None):
-        self._call("nsb_linear_to_mel", _ptr(spec), layout, self._lens(n_frames, ctypes.c_int32), len(n_frames), _ptr(out),
-                   out_dtype, space, _ptr(stream))
+        T = sum(n_frames)
+        self._call("nsb_linear_to_mel", _ptr(spec, 4 * self.num_freq * T, "spec"), layout, self._lens(n_frames, ctypes.c_int32), len(n_frames),
+                   _ptr(out, (8 if out_dtype == F64 else 4) * self.num_mels * T, "out"), out_dtype, space, _ptr(stream))
 
     def mel_basis(self):
         out = np.empty((self.num_mels, self.num_freq), dtype=np.float64)
@@ -324,7 +416,8 @@ class Handle(object):
         return out
 
     def elementwise(self, op, x, out, space=HOST, stream=None, n=None):
-        self._call("nsb_elementwise", int(op), _ptr(x), int(x.size if n is None else n), _ptr(out), space, _ptr(stream))
+        n = int(x.size if n is None else n)
+        self._call("nsb_elementwise", int(op), _ptr(x, 4 * n, "x"), n, _ptr(out, 4 * n, "out"), space, _ptr(stream))
 
     def synchronize(self, stream=None):
         self._call("nsb_synchronize", _ptr(stream))

@@ -8,23 +8,41 @@ numpy; these are the calls the BASELINE configs 2-5 time).
 * ``shard_by_frames`` / ``run_sharded`` - utterance sharding across the GPUs of one box: independent units,
                                         no collective; one host thread per GPU
 """
+import collections
 import threading
 
 import numpy as np
 
-from . import _lib, audio
+from . import _buffers, _lib, audio
 
 
-def _frames_major(spec, num_freq):
-    """[F,T] (any order) or [T,F] C-contiguous -> frame-major [T,F] float32 view/copy."""
+def _is_time_major(shape, num_freq, layout):
+    """Which axis of a 2-D spectrogram is time.  ``layout``: "FT" = the reference's [num_freq, T] (what ``audio.spectrogram``
+    returns and ``audio.inv_spectrogram`` takes), "TF" = time-major [T, num_freq] (Tacotron's outputs), None = decide from the
+    shape - refused when both axes have num_freq entries (a 1025-frame clip would otherwise be inverted transposed, silently)."""
+    if len(shape) != 2:
+        raise ValueError("expected 2-D spectrogram, got %r" % (shape,))
+    if layout is not None:
+        if layout not in ("FT", "TF"):
+            raise ValueError("layout must be 'FT', 'TF' or None, got %r" % (layout,))
+        if shape[0 if layout == "FT" else 1] != num_freq:
+            raise ValueError("layout %r: shape %r has no %d bins on that axis" % (layout, shape, num_freq))
+        return layout == "TF"
+    if shape[0] == num_freq and shape[1] == num_freq:
+        raise ValueError("shape %r is ambiguous (T == num_freq): pass layout='FT' or 'TF'" % (shape,))
+    if shape[0] == num_freq:
+        return False
+    if shape[1] == num_freq:
+        return True
+    raise ValueError("no axis of %r has num_freq=%d bins" % (shape, num_freq))
+
+
+def _frames_major(spec, num_freq, layout=None, dtype=np.float32):
+    """[F,T] (any order) or [T,F] -> frame-major [T,F] C-contiguous view/copy."""
     spec = np.asarray(spec)
-    if spec.ndim != 2:
-        raise ValueError("expected 2-D spectrogram, got %r" % (spec.shape,))
-    if spec.shape[0] == num_freq and spec.shape[1] != num_freq:
+    if not _is_time_major(spec.shape, num_freq, layout):
         spec = spec.T
-    elif spec.shape[1] != num_freq:
-        raise ValueError("no axis of %r has num_freq=%d bins" % (spec.shape, num_freq))
-    return np.ascontiguousarray(spec, dtype=np.float32)
+    return np.ascontiguousarray(spec, dtype=dtype)
 
 
 def features_batch(wavs, device=None, want_linear=True, want_mel=True):
@@ -69,15 +87,8 @@ def feeder_targets(wavs, outputs_per_step, device=None):
     return mel, lin, Ts
 
 
-def inv_spectrogram_batch(specs, init_phase=None, seed=0, iters=None, device=None, denormalize=True, deemphasis=True,
-                          out=None):
-    """Griffin-Lim inversion of a batch.
-
-    specs: list of [F,T_b] / [T_b,F] arrays, or one [N,T,F] array.  init_phase: same structure (complex) or
-    None -> device Philox keyed by ``seed``.  Returns a list of float64 waveforms (views into one buffer),
-    or float32 when ``deemphasis`` is False (what ``_griffin_lim`` returns).
-    """
-    h = audio._handle(device)
+def _gl_batch_inputs(h, specs, init_phase, layout):
+    """-> (packed [sum T, F] float32, n_frames, packed phase or None)"""
     F = h.num_freq
     if isinstance(specs, np.ndarray) and specs.ndim == 3:
         if specs.shape[2] != F:
@@ -86,32 +97,174 @@ def inv_spectrogram_batch(specs, init_phase=None, seed=0, iters=None, device=Non
         Ts = [specs.shape[1]] * specs.shape[0]
         if init_phase is not None:
             init_phase = np.ascontiguousarray(init_phase, dtype=np.complex64)
-    else:
-        mats = [_frames_major(s, F) for s in specs]
-        Ts = [m.shape[0] for m in mats]
-        packed = np.concatenate(mats) if len(mats) > 1 else mats[0]
-        if init_phase is not None:
-            ph = []
-            for p, T in zip(init_phase, Ts):
-                p = np.asarray(p)
-                if p.shape == (F, T) and T != F:
-                    p = p.T
-                ph.append(np.ascontiguousarray(p, dtype=np.complex64))
-            init_phase = np.concatenate(ph) if len(ph) > 1 else ph[0]
-    ns = [h.num_samples(T) for T in Ts]
-    dt = np.float64 if deemphasis else np.float32
+            if init_phase.shape != packed.shape:
+                raise ValueError("init_phase shape %r != batch shape %r" % (init_phase.shape, packed.shape))
+        return packed, Ts, init_phase
+    mats = [_frames_major(s, F, layout) for s in specs]
+    if not mats:
+        raise ValueError("empty batch")
+    Ts = [m.shape[0] for m in mats]
+    packed = np.concatenate(mats) if len(mats) > 1 else mats[0]
+    if init_phase is not None:
+        if len(init_phase) != len(mats):
+            raise ValueError("init_phase has %d entries for %d spectrograms" % (len(init_phase), len(mats)))
+        ph = []
+        for p, s, T in zip(init_phase, specs, Ts):
+            if np.shape(p) != np.shape(s):
+                raise ValueError("init_phase shape %r != spectrogram shape %r" % (np.shape(p), np.shape(s)))
+            ph.append(_frames_major(p, F, layout, dtype=np.complex64))
+        init_phase = np.concatenate(ph) if len(ph) > 1 else ph[0]
+    return packed, Ts, init_phase
+
+
+def _gl_out_buffer(h, ns, dt, out):
+    total = sum(ns)
     if out is None:
         # results land in pooled page-locked memory (PinnedPool): the copy out runs at PCIe speed
-        nbytes = sum(ns) * np.dtype(dt).itemsize
-        out = h.lib.pinned_pool().empty((sum(ns),), dt) if nbytes >= (1 << 20) else np.empty(sum(ns), dtype=dt)
-    flags = (_lib.GL_DENORMALIZE if denormalize else 0) | (_lib.GL_DEEMPHASIS if deemphasis else 0)
-    h.griffin_lim(packed, _lib.FRAME_MAJOR, Ts, out, init_phase=init_phase, seed=seed, iters=-1 if iters is None else iters,
-                  flags=flags, out_dtype=_lib.F64 if deemphasis else _lib.F32)
+        nbytes = total * np.dtype(dt).itemsize
+        return h.lib.pinned_pool().empty((total,), dt) if nbytes >= (1 << 20) else np.empty(total, dtype=dt)
+    if not isinstance(out, np.ndarray) or out.dtype != np.dtype(dt) or not out.flags.c_contiguous or out.size < total:
+        raise ValueError("out must be a C-contiguous numpy array of %s with at least %d elements" % (np.dtype(dt), total))
+    return out
+
+
+def _split(out, ns):
     res, off = [], 0
     for n in ns:
         res.append(out[off:off + n])
         off += n
     return res
+
+
+def _inv_spectrogram_batch_device(specs, init_phase, seed, iters, denormalize, deemphasis):
+    """uniform [N, T, F] batch that already lives on the GPU (models/tacotron.py:98): NSB_DEVICE path, device result [N, n]"""
+    specs, b, _ = audio._dev_tf_batch(specs, np.float32, "specs")
+    if b.ndim != 3:
+        raise ValueError("device batches must be one [N, T, F] array")
+    h = audio._handle(b.device)
+    if b.shape[2] != h.num_freq:
+        raise ValueError("uniform batch must be [N,T,%d]" % h.num_freq)
+    N, T = b.shape[0], b.shape[1]
+    if init_phase is not None:
+        init_phase, pb, _ = audio._dev_tf_batch(init_phase, np.complex64, "init_phase")
+        if pb.shape != b.shape:
+            raise ValueError("init_phase shape %r != batch shape %r" % (pb.shape, b.shape))
+    st = _buffers.stream_of(specs, init_phase)
+    dt = np.float64 if deemphasis else np.float32
+    out = _buffers.empty_like_source(h.lib, (N, h.num_samples(T)), dt, b.device, (specs,))
+    flags = (_lib.GL_DENORMALIZE if denormalize else 0) | (_lib.GL_DEEMPHASIS if deemphasis else 0)
+    h.griffin_lim(specs, _lib.FRAME_MAJOR, [T] * N, out, init_phase=init_phase, seed=seed, iters=-1 if iters is None else iters,
+                  flags=flags, out_dtype=_lib.F64 if deemphasis else _lib.F32, space=_lib.DEVICE, stream=st)
+    h.check_status(st)
+    return out
+
+
+def inv_spectrogram_batch(specs, init_phase=None, seed=0, iters=None, device=None, denormalize=True, deemphasis=True,
+                          out=None, layout=None):
+    """Griffin-Lim inversion of a batch.
+
+    specs: list of [F,T_b] / [T_b,F] arrays (``layout`` "FT" / "TF" says which; None decides per array from the shape and
+    refuses the ambiguous T == num_freq), or one [N,T,F] array.  init_phase: same structure (complex) or
+    None -> device Philox keyed by ``seed``.  Returns a list of float64 waveforms (views into one buffer),
+    or float32 when ``deemphasis`` is False (what ``_griffin_lim`` returns).  A [N,T,F] array that lives on the GPU
+    (torch / ``__cuda_array_interface__`` / DLPack) is inverted in place there and a device array [N, n] comes back.
+    """
+    if _buffers.is_device_array(specs):
+        return _inv_spectrogram_batch_device(specs, init_phase, seed, iters, denormalize, deemphasis)
+    h = audio._handle(device)
+    packed, Ts, init_phase = _gl_batch_inputs(h, specs, init_phase, layout)
+    ns = [h.num_samples(T) for T in Ts]
+    dt = np.float64 if deemphasis else np.float32
+    out = _gl_out_buffer(h, ns, dt, out)
+    flags = (_lib.GL_DENORMALIZE if denormalize else 0) | (_lib.GL_DEEMPHASIS if deemphasis else 0)
+    h.griffin_lim(packed, _lib.FRAME_MAJOR, Ts, out, init_phase=init_phase, seed=seed, iters=-1 if iters is None else iters,
+                  flags=flags, out_dtype=_lib.F64 if deemphasis else _lib.F32)
+    return _split(out, ns)
+
+
+def inv_spectrogram_stream(batches, seed=0, iters=None, device=None, denormalize=True, deemphasis=True, layout=None, in_flight=2):
+    """Generator over an iterable of batches (each what ``inv_spectrogram_batch`` takes as ``specs``): yields each batch's
+    list of waveforms, in order, with ``in_flight`` batches inside the library at any time (``nsb_griffin_lim_submit`` /
+    ``nsb_wait``) - batch i+1 is copied in and starts while batch i finishes and is copied out.  The caller pattern is the
+    reference's synthesis loops (eval.py:36-59: sentence after sentence) and feeder threads (datasets/datafeeder.py:110-152).
+    The phase is drawn on the device (Philox, ``seed`` + the batch's index)."""
+    h = audio._handle(device)
+    flags = (_lib.GL_DENORMALIZE if denormalize else 0) | (_lib.GL_DEEMPHASIS if deemphasis else 0)
+    dt = np.float64 if deemphasis else np.float32
+    pending = collections.deque()
+
+    def collect():
+        ticket, out, ns, _keep = pending.popleft()
+        h.wait(ticket)
+        return _split(out, ns)
+
+    try:
+        for i, specs in enumerate(batches):
+            packed, Ts, _ = _gl_batch_inputs(h, specs, None, layout)
+            ns = [h.num_samples(T) for T in Ts]
+            out = _gl_out_buffer(h, ns, dt, None)
+            t = h.griffin_lim_submit(packed, _lib.FRAME_MAJOR, Ts, out, seed=seed + i, iters=-1 if iters is None else iters,
+                                     flags=flags, out_dtype=_lib.F64 if deemphasis else _lib.F32)
+            pending.append((t, out, ns, packed))
+            if len(pending) >= max(1, in_flight):
+                yield collect()
+        while pending:
+            yield collect()
+    finally:
+        while pending:                       # the consumer stopped early: the buffers must outlive the submitted calls
+            try:
+                collect()
+            except Exception:
+                pass
+
+
+def bucket_by_length(n_frames, batch_size, rng=None):
+    """The feeder's bucketing (reference datasets/datafeeder.py:143-147): sort the group's examples by output length
+    (stable, like ``list.sort``), cut into batches of ``batch_size``, shuffle the batches with ``rng`` (an object with
+    ``shuffle``, e.g. the ``random`` module as in the reference; None: keep the sorted order).  Returns lists of indices."""
+    order = sorted(range(len(n_frames)), key=lambda i: int(n_frames[i]))
+    batches = [order[i:i + batch_size] for i in range(0, len(order), batch_size)]
+    if rng is not None:
+        rng.shuffle(batches)
+    return batches
+
+
+def feeder_groups(wavs, batch_size, outputs_per_step, rng=None, device=None):
+    """One group of the feeder (reference datasets/datafeeder.py:130-158 with ``_prepare_batch`` 190-216) from the waveforms:
+    features of ALL ``batch_size * batch_group_size`` clips in one device pass, written straight into the bucketed batches'
+    padded, time-major target tensors (``nsb_features_rows``) - no per-utterance numpy pad, no second pass over the frames.
+    Returns a list of batches (dicts): ``indices`` (into ``wavs``), ``mel_targets`` [n, Tpad, num_mels], ``linear_targets``
+    [n, Tpad, num_freq] with Tpad = round_up(max frames of the batch + 1, outputs_per_step), ``audios`` [n, max len] (padded
+    with 0 like ``_prepare_inputs``), ``n_frames``."""
+    h = audio._handle(device)
+    wavs = [audio._as_wav(w) for w in wavs]
+    ns = [w.size for w in wavs]
+    Ts = [h.num_frames(n) for n in ns]
+    buckets = bucket_by_length(Ts, batch_size, rng)
+    row_off, rows_of, base, total = [0] * len(wavs), [], [], 0
+    for idx in buckets:
+        rows = _round_up(max(Ts[i] for i in idx) + 1, outputs_per_step)
+        rows_of.append(rows)
+        base.append(total)
+        for j, i in enumerate(idx):
+            row_off[i] = total + j * rows
+        total += rows * len(idx)
+    packed = np.concatenate(wavs) if len(wavs) > 1 else wavs[0]
+    pool = h.lib.pinned_pool()
+    lin = pool.empty((total, h.num_freq), np.float32)
+    mel = pool.empty((total, h.num_mels), np.float32)
+    h.features_rows(packed, ns, row_off, total, lin, mel)
+    out = []
+    for idx, rows, r0 in zip(buckets, rows_of, base):
+        n = len(idx)
+        max_len = max(ns[i] for i in idx)
+        audios = np.zeros((n, max_len), dtype=np.float32)
+        for j, i in enumerate(idx):
+            audios[j, :ns[i]] = wavs[i]
+        out.append({"indices": list(idx), "n_frames": [Ts[i] for i in idx], "audios": audios,
+                    "mel_targets": mel[r0:r0 + n * rows].reshape(n, rows, h.num_mels),
+                    "linear_targets": lin[r0:r0 + n * rows].reshape(n, rows, h.num_freq)})
+    return out
 
 
 def _parse_cpulist(text):
@@ -188,5 +341,5 @@ def run_sharded(fn, items, lengths, devices):
 def inv_spectrogram_multi_gpu(specs, devices, **kw):
     h = audio._handle(devices[0])
     F = h.num_freq
-    lengths = [s.shape[1] if s.shape[0] == F and s.shape[1] != F else s.shape[0] for s in specs]
+    lengths = [np.shape(s)[0] if _is_time_major(np.shape(s), F, kw.get("layout")) else np.shape(s)[1] for s in specs]
     return run_sharded(lambda sub, dev: inv_spectrogram_batch(sub, device=dev, **kw), list(specs), lengths, devices)

@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
     }
     if (threadIdx.x < 16) progress[threadIdx.x] = 0;
     __syncthreads();
-    bool bad = false;
+    // (no non-finite test in this kernel: the inputs are tested by k_prepare_mag / k_synth, the result by k_deemphasis)
     const int E = C + 1;                              // events per round: C adds + 1 store
 
     // ---- (iteration, chunk) items from one global counter (see k_gl_iter for why) ----
@@ -605,7 +605,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
     __syncthreads();                                 // every thread's stores of this chunk are issued
     if (threadIdx.x == 0) { __threadfence(); gflag_store(P.done + chunk, n_it + 1); }
     }   // items
-    if (bad) atomicOr(P.status, 1);
     if (P.trace) {
         __syncthreads();
         if (threadIdx.x == 0) P.trace[3 * blockIdx.x + 2] = global_ns();

@@ -36,6 +36,7 @@ struct Batch {
     const int* tile_off;         // [batch+1] (synthesis tiles), may be null for analysis
     const int* tile_utt;         // [total tiles] GLOBAL tile index -> GLOBAL utterance index
     const int* group_off;        // [batch+1] groups of C = ceil(win/hop) hops per utterance, GLOBAL prefix sums (k_gl_stream)
+    const long long* row_off;    // [batch] or null: output row of utterance b's first feature frame (nsb_features_rows: bucketed, padded batches)
     int group_base;              // global index of this (sub-)batch's first group
     int batch;
     int utt_base;                // global index of this (sub-)batch's first utterance (pointers above are offset by it)
@@ -248,7 +249,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
                 }
             }
         } else {
-            const long long orow = P.rows_per_utt > 0 ? (long long)(P.batch.utt_base + b) * P.rows_per_utt + k : (long long)f;
+            const long long orow = P.batch.row_off ? __ldg(P.batch.row_off + b) + k
+                                 : P.rows_per_utt > 0 ? (long long)(P.batch.utt_base + b) * P.rows_per_utt + k : (long long)f;
             // magnitudes -> scratch (as floats, 1025 <= 2112), then linear dB and sparse mel
             // The linear feature goes out straight from the registers: slot p of lanes 1..31 holds 31 consecutive bins
             // (bin_of), so the stores coalesce without a trip through shared memory; only the mel projection needs the
@@ -893,6 +895,64 @@ __global__ void __launch_bounds__(256) k_find_endpoint(EndpointParams P) {
     if (threadIdx.x == 0) P.out[b] = (long long)best;
 }
 
+
+// =============================================================================================
+// save_wav's scaling (utils/audio.py:17-19): wav *= 32767 / max(0.01, np.max(np.abs(wav))), per utterance, on the first
+// limit[b] samples (the caller trims to find_endpoint before saving, synthesizer.py:53 -> eval.py:43); float64 like numpy.
+// k_peak_max: per-utterance max |x| (the bit pattern of a non-negative double orders like an unsigned integer: atomicMax);
+// k_peak_apply: x * factor -> float64, or the C cast to int16 (numpy's astype(np.int16): truncation toward zero).
+// =============================================================================================
+struct PeakParams {
+    Batch batch;
+    const double* in64;       // one of the two inputs is non-null
+    const float* in32;
+    const long long* limit;   // [batch] samples that count (and are written), null: the whole utterance
+    unsigned long long* peak; // [batch] bit pattern of max |x| (zeroed by the host)
+    double* out64;            // one of the two outputs is non-null; samples at and beyond limit[b] become 0
+    short* out16;
+    int n_seg;                // CTAs per utterance
+    int* status;
+};
+
+__global__ void __launch_bounds__(256) k_peak_max(PeakParams P) {
+    __shared__ double wmax[8];
+    const int b = blockIdx.x / P.n_seg, seg = blockIdx.x - b * P.n_seg;
+    const long long s_off = __ldg(P.batch.samp_off + b);
+    long long L = __ldg(P.batch.samp_off + b + 1) - s_off;
+    if (P.limit) L = min(L, max(0LL, __ldg(P.limit + b)));
+    const long long per = (L + P.n_seg - 1) / P.n_seg;
+    const long long i0 = seg * per, i1 = min(L, i0 + per);
+    double m = 0.0;
+    bool nan = false;
+    for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const double v = P.in64 ? __ldg(P.in64 + s_off + i) : (double)__ldg(P.in32 + s_off + i);
+        nan |= (v != v);
+        m = fmax(m, fabs(v));
+    }
+    for (int d = 16; d > 0; d >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+    if (nan && P.status) atomicOr(P.status, 1);         // np.max would propagate the NaN into every sample
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmax(m, wmax[w]);
+        atomicMax(P.peak + b, (unsigned long long)__double_as_longlong(m));
+    }
+}
+
+// samples [i_begin, i_end) of the packed buffers (a whole batch or one chunk of it)
+__global__ void __launch_bounds__(256) k_peak_apply(PeakParams P, long long i_begin, long long i_end) {
+    for (long long i = i_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < i_end; i += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = P.batch.batch;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (__ldg(P.batch.samp_off + mid) <= i) lo = mid; else hi = mid; }
+        const long long s_off = __ldg(P.batch.samp_off + lo);
+        const bool live = !P.limit || (i - s_off) < __ldg(P.limit + lo);
+        const double peak = __longlong_as_double((long long)P.peak[lo]);
+        const double factor = 32767.0 / fmax(0.01, peak);
+        const double x = P.in64 ? __ldg(P.in64 + i) : (double)__ldg(P.in32 + i);
+        const double v = live ? x * factor : 0.0;
+        if (P.out64) P.out64[i] = v; else P.out16[i] = (short)(int)v;
+    }
+}
 
 // =============================================================================================
 // frame energy: mean(|x|^2) of every centred frame (librosa.feature.rmse(y, frame_length, hop_length, center=True,

@@ -68,6 +68,8 @@ struct nsb_handle_s {
     cudaStream_t own_stream = nullptr, copy_in = nullptr, copy_out = nullptr;
     cudaStream_t chunk_stream = nullptr;   // odd chunks of a pipelined NSB_HOST Griffin-Lim call (even ones run on the call's stream)
     cudaEvent_t desc_done = nullptr, chunk_fork = nullptr, chunk_join = nullptr;
+    cudaEvent_t last_done = nullptr;       // recorded on the stream of every call when it returns (CallScope)
+    cudaStream_t last_stream = nullptr; bool have_last = false;
     // tables
     float2* d_tw = nullptr;
     float* d_win = nullptr;          // periodic Hann padded centrally to n_fft (librosa geometry)
@@ -102,8 +104,12 @@ struct nsb_handle_s {
     int host_chunks = 0;             // 0 = automatic chunking of NSB_HOST Griffin-Lim calls, n > 0 = force n chunks
     int use_generic_iter = -1;       // -1 = automatic (k_gl_stream for long batches, k_gl_iter otherwise), 0 = k_gl_stream, 1 = generic k_synth<SRC_Y>, 2 = tile kernel k_gl_iter; A-B hook: run the iterations with k_synth<SRC_Y> instead of k_gl_iter
     unsigned long long launches = 0;
+    unsigned long long launches_async = 0;   // kernels launched by the worker slots of the asynchronous entry points (guarded by async->m)
+    struct nsb_async_s* async = nullptr;     // worker slots of nsb_*_submit / nsb_wait, created by the first submit
+    int async_slots = 2;
     std::mutex mu;
 };
+static void async_shutdown(nsb_handle_s* h);
 
 static Plan make_plan(nsb_handle_s* h, bool tf = false) {
     Plan p;
@@ -256,6 +262,7 @@ extern "C" int nsb_free_pinned(void* p) {
 
 extern "C" int nsb_destroy(nsb_handle_t h) {
     if (!h) return NSB_OK;
+    async_shutdown(h);                       // runs what was submitted, joins the workers, destroys their child handles
     cudaSetDevice(h->device);
     if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
     if (h->copy_in) cudaStreamDestroy(h->copy_in);
@@ -264,6 +271,7 @@ extern "C" int nsb_destroy(nsb_handle_t h) {
     if (h->desc_done) cudaEventDestroy(h->desc_done);
     if (h->chunk_fork) cudaEventDestroy(h->chunk_fork);
     if (h->chunk_join) cudaEventDestroy(h->chunk_join);
+    if (h->last_done) cudaEventDestroy(h->last_done);
     cudaFree(h->d_tw); cudaFree(h->d_win); cudaFree(h->d_win_tf); cudaFree(h->d_rinv); cudaFree(h->d_rinv_tf); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo); cudaFree(h->d_mel_n); cudaFree(h->d_mel_ptr); cudaFree(h->d_mel_seg); cudaFree(h->d_mel_coef);
     cudaFree(h->d_status);
     if (h->h_desc) cudaFreeHost(h->h_desc);
@@ -311,6 +319,7 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
     CUB(cudaEventCreateWithFlags(&h->desc_done, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&h->chunk_fork, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&h->chunk_join, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&h->last_done, cudaEventDisableTiming));
     // twiddles w2048^(j*l), j = 1..31, l = 0..31, rounded from double
     {
         std::vector<float2> tw(kTwF2);
@@ -430,7 +439,7 @@ extern "C" int nsb_stft_parameters(nsb_handle_t h, int32_t* n_fft, int32_t* hop,
 }
 extern "C" int64_t nsb_num_frames(nsb_handle_t h, int64_t n) { return h ? 1 + n / h->hop : -1; }
 extern "C" int64_t nsb_num_samples(nsb_handle_t h, int64_t T) { return h ? (int64_t)h->hop * (T - 1) : -1; }
-extern "C" uint64_t nsb_kernel_launches(nsb_handle_t h) { return h ? h->launches : 0; }
+extern "C" uint64_t nsb_kernel_launches(nsb_handle_t h) { return h ? h->launches + h->launches_async : 0; }
 extern "C" int nsb_set_host_chunks(nsb_handle_t h, int32_t n) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");
     if (n < 0 || n > 64) return fail(NSB_ERR_INVALID, "host_chunks %d outside [0,64]", n);
@@ -493,6 +502,21 @@ static cudaStream_t pick_stream(nsb_handle_s* h, void* stream, int space = NSB_D
     return space == NSB_HOST ? h->own_stream : (cudaStream_t)0;
 }
 
+// The device state of a handle (descriptors, scheduling counters, workspaces, status flag) is shared by all of its calls, and
+// an NSB_DEVICE call returns while its kernels still run.  One stream per handle is the rule; when a call nevertheless arrives
+// on ANOTHER stream (or an NSB_HOST call, which uses the handle's private streams, follows an NSB_DEVICE call) its streams
+// first wait for the event the previous call recorded when it returned - the handle mutex only orders the host side.
+struct CallScope {
+    nsb_handle_s* h; cudaStream_t st;
+    CallScope(nsb_handle_s* h_, cudaStream_t st_, int space) : h(h_), st(st_) {
+        if (h->have_last) {
+            if (h->last_stream != st) cudaStreamWaitEvent(st, h->last_done, 0);
+            if (space == NSB_HOST) cudaStreamWaitEvent(h->copy_in, h->last_done, 0);
+        }
+    }
+    ~CallScope() { if (cudaEventRecord(h->last_done, st) == cudaSuccess) { h->last_stream = st; h->have_last = true; } }
+};
+
 extern "C" int nsb_synchronize(nsb_handle_t h, void* stream) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");
     CU(cudaSetDevice(h->device));
@@ -515,7 +539,8 @@ extern "C" int nsb_check_status(nsb_handle_t h, void* stream) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
-    return read_status(h, pick_stream(h, stream));
+    CallScope scope(h, pick_stream(h, stream), NSB_DEVICE);
+    return read_status(h, scope.st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -530,8 +555,9 @@ struct Desc {
 };
 
 static int upload_desc(nsb_handle_s* h, cudaStream_t st, const std::vector<int>& frames, const std::vector<long long>& samples,
-                       int tile_hops, Desc* d) {
+                       int tile_hops, Desc* d, const int64_t* rows = nullptr) {
     const int B = (int)frames.size();
+    h->gl.valid = false;            // the Griffin-Lim state of nsb_griffin_lim_iterate points into the descriptor buffer rewritten below
     long long n_tiles = 0;
     if (tile_hops > 0) for (int b = 0; b < B; ++b) { long long hops = (samples[b] + h->hop - 1) / h->hop; n_tiles += (hops + tile_hops - 1) / tile_hops; }
     if (n_tiles > 2000000000LL) return fail(NSB_ERR_INVALID, "batch too large: more than 2e9 tiles");
@@ -539,7 +565,8 @@ static int upload_desc(nsb_handle_s* h, cudaStream_t st, const std::vector<int>&
     const size_t off_samp = (n_int * sizeof(int) + 7) & ~(size_t)7;
     const size_t off_tutt = off_samp + (size_t)(B + 1) * sizeof(long long);
     const size_t off_goff = off_tutt + (size_t)(n_tiles > 0 ? n_tiles : 1) * sizeof(int);
-    const size_t bytes = off_goff + (size_t)(B + 1) * sizeof(int);
+    const size_t off_rows = (off_goff + (size_t)(B + 1) * sizeof(int) + 7) & ~(size_t)7;
+    const size_t bytes = off_rows + (rows ? (size_t)B * sizeof(long long) : 0);
     if (bytes > h->h_desc_cap) {
         if (h->h_desc) { CU(cudaEventSynchronize(h->desc_done)); cudaFreeHost(h->h_desc); h->h_desc = nullptr; h->h_desc_cap = 0; }
         CU(cudaHostAlloc(&h->h_desc, bytes * 2, cudaHostAllocDefault));
@@ -556,6 +583,7 @@ static int upload_desc(nsb_handle_s* h, cudaStream_t st, const std::vector<int>&
     int* tu = reinterpret_cast<int*>(hb + off_tutt);
     int* go = reinterpret_cast<int*>(hb + off_goff);
     fo[0] = 0; to[0] = 0; so[0] = 0; go[0] = 0;
+    if (rows) { long long* ro = reinterpret_cast<long long*>(hb + off_rows); for (int b = 0; b < B; ++b) ro[b] = rows[b]; }
     for (int b = 0; b < B; ++b) {
         long long nf = (long long)fo[b] + frames[b];
         if (nf > 2000000000LL) return fail(NSB_ERR_INVALID, "batch too large: more than 2e9 frames");
@@ -578,6 +606,7 @@ static int upload_desc(nsb_handle_s* h, cudaStream_t st, const std::vector<int>&
     d->dev.samp_off = reinterpret_cast<const long long*>(db + off_samp);
     d->dev.tile_utt = reinterpret_cast<const int*>(db + off_tutt);
     d->dev.group_off = reinterpret_cast<const int*>(db + off_goff);
+    d->dev.row_off = rows ? reinterpret_cast<const long long*>(db + off_rows) : nullptr;
     d->dev.batch = B;
     d->dev.frame_base = 0; d->dev.tile_base = 0; d->dev.utt_base = 0; d->dev.group_base = 0;
     d->total_groups = go[B];
@@ -605,7 +634,8 @@ static int grid_1d(long long n, int threads, int max_blocks) {
 // analysis entry points
 // ---------------------------------------------------------------------------------------------
 static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wav, const int64_t* n_samples, int batch,
-                        float* out_complex, float* lin_out, float* mel_out, int space, void* stream, bool tf = false, int rows_per_utt = 0) {
+                        float* out_complex, float* lin_out, float* mel_out, int space, void* stream, bool tf = false, int rows_per_utt = 0,
+                        const int64_t* row_off = nullptr, int64_t total_rows = 0) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");
     if (!wav || !n_samples || batch < 1) return fail(NSB_ERR_INVALID, "null/empty input");
     if (mode == ANALYSIS_COMPLEX && !out_complex) return fail(NSB_ERR_INVALID, "out_complex is null");
@@ -613,6 +643,7 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
     cudaStream_t st = pick_stream(h, stream, space);
+    CallScope scope(h, st, space);
     std::vector<int> frames(batch);
     std::vector<long long> samples(batch);
     for (int b = 0; b < batch; ++b) {
@@ -621,12 +652,14 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
         samples[b] = n_samples[b];
         frames[b] = tf ? (int)(1 + (n_samples[b] - h->win) / h->hop) : (int)(1 + n_samples[b] / h->hop);
         if (rows_per_utt > 0 && frames[b] > rows_per_utt) return fail(NSB_ERR_INVALID, "utterance %d has %d frames, more than rows_per_utt = %d", b, frames[b], rows_per_utt);
+        if (row_off && (row_off[b] < 0 || row_off[b] + frames[b] > total_rows))
+            return fail(NSB_ERR_INVALID, "utterance %d: rows [%lld, %lld) leave the output of %lld rows", b, (long long)row_off[b], (long long)row_off[b] + frames[b], (long long)total_rows);
     }
     Desc d;
-    int rc = upload_desc(h, st, frames, samples, 0, &d);
+    int rc = upload_desc(h, st, frames, samples, 0, &d, row_off);
     if (rc) return rc;
     const size_t F = kBins, M = h->num_mels;
-    const size_t out_rows = rows_per_utt > 0 ? (size_t)rows_per_utt * batch : (size_t)d.total_frames;     // padded or packed
+    const size_t out_rows = row_off ? (size_t)total_rows : rows_per_utt > 0 ? (size_t)rows_per_utt * batch : (size_t)d.total_frames;     // scattered, padded or packed
     const float* d_wav = wav;
     float2* d_c = reinterpret_cast<float2*>(out_complex);
     float *d_lin = lin_out, *d_mel = mel_out;
@@ -658,7 +691,7 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
     // out.  Chunks of whole utterances keep both PCIe directions and the GPU busy at once: chunk c+1 is copied in (copy_in
     // stream) and transformed while chunk c is copied out (copy_out stream).  Device buffers: one chunk.
     std::vector<int> cuts(1, 0);
-    if (space == NSB_HOST && batch > 1) {
+    if (space == NSB_HOST && batch > 1 && !row_off) {          // (scattered rows: one chunk, the output rows of a chunk are not one range)
         const size_t out_bytes = (mode == ANALYSIS_COMPLEX ? sizeof(float2) * F : sizeof(float) * ((lin_out ? F : 0) + (mel_out ? M : 0))) * (size_t)d.total_frames;
         int want = h->host_chunks > 0 ? h->host_chunks : (int)(out_bytes / (24u << 20));      // ~24 MB of results per chunk
         if (want > 32) want = 32;
@@ -685,7 +718,7 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
             CUA(cudaEventRecord(ev_in[c], h->copy_in));
         }
     }
-    if (rows_per_utt > 0) {             // the padding rows are zeros (_pad = 0, datafeeder.py:216)
+    if (rows_per_utt > 0 || row_off) {  // the padding rows are zeros (_pad = 0, datafeeder.py:216)
         if (d_lin) CUA(cudaMemsetAsync(d_lin, 0, sizeof(float) * F * out_rows, st));
         if (d_mel) CUA(cudaMemsetAsync(d_mel, 0, sizeof(float) * M * out_rows, st));
     }
@@ -715,8 +748,8 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
             CUA(cudaEventRecord(ev_done[c], st));
             CUA(cudaStreamWaitEvent(h->copy_out, ev_done[c], 0));
             // rows of this chunk: packed = its frames, padded = rows_per_utt per utterance
-            const size_t r0 = rows_per_utt > 0 ? (size_t)rows_per_utt * b0 : (size_t)h->h_frame_off[b0];
-            const size_t r1 = rows_per_utt > 0 ? (size_t)rows_per_utt * b1 : (size_t)h->h_frame_off[b1];
+            const size_t r0 = row_off ? 0 : rows_per_utt > 0 ? (size_t)rows_per_utt * b0 : (size_t)h->h_frame_off[b0];
+            const size_t r1 = row_off ? out_rows : rows_per_utt > 0 ? (size_t)rows_per_utt * b1 : (size_t)h->h_frame_off[b1];
             if (mode == ANALYSIS_COMPLEX)
                 CUA(cudaMemcpyAsync(reinterpret_cast<float2*>(out_complex) + F * r0, d_c + F * r0, sizeof(float2) * F * (r1 - r0), cudaMemcpyDeviceToHost, h->copy_out));
             else {
@@ -819,6 +852,7 @@ static int run_istft(nsb_handle_t h, const float* spec, int32_t layout, const in
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
     cudaStream_t st = pick_stream(h, stream, space);
+    CallScope scope(h, st, space);
     std::vector<int> frames; std::vector<long long> samples;
     int rc = validate_frames(h, n_frames, batch, frames, samples, tf);
     if (rc) return rc;
@@ -996,11 +1030,17 @@ extern "C" int nsb_griffin_lim_iterate(nsb_handle_t h, int32_t iters, void* stre
     std::lock_guard<std::mutex> lk(h->mu);
     if (!h->gl.valid) return fail(NSB_ERR_INVALID, "no device-resident Griffin-Lim state (call nsb_griffin_lim with NSB_DEVICE first)");
     CU(cudaSetDevice(h->device));
-    return gl_iterations(h, h->gl.batch, h->gl.total_tiles, h->gl.total_groups, h->gl.tile_hops, h->gl.cur, iters, pick_stream(h, stream), h->gl.tf, h->gl.inv_thr);
+    CallScope scope(h, pick_stream(h, stream), NSB_DEVICE);
+    return gl_iterations(h, h->gl.batch, h->gl.total_tiles, h->gl.total_groups, h->gl.tile_hops, h->gl.cur, iters, scope.st, h->gl.tf, h->gl.inv_thr);
 }
 
 // endpoint search fused into the Griffin-Lim pipeline (nsb_synthesize): per chunk, on the device result
-struct EndpointReq { int64_t* out = nullptr; double threshold_db = -40.0, min_silence_sec = 0.8; };
+struct EndpointReq {
+    int64_t* out = nullptr; double threshold_db = -40.0, min_silence_sec = 0.8;
+    int peak = 0;                     // save_wav's scaling (audio.py:17-19) on the trimmed waveform
+    int final_dtype = NSB_F64;        // NSB_F64, or NSB_I16 (the scaled waveform cast like numpy's astype(np.int16))
+};
+static size_t dtype_size(int dt) { return dt == NSB_F64 ? sizeof(double) : dt == NSB_I16 ? sizeof(short) : sizeof(float); }
 static void endpoint_params(const nsb_handle_s* h, double threshold_db, double min_silence_sec, EndpointParams& E) {
     E.window = (long long)(h->hp.sample_rate * min_silence_sec);            // int(sample_rate * min_silence_sec), audio.py:68
     E.hop = E.window / 4;                                                    // int(window_length / 4), audio.py:69
@@ -1018,6 +1058,7 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
     cudaStream_t st = pick_stream(h, stream, space);
+    CallScope scope(h, st, space);
     const bool tf = (flags & NSB_GL_TF_TWIN) != 0;
     if (tf) init_phase = nullptr;            // the TF twin always starts from zero phase (audio.py:97-98)
     std::vector<int> frames; std::vector<long long> samples;
@@ -1026,13 +1067,21 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
     const int H = choose_tile_hops(h, samples, tf);
     Desc d;
     if ((rc = upload_desc(h, st, frames, samples, H, &d))) return rc;
-    const size_t out_elt = out_dtype == NSB_F64 ? sizeof(double) : sizeof(float);
+    // out_dtype is what the de-emphasis writes; the synthesis stage may end in another type (peak-normalised int16)
+    const bool to_i16 = ep && ep->final_dtype == NSB_I16;
+    const size_t out_elt = to_i16 ? sizeof(short) : dtype_size(out_dtype);
     if (!(flags & NSB_GL_DEEMPHASIS) && out_dtype != NSB_F32)
         return fail(NSB_ERR_INVALID, "NSB_F64 output without NSB_GL_DEEMPHASIS is not provided (_griffin_lim returns float32)");
     const size_t n_spec = (size_t)kBins * d.total_frames;
     const float* d_spec = spec;
     const float2* d_phase = reinterpret_cast<const float2*>(init_phase);
-    char* d_out = reinterpret_cast<char*>(wav_out);
+    char* d_out = reinterpret_cast<char*>(wav_out);           // de-emphasis output (out_dtype)
+    char* d_final = d_out;                                      // what the caller receives
+    if (to_i16) {
+        if ((rc = h->ws_out.reserve(dtype_size(out_dtype) * d.total_samples))) return rc;
+        d_out = reinterpret_cast<char*>(h->ws_out.p);
+        if (space == NSB_HOST) { if ((rc = h->ws_out2.reserve(sizeof(short) * d.total_samples))) return rc; d_final = reinterpret_cast<char*>(h->ws_out2.p); }
+    }
     if (space == NSB_HOST) {
         if ((rc = h->ws_in.reserve(sizeof(float) * n_spec))) return rc;
         d_spec = reinterpret_cast<const float*>(h->ws_in.p);
@@ -1040,8 +1089,10 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
             if ((rc = h->ws_in2.reserve(sizeof(float2) * n_spec))) return rc;
             d_phase = reinterpret_cast<const float2*>(h->ws_in2.p);
         }
-        if ((rc = h->ws_out.reserve(out_elt * d.total_samples))) return rc;
-        d_out = reinterpret_cast<char*>(h->ws_out.p);
+        if (!to_i16) {
+            if ((rc = h->ws_out.reserve(out_elt * d.total_samples))) return rc;
+            d_out = d_final = reinterpret_cast<char*>(h->ws_out.p);
+        }
     }
     if ((rc = h->ws_mag.reserve(sizeof(float) * kMagPitch * (size_t)d.total_frames))) return rc;
     if ((rc = h->ws_y0.reserve(sizeof(float) * d.total_samples))) return rc;
@@ -1150,7 +1201,7 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
     h->gl.valid = false;
     int cur = 0;
     const float inv_thr = (float)(1.0 / (2.0e-8 * gscale));      // est / max(1e-8, |est|) on slots that hold 2*g*est
-    if (ep && (rc = h->ws_ep.reserve(sizeof(long long) * (size_t)batch))) { cleanup(); return rc; }
+    if (ep && (rc = h->ws_ep.reserve(2 * sizeof(long long) * (size_t)batch))) { cleanup(); return rc; }      // endpoints | peaks
     // the utterances [b0, b1) as a batch of their own (descriptor pointers shifted, bases remembered)
     struct Sub { Batch B; int groups, frames, tiles; };
     auto sub_batch = [&](int b0, int b1) {
@@ -1230,11 +1281,26 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
             NSB_LAUNCH(k_find_endpoint, b1 - b0, 256, 0, s_, EP);
             int r_ = check_launch(h, "k_find_endpoint");
             if (r_) return r_;
+            if (ep->peak) {
+                // save_wav's scaling on what the caller keeps: wav[:endpoint] *= 32767 / max(0.01, max |wav[:endpoint]|)  (audio.py:17-19)
+                PeakParams K{};
+                K.batch = u.B; K.limit = EP.out; K.peak = reinterpret_cast<unsigned long long*>(h->ws_ep.p) + batch + b0; K.status = h->d_status;
+                if (out_dtype == NSB_F64) K.in64 = reinterpret_cast<const double*>(d_out); else K.in32 = reinterpret_cast<const float*>(d_out);
+                if (to_i16) K.out16 = reinterpret_cast<short*>(d_final); else K.out64 = reinterpret_cast<double*>(d_final);
+                long long max_len = 0;
+                for (int b = b0; b < b1; ++b) max_len = std::max(max_len, (long long)(h->h_samp_off[b + 1] - h->h_samp_off[b]));
+                K.n_seg = (int)std::min<long long>(64, std::max<long long>(1, max_len / 16384));
+                CUL(cudaMemsetAsync(K.peak, 0, sizeof(unsigned long long) * (size_t)(b1 - b0), s_));
+                NSB_LAUNCH(k_peak_max, (b1 - b0) * K.n_seg, 256, 0, s_, K);
+                if ((r_ = check_launch(h, "k_peak_max"))) return r_;
+                NSB_LAUNCH(k_peak_apply, grid_1d(s_cnt, 256, 8 * h->num_sms), 256, 0, s_, K, s_base, s_base + s_cnt);
+                if ((r_ = check_launch(h, "k_peak_apply"))) return r_;
+            }
         }
         if (space == NSB_HOST) {
             CUL(cudaEventRecord(ev_done[c], s_));
             CUL(cudaStreamWaitEvent(h->copy_out, ev_done[c], 0));
-            CUL(cudaMemcpyAsync(reinterpret_cast<char*>(wav_out) + s_base * out_elt, d_out + s_base * out_elt, out_elt * s_cnt,
+            CUL(cudaMemcpyAsync(reinterpret_cast<char*>(wav_out) + s_base * out_elt, d_final + s_base * out_elt, out_elt * s_cnt,
                                 cudaMemcpyDeviceToHost, h->copy_out));
         }
         return NSB_OK;
@@ -1289,7 +1355,7 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
         CUE(cudaStreamWaitEvent(st, h->chunk_join, 0));
     }
     // device-resident state for nsb_griffin_lim_iterate: the whole batch
-    h->gl.valid = true; h->gl.batch = d.dev; h->gl.total_frames = d.total_frames; h->gl.tile_hops = H;
+    h->gl.valid = (space == NSB_DEVICE); h->gl.batch = d.dev; h->gl.total_frames = d.total_frames; h->gl.tile_hops = H;
     h->gl.total_tiles = d.total_tiles; h->gl.total_groups = d.total_groups; h->gl.cur = cur; h->gl.tf = tf; h->gl.inv_thr = (float)(1.0 / (2.0e-8 * gscale));
     if (ep) CUE(cudaMemcpyAsync(ep->out, h->ws_ep.p, sizeof(long long) * (size_t)batch,
                                 space == NSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
@@ -1309,20 +1375,35 @@ extern "C" int nsb_griffin_lim(nsb_handle_t h, const float* spec, int32_t layout
     return griffin_lim_impl(h, spec, layout, n_frames, batch, init_phase, seed, iters, flags, wav_out, out_dtype, space, stream, nullptr);
 }
 
-extern "C" int nsb_synthesize(nsb_handle_t h, const float* spec, const int32_t* n_frames, int32_t batch, int32_t iters,
-                              double threshold_db, double min_silence_sec, double* wav_out, int64_t* endpoints, int32_t space, void* stream) {
+extern "C" int nsb_synthesize_ex(nsb_handle_t h, const float* spec, const int32_t* n_frames, int32_t batch, int32_t iters,
+                                 double threshold_db, double min_silence_sec, int32_t flags, void* wav_out, int32_t out_dtype,
+                                 int64_t* endpoints, int32_t space, void* stream) {
     if (!endpoints) return fail(NSB_ERR_INVALID, "null endpoints");
     if (!(min_silence_sec > 0.0)) return fail(NSB_ERR_INVALID, "min_silence_sec must be positive");
+    if (out_dtype != NSB_F64 && out_dtype != NSB_I16) return fail(NSB_ERR_INVALID, "out_dtype must be NSB_F64 or NSB_I16");
+    if (out_dtype == NSB_I16 && !(flags & NSB_SYNTH_PEAK_NORMALIZE)) return fail(NSB_ERR_INVALID, "NSB_I16 output needs NSB_SYNTH_PEAK_NORMALIZE (save_wav's scaling)");
     EndpointReq ep;
     ep.out = endpoints; ep.threshold_db = threshold_db; ep.min_silence_sec = min_silence_sec;
+    ep.peak = (flags & NSB_SYNTH_PEAK_NORMALIZE) ? 1 : 0; ep.final_dtype = out_dtype;
     return griffin_lim_impl(h, spec, NSB_FRAME_MAJOR, n_frames, batch, nullptr, 0, iters,
                             NSB_GL_TF_TWIN | NSB_GL_DENORMALIZE | NSB_GL_DEEMPHASIS, wav_out, NSB_F64, space, stream, &ep);
+}
+extern "C" int nsb_synthesize(nsb_handle_t h, const float* spec, const int32_t* n_frames, int32_t batch, int32_t iters,
+                              double threshold_db, double min_silence_sec, double* wav_out, int64_t* endpoints, int32_t space, void* stream) {
+    return nsb_synthesize_ex(h, spec, n_frames, batch, iters, threshold_db, min_silence_sec, 0, wav_out, NSB_F64, endpoints, space, stream);
 }
 
 extern "C" int nsb_features_padded(nsb_handle_t h, const float* wav, const int64_t* n_samples, int32_t batch, int32_t rows_per_utt,
                                    float* lin_out, float* mel_out, int32_t space, void* stream) {
     if (rows_per_utt < 1) return fail(NSB_ERR_INVALID, "rows_per_utt must be positive");
     return run_analysis(h, ANALYSIS_FEATURES, true, wav, n_samples, batch, nullptr, lin_out, mel_out, space, stream, false, rows_per_utt);
+}
+
+extern "C" int nsb_features_rows(nsb_handle_t h, const float* wav, const int64_t* n_samples, int32_t batch, const int64_t* row_off, int64_t total_rows,
+                                 float* lin_out, float* mel_out, int32_t space, void* stream) {
+    if (!row_off || total_rows < 1) return fail(NSB_ERR_INVALID, "row_off is null or total_rows < 1");
+    if (total_rows > 2000000000LL) return fail(NSB_ERR_INVALID, "more than 2e9 output rows");
+    return run_analysis(h, ANALYSIS_FEATURES, true, wav, n_samples, batch, nullptr, lin_out, mel_out, space, stream, false, 0, row_off, total_rows);
 }
 
 extern "C" int nsb_frame_energy(nsb_handle_t h, const float* wav, const int64_t* n_samples, int32_t batch, int32_t frame_length,
@@ -1333,6 +1414,7 @@ extern "C" int nsb_frame_energy(nsb_handle_t h, const float* wav, const int64_t*
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
     cudaStream_t st = pick_stream(h, stream, space);
+    CallScope scope(h, st, space);
     std::vector<int> frames(batch); std::vector<long long> samples(batch);
     for (int b = 0; b < batch; ++b) {
         if (n_samples[b] < 1) return fail(NSB_ERR_INVALID, "utterance %d is empty", b);
@@ -1371,6 +1453,7 @@ extern "C" int nsb_find_endpoint(nsb_handle_t h, const void* wav, int32_t wav_dt
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
     cudaStream_t st = pick_stream(h, stream, space);
+    CallScope scope(h, st, space);
     std::vector<int> frames(batch, 0); std::vector<long long> samples(batch);
     for (int b = 0; b < batch; ++b) {
         if (n_samples[b] < 0) return fail(NSB_ERR_INVALID, "utterance %d has a negative length", b);
@@ -1411,6 +1494,7 @@ static int run_emph(nsb_handle_s* h, bool inverse, const float* x, const int64_t
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
     cudaStream_t st = pick_stream(h, stream, space);
+    CallScope scope(h, st, space);
     std::vector<int> frames(batch, 1);
     std::vector<long long> samples(batch);
     for (int b = 0; b < batch; ++b) { if (n_samples[b] < 0) return fail(NSB_ERR_INVALID, "negative length"); samples[b] = n_samples[b]; }
@@ -1460,6 +1544,7 @@ extern "C" int nsb_linear_to_mel(nsb_handle_t h, const float* spec, int32_t layo
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
     cudaStream_t st = pick_stream(h, stream, space);
+    CallScope scope(h, st, space);
     std::vector<int> frames(batch);
     std::vector<long long> samples(batch, 0);
     for (int b = 0; b < batch; ++b) { if (n_frames[b] < 1) return fail(NSB_ERR_INVALID, "utterance %d has no frames", b); frames[b] = n_frames[b]; }
@@ -1497,6 +1582,7 @@ extern "C" int nsb_elementwise(nsb_handle_t h, int32_t op, const float* in, int6
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
     cudaStream_t st = pick_stream(h, stream, space);
+    CallScope scope(h, st, space);
     const float* d_in = in;
     float* d_out = out;
     int rc;
@@ -1514,4 +1600,258 @@ extern "C" int nsb_elementwise(nsb_handle_t h, int32_t op, const float* in, int6
         CU(cudaStreamSynchronize(st));
     }
     return NSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// save_wav's scaling as an entry point of its own (utils/audio.py:17-19)
+// ---------------------------------------------------------------------------------------------
+extern "C" int nsb_peak_normalize(nsb_handle_t h, const void* wav, int32_t wav_dtype, const int64_t* n_samples, int32_t batch,
+                                  const int64_t* limit, void* out, int32_t out_dtype, int32_t space, void* stream) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    if (!wav || !n_samples || !out || batch < 1) return fail(NSB_ERR_INVALID, "null/empty argument");
+    if (wav_dtype != NSB_F32 && wav_dtype != NSB_F64) return fail(NSB_ERR_INVALID, "bad wav_dtype");
+    if (out_dtype != NSB_F64 && out_dtype != NSB_I16) return fail(NSB_ERR_INVALID, "out_dtype must be NSB_F64 or NSB_I16");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = pick_stream(h, stream, space);
+    CallScope scope(h, st, space);
+    std::vector<int> frames(batch, 0); std::vector<long long> samples(batch);
+    long long max_len = 0;
+    for (int b = 0; b < batch; ++b) {
+        if (n_samples[b] < 0) return fail(NSB_ERR_INVALID, "utterance %d has a negative length", b);
+        samples[b] = n_samples[b];
+        max_len = std::max(max_len, samples[b]);
+    }
+    Desc d;
+    int rc = upload_desc(h, st, frames, samples, 0, &d);
+    if (rc) return rc;
+    if (d.total_samples == 0) return NSB_OK;
+    const size_t in_elt = dtype_size(wav_dtype), out_elt = dtype_size(out_dtype);
+    const void* d_in = wav;
+    void* d_out = out;
+    if ((rc = h->ws_ep.reserve(2 * sizeof(long long) * (size_t)batch))) return rc;
+    long long* d_limit = nullptr;
+    if (space == NSB_HOST) {
+        if ((rc = h->ws_in.reserve(in_elt * (size_t)d.total_samples))) return rc;
+        if ((rc = h->ws_out.reserve(out_elt * (size_t)d.total_samples))) return rc;
+        CU(cudaMemcpyAsync(h->ws_in.p, wav, in_elt * (size_t)d.total_samples, cudaMemcpyHostToDevice, st));
+        d_in = h->ws_in.p; d_out = h->ws_out.p;
+        if (limit) {
+            d_limit = reinterpret_cast<long long*>(h->ws_ep.p);
+            CU(cudaMemcpyAsync(d_limit, limit, sizeof(long long) * (size_t)batch, cudaMemcpyHostToDevice, st));
+        }
+    } else if (limit) {
+        d_limit = const_cast<long long*>(reinterpret_cast<const long long*>(limit));
+    }
+    PeakParams K{};
+    K.batch = d.dev; K.limit = d_limit; K.peak = reinterpret_cast<unsigned long long*>(h->ws_ep.p) + batch; K.status = h->d_status;
+    if (wav_dtype == NSB_F64) K.in64 = reinterpret_cast<const double*>(d_in); else K.in32 = reinterpret_cast<const float*>(d_in);
+    if (out_dtype == NSB_I16) K.out16 = reinterpret_cast<short*>(d_out); else K.out64 = reinterpret_cast<double*>(d_out);
+    K.n_seg = (int)std::min<long long>(64, std::max<long long>(1, max_len / 16384));
+    CU(cudaMemsetAsync(K.peak, 0, sizeof(unsigned long long) * (size_t)batch, st));
+    NSB_LAUNCH(k_peak_max, batch * K.n_seg, 256, 0, st, K);
+    if ((rc = check_launch(h, "k_peak_max"))) return rc;
+    NSB_LAUNCH(k_peak_apply, grid_1d(d.total_samples, 256, 8 * h->num_sms), 256, 0, st, K, 0LL, d.total_samples);
+    if ((rc = check_launch(h, "k_peak_apply"))) return rc;
+    if (space == NSB_HOST) {
+        CU(cudaMemcpyAsync(out, d_out, out_elt * (size_t)d.total_samples, cudaMemcpyDeviceToHost, st));
+        return read_status(h, st);
+    }
+    return NSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device memory for results handed to other frameworks (nspeech_b200/_buffers.py: DLPack / CUDA array interface)
+// ---------------------------------------------------------------------------------------------
+extern "C" int nsb_device_alloc(int device, uint64_t bytes, void** out) {
+    if (!out) return fail(NSB_ERR_INVALID, "out is null");
+    *out = nullptr;
+    CU(cudaSetDevice(device));
+    CU(cudaMalloc(out, bytes ? bytes : 1));
+    return NSB_OK;
+}
+extern "C" int nsb_device_free(int device, void* p) {
+    if (!p) return NSB_OK;
+    CU(cudaSetDevice(device));
+    CU(cudaFree(p));
+    return NSB_OK;
+}
+// kind: 1 host -> device, 2 device -> host, 3 device -> device; synchronous
+extern "C" int nsb_device_copy(int device, void* dst, const void* src, uint64_t bytes, int32_t kind) {
+    if (kind < 1 || kind > 3) return fail(NSB_ERR_INVALID, "bad copy kind %d", kind);
+    if (bytes == 0) return NSB_OK;
+    if (!dst || !src) return fail(NSB_ERR_INVALID, "null pointer");
+    CU(cudaSetDevice(device));
+    CU(cudaMemcpy(dst, src, bytes, kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice));
+    return NSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// asynchronous host calls: submit -> ticket, wait(ticket)
+//
+// A synchronous NSB_HOST call keeps its caller inside the library for the whole batch, so consecutive batches cannot overlap
+// one's copy-out and pipeline tail with the next one's copy-in and ramp.  The asynchronous entry points hand the call to one
+// of `slots` (default 2) worker threads of the handle.  Every slot owns a CHILD handle - private streams, descriptors,
+// scheduling counters and workspaces, nothing shared with its siblings - and runs the ordinary synchronous call on it, so two
+// batches are in flight on the GPU at once: the second one's H2D copies and first waves fill what the first one's tail leaves
+// idle.  The caller's buffers must stay valid until nsb_wait(ticket) returns; n_frames / n_samples are copied at submit.
+// (The feeder threads of datasets/datafeeder.py:110-152 are this pattern on the reference's side.)
+// ---------------------------------------------------------------------------------------------
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <unordered_map>
+
+struct AsyncJob {
+    std::function<int(nsb_handle_s*)> run;
+    int status = NSB_OK;
+    std::string err;
+    bool done = false;
+};
+struct AsyncSlot {
+    nsb_handle_s* child = nullptr;
+    std::thread th;
+    std::deque<std::shared_ptr<AsyncJob>> q;
+};
+struct nsb_async_s {
+    std::mutex m;
+    std::condition_variable cv_work, cv_done;
+    std::vector<std::unique_ptr<AsyncSlot>> slots;
+    std::unordered_map<uint64_t, std::shared_ptr<AsyncJob>> jobs;
+    uint64_t next_ticket = 1;
+    bool stop = false;
+};
+
+static void async_worker(nsb_handle_s* parent, nsb_async_s* A, AsyncSlot* S) {
+    for (;;) {
+        std::shared_ptr<AsyncJob> job;
+        {
+            std::unique_lock<std::mutex> lk(A->m);
+            A->cv_work.wait(lk, [&] { return A->stop || !S->q.empty(); });
+            if (S->q.empty()) return;              // stop requested and nothing left to run
+            job = S->q.front();
+            S->q.pop_front();
+        }
+        int rc = NSB_OK;
+        if (!S->child) {
+            rc = nsb_create(&parent->hp, parent->device, &S->child);
+            if (rc) S->child = nullptr;
+        }
+        if (!rc) {
+            // the tuning state of the parent at the time the job runs
+            S->child->host_chunks = parent->host_chunks; S->child->wave_schedule = parent->wave_schedule;
+            S->child->overlap_chunks = parent->overlap_chunks; S->child->use_generic_iter = parent->use_generic_iter;
+            S->child->stream_sync_mode = parent->stream_sync_mode; S->child->fuse_iterations = parent->fuse_iterations;
+            S->child->wide_mode = parent->wide_mode; S->child->mel_lines = parent->mel_lines;
+            rc = job->run(S->child);
+        }
+        {
+            std::lock_guard<std::mutex> lk(A->m);
+            job->status = rc;
+            if (rc) job->err = g_err;
+            job->done = true;
+            if (S->child) parent->launches_async += S->child->launches, S->child->launches = 0;
+        }
+        A->cv_done.notify_all();
+    }
+}
+
+static int async_submit(nsb_handle_s* h, std::function<int(nsb_handle_s*)> fn, uint64_t* ticket) {
+    if (!ticket) return fail(NSB_ERR_INVALID, "ticket is null");
+    nsb_async_s* A;
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        if (!h->async) {
+            h->async = new nsb_async_s();
+            const int n = h->async_slots < 1 ? 1 : h->async_slots;
+            for (int i = 0; i < n; ++i) {
+                h->async->slots.emplace_back(new AsyncSlot());
+                AsyncSlot* S = h->async->slots.back().get();
+                S->th = std::thread(async_worker, h, h->async, S);
+            }
+        }
+        A = h->async;
+    }
+    auto job = std::make_shared<AsyncJob>();
+    job->run = std::move(fn);
+    {
+        std::lock_guard<std::mutex> lk(A->m);
+        const uint64_t t = A->next_ticket++;
+        A->jobs[t] = job;
+        A->slots[t % A->slots.size()]->q.push_back(job);
+        *ticket = t;
+    }
+    A->cv_work.notify_all();
+    return NSB_OK;
+}
+
+static void async_shutdown(nsb_handle_s* h) {
+    nsb_async_s* A = h->async;
+    if (!A) return;
+    { std::lock_guard<std::mutex> lk(A->m); A->stop = true; }
+    A->cv_work.notify_all();
+    for (auto& S : A->slots) if (S->th.joinable()) S->th.join();          // the workers drain their queues first
+    for (auto& S : A->slots) if (S->child) nsb_destroy(S->child);
+    delete A;
+    h->async = nullptr;
+}
+
+extern "C" int nsb_wait(nsb_handle_t h, uint64_t ticket) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    nsb_async_s* A = h->async;
+    if (!A) return fail(NSB_ERR_INVALID, "ticket %llu: nothing was submitted on this handle", (unsigned long long)ticket);
+    std::shared_ptr<AsyncJob> job;
+    {
+        std::unique_lock<std::mutex> lk(A->m);
+        auto it = A->jobs.find(ticket);
+        if (it == A->jobs.end()) return fail(NSB_ERR_INVALID, "unknown or already collected ticket %llu", (unsigned long long)ticket);
+        job = it->second;
+        A->cv_done.wait(lk, [&] { return job->done; });
+        A->jobs.erase(ticket);
+    }
+    if (job->status) g_err = job->err;
+    return job->status;
+}
+
+extern "C" int nsb_set_async_slots(nsb_handle_t h, int32_t n) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    if (n < 1 || n > 8) return fail(NSB_ERR_INVALID, "async slots %d outside [1,8]", n);
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->async) return fail(NSB_ERR_INVALID, "the worker slots already run; set their number before the first submit");
+    h->async_slots = n;
+    return NSB_OK;
+}
+
+extern "C" int nsb_griffin_lim_submit(nsb_handle_t h, const float* spec, int32_t layout, const int32_t* n_frames, int32_t batch,
+                                      const float* init_phase_complex, uint64_t seed, int32_t iters, int32_t flags,
+                                      void* wav_out, int32_t out_dtype, uint64_t* ticket) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    if (!spec || !n_frames || !wav_out || batch < 1) return fail(NSB_ERR_INVALID, "null/empty argument");
+    std::vector<int32_t> nf(n_frames, n_frames + batch);
+    return async_submit(h, [=](nsb_handle_s* c) {
+        return nsb_griffin_lim(c, spec, layout, nf.data(), batch, init_phase_complex, seed, iters, flags, wav_out, out_dtype, NSB_HOST, nullptr);
+    }, ticket);
+}
+
+extern "C" int nsb_features_submit(nsb_handle_t h, const float* wav, const int64_t* n_samples, int32_t batch,
+                                   float* lin_out, float* mel_out, uint64_t* ticket) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    if (!wav || !n_samples || batch < 1) return fail(NSB_ERR_INVALID, "null/empty argument");
+    std::vector<int64_t> ns(n_samples, n_samples + batch);
+    return async_submit(h, [=](nsb_handle_s* c) {
+        return nsb_features(c, wav, ns.data(), batch, lin_out, mel_out, NSB_HOST, nullptr);
+    }, ticket);
+}
+
+extern "C" int nsb_synthesize_submit(nsb_handle_t h, const float* spec, const int32_t* n_frames, int32_t batch, int32_t iters,
+                                     double threshold_db, double min_silence_sec, int32_t flags, void* wav_out, int32_t out_dtype,
+                                     int64_t* endpoints, uint64_t* ticket) {
+    if (!h) return fail(NSB_ERR_INVALID, "null handle");
+    if (!spec || !n_frames || !wav_out || !endpoints || batch < 1) return fail(NSB_ERR_INVALID, "null/empty argument");
+    std::vector<int32_t> nf(n_frames, n_frames + batch);
+    return async_submit(h, [=](nsb_handle_s* c) {
+        return nsb_synthesize_ex(c, spec, nf.data(), batch, iters, threshold_db, min_silence_sec, flags, wav_out, out_dtype, endpoints, NSB_HOST, nullptr);
+    }, ticket);
 }

@@ -126,6 +126,14 @@ def find_endpoint(wav, hp, threshold_db=-40, min_silence_sec=0.8):
     return len(wav)
 
 
+def save_wav_scaling(wav):
+    # audio.py:17-18: the arithmetic of save_wav (in place there; a copy here); the file itself is written by
+    # librosa.output.write_wav -> scipy.io.wavfile.write
+    wav = np.array(wav, copy=True)
+    wav *= 32767 / max(0.01, np.max(np.abs(wav)))
+    return wav
+
+
 # ---- metrics used by the parity tests and the bench (not in the reference) ----
 
 def rel_l2(a, b):

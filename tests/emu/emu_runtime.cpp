@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE ONLY: thread-per-CUDA-thread block executor for cuda_emu.h, plus lane-level
 // entry points used by tests/test_emulated_kernels.py.  See cuda_emu.h.
+#include <mutex>
 #include "cuda_emu.h"
 #include "../../nspeech_b200/csrc/frame_fft.cuh"
 
@@ -10,8 +11,13 @@ thread_local dim3 g_bdim, g_gdim;
 alignas(256) static unsigned char g_smem[256 * 1024];
 unsigned char* dyn_smem() { return g_smem; }
 
+// one kernel at a time: the emulated shared memory (g_smem, the kernels' `static` __shared__ variables) exists once, and the
+// asynchronous entry points launch from several host threads
+static std::mutex g_launch_mu;
+
 void launch(unsigned grid, unsigned block, size_t smem, const std::function<void()>& body) {
     if (smem > sizeof g_smem) abort();
+    std::lock_guard<std::mutex> lk(g_launch_mu);
     const unsigned nwarps = (block + 31) / 32;
     for (unsigned b = 0; b < grid; ++b) {
         BlockCtx ctx;

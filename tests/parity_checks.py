@@ -360,3 +360,175 @@ def check_feeder_targets():
         assert ao.rel_l2(lin[i, :Ts[i]], ao.spectrogram(w, ohp).T) < 1e-5
         assert ao.rel_l2(mel[i, :Ts[i]], ao.melspectrogram(w, ohp).T) < 1e-5
         assert not lin[i, Ts[i]:].any() and not mel[i, Ts[i]:].any()          # _pad = 0
+
+
+def check_save_wav_scaling_and_int16(golden=None):
+    """save_wav's scaling (reference audio.py:17-19) on the device: bit-exact float64, bit-exact int16 (integer work), alone
+    and fused into the synthesis stage (synthesizer.py:51-53 -> eval.py:43); ragged lists of spectrograms."""
+    ohp = _load(min_level_db=-100)
+    rs = np.random.RandomState(12)
+    for wav in (speechlike(33000, 21).astype(np.float64) * 0.37, speechlike(5000, 22), rs.randn(70001) * 3.0,
+                np.zeros(300), np.full(10, 1e-5), -np.abs(speechlike(2000, 23)).astype(np.float64)):
+        ref = ao.save_wav_scaling(wav.astype(np.float64))
+        got = audio.peak_normalize(wav)
+        assert got.dtype == np.float64
+        np.testing.assert_array_equal(got, ref)                       # one IEEE multiply per sample by the same factor
+        np.testing.assert_array_equal(audio.peak_normalize(wav, dtype=np.int16), ref.astype(np.int16))
+    w = speechlike(4000, 24).astype(np.float64)
+    w2 = w.copy()
+    import os, tempfile
+    from scipy.io import wavfile
+    with tempfile.TemporaryDirectory() as d:
+        audio.save_wav(w2, os.path.join(d, "a.wav"))                  # mutates its argument like the reference
+        np.testing.assert_array_equal(w2, ao.save_wav_scaling(w))
+        sr, back = wavfile.read(os.path.join(d, "a.wav"))
+        assert sr == 20000
+        np.testing.assert_array_equal(back, w2)
+        lin = audio.spectrogram(speechlike(3000, 25))
+        audio.save_spectrogram(lin, os.path.join(d, "s.npy"))
+        spec, n = audio.load_spectrogram(os.path.join(d, "s.npy"))
+        assert n == lin.shape[1] and spec.flags.f_contiguous
+        np.testing.assert_array_equal(spec, lin)
+    # fused: ragged list, trimmed at the endpoint, scaled by the peak of the TRIMMED waveform
+    Ts = [140, 33, 90]
+    specs = [rs.rand(T, 1025).astype(np.float32) for T in Ts]
+    specs[0][50:] = 0.0
+    plain = audio.synthesize_waveforms(specs, iters=3)
+    scaled = audio.synthesize_waveforms(specs, iters=3, peak_normalize=True)
+    ints = audio.synthesize_waveforms(specs, iters=3, peak_normalize=True, dtype=np.int16)
+    assert len(plain) == len(scaled) == len(ints) == 3
+    for i in range(3):
+        ref = ao.inv_preemphasis(tfo.inv_spectrogram_tensorflow(specs[i], ohp, iters=3), ohp)
+        ref = ref[:ao.find_endpoint(ref, ohp)]
+        assert plain[i].shape == ref.shape and ao.snr_db(plain[i], ref) > 60
+        np.testing.assert_array_equal(scaled[i], ao.save_wav_scaling(plain[i]))         # the same device result, scaled like numpy does
+        assert ints[i].dtype == np.int16
+        np.testing.assert_array_equal(ints[i], scaled[i].astype(np.int16))
+        assert np.abs(ints[i].astype(np.int64) - ao.save_wav_scaling(ref).astype(np.int16)).max() <= 1   # vs the oracle's own pipeline
+        np.testing.assert_array_equal(audio.synthesize_waveforms(specs[i], iters=3), plain[i])            # batch == single, bitwise
+    assert plain[0].size < audio._handle().num_samples_tf(Ts[0])
+    with pytest.raises(ValueError):
+        audio.synthesize_waveforms(specs, iters=1, dtype=np.int16)
+
+
+def check_feeder_groups():
+    """batch.feeder_groups = one group of the reference feeder (datasets/datafeeder.py:130-158, 190-216): bucket by length,
+    pad every batch on its own - the feature kernel writes the padded batch tensors directly (nsb_features_rows)."""
+    from nspeech_b200 import batch
+    from oracle import feeder_oracle as fo
+    ohp = _load(min_level_db=-100)
+    lens = (5200, 900, 12345, 2500, 2500, 777, 9000)
+    wavs = [speechlike(n, 40 + i) for i, n in enumerate(lens)]
+    n, r = 3, 5
+    groups = batch.feeder_groups(wavs, n, r)
+    examples = [(i, w, ao.melspectrogram(w, ohp).T, ao.spectrogram(w, ohp).T, 1 + w.size // 250) for i, w in enumerate(wavs)]
+    want = fo.bucket(examples, n)
+    assert [g["indices"] for g in groups] == [[e[0] for e in b] for b in want]
+    for g, b in zip(groups, want):
+        mel_ref = fo._prepare_targets([e[2] for e in b], r)
+        lin_ref = fo._prepare_targets([e[3] for e in b], r)
+        assert g["mel_targets"].shape == mel_ref.shape and g["linear_targets"].shape == lin_ref.shape
+        assert ao.rel_l2(g["mel_targets"], mel_ref) < 1e-5 and ao.rel_l2(g["linear_targets"], lin_ref) < 1e-5
+        np.testing.assert_array_equal(g["mel_targets"] == 0, mel_ref == 0)           # the padding (and only it) is exactly _pad = 0
+        np.testing.assert_array_equal(g["audios"], fo._prepare_inputs([e[1] for e in b]))
+    import random
+    shuffled = batch.bucket_by_length([e[4] for e in examples], n, rng=random.Random(3))
+    assert sorted(map(tuple, shuffled)) == sorted(tuple(e[0] for e in b) for b in want)
+
+
+def check_async_submit_wait():
+    """nsb_*_submit / nsb_wait: two batches in flight on private worker slots; results must equal the synchronous calls bit
+    for bit, in any wait order; a ticket is good for one wait."""
+    from nspeech_b200 import batch
+    _load(min_level_db=-100)
+    h = audio._handle()
+    rs = np.random.RandomState(31)
+    jobs = []
+    for i, Ts in enumerate(([9, 41], [17], [5, 6, 7])):
+        spec = np.concatenate([rs.rand(T, 1025).astype(np.float32) for T in Ts])
+        sync = np.empty(sum(h.num_samples(T) for T in Ts), np.float64)
+        h.griffin_lim(spec, _lib.FRAME_MAJOR, Ts, sync, seed=5 + i, iters=3, flags=_lib.GL_DENORMALIZE | _lib.GL_DEEMPHASIS, out_dtype=_lib.F64)
+        out = np.full_like(sync, np.nan)
+        jobs.append((Ts, spec, sync, out))
+    tickets = [h.griffin_lim_submit(spec, _lib.FRAME_MAJOR, Ts, out, seed=5 + i, iters=3, flags=_lib.GL_DENORMALIZE | _lib.GL_DEEMPHASIS,
+                                    out_dtype=_lib.F64) for i, (Ts, spec, sync, out) in enumerate(jobs)]
+    assert len(set(tickets)) == 3
+    for t in (tickets[2], tickets[0], tickets[1]):
+        h.wait(t)
+    for Ts, spec, sync, out in jobs:
+        np.testing.assert_array_equal(out, sync)
+    with pytest.raises(ValueError):
+        h.wait(tickets[0])                       # collected already
+    with pytest.raises(ValueError):
+        h.wait(10 ** 9)
+    # a failing job reports through its ticket
+    bad, bad_out = np.full((4, 1025), np.inf, np.float32), np.empty(h.num_samples(4))     # (buffers must outlive the call: keep the names)
+    t = h.griffin_lim_submit(bad, _lib.FRAME_MAJOR, [4], bad_out, iters=1, flags=_lib.GL_DENORMALIZE | _lib.GL_DEEMPHASIS,
+                             out_dtype=_lib.F64)
+    with pytest.raises(audio.ParameterError):
+        h.wait(t)
+    # features, and the generator front end
+    wav = speechlike(6000, 33)
+    T = h.num_frames(wav.size)
+    lin, mel = np.empty((T, 1025), np.float32), np.empty((T, 80), np.float32)
+    h.wait(h.features_submit(wav, [wav.size], lin, mel))
+    l2, m2 = audio.spectrogram_and_mel(wav)
+    np.testing.assert_array_equal(lin.T, l2)
+    np.testing.assert_array_equal(mel.T, m2)
+    batches = [[rs.rand(1025, T).astype(np.float32) for T in Ts] for Ts in ([4, 9], [12], [3, 3, 3], [8])]
+    got = list(batch.inv_spectrogram_stream(batches, seed=11, iters=2, layout="FT"))
+    assert len(got) == 4
+    for i, (b, outs) in enumerate(zip(batches, got)):
+        ref = batch.inv_spectrogram_batch(b, seed=11 + i, iters=2, layout="FT")
+        for a, c in zip(outs, ref):
+            np.testing.assert_array_equal(a, c)
+
+
+def check_api_guards():
+    """stale Griffin-Lim state, ambiguous layouts, undersized buffers."""
+    from nspeech_b200 import batch
+    _load(min_level_db=-100)
+    h = audio._handle()
+    rs = np.random.RandomState(2)
+    with pytest.raises(ValueError):
+        batch.inv_spectrogram_batch([rs.rand(1025, 1025).astype(np.float32)], iters=1)          # square: which axis is time?
+    S = rs.rand(1025, 7).astype(np.float32)
+    a = batch.inv_spectrogram_batch([S], seed=1, iters=2, layout="FT")[0]
+    b = batch.inv_spectrogram_batch([np.ascontiguousarray(S.T)], seed=1, iters=2, layout="TF")[0]
+    np.testing.assert_array_equal(a, b)
+    with pytest.raises(ValueError):
+        batch.inv_spectrogram_batch([S], iters=1, layout="TF")
+    with pytest.raises(ValueError):
+        batch.inv_spectrogram_batch([S], iters=1, out=np.empty(10, np.float64))                 # too small
+    with pytest.raises(ValueError):
+        batch.inv_spectrogram_batch([S], iters=1, out=np.empty(h.num_samples(7), np.float32))   # wrong dtype
+    with pytest.raises(ValueError):
+        batch.inv_spectrogram_batch([S], iters=1, init_phase=[np.ones((1025, 6), np.complex64)])
+    with pytest.raises(ValueError):
+        h.griffin_lim(S.T.copy(), _lib.FRAME_MAJOR, [7], np.empty(5, np.float64), iters=1, flags=_lib.GL_DEEMPHASIS, out_dtype=_lib.F64)
+    with pytest.raises(ValueError):
+        h.features(speechlike(1000, 1), [1000], np.empty((2, 1025), np.float32), None)
+
+
+def check_stale_griffin_lim_state(to_dev, stream=None):
+    """nsb_griffin_lim_iterate runs on the state of the last NSB_DEVICE Griffin-Lim call; any later call that rewrites the
+    handle's descriptors must invalidate it.  ``to_dev`` puts a numpy array where NSB_DEVICE pointers live."""
+    _load(min_level_db=-100)
+    h = audio._handle()
+    rs = np.random.RandomState(4)
+    spec = to_dev(rs.rand(9, 1025).astype(np.float32))
+    out = to_dev(np.zeros(h.num_samples(9), np.float64))
+    flags = _lib.GL_DENORMALIZE | _lib.GL_DEEMPHASIS
+    h.griffin_lim(spec, _lib.FRAME_MAJOR, [9], out, seed=1, iters=1, flags=flags, out_dtype=_lib.F64, space=_lib.DEVICE, stream=stream)
+    h.griffin_lim_iterate(1, stream)
+    wav = to_dev(speechlike(2000, 1))
+    lin = to_dev(np.zeros((h.num_frames(2000), 1025), np.float32))
+    h.features(wav, [2000], lin, None, space=_lib.DEVICE, stream=stream)
+    with pytest.raises(ValueError):
+        h.griffin_lim_iterate(1, stream)
+    h.synchronize(stream)
+    # a HOST call leaves no device-resident state either
+    host_out = np.empty(h.num_samples(9), np.float64)
+    h.griffin_lim(rs.rand(9, 1025).astype(np.float32), _lib.FRAME_MAJOR, [9], host_out, seed=1, iters=1, flags=flags, out_dtype=_lib.F64)
+    with pytest.raises(ValueError):
+        h.griffin_lim_iterate(1, stream)

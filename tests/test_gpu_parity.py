@@ -15,8 +15,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(autouse=True)
 def _native():
-    assert audio._lib_override is None
     lib = _lib.default_lib()                       # raises if libnspeech_b200.so is missing: no fallback
+    assert lib.path == _lib.DEFAULT_LIB            # the sm_100a build, not the CPU-emulated test library
     assert lib.device_count() >= 1
     yield
     hparams.load()
@@ -64,6 +64,27 @@ def test_feeder_targets():
 
 def test_errors_and_edge_cases():
     pc.check_errors_and_edge_cases()
+
+
+def test_save_wav_scaling_and_int16():
+    pc.check_save_wav_scaling_and_int16()
+
+
+def test_feeder_groups():
+    pc.check_feeder_groups()
+
+
+def test_async_submit_wait():
+    pc.check_async_submit_wait()
+
+
+def test_api_guards():
+    pc.check_api_guards()
+
+
+def test_stale_griffin_lim_state():
+    torch = pytest.importorskip("torch")
+    pc.check_stale_griffin_lim_state(lambda a: torch.from_numpy(a).cuda(), torch.cuda.current_stream().cuda_stream)
 
 
 def test_device_random_phase_is_deterministic_per_seed():

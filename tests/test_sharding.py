@@ -64,7 +64,7 @@ def _rank_main(rank, world, port, emu_so, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    audio._lib_override = _lib.NativeLib(emu_so)
+    _lib._default = _lib.NativeLib(emu_so)          # test process only: the loader's cached library is the CPU-emulated build
     hparams.load().parse("min_level_db=-100")
     Ts, specs, phases = _make_batch()
     mine = b.shard_by_frames(Ts, world)[rank]
@@ -97,14 +97,14 @@ def test_two_rank_gloo_shards_equal_single_process():
     merged = q.get(timeout=300)
     [p.join(timeout=60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
-    old = audio._lib_override
-    audio._lib_override = _lib.NativeLib(tek.EMU_SO)
+    old = _lib._default
+    _lib._default = _lib.NativeLib(tek.EMU_SO)
     try:
         hparams.load().parse("min_level_db=-100")
         Ts, specs, phases = _make_batch()
         single = batch.inv_spectrogram_batch(specs, init_phase=phases, iters=2)
     finally:
-        audio._lib_override = old
+        _lib._default = old
         hparams.load()
     assert sorted(merged) == list(range(len(Ts)))
     for i, ref in enumerate(single):
