@@ -10,6 +10,7 @@
 #include "../../include/nspeech_b200.h"
 #include "kernels.cuh"
 #include "gl_stream.cuh"
+#include "gen_kernels.cuh"
 
 using namespace nsb;
 
@@ -64,6 +65,11 @@ struct nsb_handle_s {
     nsb_hparams hp{};
     int n_fft = 0, hop = 0, win = 0, lo = 0, colours = 0, prune = 0, defcfg = 0, num_mels = 0;
     int num_sms = 0;
+    int F = 0;                       // num_freq = n_fft / 2 + 1
+    int generic = 0;                 // n_fft != 2048: every operator runs the generic-size kernels (gen_kernels.cuh)
+    GenPlan gen{}, gen_tf{};         // their plan in the librosa and the tf.contrib.signal geometry
+    float2* d_wt = nullptr;          // [n_fft] exp(-2 pi i m / n_fft)
+    DevBuf ws_frames;                // generic path: windowed frames before the overlap-add [frames][win]
     int user_tile_hops = 0, user_stream_grid = 0;
     cudaStream_t own_stream = nullptr, copy_in = nullptr, copy_out = nullptr;
     cudaStream_t chunk_stream = nullptr;   // odd chunks of a pipelined NSB_HOST Griffin-Lim call (even ones run on the call's stream)
@@ -273,7 +279,7 @@ extern "C" int nsb_destroy(nsb_handle_t h) {
     if (h->chunk_join) cudaEventDestroy(h->chunk_join);
     if (h->last_done) cudaEventDestroy(h->last_done);
     cudaFree(h->d_tw); cudaFree(h->d_win); cudaFree(h->d_win_tf); cudaFree(h->d_rinv); cudaFree(h->d_rinv_tf); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo); cudaFree(h->d_mel_n); cudaFree(h->d_mel_ptr); cudaFree(h->d_mel_seg); cudaFree(h->d_mel_coef);
-    cudaFree(h->d_status);
+    cudaFree(h->d_status); cudaFree(h->d_wt); h->ws_frames.release();
     if (h->h_desc) cudaFreeHost(h->h_desc);
     h->d_desc.release(); h->d_trace.release(); h->d_done.release(); h->d_done2.release(); h->ws_mag.release(); h->ws_y0.release(); h->ws_y1.release();
     h->ws_in.release(); h->ws_in2.release(); h->ws_out.release(); h->ws_out2.release(); h->ws_ep.release();
@@ -288,7 +294,7 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
     const int n_fft = (hp->num_freq - 1) * 2;
     const int hop = (int)(hp->frame_shift_ms / 1000 * hp->sample_rate);
     const int win = (int)(hp->frame_length_ms / 1000 * hp->sample_rate);
-    if (n_fft != kNfft) return fail(NSB_ERR_UNSUPPORTED, "num_freq=%d (n_fft=%d): only n_fft=2048 is implemented", hp->num_freq, n_fft);
+    if (hp->num_freq < 3 || n_fft > 16384) return fail(NSB_ERR_UNSUPPORTED, "num_freq=%d (n_fft=%d): n_fft must be in [4, 16384]", hp->num_freq, n_fft);
     if (win < 1 || win > n_fft) return fail(NSB_ERR_UNSUPPORTED, "win_length=%d must be in [1, n_fft]", win);
     if (hop < 1) return fail(NSB_ERR_INVALID, "hop_length=%d must be >= 1", hop);
     if (hp->num_mels < 1 || hp->num_mels > 1024) return fail(NSB_ERR_INVALID, "num_mels=%d out of range", hp->num_mels);
@@ -306,7 +312,9 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
     nsb_handle_s* h = new nsb_handle_s();
     h->device = device; h->hp = *hp; h->n_fft = n_fft; h->hop = hop; h->win = win; h->lo = (n_fft - win) / 2;
     h->colours = (win + hop - 1) / hop;
-    h->prune = (h->lo >= 512 && h->lo + win <= 1536) ? 1 : 0;
+    h->F = n_fft / 2 + 1;
+    h->generic = (n_fft != kNfft) ? 1 : 0;
+    h->prune = (!h->generic && h->lo >= 512 && h->lo + win <= 1536) ? 1 : 0;
     h->num_mels = hp->num_mels;
     h->num_sms = prop.multiProcessorCount;
     int rc = NSB_OK;
@@ -333,28 +341,28 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
     }
     // periodic Hann (scipy.signal.get_window('hann', win, fftbins=True)) padded centrally (librosa.util.pad_center)
     {
-        std::vector<float> w(kNfft, 0.f);
+        std::vector<float> w(n_fft, 0.f);
         for (int i = 0; i < win; ++i) w[h->lo + i] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * i / win));
-        CUB(cudaMalloc(&h->d_win, sizeof(float) * kNfft));
-        CUB(cudaMemcpy(h->d_win, w.data(), sizeof(float) * kNfft, cudaMemcpyHostToDevice));
+        CUB(cudaMalloc(&h->d_win, sizeof(float) * n_fft));
+        CUB(cudaMemcpy(h->d_win, w.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
         // tf.contrib.signal.stft / inverse_stft: the same periodic Hann on the first `win` samples, zero-padded at the END
-        std::vector<float> wt(kNfft, 0.f);
+        std::vector<float> wt(n_fft, 0.f);
         for (int i = 0; i < win; ++i) wt[i] = w[h->lo + i];
-        CUB(cudaMalloc(&h->d_win_tf, sizeof(float) * kNfft));
-        CUB(cudaMemcpy(h->d_win_tf, wt.data(), sizeof(float) * kNfft, cudaMemcpyHostToDevice));
-        h->prune_tf = (win <= 1024) ? 2 : 0;
+        CUB(cudaMalloc(&h->d_win_tf, sizeof(float) * n_fft));
+        CUB(cudaMemcpy(h->d_win_tf, wt.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
+        h->prune_tf = (!h->generic && win <= 1024) ? 2 : 0;
         h->colours_tf = h->colours;
         // reciprocal of the interior window sum per offset inside a hop, in the arithmetic the kernels use
         // (float fmaf chain over the covering frames, IEEE division), times 1/n_fft of the unnormalised inverse FFT
         const int GHs = h->colours * hop;                    // k_gl_stream indexes the table by the sample inside a group of C hops
         std::vector<float> ri(GHs), rt(GHs);
         for (int geo = 0; geo < 2; ++geo) {
-            const int lo_g = geo ? 0 : h->lo, a = geo ? 0 : kNfft / 2 - h->lo;
+            const int lo_g = geo ? 0 : h->lo, a = geo ? 0 : n_fft / 2 - h->lo;
             const std::vector<float>& wg = geo ? wt : w;
             for (int j = 0; j < hop; ++j) {
                 float sum = 0.f;
                 for (int idx = (j + a) % hop; idx < win; idx += hop) sum = std::fmaf(wg[lo_g + idx], wg[lo_g + idx], sum);
-                const float v = ((geo == 0 && sum > 1.17549435e-38f) ? 1.0f / sum : 1.0f) * (1.0f / (float)kNfft);
+                const float v = ((geo == 0 && sum > 1.17549435e-38f) ? 1.0f / sum : 1.0f) * (1.0f / (float)n_fft);
                 for (int c = 0; c < h->colours; ++c) (geo ? rt : ri)[c * hop + j] = v;
             }
         }
@@ -369,10 +377,10 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
         std::vector<float> wts; std::vector<int> lo(hp->num_mels), n(hp->num_mels), ptr(hp->num_mels);
         for (int m = 0; m < hp->num_mels; ++m) {
             int first = -1, last = -1;
-            for (int k = 0; k < kBins; ++k) if (h->mel_dense[(size_t)m * kBins + k] != 0.0) { if (first < 0) first = k; last = k; }
+            for (int k = 0; k < h->F; ++k) if (h->mel_dense[(size_t)m * h->F + k] != 0.0) { if (first < 0) first = k; last = k; }
             if (first < 0) { first = 0; last = -1; }
             lo[m] = first; n[m] = last - first + 1; ptr[m] = (int)wts.size();
-            for (int k = first; k <= last; ++k) wts.push_back((float)h->mel_dense[(size_t)m * kBins + k]);
+            for (int k = first; k <= last; ++k) wts.push_back((float)h->mel_dense[(size_t)m * h->F + k]);
         }
         if (wts.empty()) wts.push_back(0.f);
         CUB(cudaMalloc(&h->d_mel_w, sizeof(float) * wts.size()));
@@ -385,7 +393,7 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
         CUB(cudaMemcpy(h->d_mel_ptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice));
         std::vector<int> seg; std::vector<float> coef;
         // (the two moments per segment live behind the magnitude row in the warp's scratch tile: 1028 + 2 (M + 1) <= 2 kScratchF2 floats)
-        if (1028 + 2 * (hp->num_mels + 1) <= 2 * kScratchF2 && build_mel_lines(hp->sample_rate, n_fft, hp->num_mels, h->mel_dense, seg, coef)) {
+        if (!h->generic && 1028 + 2 * (hp->num_mels + 1) <= 2 * kScratchF2 && build_mel_lines(hp->sample_rate, n_fft, hp->num_mels, h->mel_dense, seg, coef)) {
             CUB(cudaMalloc(&h->d_mel_seg, sizeof(int) * seg.size()));
             CUB(cudaMemcpy(h->d_mel_seg, seg.data(), sizeof(int) * seg.size(), cudaMemcpyHostToDevice));
             CUB(cudaMalloc(&h->d_mel_coef, sizeof(float) * coef.size()));
@@ -398,8 +406,32 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
     // The opt-in limit is a per-FUNCTION attribute shared by every handle of the process: always raise it to the
     // device maximum (a handle with a smaller hop must not lower it under another handle's launches).
     const size_t as = prop.sharedMemPerBlockOptin, ss = prop.sharedMemPerBlockOptin, gs = prop.sharedMemPerBlockOptin;
-    h->defcfg = (hop == 250 && win == 1000 && h->lo == 524) ? 1 : 0;
 #define SET(k, b) do { rc = set_smem(k, b); if (rc) return bail(rc); } while (0)
+    h->defcfg = (!h->generic && hop == 250 && win == 1000 && h->lo == 524) ? 1 : 0;
+    if (h->generic) {
+        // mixed-radix plan of the complex FFT of length M = n_fft / 2: 8s, 4s, 2s, then the odd prime factors
+        GenPlan& G = h->gen;
+        G.n_fft = n_fft; G.M = n_fft / 2; G.F = h->F; G.n_stages = 0;
+        int m = G.M;
+        auto take = [&](int r) { while (m % r == 0 && G.n_stages < kGenMaxStages) { G.radix[G.n_stages++] = r; m /= r; } };
+        take(8); take(4); take(2);
+        for (int pfac = 3; m > 1; pfac += 2) take(pfac);
+        if (m != 1) return bail(fail(NSB_ERR_UNSUPPORTED, "n_fft=%d has too many prime factors", n_fft));
+        std::vector<float2> wt(n_fft);
+        for (int i = 0; i < n_fft; ++i) { const double a = -2.0 * M_PI * (double)i / (double)n_fft; wt[i] = make_float2((float)std::cos(a), (float)std::sin(a)); }
+        CUB(cudaMalloc(&h->d_wt, sizeof(float2) * n_fft));
+        CUB(cudaMemcpy(h->d_wt, wt.data(), sizeof(float2) * n_fft, cudaMemcpyHostToDevice));
+        G.wt = h->d_wt; G.hop = hop; G.win_len = win; G.num_mels = hp->num_mels;
+        G.mel_w = h->d_mel_w; G.mel_lo = h->d_mel_lo; G.mel_n = h->d_mel_n; G.mel_ptr = h->d_mel_ptr;
+        h->gen_tf = G;
+        G.win = h->d_win; G.lo = h->lo; G.origin = n_fft / 2; G.norm_wss = 1;
+        h->gen_tf.win = h->d_win_tf; h->gen_tf.lo = 0; h->gen_tf.origin = 0; h->gen_tf.norm_wss = 0;
+        SET(k_gen_analysis, as); SET(k_gen_synth, as);
+        if ((size_t)(3 * G.M + 1) * sizeof(float2) > prop.sharedMemPerBlockOptin)
+            return bail(fail(NSB_ERR_UNSUPPORTED, "n_fft=%d needs more shared memory than the device has", n_fft));
+        *out = h;
+        return NSB_OK;
+    }
     SET((k_analysis<ANALYSIS_COMPLEX, false, 0>), as); SET((k_analysis<ANALYSIS_COMPLEX, false, 1>), as); SET((k_analysis<ANALYSIS_COMPLEX, false, 2>), as);
     SET((k_analysis<ANALYSIS_COMPLEX, true, 0>), as);  SET((k_analysis<ANALYSIS_COMPLEX, true, 1>), as);
     SET((k_analysis<ANALYSIS_FEATURES, true, 0>), as); SET((k_analysis<ANALYSIS_FEATURES, true, 1>), as);
@@ -630,6 +662,30 @@ static int grid_1d(long long n, int threads, int max_blocks) {
     return (int)g;
 }
 
+// ---- generic-size path (gen_kernels.cuh): launch helpers ----
+static size_t gen_smem_analysis(const GenPlan& G) { return (size_t)2 * G.M * sizeof(float2); }
+static size_t gen_smem_synth(const GenPlan& G) { return (size_t)(3 * G.M + 1) * sizeof(float2); }
+static int gen_grid(const nsb_handle_s* h, long long frames) {
+    const long long cap = 8LL * h->num_sms;
+    return (int)(frames < 1 ? 1 : (frames < cap ? frames : cap));
+}
+// frames of the (sub-)batch B from `src` -> windowed inverse transforms -> overlap-add into y_out (packed samples of the batch)
+static int gen_synthesize(nsb_handle_s* h, const GenPlan& G, const Batch& B, int frames, long long total_samples, int src, const float* y_in,
+                          const float* mag, const float2* spec, int spec_bin_major, int tf_renorm, unsigned long long seed, float* y_out, cudaStream_t st) {
+    int rc = h->ws_frames.reserve(sizeof(float) * (size_t)frames * G.win_len);
+    if (rc) return rc;
+    GenSynthParams S{};
+    S.plan = G; S.batch = B; S.src = src; S.y_in = y_in; S.mag = mag; S.spec = spec; S.spec_bin_major = spec_bin_major;
+    S.frames_out = reinterpret_cast<float*>(h->ws_frames.p) - (size_t)B.frame_base * G.win_len;     // indexed by the GLOBAL frame number
+    S.total_frames = frames; S.tf_renorm = tf_renorm; S.seed = seed; S.status = h->d_status;
+    NSB_LAUNCH(k_gen_synth, gen_grid(h, frames), kGenThreads, gen_smem_synth(G), st, S);
+    if ((rc = check_launch(h, "k_gen_synth"))) return rc;
+    GenOlaParams O{};
+    O.plan = G; O.batch = B; O.frames = S.frames_out; O.y_out = y_out; O.total_samples = total_samples;
+    NSB_LAUNCH(k_gen_ola, grid_1d(total_samples, 256, 16 * h->num_sms), 256, 0, st, O);
+    return check_launch(h, "k_gen_ola");
+}
+
 // ---------------------------------------------------------------------------------------------
 // analysis entry points
 // ---------------------------------------------------------------------------------------------
@@ -658,7 +714,7 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
     Desc d;
     int rc = upload_desc(h, st, frames, samples, 0, &d, row_off);
     if (rc) return rc;
-    const size_t F = kBins, M = h->num_mels;
+    const size_t F = h->F, M = h->num_mels;
     const size_t out_rows = row_off ? (size_t)total_rows : rows_per_utt > 0 ? (size_t)rows_per_utt * batch : (size_t)d.total_frames;     // scattered, padded or packed
     const float* d_wav = wav;
     float2* d_c = reinterpret_cast<float2*>(out_complex);
@@ -730,7 +786,15 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
         P.total_frames = h->h_frame_off[b1] - h->h_frame_off[b0];
         if (space == NSB_HOST) CUA(cudaStreamWaitEvent(st, ev_in[c], 0));
         const int grid = grid_1d(P.total_frames, kWarpsPerCta, 2 * h->num_sms);
-        if (mode == ANALYSIS_COMPLEX) {
+        if (h->generic) {
+            GenAnalysisParams Q{};
+            Q.plan = tf ? h->gen_tf : h->gen; Q.batch = P.batch; Q.wav = P.wav; Q.total_frames = P.total_frames; Q.rows_per_utt = rows_per_utt;
+            Q.out_complex = mode == ANALYSIS_COMPLEX ? d_c : nullptr; Q.out_lin = mode == ANALYSIS_COMPLEX ? nullptr : d_lin;
+            Q.out_mel = mode == ANALYSIS_COMPLEX ? nullptr : d_mel;
+            Q.preemph_on = preemph ? 1 : 0; Q.preemph = P.preemph;
+            Q.db_scale = P.db_scale; Q.db_offset_lin = P.db_offset_lin; Q.db_offset_mel = P.db_offset_mel; Q.status = h->d_status;
+            NSB_LAUNCH(k_gen_analysis, gen_grid(h, P.total_frames), kGenThreads, gen_smem_analysis(Q.plan), st, Q);
+        } else if (mode == ANALYSIS_COMPLEX) {
             if (preemph) {
                 if (prune == 1) NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, true, 1>), grid, kThreads, smem, st, P);
                 else NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, true, 0>), grid, kThreads, smem, st, P);
@@ -856,19 +920,28 @@ static int run_istft(nsb_handle_t h, const float* spec, int32_t layout, const in
     std::vector<int> frames; std::vector<long long> samples;
     int rc = validate_frames(h, n_frames, batch, frames, samples, tf);
     if (rc) return rc;
-    const int H = choose_tile_hops(h, samples, tf);
+    const int H = h->generic ? 0 : choose_tile_hops(h, samples, tf);
     Desc d;
     if ((rc = upload_desc(h, st, frames, samples, H, &d))) return rc;
     const float2* d_spec = reinterpret_cast<const float2*>(spec);
     float* d_out = wav_out;
     if (space == NSB_HOST) {
-        if ((rc = h->ws_in.reserve(sizeof(float2) * kBins * (size_t)d.total_frames))) return rc;
+        if ((rc = h->ws_in.reserve(sizeof(float2) * h->F * (size_t)d.total_frames))) return rc;
         if ((rc = h->ws_out.reserve(sizeof(float) * d.total_samples))) return rc;
-        CU(cudaMemcpyAsync(h->ws_in.p, spec, sizeof(float2) * kBins * (size_t)d.total_frames, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(h->ws_in.p, spec, sizeof(float2) * h->F * (size_t)d.total_frames, cudaMemcpyHostToDevice, st));
         d_spec = reinterpret_cast<const float2*>(h->ws_in.p);
         d_out = reinterpret_cast<float*>(h->ws_out.p);
     }
     h->gl.valid = false;
+    if (h->generic) {
+        if ((rc = gen_synthesize(h, tf ? h->gen_tf : h->gen, d.dev, d.total_frames, d.total_samples, SRC_SPEC, nullptr, nullptr, d_spec,
+                                 layout == NSB_BIN_MAJOR, 0, 0, d_out, st))) return rc;
+        if (space == NSB_HOST) {
+            CU(cudaMemcpyAsync(wav_out, d_out, sizeof(float) * d.total_samples, cudaMemcpyDeviceToHost, st));
+            return read_status(h, st);
+        }
+        return NSB_OK;
+    }
     SynthParams P{};
     P.plan = make_plan(h, tf); P.batch = d.dev; P.spec = d_spec; P.spec_bin_major = (layout == NSB_BIN_MAJOR);
     P.y_out = d_out; P.tile_hops = H; P.colours = h->colours; P.status = h->d_status; P.mag = nullptr;
@@ -1064,7 +1137,7 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
     std::vector<int> frames; std::vector<long long> samples;
     int rc = validate_frames(h, n_frames, batch, frames, samples, tf);
     if (rc) return rc;
-    const int H = choose_tile_hops(h, samples, tf);
+    const int H = h->generic ? 0 : choose_tile_hops(h, samples, tf);
     Desc d;
     if ((rc = upload_desc(h, st, frames, samples, H, &d))) return rc;
     // out_dtype is what the de-emphasis writes; the synthesis stage may end in another type (peak-normalised int16)
@@ -1072,7 +1145,8 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
     const size_t out_elt = to_i16 ? sizeof(short) : dtype_size(out_dtype);
     if (!(flags & NSB_GL_DEEMPHASIS) && out_dtype != NSB_F32)
         return fail(NSB_ERR_INVALID, "NSB_F64 output without NSB_GL_DEEMPHASIS is not provided (_griffin_lim returns float32)");
-    const size_t n_spec = (size_t)kBins * d.total_frames;
+    const size_t n_spec = (size_t)h->F * d.total_frames;
+    const size_t mag_pitch = h->generic ? (size_t)h->F : (size_t)kMagPitch;
     const float* d_spec = spec;
     const float2* d_phase = reinterpret_cast<const float2*>(init_phase);
     char* d_out = reinterpret_cast<char*>(wav_out);           // de-emphasis output (out_dtype)
@@ -1094,14 +1168,14 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
             d_out = d_final = reinterpret_cast<char*>(h->ws_out.p);
         }
     }
-    if ((rc = h->ws_mag.reserve(sizeof(float) * kMagPitch * (size_t)d.total_frames))) return rc;
+    if ((rc = h->ws_mag.reserve(sizeof(float) * mag_pitch * (size_t)d.total_frames))) return rc;
     if ((rc = h->ws_y0.reserve(sizeof(float) * d.total_samples))) return rc;
     if ((rc = h->ws_y1.reserve(sizeof(float) * d.total_samples))) return rc;
 
     // Griffin-Lim is linear in S: run it on g*S with g a power of two that brings the largest possible magnitude
     // below 1 (the yaml's +100 dB floor gives S up to 1e9 whose squares would overflow fp32), undo g on output.
     double gscale = 1.0;
-    if (flags & NSB_GL_DENORMALIZE) {
+    if ((flags & NSB_GL_DENORMALIZE) && !h->generic) {       // (the generic kernels renormalise with a guarded square: no pre-scale needed)
         const double e0 = (h->hp.min_level_db + h->hp.ref_level_db) * 0.05 * h->hp.power, e1 = h->hp.ref_level_db * 0.05 * h->hp.power;
         const double smax = std::pow(10.0, e0 > e1 ? e0 : e1);
         gscale = std::ldexp(1.0, -(int)std::ceil(std::log2(smax)));
@@ -1112,7 +1186,7 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
     // (copy_in stream) and chunk c-1 copied out (copy_out stream) while chunk c computes.  Device buffers: one chunk.
     std::vector<int> cuts;           // utterance index where each chunk starts, plus the end
     cuts.push_back(0);
-    if (space == NSB_HOST && batch > 1 && (h->host_chunks > 0 || n_spec * sizeof(float) > (8u << 20))) {
+    if (space == NSB_HOST && batch > 1 && !h->generic && (h->host_chunks > 0 || n_spec * sizeof(float) > (8u << 20))) {
         // Only the first chunk's copy-in and the last chunk's copy-out are exposed, so those two chunks should be small -
         // but below ~16k frames the iteration kernels are latency-bound, and the streaming kernel (the fastest) needs
         // ~35k frames.  Automatic mode: long batches (>= 60k frames) are cut 16k | rest | 12k frames, shorter ones into up
@@ -1144,7 +1218,7 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
     // arrived and are not finished: the launches grow with the data, only the very first ones are small, and a finished chunk's
     // de-emphasis and copy-out hide behind the later waves.  Chunk g+1 is sized to arrive while wave g runs.
     int waves = 0, wave_iters = 0;
-    if (space == NSB_HOST && batch > 1 && h->wave_schedule && h->host_chunks == 0 && !h->trace_on && h->fuse_iterations
+    if (space == NSB_HOST && batch > 1 && !h->generic && h->wave_schedule && h->host_chunks == 0 && !h->trace_on && h->fuse_iterations
         && !(std::getenv("NSB_CHUNK_CUTS") && *std::getenv("NSB_CHUNK_CUTS")) && d.total_frames >= 40000) {
         const int ie = iters - (iters & 1);
         const char* ew = std::getenv("NSB_WAVES");                 // tuning hooks
@@ -1190,11 +1264,12 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
         // all input copies are queued up front on the copy-in stream, in chunk order
         for (int c = 0; c < n_chunks; ++c) {
             const size_t f0 = h->h_frame_off[cuts[c]], f1 = h->h_frame_off[cuts[c + 1]];
-            CUE(cudaMemcpyAsync(reinterpret_cast<float*>(h->ws_in.p) + f0 * kBins, spec + f0 * kBins, sizeof(float) * (f1 - f0) * kBins,
+            const size_t Fb = h->F;
+            CUE(cudaMemcpyAsync(reinterpret_cast<float*>(h->ws_in.p) + f0 * Fb, spec + f0 * Fb, sizeof(float) * (f1 - f0) * Fb,
                                 cudaMemcpyHostToDevice, h->copy_in));
             if (init_phase)
-                CUE(cudaMemcpyAsync(reinterpret_cast<float2*>(h->ws_in2.p) + f0 * kBins, reinterpret_cast<const float2*>(init_phase) + f0 * kBins,
-                                    sizeof(float2) * (f1 - f0) * kBins, cudaMemcpyHostToDevice, h->copy_in));
+                CUE(cudaMemcpyAsync(reinterpret_cast<float2*>(h->ws_in2.p) + f0 * Fb, reinterpret_cast<const float2*>(init_phase) + f0 * Fb,
+                                    sizeof(float2) * (f1 - f0) * Fb, cudaMemcpyHostToDevice, h->copy_in));
             CUE(cudaEventRecord(ev_in[c], h->copy_in));
         }
     }
@@ -1230,6 +1305,14 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
             Q.e_offset = (h->hp.min_level_db + h->hp.ref_level_db) * 0.05 * h->hp.power * l2_10 + std::log2(gscale);
         }
         Q.mag = reinterpret_cast<float*>(h->ws_mag.p); Q.total_frames = u.frames; Q.status = h->d_status; Q.scale = (float)gscale;
+        if (h->generic) {
+            NSB_LAUNCH(k_gen_prepare_mag, grid_1d((long long)u.frames * h->F, 256, 16 * h->num_sms), 256, 0, s_, Q, h->F);
+            int r_ = check_launch(h, "k_gen_prepare_mag");
+            if (r_) return r_;
+            const long long s_cnt = h->h_samp_off[cuts[c + 1]] - h->h_samp_off[cuts[c]];
+            return gen_synthesize(h, tf ? h->gen_tf : h->gen, u.B, u.frames, s_cnt, tf ? SRC_MAGZERO : (init_phase ? SRC_MAGPHASE : SRC_MAGRAND), nullptr,
+                                  Q.mag, d_phase, layout == NSB_BIN_MAJOR, 0, seed, reinterpret_cast<float*>(h->ws_y0.p), s_);
+        }
         if (Q.bin_major) {
             CUL(cudaMemsetAsync(Q.mag + (size_t)u.B.frame_base * kMagPitch, 0, sizeof(float) * kMagPitch * (size_t)u.frames, s_));
             NSB_LAUNCH(k_prepare_mag, (u.frames + 31) / 32, 256, 0, s_, Q);
@@ -1250,6 +1333,17 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
     // n iterations on the utterances [b0, b1); cur_ says which of the two waveform buffers holds their y
     auto iterate = [&](int b0, int b1, int n, int& cur_, cudaStream_t s_, DevBuf* done_buf) -> int {
         const Sub u = sub_batch(b0, b1);
+        if (h->generic) {
+            float* yb[2] = {reinterpret_cast<float*>(h->ws_y0.p), reinterpret_cast<float*>(h->ws_y1.p)};
+            const long long s_cnt = h->h_samp_off[b1] - h->h_samp_off[b0];
+            for (int it = 0; it < n; ++it) {
+                int r_ = gen_synthesize(h, tf ? h->gen_tf : h->gen, u.B, u.frames, s_cnt, SRC_Y, yb[cur_], reinterpret_cast<const float*>(h->ws_mag.p),
+                                        nullptr, 0, tf ? 1 : 0, 0, yb[cur_ ^ 1], s_);
+                if (r_) return r_;
+                cur_ ^= 1;
+            }
+            return NSB_OK;
+        }
         return gl_iterations(h, u.B, u.tiles, u.groups, H, cur_, n, s_, tf, inv_thr, done_buf);
     };
     // chunk c is finished: de-emphasis (+ endpoint search) and the copy out
@@ -1355,7 +1449,7 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
         CUE(cudaStreamWaitEvent(st, h->chunk_join, 0));
     }
     // device-resident state for nsb_griffin_lim_iterate: the whole batch
-    h->gl.valid = (space == NSB_DEVICE); h->gl.batch = d.dev; h->gl.total_frames = d.total_frames; h->gl.tile_hops = H;
+    h->gl.valid = (space == NSB_DEVICE) && !h->generic; h->gl.batch = d.dev; h->gl.total_frames = d.total_frames; h->gl.tile_hops = H;
     h->gl.total_tiles = d.total_tiles; h->gl.total_groups = d.total_groups; h->gl.cur = cur; h->gl.tf = tf; h->gl.inv_thr = (float)(1.0 / (2.0e-8 * gscale));
     if (ep) CUE(cudaMemcpyAsync(ep->out, h->ws_ep.p, sizeof(long long) * (size_t)batch,
                                 space == NSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
@@ -1552,7 +1646,7 @@ extern "C" int nsb_linear_to_mel(nsb_handle_t h, const float* spec, int32_t layo
     int rc = upload_desc(h, st, frames, samples, 0, &d);
     if (rc) return rc;
     const size_t out_elt = out_dtype == NSB_F64 ? sizeof(double) : sizeof(float);
-    const size_t n_in = (size_t)kBins * d.total_frames, n_out = (size_t)h->num_mels * d.total_frames;
+    const size_t n_in = (size_t)h->F * d.total_frames, n_out = (size_t)h->num_mels * d.total_frames;
     const float* d_in = spec;
     void* d_out = out;
     if (space == NSB_HOST) {
@@ -1565,7 +1659,8 @@ extern "C" int nsb_linear_to_mel(nsb_handle_t h, const float* spec, int32_t layo
     MelParams M{};
     M.plan = make_plan(h); M.batch = d.dev; M.in = d_in; M.bin_major = (layout == NSB_BIN_MAJOR); M.total_frames = d.total_frames;
     if (out_dtype == NSB_F64) M.out64 = reinterpret_cast<double*>(d_out); else M.out32 = reinterpret_cast<float*>(d_out);
-    NSB_LAUNCH(k_linear_to_mel, grid_1d(d.total_frames, kWarpsPerCta, 4 * h->num_sms), kThreads, 0, st, M);
+    if (h->generic) NSB_LAUNCH(k_gen_linear_to_mel, grid_1d((long long)d.total_frames * h->num_mels, 256, 8 * h->num_sms), 256, 0, st, M, h->F);
+    else NSB_LAUNCH(k_linear_to_mel, grid_1d(d.total_frames, kWarpsPerCta, 4 * h->num_sms), kThreads, 0, st, M);
     if ((rc = check_launch(h, "k_linear_to_mel"))) return rc;
     if (space == NSB_HOST) {
         CU(cudaMemcpyAsync(out, d_out, out_elt * n_out, cudaMemcpyDeviceToHost, st));

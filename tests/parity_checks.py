@@ -10,6 +10,12 @@ from oracle import audio_oracle as ao
 from oracle import tf_signal17 as tfo
 
 CONFIGS = [{"min_level_db": -100}, {}, {"min_level_db": -100, "sample_rate": 22050}]
+# hparams-driven num_freq (audio.py:126-130): every n_fft != 2048 runs the generic-size kernels (csrc/gen_kernels.cuh) - powers of
+# two, the yaml's commented alternative num_freq 2048 (n_fft 4094 = 2 * 23 * 89, audio.yaml:7) with its 24 kHz (audio.yaml:8),
+# a 2^5 * 5^2 size, and a window as long as the transform
+GENERIC_CONFIGS = [{"min_level_db": -100, "num_freq": 513}, {"min_level_db": -100, "num_freq": 2049},
+                   {"num_freq": 2048, "sample_rate": 24000}, {"min_level_db": -100, "num_freq": 401, "sample_rate": 16000},
+                   {"min_level_db": -100, "num_freq": 501, "frame_length_ms": 50, "sample_rate": 20000}]
 
 
 def _load(**over):
@@ -33,7 +39,7 @@ def check_single_ops_vs_oracle(over):
     assert ao.rel_l2(y, yref) < 1e-5
     assert ao.rel_l2(audio._istft(np.ascontiguousarray(Dref)), yref) < 1e-5   # bin-major input
     lin, mel = audio.spectrogram_and_mel(wav)
-    assert lin.shape == (1025, D.shape[1]) and mel.shape == (80, D.shape[1]) and lin.dtype == np.float32
+    assert lin.shape == (ohp.num_freq, D.shape[1]) and mel.shape == (80, D.shape[1]) and lin.dtype == np.float32
     assert ao.rel_l2(lin, ao.spectrogram(wav, ohp)) < 1e-5
     assert ao.rel_l2(mel, ao.melspectrogram(wav, ohp)) < 1e-5
     np.testing.assert_array_equal(audio.spectrogram(wav), lin)
@@ -164,10 +170,11 @@ def check_errors_and_edge_cases():
     # silence: phase of an all-zero STFT is 0 (np.angle(0) == 0) -> finite output, no NaN from 0/0
     y = audio._griffin_lim(np.zeros((1025, 6), np.float32), init_phase=np.ones((1025, 6), np.complex64), iters=2)
     assert np.all(y == 0)
-    hp = hparams.load()
-    hp.parse("num_freq=513")
-    with pytest.raises(ValueError):
-        audio._stft(wav)
+    for bad_hp in ("num_freq=2", "num_freq=257", "num_freq=9000"):     # n_fft 2; window (1000) longer than n_fft 512; n_fft > 16384
+        hp = hparams.load()
+        hp.parse(bad_hp)
+        with pytest.raises(ValueError):
+            audio._stft(wav)
     hparams.load()
 
 
@@ -532,3 +539,56 @@ def check_stale_griffin_lim_state(to_dev, stream=None):
     h.griffin_lim(rs.rand(9, 1025).astype(np.float32), _lib.FRAME_MAJOR, [9], host_out, seed=1, iters=1, flags=flags, out_dtype=_lib.F64)
     with pytest.raises(ValueError):
         h.griffin_lim_iterate(1, stream)
+
+
+def check_generic_tf_twin_and_stages():
+    """The generic-size kernels behind the rest of the interface at num_freq = 513 (n_fft 1024): the TensorFlow twin
+    (audio.py:51-58, 90-123), the fused synthesis stage (synthesizer.py:51-53), ragged batches in both layouts, the device RNG."""
+    from nspeech_b200 import batch
+    ohp = _load(min_level_db=-100, num_freq=513)
+    h = audio._handle()
+    F = 513
+    assert (h.n_fft, h.num_freq) == (1024, F)
+    wav = speechlike(5300, 1)
+    D = audio._stft_tensorflow(wav)
+    Dref = tfo._stft_tensorflow(wav, ohp)
+    assert D.shape == Dref.shape == (h.num_frames_tf(wav.size), F)
+    assert ao.rel_l2(D, Dref) < 1e-5
+    assert ao.rel_l2(audio._istft_tensorflow(Dref), tfo._istft_tensorflow(Dref, ohp)) < 1e-5
+    rs = np.random.RandomState(0)
+    S3 = rs.rand(3, 9, F).astype(np.float32)
+    g3 = audio.inv_spectrogram_tensorflow(S3, iters=3)
+    for i in range(3):
+        assert ao.snr_db(g3[i], tfo.inv_spectrogram_tensorflow(S3[i], ohp, iters=3)) > 60
+    assert np.all(audio._griffin_lim_tensorflow(np.zeros((5, F), np.float32), iters=2) == 0)
+    specs = rs.rand(2, 140, F).astype(np.float32)
+    specs[0, 50:] = 0.0
+    outs = audio.synthesize_waveforms(specs, iters=3, peak_normalize=True)
+    for i in range(2):
+        ref = ao.inv_preemphasis(tfo.inv_spectrogram_tensorflow(specs[i], ohp, iters=3), ohp)
+        ref = ao.save_wav_scaling(ref[:ao.find_endpoint(ref, ohp)])
+        assert outs[i].shape == ref.shape and ao.snr_db(outs[i], ref) > 60
+    # ragged Griffin-Lim batch, [F,T] and [T,F] members, against one-at-a-time calls (bitwise) and the oracle
+    Ts = [2, 17, 5]
+    mats = [rs.rand(F, T).astype(np.float32) for T in Ts]
+    phs = [np.exp(2j * np.pi * rs.rand(F, T)).astype(np.complex64) for T in Ts]
+    outs = batch.inv_spectrogram_batch(mats, init_phase=phs, iters=3, layout="FT")
+    outs_t = batch.inv_spectrogram_batch([np.ascontiguousarray(m.T) for m in mats], init_phase=[np.ascontiguousarray(p.T) for p in phs], iters=3, layout="TF")
+    for m, p, o, ot in zip(mats, phs, outs, outs_t):
+        assert ao.snr_db(o, ao.inv_spectrogram(m, ohp, angles=p, iters=3)) > 60
+        np.testing.assert_array_equal(o, ot)
+        np.testing.assert_array_equal(o, audio.inv_spectrogram(m, init_phase=p, iters=3))
+        np.testing.assert_array_equal(o, audio.inv_spectrogram(np.ascontiguousarray(m), init_phase=np.ascontiguousarray(p), iters=3))   # bin-major
+    a = audio.inv_spectrogram(mats[1], seed=7, iters=2)
+    np.testing.assert_array_equal(a, audio.inv_spectrogram(mats[1], seed=7, iters=2))
+    assert np.isfinite(a).all() and not np.array_equal(a, audio.inv_spectrogram(mats[1], seed=8, iters=2))
+    # ragged features + the feeder's padded tensors
+    wavs = [speechlike(n, i) for i, n in enumerate((3000, 5118, 700))]
+    feats = batch.features_batch(wavs)
+    mel_t, lin_t, Tn = batch.feeder_targets(wavs, 5)
+    for i, (w, (lin, mel)) in enumerate(zip(wavs, feats)):
+        assert lin.shape == (F, Tn[i]) and ao.rel_l2(lin, ao.spectrogram(w, ohp)) < 1e-5 and ao.rel_l2(mel, ao.melspectrogram(w, ohp)) < 1e-5
+        np.testing.assert_array_equal(lin_t[i, :Tn[i]], lin.T)
+        assert not lin_t[i, Tn[i]:].any()
+    with pytest.raises(audio.ParameterError):
+        audio.inv_spectrogram(np.full((F, 4), np.inf, np.float32), iters=1)

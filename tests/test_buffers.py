@@ -71,6 +71,7 @@ def test_exported_dlpack_capsule_round_trips():
     assert tb.shape == (4, 3) and tb.f_contiguous and tb.ptr == arr.ptr
     assert arr.T.__cuda_array_interface__["strides"] == (8, 32)
     import gc
+    del back, tb
     gc.collect()
     assert len(_buffers.DeviceArray._live) == 0       # the capsules read back above were never consumed: dropping them released the pins
     cap = arr.__dlpack__()

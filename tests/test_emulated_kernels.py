@@ -56,6 +56,16 @@ def test_single_ops_vs_oracle(emu, over):
     pc.check_single_ops_vs_oracle(over)
 
 
+@pytest.mark.parametrize("over", pc.GENERIC_CONFIGS)
+def test_generic_num_freq_vs_oracle(emu, over):
+    pc.check_single_ops_vs_oracle(over)
+    pc.check_griffin_lim_vs_oracle(over)
+
+
+def test_generic_num_freq_tf_twin_and_stages(emu):
+    pc.check_generic_tf_twin_and_stages()
+
+
 @pytest.mark.parametrize("over", pc.CONFIGS)
 def test_griffin_lim_vs_oracle(emu, over):
     pc.check_griffin_lim_vs_oracle(over)

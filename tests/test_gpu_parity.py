@@ -32,6 +32,16 @@ def test_griffin_lim_vs_oracle(over):
     pc.check_griffin_lim_vs_oracle(over)
 
 
+@pytest.mark.parametrize("over", pc.GENERIC_CONFIGS)
+def test_generic_num_freq_vs_oracle(over):
+    pc.check_single_ops_vs_oracle(over)
+    pc.check_griffin_lim_vs_oracle(over)
+
+
+def test_generic_num_freq_tf_twin_and_stages():
+    pc.check_generic_tf_twin_and_stages()
+
+
 def test_golden_fixtures_through_kernels(golden):
     pc.check_golden_fixtures_through_kernels(golden)
 
@@ -310,3 +320,113 @@ def test_feature_host_pipeline_matches_one_chunk():
             assert ref[4] == cur[4]
     finally:
         h.set_host_chunks(0)
+
+
+class _CaiOnly(object):
+    """a device array of 'some other framework': exposes nothing but the CUDA array interface (keeps the torch tensor alive)"""
+
+    def __init__(self, t):
+        self._t = t
+        self.__cuda_array_interface__ = t.__cuda_array_interface__
+
+
+class _DlpackOnly(object):
+    def __init__(self, t):
+        self._t = t
+
+    def __dlpack__(self, stream=None):
+        return self._t.__dlpack__()
+
+    def __dlpack_device__(self):
+        return self._t.__dlpack_device__()
+
+
+def test_device_arrays_at_the_python_boundary():
+    """torch CUDA tensors, CUDA-array-interface and DLPack producers go in without a host round trip and device arrays come
+    back (north-star: 'numpy/DLPack buffers'); the results equal the host path bit for bit."""
+    torch = pytest.importorskip("torch")
+    from nspeech_b200 import _buffers
+    pc._load(min_level_db=-100)
+    h = audio._handle()
+    rs = np.random.RandomState(8)
+    wav = speechlike(9000, 3)
+    lin, mel = audio.spectrogram_and_mel(wav)
+    D = audio._stft(wav)
+    y = audio._istft(D)
+    S = rs.rand(1025, 23).astype(np.float32)
+    ang = np.exp(2j * np.pi * rs.rand(1025, 23)).astype(np.complex64)
+    g = audio.inv_spectrogram(S, init_phase=ang, iters=4)
+    twin = audio.inv_spectrogram_tensorflow(S.T.copy(), iters=3)
+    tw = torch.from_numpy(wav).cuda()
+    # torch in -> torch out
+    tl, tm = audio.spectrogram_and_mel(tw)
+    assert isinstance(tl, torch.Tensor) and tl.is_cuda and tl.shape == lin.shape and tl.dtype == torch.float32
+    np.testing.assert_array_equal(tl.cpu().numpy(), lin)
+    np.testing.assert_array_equal(tm.cpu().numpy(), mel)
+    np.testing.assert_array_equal(audio.spectrogram(tw).cpu().numpy(), lin)
+    np.testing.assert_array_equal(audio.melspectrogram(tw).cpu().numpy(), mel)
+    tD = audio._stft(tw)
+    assert tD.dtype == torch.complex64
+    np.testing.assert_array_equal(tD.cpu().numpy(), D)
+    np.testing.assert_array_equal(audio._istft(tD).cpu().numpy(), y)                     # Fortran-ordered [F,T] view: frame-major
+    np.testing.assert_array_equal(audio._istft(tD.contiguous()).cpu().numpy(), y)        # C-ordered: bin-major
+    tS, ta = torch.from_numpy(S).cuda(), torch.from_numpy(ang).cuda()
+    tg = audio.inv_spectrogram(tS, init_phase=ta, iters=4)
+    assert tg.dtype == torch.float64 and tg.is_cuda
+    np.testing.assert_array_equal(tg.cpu().numpy(), g)
+    np.testing.assert_array_equal(audio.inv_spectrogram(tS.T.contiguous().T, init_phase=ta.T.contiguous().T, iters=4).cpu().numpy(), g)
+    np.testing.assert_array_equal(audio.inv_spectrogram_tensorflow(tS.T.contiguous(), iters=3).cpu().numpy(), twin)
+    np.testing.assert_array_equal(audio.inv_preemphasis(tw).cpu().numpy(), audio.inv_preemphasis(wav))
+    # float64 torch input is converted on the device
+    np.testing.assert_array_equal(audio.spectrogram(tw.double()).cpu().numpy(), lin)
+    # another framework's arrays (CUDA array interface / DLPack only) -> DeviceArray, adoptable without a copy
+    for wrap in (_CaiOnly, _DlpackOnly):
+        r = audio.inv_spectrogram(wrap(tS.T.contiguous().T), init_phase=wrap(ta.T.contiguous().T), iters=4)
+        assert isinstance(r, _buffers.DeviceArray) and r.shape == g.shape and r.dtype == np.float64
+        np.testing.assert_array_equal(r.copy_to_host(), g)
+        adopted = torch.from_dlpack(r)
+        assert adopted.is_cuda and adopted.data_ptr() == r.ptr
+        np.testing.assert_array_equal(adopted.cpu().numpy(), g)
+        np.testing.assert_array_equal(torch.as_tensor(r, device="cuda").cpu().numpy(), g)          # __cuda_array_interface__
+        rl, rm = audio.spectrogram_and_mel(wrap(tw))
+        assert rl.shape == lin.shape and rm.shape == mel.shape
+        np.testing.assert_array_equal(np.asarray(rl), lin)
+        np.testing.assert_array_equal(torch.from_dlpack(rm).cpu().numpy(), mel)
+        del adopted, r, rl, rm
+    # Tacotron's [N, T, F] batch on the GPU (models/tacotron.py:98, 107)
+    B = rs.rand(3, 31, 1025).astype(np.float32)
+    ref = batch.inv_spectrogram_batch(B, seed=9, iters=3)
+    got = batch.inv_spectrogram_batch(torch.from_numpy(B).cuda(), seed=9, iters=3)
+    assert got.shape == (3, h.num_samples(31)) and got.is_cuda
+    for i in range(3):
+        np.testing.assert_array_equal(got[i].cpu().numpy(), ref[i])
+    with pytest.raises(audio.ParameterError):
+        audio.spectrogram(torch.full((3000,), float("nan"), device="cuda"))
+    with pytest.raises(TypeError):
+        audio.inv_spectrogram(tS, init_phase=ang, iters=1)              # phase on the host, spectrogram on the device
+
+
+def test_two_streams_on_one_handle_are_ordered():
+    """NSB_DEVICE calls on different streams share the handle's descriptors and counters - the second call must
+    wait for the first on the device.  Results equal the single-stream run; nothing hangs."""
+    torch = pytest.importorskip("torch")
+    pc._load()
+    h = audio._handle()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    Ts = [400] * 40
+    spec = torch.rand((sum(Ts), 1025), device="cuda", generator=g)
+    flags = _lib.GL_DENORMALIZE | _lib.GL_DEEMPHASIS
+    n = sum(h.num_samples(t) for t in Ts)
+    ref = torch.empty(n, dtype=torch.float64, device="cuda")
+    s0 = torch.cuda.current_stream().cuda_stream
+    h.griffin_lim(spec, _lib.FRAME_MAJOR, Ts, ref, seed=1, iters=10, flags=flags, out_dtype=_lib.F64, space=_lib.DEVICE, stream=s0)
+    h.check_status(s0)
+    a, b = torch.cuda.Stream(), torch.cuda.Stream()
+    o1, o2 = torch.empty_like(ref), torch.empty_like(ref)
+    torch.cuda.synchronize()
+    h.griffin_lim(spec, _lib.FRAME_MAJOR, Ts, o1, seed=1, iters=10, flags=flags, out_dtype=_lib.F64, space=_lib.DEVICE, stream=a.cuda_stream)
+    h.griffin_lim(spec, _lib.FRAME_MAJOR, Ts, o2, seed=1, iters=10, flags=flags, out_dtype=_lib.F64, space=_lib.DEVICE, stream=b.cuda_stream)
+    host = np.empty(h.num_samples(50), np.float64)                      # and a synchronous HOST call right behind them
+    h.griffin_lim(np.random.RandomState(1).rand(50, 1025).astype(np.float32), _lib.FRAME_MAJOR, [50], host, seed=1, iters=2, flags=flags, out_dtype=_lib.F64)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, ref) and torch.equal(o2, ref) and np.isfinite(host).all()
