@@ -199,6 +199,121 @@ __device__ __forceinline__ float amp_to_db_norm(float amp, float ref_db, float m
     return fminf(fmaxf(v, 0.f), 1.f);
 }
 
+// a kernel parameter pinned in a register: ptxas otherwise re-reads it from the constant bank at every use (LDC / LDCU per bin
+// of the feature epilogue: 74 of its instructions per frame)
+__device__ __forceinline__ float pin_reg(float v) {
+#ifndef NSB_EMULATE
+    asm volatile("mov.f32 %0, %0;" : "+f"(v));
+#endif
+    return v;
+}
+
+// position of bin kb in the warp's magnitude row: one pad word per 32 bins.  The mel moment loop gives every lane its own
+// segment of consecutive bins; the segments of neighbouring lanes start 4, 8, ... bins apart (the low mel bands), i.e. lanes
+// 8 (or 4) apart would hit the same bank at every step - a quarter of the kernel's shared-memory wavefronts were such
+// conflicts (profiles/r1/ncu_full_k_analysis_features.txt).  With the pad they walk different banks.
+constexpr int kMagSkewLen = 1025 + 32 + 3;          // 1060 floats: skewed row, then the moments
+__device__ __forceinline__ int mag_skew(int kb) { return kb + (kb >> 5); }
+
+// Feature epilogue of one frame (registers of fwd_phase2 -> linear dB row, mel dB row).
+// Slot p of lane l >= 1 holds bin l + 64p (p < 16) or (64 - l) + 64(31 - p) (p >= 16): from a per-lane base every address of the
+// unrolled loops is an immediate offset (64 floats in the output row, 66 in the skewed magnitude row), stores are predicated
+// off for lane 0.  Lane 0's slots are the bins 32 j: it hands them over through shared memory and lane j finishes bin 32 j.
+// The linear dB comes from |D|^2 (10 log10 |D|^2 = 20 log10 |D|): the square root is only on the mel path and the two
+// MUFU operations of a bin no longer depend on each other.
+template <bool LIN>
+__device__ __forceinline__ void feature_epilogue(const AnalysisParams& P, c2 (&z)[32], int lane, float2* scratch, float* o_lin, float* o_mel,
+                                                 float db_scale, float db_off_lin, float db_off_mel, bool& bad) {
+    float* magrow = reinterpret_cast<float*>(scratch);
+    float* mom = magrow + kMagSkewLen;                             // [num_mels + 1][2] (the host checks that it fits the scratch tile)
+    float2* xch = reinterpret_cast<float2*>(magrow + kMagSkewLen + 2 * 96 + 4);   // lane 0's 32 slots (8-byte aligned: 1256 floats in)
+    const float half_scale = 0.5f * db_scale;
+    const bool main = lane != 0;
+    float* mr_lo = magrow + lane;                                  // bin l + 64p        -> skewed l + 66p
+    float* mr_hi = magrow + (66 * 32 - 1) - lane;                  // bin 2048 - l - 64p -> skewed 66(32 - p) - l - 1
+    float* ol_lo = o_lin + lane;
+    float* ol_hi = o_lin + 2048 - lane;
+    float chk = 0.f;
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) xch[q] = z[q];
+    }
+#pragma unroll
+    for (int p = 0; p < 32; ++p) {
+        const float m2 = fmaf(z[p].x, z[p].x, z[p].y * z[p].y);
+        if (main) {
+            chk += m2;
+            const float mg = sqrt_approx(m2);
+            if (p < 16) mr_lo[66 * p] = mg; else mr_hi[-66 * p] = mg;
+            if (LIN) {
+                const float v = __saturatef(fmaf(lg2_approx(fmaxf(1e-10f, m2)), half_scale, db_off_lin));
+                if (p < 16) ol_lo[64 * p] = v; else ol_hi[-64 * p] = v;
+            }
+        }
+    }
+    __syncwarp();
+    {
+        // bins 32 j from lane 0's slots: lane 0 itself takes the real pair (DC, Nyquist), lane j >= 1 the complex X[32 j]
+        const float2 v = xch[lane];
+        const float m2 = main ? fmaf(v.x, v.x, v.y * v.y) : v.x * v.x;
+        chk += m2;
+        const float mg = main ? sqrt_approx(m2) : fabsf(v.x);
+        magrow[33 * lane] = mg;
+        if (LIN) o_lin[32 * lane] = __saturatef(fmaf(lg2_approx(fmaxf(1e-10f, m2)), half_scale, db_off_lin));
+        if (!main) {
+            const float n2 = v.y * v.y;
+            chk += n2;
+            magrow[1024 + 32] = fabsf(v.y);
+            if (LIN) o_lin[1024] = __saturatef(fmaf(lg2_approx(fmaxf(1e-10f, n2)), half_scale, db_off_lin));
+        }
+    }
+    // non-finite input shows up in every bin of its frames: ONE test per frame and lane on the sum of the squared magnitudes
+    // (squares beyond 3e38, i.e. |D| > 1e19, also count as non-finite)
+    bad |= !isfinite(chk);
+    __syncwarp();
+    if (o_mel && P.plan.mel_seg) {
+        // mel[m] = sum_k W[m,k] |D[k]| with W[m,.] a triangle: per segment j two moments S0 = sum |D|, S1 = sum (end - k) |D|
+        // (every bin read ONCE, no weight loads), then every row is four multiply-adds of its two segments' moments.
+        // a1 = sum of the running sums = sum (k1 - k) |D[k]|: the first moment counted from the segment's END costs one add
+        // per bin; the host folds the change of origin into the coefficients.  The adds run in bin order whatever the unrolling.
+        const int M = P.plan.num_mels;
+        for (int j = lane; j <= M; j += 32) {
+            const int k0 = __ldg(P.plan.mel_seg + j), k1 = __ldg(P.plan.mel_seg + j + 1);
+            float a0 = 0.f, a1 = 0.f;
+            int kb = k0;
+            const float* q = magrow + mag_skew(k0);
+            while (kb < k1) {
+                const int e = min(k1, (kb | 31) + 1);              // end of this run of consecutive words (a pad word follows bin 32i + 31)
+                int n = e - kb;
+                for (; n >= 4; n -= 4, q += 4) {
+                    a0 += q[0]; a1 += a0; a0 += q[1]; a1 += a0; a0 += q[2]; a1 += a0; a0 += q[3]; a1 += a0;
+                }
+                for (; n > 0; --n, ++q) { a0 += q[0]; a1 += a0; }
+                kb = e;
+                ++q;
+            }
+            mom[2 * j] = a0; mom[2 * j + 1] = a1;
+        }
+        __syncwarp();
+        for (int m = lane; m < M; m += 32) {
+            const float4 c = __ldg(P.plan.mel_coef + m);
+            const float2 r = *reinterpret_cast<const float2*>(mom + 2 * m), f = *reinterpret_cast<const float2*>(mom + 2 * m + 2);
+            float acc = c.x * r.x;
+            acc = fmaf(c.y, r.y, acc); acc = fmaf(c.z, f.x, acc); acc = fmaf(c.w, f.y, acc);
+            o_mel[m] = amp_to_db_norm_fast(fmaxf(acc, 0.f), db_scale, db_off_mel);   // melspectrogram subtracts no ref_level_db (audio.py:63)
+        }
+    } else if (o_mel) {
+        for (int m = lane; m < P.plan.num_mels; m += 32) {
+            const int lo = __ldg(P.plan.mel_lo + m), n = __ldg(P.plan.mel_n + m);
+            const float* w = P.plan.mel_w + __ldg(P.plan.mel_ptr + m);
+            float acc = 0.f;
+            for (int i = 0; i < n; ++i) acc = fmaf(__ldg(w + i), magrow[mag_skew(lo + i)], acc);
+            o_mel[m] = amp_to_db_norm_fast(acc, db_scale, db_off_mel);   // melspectrogram subtracts no ref_level_db (audio.py:63)
+        }
+    }
+    __syncwarp();
+}
+
 template <int MODE, bool PREEMPH, int PRUNE>
 __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
     NSB_DYN_SMEM(smem_raw);
@@ -215,6 +330,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
     float2* scratch = scratch_all + warp * kScratchF2;
     const int hop = P.plan.hop;
     bool bad = false;
+    const float db_scale = pin_reg(P.db_scale), db_off_lin = pin_reg(P.db_offset_lin), db_off_mel = pin_reg(P.db_offset_mel);
     // every CTA takes one contiguous block of frames (its 8 warps side by side on 8 consecutive frames, which share three
     // quarters of their samples in L1): the utterance index then only creeps forward.  With the frames dealt round-robin over
     // the grid every step landed in another utterance and paid a binary search of dependent loads (10 % of the stall samples).
@@ -251,71 +367,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
         } else {
             const long long orow = P.batch.row_off ? __ldg(P.batch.row_off + b) + k
                                  : P.rows_per_utt > 0 ? (long long)(P.batch.utt_base + b) * P.rows_per_utt + k : (long long)f;
-            // magnitudes -> scratch (as floats, 1025 <= 2112), then linear dB and sparse mel
-            // The linear feature goes out straight from the registers: slot p of lanes 1..31 holds 31 consecutive bins
-            // (bin_of), so the stores coalesce without a trip through shared memory; only the mel projection needs the
-            // magnitudes in bin order.  Non-finite input shows up in every bin of its frames: ONE test per frame on the sum
-            // of the squared magnitudes (squares beyond 3e38, i.e. |D| > 1e19, also count as non-finite).
-            float* magrow = reinterpret_cast<float*>(scratch);
             float* o_lin = P.out_lin ? P.out_lin + (size_t)orow * kBins : nullptr;
-            float chk = 0.f;
-#pragma unroll
-            for (int p = 0; p < 32; ++p) {
-                if (lane == 0 && p == 0) {
-                    const float m0 = fabsf(z[0].x), m1 = fabsf(z[0].y);
-                    chk += m0 + m1;
-                    magrow[0] = m0;
-                    magrow[1024] = m1;
-                    if (o_lin) {
-                        o_lin[0] = amp_to_db_norm_fast(m0, P.db_scale, P.db_offset_lin);
-                        o_lin[1024] = amp_to_db_norm_fast(m1, P.db_scale, P.db_offset_lin);
-                    }
-                } else {
-                    const float m2 = fmaf(z[p].x, z[p].x, z[p].y * z[p].y);
-                    chk += m2;
-                    const float mg = sqrt_approx(m2);
-                    const int kb = bin_of(lane, p);
-                    magrow[kb] = mg;
-                    if (o_lin) o_lin[kb] = amp_to_db_norm_fast(mg, P.db_scale, P.db_offset_lin);
-                }
-            }
-            bad |= !isfinite(chk);
-            __syncwarp();
-            if (P.out_mel && P.plan.mel_seg) {
-                // mel[m] = sum_k W[m,k] |D[k]| with W[m,.] a triangle: per segment j two moments S0 = sum |D|, S1 = sum (end - k) |D|
-                // (every bin read ONCE, no weight loads: 68 dependent steps per lane instead of 135 with two loads each), then
-                // every row is four multiply-adds of its two segments' moments
-                float* o = P.out_mel + (size_t)orow * P.plan.num_mels;
-                float* mom = magrow + 1028;                       // [num_mels + 1][2] (the host checks that it fits the scratch tile)
-                const int M = P.plan.num_mels;
-                for (int j = lane; j <= M; j += 32) {
-                    const int k0 = __ldg(P.plan.mel_seg + j), k1 = __ldg(P.plan.mel_seg + j + 1);
-                    // a1 = sum of the running sums = sum (k1 - k) |D[k]|: the first moment counted from the segment's END costs one
-                    // add per bin instead of a multiply-add and an index increment; the host folds the change of origin into c
-                    float a0 = 0.f, a1 = 0.f;
-                    for (int kb = k0; kb < k1; ++kb) { a0 += magrow[kb]; a1 += a0; }
-                    mom[2 * j] = a0; mom[2 * j + 1] = a1;
-                }
-                __syncwarp();
-                for (int m = lane; m < M; m += 32) {
-                    const float4 c = __ldg(P.plan.mel_coef + m);
-                    const float2 r = *reinterpret_cast<const float2*>(mom + 2 * m), f = *reinterpret_cast<const float2*>(mom + 2 * m + 2);
-                    float acc = c.x * r.x;
-                    acc = fmaf(c.y, r.y, acc); acc = fmaf(c.z, f.x, acc); acc = fmaf(c.w, f.y, acc);
-                    o[m] = amp_to_db_norm_fast(fmaxf(acc, 0.f), P.db_scale, P.db_offset_mel);   // melspectrogram subtracts no ref_level_db (audio.py:63)
-                }
-            } else if (P.out_mel) {
-                float* o = P.out_mel + (size_t)orow * P.plan.num_mels;
-                for (int m = lane; m < P.plan.num_mels; m += 32) {
-                    const int lo = __ldg(P.plan.mel_lo + m), n = __ldg(P.plan.mel_n + m);
-                    const float* w = P.plan.mel_w + __ldg(P.plan.mel_ptr + m);
-                    float acc = 0.f;
-                    // (#pragma unroll 4 here: 173 -> 160 M frames/s, rejected)
-                    for (int i = 0; i < n; ++i) acc = fmaf(__ldg(w + i), magrow[lo + i], acc);
-                    o[m] = amp_to_db_norm_fast(acc, P.db_scale, P.db_offset_mel);   // melspectrogram subtracts no ref_level_db (audio.py:63)
-                }
-            }
-            __syncwarp();
+            float* o_mel = P.out_mel ? P.out_mel + (size_t)orow * P.plan.num_mels : nullptr;
+            if (o_lin) feature_epilogue<true>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad);
+            else feature_epilogue<false>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad);
         }
     }
     if (bad) atomicOr(P.status, 1);

@@ -392,8 +392,8 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
         CUB(cudaMalloc(&h->d_mel_ptr, sizeof(int) * ptr.size()));
         CUB(cudaMemcpy(h->d_mel_ptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice));
         std::vector<int> seg; std::vector<float> coef;
-        // (the two moments per segment live behind the magnitude row in the warp's scratch tile: 1028 + 2 (M + 1) <= 2 kScratchF2 floats)
-        if (!h->generic && 1028 + 2 * (hp->num_mels + 1) <= 2 * kScratchF2 && build_mel_lines(hp->sample_rate, n_fft, hp->num_mels, h->mel_dense, seg, coef)) {
+        // (the two moments per segment live behind the skewed magnitude row in the warp's scratch tile, room for 95 mel bands; lane 0's exchange area after them)
+        if (!h->generic && hp->num_mels <= 95 && build_mel_lines(hp->sample_rate, n_fft, hp->num_mels, h->mel_dense, seg, coef)) {
             CUB(cudaMalloc(&h->d_mel_seg, sizeof(int) * seg.size()));
             CUB(cudaMemcpy(h->d_mel_seg, seg.data(), sizeof(int) * seg.size(), cudaMemcpyHostToDevice));
             CUB(cudaMalloc(&h->d_mel_coef, sizeof(float) * coef.size()));

@@ -99,6 +99,7 @@ static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+static inline float __saturatef(float x) { return fminf(fmaxf(x, 0.f), 1.f); }
 static inline void sincospif(float x, float* s, float* c) { *s = (float)std::sin(M_PI * (double)x); *c = (float)std::cos(M_PI * (double)x); }
 using std::isfinite;
 using std::min;

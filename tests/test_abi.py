@@ -35,7 +35,7 @@ def test_header_symbols_are_exported_and_bound(built_lib):
     for s in syms:
         assert hasattr(built_lib.dll, s), "not exported: " + s
     assert sorted(_lib.SIGNATURES) == syms
-    assert built_lib.dll.nsb_abi_version() == 1
+    assert built_lib.dll.nsb_abi_version() == 2
 
 
 def test_no_device_is_an_error_not_a_fallback(built_lib):
