@@ -45,6 +45,9 @@ FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_gl_iter launch, from the committed ncu --set full capture
 NCU_TRAFFIC_BYTES_PER_LAUNCH = 20.580e9 + 3.885e9
 NCU_TRAFFIC_SOURCE = "profiles/r1/ncu_full_k_gl_stream_fused60.txt (dram__bytes_read.sum + dram__bytes_write.sum of one 60-iteration launch)"
+# the feature kernel: DRAM bytes per frame of one k_analysis<FEATURES> launch (268,734 frames) from the committed ncu --set full capture
+NCU_FEATURES_TRAFFIC_BYTES_PER_FRAME = (270.27e6 + 1130.87e6) / 268734
+NCU_FEATURES_TRAFFIC_SOURCE = "profiles/r2/ncu_full_k_analysis_features.txt (dram__bytes_read.sum + dram__bytes_write.sum per frame of a 268,734-frame launch, scaled to this launch's frames)"
 
 
 def oracle_hp():
@@ -184,7 +187,64 @@ def workload_config():
                         "(12.5 s each) per GPU, default hparams" % (ITERS, N_UTT, N_FRAMES),
             "batch_per_gpu": N_UTT, "frames": N_FRAMES, "num_freq": N_BINS, "n_fft": 2048, "hop": HOP, "win": 1000,
             "griffin_lim_iters": ITERS, "sharding": "by utterance, no collective",
+            "reference_arm_sample": "the CPU arm times one 12.5 s utterance per host core (a bounded sample of the same workload); the rate is per audio second either way",
             "l2": "working set per step (270 MB magnitudes + 128 MB waveforms) exceeds the 126 MB L2"}
+
+
+def _features_cpu_one(args):
+    """spectrogram + melspectrogram of one clip through the oracle, as datasets/process.py:30,33 does (worker process)"""
+    seed, n = args
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[k] = "1"
+    from oracle import audio_oracle as ao
+    hp = oracle_hp()
+    rs = np.random.RandomState(seed)
+    wav = (0.3 * rs.standard_normal(n)).astype(np.float32)
+    t0 = time.perf_counter()
+    lin = ao.spectrogram(wav, hp)
+    ao.melspectrogram(wav, hp)
+    return time.perf_counter() - t0, lin.shape[1]
+
+
+def features_cpu_baseline(clips_per_core=3, cores=None):
+    from concurrent.futures import ProcessPoolExecutor
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    rs = np.random.default_rng(1234)
+    durs = np.clip(rs.normal(6.57, 2.19, size=cores * clips_per_core), 1.0, 10.0)
+    jobs = [(2000 + i, int(d * SR)) for i, d in enumerate(durs)]
+    t0 = time.perf_counter()
+    with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("spawn")) as ex:
+        res = list(ex.map(_features_cpu_one, jobs, chunksize=clips_per_core))
+    wall = time.perf_counter() - t0
+    busy = max(sum(t for t, _ in res[c * clips_per_core:(c + 1) * clips_per_core]) for c in range(cores))
+    frames = sum(n for _, n in res)
+    return frames / busy, cores, "%d clips (%d per core, durations clip(N(6.57,2.19),1,10) s), spectrogram + melspectrogram per clip as datasets/process.py:30,33, numpy oracle; busiest worker %.1f s, wall incl. spawn %.1f s" % (
+        len(jobs), clips_per_core, busy, wall)
+
+
+def speechlike_corpus(torch, dev, n_clips, seed=1234):
+    """BASELINE config 2: n_clips at 20 kHz, durations clip(N(6.57, 2.19), 1, 10) s from default_rng(seed); content = harmonic
+    stack (f0 100-250 Hz, 30 harmonics 1/k, 3 Hz amplitude modulation) + white noise at -50 dB, peak 0.9.  Synthesised on the GPU
+    (there is no dataset offline); returns (device float32 samples packed back to back, lengths)."""
+    rs = np.random.default_rng(seed)
+    durs = np.clip(rs.normal(6.57, 2.19, size=n_clips), 1.0, 10.0)
+    ns = [int(d * SR) for d in durs]
+    f0 = torch.from_numpy(rs.uniform(100.0, 250.0, size=n_clips)).to(dev, torch.float32)
+    lens = torch.tensor(ns, device=dev)
+    clip_of = torch.repeat_interleave(torch.arange(n_clips, device=dev), lens)
+    starts = torch.cumsum(lens, 0) - lens
+    t = (torch.arange(int(lens.sum()), device=dev) - starts[clip_of]).to(torch.float32) / SR
+    w = 2 * np.pi * f0[clip_of] * t
+    x = torch.zeros_like(t)
+    for k in range(1, 31):
+        x += torch.sin(k * w + 0.7 * k) / k
+    x *= 0.6 + 0.4 * torch.sin(2 * np.pi * 3 * t)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    x += 10 ** (-50 / 20) * torch.randn(x.shape, device=dev, generator=g)
+    peak = torch.zeros(n_clips, device=dev).scatter_reduce(0, clip_of, x.abs(), reduce="amax")
+    x *= 0.9 / peak[clip_of]
+    return x.contiguous(), ns
 
 
 def main():
@@ -195,6 +255,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-features", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -240,13 +301,26 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- synthetic inputs: pinned host copy for the e2e leg, device copy for the kernel-only leg ----
+    def ev_ms(fn, reps, warm=1):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    # ---- synthetic inputs: pinned host copies for the e2e legs, device copy for the kernel-only leg ----
     gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
-    pin_in = _lib.PinnedArray((N_UTT, N_FRAMES, N_BINS), np.float32)
-    pin_in.array[...] = torch.rand((N_UTT, N_FRAMES, N_BINS), generator=gen, dtype=torch.float32).numpy()
+    pin_in = [_lib.PinnedArray((N_UTT, N_FRAMES, N_BINS), np.float32) for _ in range(2)]      # two batches alternate (two in flight)
+    for p_ in pin_in:
+        p_.array[...] = torch.rand((N_UTT, N_FRAMES, N_BINS), generator=gen, dtype=torch.float32).numpy()
     n_samp = HOP * (N_FRAMES - 1)
     pin_out = _lib.PinnedArray((N_UTT * n_samp,), np.float64)
-    d_spec = torch.from_numpy(pin_in.array).to(dev)
+    d_spec = torch.from_numpy(pin_in[0].array).to(dev)
     d_out = torch.empty(N_UTT * n_samp, dtype=torch.float64, device=dev)
     Ts = [N_FRAMES] * N_UTT
     flags = _lib.GL_DENORMALIZE | _lib.GL_DEEMPHASIS
@@ -255,9 +329,6 @@ def main():
     def step_device(seed):
         h.griffin_lim(d_spec, _lib.FRAME_MAJOR, Ts, d_out, init_phase=None, seed=seed, iters=ITERS, flags=flags,
                       out_dtype=_lib.F64, space=_lib.DEVICE, stream=st)
-
-    def step_host(seed):
-        batch.inv_spectrogram_batch(pin_in.array, seed=seed, iters=ITERS, out=pin_out.array)
 
     # ---- kernel-only (device-resident) ----
     for i in range(args.warmup):
@@ -280,7 +351,7 @@ def main():
     barrier()
     h.check_status(st)
 
-    # ---- the dominant kernel alone: one launch of k_gl_iter = all ITERS Griffin-Lim iterations over the batch ----
+    # ---- the dominant kernel alone: one launch of k_gl_stream = all ITERS Griffin-Lim iterations over the batch ----
     n_launch = 3
     h.griffin_lim_iterate(ITERS, st)
     torch.cuda.synchronize()
@@ -298,55 +369,117 @@ def main():
     achieved_gbs = frames * BYTES_PER_FRAME_ITER / (ms_iter * 1e-3) / 1e9
     achieved_tflops = frames * FLOPS_PER_FRAME_ITER / (ms_iter * 1e-3) / 1e12
 
-    # ---- end to end through the public API on pinned host buffers ----
-    for i in range(max(1, args.warmup // 2)):
-        step_host(i)
-    barrier()
+    # ---- end to end through the public API on host buffers: every step copies its batch in and its waveforms out ----
+    # headline: batch.inv_spectrogram_stream (nsb_griffin_lim_submit / nsb_wait, two batches in flight, results in pooled page-locked
+    # memory); beside it the synchronous call (round 1's e2e) and the same stream fed from PAGEABLE numpy arrays
+    def e2e_stream(n_steps, inputs, seed0):
+        got = 0
+        for outs in batch.inv_spectrogram_stream((inputs[i % len(inputs)] for i in range(n_steps)), seed=seed0, iters=ITERS):
+            got += len(outs)
+            last = outs[-1]
+        assert got == n_steps * N_UTT and np.isfinite(last[:1000]).all()
+
+    def wall_ms(fn):
+        barrier()
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        return max_over_ranks((time.perf_counter() - t0) * 1e3)
+
+    pinned_inputs = [p_.array for p_ in pin_in]
+    e2e_stream(max(2, args.warmup // 2 + 1), pinned_inputs, 0)
     sampler.mark()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step_host(200 + i)
-    torch.cuda.synchronize()
-    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    ms_e2e = wall_ms(lambda: e2e_stream(args.steps, pinned_inputs, 200))
     sampler.mark()
     clocks = sampler.stop()
-    barrier()
-    assert np.isfinite(pin_out.array[:1000]).all()
 
-    # ---- secondary metric: feature extraction (mel frames/s), BASELINE config 2 sample ----
+    def sync_steps(n):
+        for i in range(n):
+            batch.inv_spectrogram_batch(pin_in[0].array, seed=300 + i, iters=ITERS, out=pin_out.array)
+    sync_steps(1)
+    ms_e2e_sync = wall_ms(lambda: sync_steps(args.steps))
+    pageable_inputs = [np.array(p_.array) for p_ in pin_in]          # plain numpy memory, what a drop-in caller holds
+    n_pg = max(2, args.steps // 2)
+    e2e_stream(2, pageable_inputs, 0)
+    ms_e2e_pageable = wall_ms(lambda: e2e_stream(n_pg, pageable_inputs, 400)) * args.steps / n_pg
+    barrier()
+
     extra = {}
+    # ---- second BASELINE metric: mel frames/s of spectrogram + melspectrogram, BASELINE config 2 (13,100 LJSpeech-shaped clips) ----
     if not args.no_features:
-        rs = np.random.RandomState(1234)
-        durs = np.clip(rs.normal(6.57, 2.19, size=512), 1.0, 10.0)
-        ns = [int(d * SR) for d in durs]
-        wav_host = _lib.PinnedArray((sum(ns),), np.float32)
-        wav_host.array[...] = (0.3 * rs.standard_normal(sum(ns))).astype(np.float32)
+        d_wav, ns = speechlike_corpus(torch, dev, 13100)
         Tn = [h.num_frames(n) for n in ns]
-        d_wav = torch.from_numpy(wav_host.array).to(dev)
-        d_lin = torch.empty((sum(Tn), N_BINS), dtype=torch.float32, device=dev)
-        d_mel = torch.empty((sum(Tn), 80), dtype=torch.float32, device=dev)
-        for _ in range(3):
-            h.features(d_wav, ns, d_lin, d_mel, space=_lib.DEVICE, stream=st)
-        torch.cuda.synchronize()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(10):
-            h.features(d_wav, ns, d_lin, d_mel, space=_lib.DEVICE, stream=st)
-        f1.record()
-        torch.cuda.synchronize()
-        ms_feat = f0.elapsed_time(f1) / 10
-        lin_h = _lib.PinnedArray((sum(Tn), N_BINS), np.float32)
-        mel_h = _lib.PinnedArray((sum(Tn), 80), np.float32)
-        h.features(wav_host.array, ns, lin_h.array, mel_h.array)
+        n_fr = sum(Tn)
+        d_lin = torch.empty((n_fr, N_BINS), dtype=torch.float32, device=dev)
+        d_mel = torch.empty((n_fr, 80), dtype=torch.float32, device=dev)
+        ms_feat = max_over_ranks(ev_ms(lambda: h.features(d_wav, ns, d_lin, d_mel, space=_lib.DEVICE, stream=st), 5, warm=2))
+        h.check_status(st)
+        assert 0.0 < float(d_mel[:1000].mean()) <= 1.0
+        del d_lin, d_mel
+        # end to end from host memory on a bounded sample (every 8th clip: the full corpus would need 30 GB of page-locked results)
+        sub = list(range(0, 13100, 8))
+        offs = np.concatenate([[0], np.cumsum(ns)])
+        sub_wavs = [d_wav[offs[i]:offs[i + 1]].cpu().numpy() for i in sub]
+        sub_frames = sum(Tn[i] for i in sub)
+        batch.features_batch(sub_wavs[:64])
+        t0 = time.perf_counter()
+        feats = batch.features_batch(sub_wavs)
+        ms_feat_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        in_bytes, out_bytes = 4 * sum(len(w) for w in sub_wavs), 4 * sub_frames * (N_BINS + 80)
+        del feats, d_wav
+        feat_bytes = 4 * HOP + 4 * N_BINS + 4 * 80
+        extra["features"] = {
+            "metric": "mel_frames_per_sec", "unit": "mel frames/s", "value": world * n_fr / (ms_feat * 1e-3), "ms_per_pass": ms_feat,
+            "workload": "BASELINE config 2: spectrogram + melspectrogram (one pass) over 13,100 synthetic LJSpeech-shaped clips per GPU "
+                        "(durations clip(N(6.57,2.19),1,10) s from default_rng(1234), speech-like harmonic stack + noise), device-resident",
+            "frames": n_fr, "audio_hours": sum(ns) / SR / 3600.0,
+            "roofline": {"bound": "hbm", "kernel": "k_analysis<FEATURES>", "achieved": n_fr * feat_bytes / (ms_feat * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": n_fr * feat_bytes / (ms_feat * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         "algorithmic_bytes_per_frame": feat_bytes, "traffic": NCU_FEATURES_TRAFFIC_BYTES_PER_FRAME * n_fr,
+                         "traffic_source": NCU_FEATURES_TRAFFIC_SOURCE},
+            "e2e": {"value": world * sub_frames / (ms_feat_e2e * 1e-3), "unit": "mel frames/s", "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(out_bytes),
+                    "sample": "every 8th clip of the corpus (%d clips, %d frames) through batch.features_batch from numpy arrays, results in pooled page-locked memory" % (len(sub), sub_frames)}}
+        if rank == 0 and not args.no_cpu_baseline and world == 1:
+            v, cores, sample = features_cpu_baseline()
+            extra["features"]["cpu_baseline"] = {"value": v, "unit": "mel frames/s", "cores": cores, "kind": "port", "sample": sample}
+
+    # ---- the other BASELINE configurations, driver-run: config 1 (latency), config 4 (synthesis stage at batch 32), config 5 (sweep) ----
+    if not args.no_configs:
+        cfgs = {}
+        S1 = np.random.default_rng(0).random((N_BINS, 401)).astype(np.float32)
+        ang = np.exp(2j * np.pi * np.random.default_rng(0).random((N_BINS, 401))).astype(np.complex64)
+        audio.inv_spectrogram(S1, init_phase=ang)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            audio.inv_spectrogram(S1, init_phase=ang)
+        lat = (time.perf_counter() - t0) / 5 * 1e3
+        dS, dA = torch.from_numpy(S1).to(dev), torch.from_numpy(ang).to(dev)
+        lat_dev = ev_ms(lambda: audio.inv_spectrogram(dS, init_phase=dA), 5)
+        cfgs["config1_single_5s_utterance"] = {"latency_ms_host_numpy": lat, "latency_ms_device_arrays": lat_dev, "audio_s_per_s_host_numpy": 5.0 / (lat * 1e-3),
+                                               "what": "audio.inv_spectrogram on one [1025,401] spectrogram, 60 iterations, supplied initial phase"}
+        lin4 = _lib.PinnedArray((32, 1500, N_BINS), np.float32)
+        lin4.array[...] = torch.rand((32, 1500, N_BINS), generator=gen, dtype=torch.float32).numpy()
+        audio.synthesize_waveforms(lin4.array)
         t0 = time.perf_counter()
         for _ in range(3):
-            h.features(wav_host.array, ns, lin_h.array, mel_h.array)
-        ms_feat_e2e = (time.perf_counter() - t0) * 1e3 / 3
-        extra["features"] = {
-            "workload": "BASELINE config 2 sample: 512 clips, durations clip(N(6.57,2.19),1,10) s, spectrogram+melspectrogram in one pass",
-            "mel_frames_per_s_device": sum(Tn) / (ms_feat * 1e-3), "mel_frames_per_s_e2e": sum(Tn) / (ms_feat_e2e * 1e-3),
-            "frames": sum(Tn), "hbm_gbs_algorithmic": sum(Tn) * (4 * HOP + 4 * N_BINS + 4 * 80) / (ms_feat * 1e-3) / 1e9,
-            "hbm_frac": sum(Tn) * (4 * HOP + 4 * N_BINS + 4 * 80) / (ms_feat * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+            w4 = audio.synthesize_waveforms(lin4.array, peak_normalize=True, dtype=np.int16)
+        ms4 = max_over_ranks((time.perf_counter() - t0) / 3 * 1e3)
+        cfgs["config4_synthesis_stage_batch32"] = {"ms_per_batch": ms4, "audio_s_per_s": world * 32 * (HOP * 1499 + 1000) / SR / (ms4 * 1e-3),
+                                                   "what": "audio.synthesize_waveforms on [32,1500,1025] from host memory: TF-twin Griffin-Lim (60 iterations) + de-emphasis + "
+                                                           "find_endpoint + save_wav scaling to int16, the stage after the network in synthesizer.py:51-53 / eval.py:43"}
+        del w4, lin4
+        sweep = []
+        for nb in (8, 64, 256, 1024):
+            spec5 = torch.rand((nb * N_FRAMES, N_BINS), device=dev)
+            out5 = torch.empty(nb * n_samp, dtype=torch.float64, device=dev)
+            for it in (60, 100):
+                ms5 = max_over_ranks(ev_ms(lambda: h.griffin_lim(spec5, _lib.FRAME_MAJOR, [N_FRAMES] * nb, out5, seed=1, iters=it, flags=flags, out_dtype=_lib.F64,
+                                                                 space=_lib.DEVICE, stream=st), 2 if nb >= 256 else 5))
+                sweep.append({"batch_per_gpu": nb, "iters": it, "ms": ms5, "audio_s_per_s": world * nb * n_samp / SR / (ms5 * 1e-3)})
+            h.check_status(st)
+            del spec5, out5
+        cfgs["config5_sweep_device_resident"] = {"gpus": world, "frames_per_utterance": N_FRAMES, "points": sweep}
+        extra["configs"] = cfgs
 
     value = world * audio_s_per_step * args.steps / (ms_dev * 1e-3)
     e2e_value = world * audio_s_per_step * args.steps / (ms_e2e * 1e-3)
@@ -354,9 +487,15 @@ def main():
         "metric": "griffin_lim_audio_sec_per_sec", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(), host_binding=("rank 0 pinned to its GPU's %d NUMA-local CPUs" % len(host_cpus)) if host_cpus else "none"),
-        "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(pin_in.array.nbytes),
-                "d2h_bytes_per_step": int(pin_out.array.nbytes), "ms_per_step": ms_e2e / args.steps},
+        "config": workload_config(),
+        "host_binding": ("every rank pinned to its GPU's %d NUMA-local CPUs" % len(host_cpus)) if host_cpus else "none",
+        "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(pin_in[0].array.nbytes),
+                "d2h_bytes_per_step": int(pin_out.array.nbytes), "ms_per_step": ms_e2e / args.steps,
+                "api": "nspeech_b200.batch.inv_spectrogram_stream (nsb_griffin_lim_submit / nsb_wait, two batches in flight), page-locked input arrays, results in pooled page-locked memory"},
+        "e2e_sync": {"value": world * audio_s_per_step * args.steps / (ms_e2e_sync * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e_sync / args.steps,
+                     "api": "nspeech_b200.batch.inv_spectrogram_batch, one synchronous call per step (round 1's e2e)"},
+        "e2e_pageable": {"value": world * audio_s_per_step * args.steps / (ms_e2e_pageable * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e_pageable / args.steps,
+                         "api": "the same stream fed from pageable numpy arrays (what a drop-in caller holds)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_gl_stream (one launch = all %d Griffin-Lim iterations over the batch)" % ITERS,
                      "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"],

@@ -160,6 +160,7 @@ struct AnalysisParams {
     // _normalize(_amp_to_db(amp) - ref) = clip(log2(max(1e-5, amp)) * db_scale + db_offset, 0, 1) with
     // db_scale = 20 log10(2) / (-min_level_db), db_offset = (-ref - min_level_db) / (-min_level_db) (host, from double)
     float db_scale, db_offset_lin, db_offset_mel;
+    int mel_skew;          // 1: magnitude row with a pad word per 32 bins (A/B: NSB_OPT_MEL_LINES 2)
     int* status;           // device flag: bit0 = non-finite input
 };
 
@@ -213,7 +214,7 @@ __device__ __forceinline__ float pin_reg(float v) {
 // 8 (or 4) apart would hit the same bank at every step - a quarter of the kernel's shared-memory wavefronts were such
 // conflicts (profiles/r1/ncu_full_k_analysis_features.txt).  With the pad they walk different banks.
 constexpr int kMagSkewLen = 1025 + 32 + 3;          // 1060 floats: skewed row, then the moments
-__device__ __forceinline__ int mag_skew(int kb) { return kb + (kb >> 5); }
+template <bool SKEW> __device__ __forceinline__ int mag_skew(int kb) { return SKEW ? kb + (kb >> 5) : kb; }
 
 // Feature epilogue of one frame (registers of fwd_phase2 -> linear dB row, mel dB row).
 // Slot p of lane l >= 1 holds bin l + 64p (p < 16) or (64 - l) + 64(31 - p) (p >= 16): from a per-lane base every address of the
@@ -221,7 +222,7 @@ __device__ __forceinline__ int mag_skew(int kb) { return kb + (kb >> 5); }
 // off for lane 0.  Lane 0's slots are the bins 32 j: it hands them over through shared memory and lane j finishes bin 32 j.
 // The linear dB comes from |D|^2 (10 log10 |D|^2 = 20 log10 |D|): the square root is only on the mel path and the two
 // MUFU operations of a bin no longer depend on each other.
-template <bool LIN>
+template <bool LIN, bool SKEW>
 __device__ __forceinline__ void feature_epilogue(const AnalysisParams& P, c2 (&z)[32], int lane, float2* scratch, float* o_lin, float* o_mel,
                                                  float db_scale, float db_off_lin, float db_off_mel, bool& bad) {
     float* magrow = reinterpret_cast<float*>(scratch);
@@ -229,8 +230,9 @@ __device__ __forceinline__ void feature_epilogue(const AnalysisParams& P, c2 (&z
     float2* xch = reinterpret_cast<float2*>(magrow + kMagSkewLen + 2 * 96 + 4);   // lane 0's 32 slots (8-byte aligned: 1256 floats in)
     const float half_scale = 0.5f * db_scale;
     const bool main = lane != 0;
+    constexpr int MS = SKEW ? 66 : 64;                             // stride of the magnitude row per slot
     float* mr_lo = magrow + lane;                                  // bin l + 64p        -> skewed l + 66p
-    float* mr_hi = magrow + (66 * 32 - 1) - lane;                  // bin 2048 - l - 64p -> skewed 66(32 - p) - l - 1
+    float* mr_hi = magrow + (SKEW ? (66 * 32 - 1) : 2048) - lane;  // bin 2048 - l - 64p -> skewed 66(32 - p) - l - 1
     float* ol_lo = o_lin + lane;
     float* ol_hi = o_lin + 2048 - lane;
     float chk = 0.f;
@@ -244,7 +246,7 @@ __device__ __forceinline__ void feature_epilogue(const AnalysisParams& P, c2 (&z
         if (main) {
             chk += m2;
             const float mg = sqrt_approx(m2);
-            if (p < 16) mr_lo[66 * p] = mg; else mr_hi[-66 * p] = mg;
+            if (p < 16) mr_lo[MS * p] = mg; else mr_hi[-MS * p] = mg;
             if (LIN) {
                 const float v = __saturatef(fmaf(lg2_approx(fmaxf(1e-10f, m2)), half_scale, db_off_lin));
                 if (p < 16) ol_lo[64 * p] = v; else ol_hi[-64 * p] = v;
@@ -258,12 +260,12 @@ __device__ __forceinline__ void feature_epilogue(const AnalysisParams& P, c2 (&z
         const float m2 = main ? fmaf(v.x, v.x, v.y * v.y) : v.x * v.x;
         chk += m2;
         const float mg = main ? sqrt_approx(m2) : fabsf(v.x);
-        magrow[33 * lane] = mg;
+        magrow[(SKEW ? 33 : 32) * lane] = mg;
         if (LIN) o_lin[32 * lane] = __saturatef(fmaf(lg2_approx(fmaxf(1e-10f, m2)), half_scale, db_off_lin));
         if (!main) {
             const float n2 = v.y * v.y;
             chk += n2;
-            magrow[1024 + 32] = fabsf(v.y);
+            magrow[1024 + (SKEW ? 32 : 0)] = fabsf(v.y);
             if (LIN) o_lin[1024] = __saturatef(fmaf(lg2_approx(fmaxf(1e-10f, n2)), half_scale, db_off_lin));
         }
     }
@@ -280,17 +282,17 @@ __device__ __forceinline__ void feature_epilogue(const AnalysisParams& P, c2 (&z
         for (int j = lane; j <= M; j += 32) {
             const int k0 = __ldg(P.plan.mel_seg + j), k1 = __ldg(P.plan.mel_seg + j + 1);
             float a0 = 0.f, a1 = 0.f;
-            int kb = k0;
-            const float* q = magrow + mag_skew(k0);
-            while (kb < k1) {
-                const int e = min(k1, (kb | 31) + 1);              // end of this run of consecutive words (a pad word follows bin 32i + 31)
-                int n = e - kb;
-                for (; n >= 4; n -= 4, q += 4) {
-                    a0 += q[0]; a1 += a0; a0 += q[1]; a1 += a0; a0 += q[2]; a1 += a0; a0 += q[3]; a1 += a0;
-                }
-                for (; n > 0; --n, ++q) { a0 += q[0]; a1 += a0; }
-                kb = e;
-                ++q;
+            // four bins per trip: the loads do not depend on the running sums, so four of them are in flight together (one load
+            // and its two dependent adds per trip made this loop a 35-cycle latency chain per bin); the tail is predicated, not branched
+            for (int kb = k0; kb < k1; kb += 4) {
+                const float v0 = magrow[mag_skew<SKEW>(kb)];
+                const float v1 = kb + 1 < k1 ? magrow[mag_skew<SKEW>(kb + 1)] : 0.f;
+                const float v2 = kb + 2 < k1 ? magrow[mag_skew<SKEW>(kb + 2)] : 0.f;
+                const float v3 = kb + 3 < k1 ? magrow[mag_skew<SKEW>(kb + 3)] : 0.f;
+                a0 += v0; a1 += a0;
+                if (kb + 1 < k1) { a0 += v1; a1 += a0; }
+                if (kb + 2 < k1) { a0 += v2; a1 += a0; }
+                if (kb + 3 < k1) { a0 += v3; a1 += a0; }
             }
             mom[2 * j] = a0; mom[2 * j + 1] = a1;
         }
@@ -307,7 +309,7 @@ __device__ __forceinline__ void feature_epilogue(const AnalysisParams& P, c2 (&z
             const int lo = __ldg(P.plan.mel_lo + m), n = __ldg(P.plan.mel_n + m);
             const float* w = P.plan.mel_w + __ldg(P.plan.mel_ptr + m);
             float acc = 0.f;
-            for (int i = 0; i < n; ++i) acc = fmaf(__ldg(w + i), magrow[mag_skew(lo + i)], acc);
+            for (int i = 0; i < n; ++i) acc = fmaf(__ldg(w + i), magrow[mag_skew<SKEW>(lo + i)], acc);
             o_mel[m] = amp_to_db_norm_fast(acc, db_scale, db_off_mel);   // melspectrogram subtracts no ref_level_db (audio.py:63)
         }
     }
@@ -369,8 +371,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
                                  : P.rows_per_utt > 0 ? (long long)(P.batch.utt_base + b) * P.rows_per_utt + k : (long long)f;
             float* o_lin = P.out_lin ? P.out_lin + (size_t)orow * kBins : nullptr;
             float* o_mel = P.out_mel ? P.out_mel + (size_t)orow * P.plan.num_mels : nullptr;
-            if (o_lin) feature_epilogue<true>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad);
-            else feature_epilogue<false>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad);
+            if (P.mel_skew) {
+                if (o_lin) feature_epilogue<true, true>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad);
+                else feature_epilogue<false, true>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad);
+            } else {
+                if (o_lin) feature_epilogue<true, false>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad);
+                else feature_epilogue<false, false>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad);
+            }
         }
     }
     if (bad) atomicOr(P.status, 1);

@@ -94,7 +94,8 @@ struct nsb_handle_s {
     float* d_mel_w = nullptr;
     int *d_mel_lo = nullptr, *d_mel_n = nullptr, *d_mel_ptr = nullptr;
     int* d_mel_seg = nullptr; float4* d_mel_coef = nullptr;      // the filters as line segments (null: not representable, sparse rows are used)
-    int mel_lines = 1;               // A/B hook: 0 = sparse mel rows even when the line form exists
+    int mel_lines = 1;               // A/B hook: 0 = sparse mel rows even when the line form exists, 2 = line form on the skewed magnitude row
+    int stream_bulk = 0;             // k_gl_stream at the default hparams: rows and staged samples by bulk asynchronous copies (TMA) instead of cp.async
     int* d_status = nullptr;
     std::vector<double> mel_dense;   // [num_mels][num_freq]
     // descriptors
@@ -211,7 +212,7 @@ static size_t gl_smem(int hop, int H) { return synth_smem(hop, H) + 64 + 16; }  
 static size_t stream_smem(int hop, int win, int a, int colours, int prune) {
     const int kfirst0 = (a - win >= 0) ? (a - win) / hop + 1 : -((win - a - 1) / hop + 1) + 1, klast0 = (hop - 1 + a) / hop;
     const int back = klast0 - kfirst0 < colours ? klast0 - kfirst0 : colours;
-    size_t fl = 2 * kTwF2 + (prune == 0 ? kNfft : 1024) + (((size_t)(kWarpsPerCta * colours + back) * hop + 3) & ~(size_t)3) + 16;
+    size_t fl = 2 * kTwF2 + (prune == 0 ? kNfft : 1024) + (((size_t)(kWarpsPerCta * colours + back) * hop + 3) & ~(size_t)3) + 16 + 4 * kWarpsPerCta;   // ... + counters + mbarriers
     return fl * sizeof(float) + sizeof(float2) * kScratchF2 * kWarpsPerCta;
 }
 static const size_t kSmemPerCtaTwoResident = (227 * 1024) / 2 - 1024;   // two CTAs per SM, 1 KB reserved each
@@ -442,7 +443,7 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
     SET((k_synth<SRC_MAGZERO, 0>), ss);  SET((k_synth<SRC_MAGZERO, 2>), ss);
     SET((k_gl_iter<1, true, false>), gs); SET((k_gl_iter<1, false, false>), gs); SET((k_gl_iter<0, false, false>), gs);
     SET((k_gl_iter<2, false, true>), gs); SET((k_gl_iter<0, false, true>), gs);
-    SET((k_gl_stream<1, true, false, true>), gs); SET((k_gl_stream<1, false, false, true>), gs); SET((k_gl_stream<0, false, false, true>), gs);
+    SET((k_gl_stream<1, true, false, true>), gs); SET((k_gl_stream<1, true, false, true, true>), gs); SET((k_gl_stream<1, false, false, true>), gs); SET((k_gl_stream<0, false, false, true>), gs);
     SET((k_gl_stream<2, false, true, true>), gs); SET((k_gl_stream<0, false, true, true>), gs);
     SET((k_gl_stream<1, false, false, false>), gs); SET((k_gl_stream<0, false, false, false>), gs);
     SET((k_gl_stream<2, false, true, false>), gs); SET((k_gl_stream<0, false, true, false>), gs);
@@ -510,7 +511,8 @@ extern "C" int nsb_set_option(nsb_handle_t h, int32_t key, int32_t value) {
         case NSB_OPT_WIDE_MODE: if (value < -1 || value > 1) return fail(NSB_ERR_INVALID, "wide mode %d outside [-1,1]", value); h->wide_mode = value; return NSB_OK;
         case NSB_OPT_OVERLAP_CHUNKS: h->overlap_chunks = value != 0; return NSB_OK;
         case NSB_OPT_WAVE_SCHEDULE: h->wave_schedule = value != 0; return NSB_OK;
-        case NSB_OPT_MEL_LINES: h->mel_lines = value != 0; return NSB_OK;
+        case NSB_OPT_STREAM_BULK: h->stream_bulk = value != 0; return NSB_OK;
+        case NSB_OPT_MEL_LINES: h->mel_lines = value < 0 ? 0 : (value > 2 ? 2 : value); return NSB_OK;
         default: return fail(NSB_ERR_INVALID, "unknown option %d", key);
     }
 }
@@ -733,7 +735,7 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
     AnalysisParams P;
     P.plan = make_plan(h, tf); P.batch = d.dev; P.wav = d_wav; P.out_complex = d_c; P.out_lin = d_lin; P.out_mel = d_mel;
     P.total_frames = d.total_frames; P.preemph = (float)h->hp.preemphasis; P.rows_per_utt = rows_per_utt;
-    P.ref_level_db = (float)h->hp.ref_level_db; P.min_level_db = (float)h->hp.min_level_db; P.status = h->d_status;
+    P.ref_level_db = (float)h->hp.ref_level_db; P.min_level_db = (float)h->hp.min_level_db; P.status = h->d_status; P.mel_skew = h->mel_lines == 2;
     {
         const double inv = 1.0 / (-h->hp.min_level_db);
         P.db_scale = (float)(20.0 * 0.30102999566398119521 * inv);      // 20 log10(2) / (-min_level_db)
@@ -1039,7 +1041,8 @@ static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int t
                 if (tf) {
                     if (S.plan.prune == 2) NSB_LAUNCH((k_gl_stream<2, false, true, true>), grid, kThreads, smem, st, S);
                     else NSB_LAUNCH((k_gl_stream<0, false, true, true>), grid, kThreads, smem, st, S);
-                } else if (h->defcfg) NSB_LAUNCH((k_gl_stream<1, true, false, true>), grid, kThreads, smem, st, S);
+                } else if (h->defcfg && h->stream_bulk) NSB_LAUNCH((k_gl_stream<1, true, false, true, true>), grid, kThreads, smem, st, S);
+                else if (h->defcfg) NSB_LAUNCH((k_gl_stream<1, true, false, true>), grid, kThreads, smem, st, S);
                 else if (h->prune == 1) NSB_LAUNCH((k_gl_stream<1, false, false, true>), grid, kThreads, smem, st, S);
                 else NSB_LAUNCH((k_gl_stream<0, false, false, true>), grid, kThreads, smem, st, S);
             } else {
@@ -1839,7 +1842,7 @@ static void async_worker(nsb_handle_s* parent, nsb_async_s* A, AsyncSlot* S) {
             S->child->host_chunks = parent->host_chunks; S->child->wave_schedule = parent->wave_schedule;
             S->child->overlap_chunks = parent->overlap_chunks; S->child->use_generic_iter = parent->use_generic_iter;
             S->child->stream_sync_mode = parent->stream_sync_mode; S->child->fuse_iterations = parent->fuse_iterations;
-            S->child->wide_mode = parent->wide_mode; S->child->mel_lines = parent->mel_lines;
+            S->child->wide_mode = parent->wide_mode; S->child->mel_lines = parent->mel_lines; S->child->stream_bulk = parent->stream_bulk;
             rc = job->run(S->child);
         }
         {

@@ -57,3 +57,8 @@ def trim_signals():
 @pytest.fixture(scope="session")
 def golden_process():
     return dict(np.load(os.path.join(ROOT, "tests", "golden", "reference_process.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_tf():
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "reference_tf_twin.npz")))

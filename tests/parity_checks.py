@@ -592,3 +592,47 @@ def check_generic_tf_twin_and_stages():
         assert not lin_t[i, Tn[i]:].any()
     with pytest.raises(audio.ParameterError):
         audio.inv_spectrogram(np.full((F, 4), np.inf, np.float32), iters=1)
+
+
+def check_tf_twin_golden(golden_tf):
+    """Fixtures written by the reference's OWN TF-twin functions (tests/golden/make_golden_tf.py: audio.py:51-58, 90-123 run
+    unmodified on an eager numpy stand-in for tf) through the kernels and the oracle."""
+    for tag, mn in (("yaml", 100), ("neg", -100)):
+        ohp = _load(min_level_db=mn)
+        S, mag = golden_tf[tag + "_tw_in"], golden_tf[tag + "_tw_S"]
+        assert ao.snr_db(tfo.inv_spectrogram_tensorflow(S, make_hp(min_level_db=mn, griffin_lim_iters=4), iters=4), golden_tf[tag + "_tw_wav"]) > 100   # oracle == reference
+        y = audio.inv_spectrogram_tensorflow(S, iters=4)
+        assert y.dtype == np.float32 and y.shape == golden_tf[tag + "_tw_wav"].shape
+        assert ao.snr_db(y, golden_tf[tag + "_tw_wav"]) > 60
+        assert ao.snr_db(audio._griffin_lim_tensorflow(mag, iters=4), golden_tf[tag + "_tw_raw"]) > 60
+    _load()
+    assert ao.rel_l2(audio._stft_tensorflow(golden_tf["tw_sig"]), golden_tf["tw_stft"]) < 1e-5
+    assert ao.rel_l2(audio._istft_tensorflow(golden_tf["tw_stft"]), golden_tf["tw_istft"]) < 1e-5
+
+
+def check_length_and_hparams_sweep(cases):
+    """(n_samples, sample_rate, frame_length_ms, num_freq) cases: the STFT, both features and the iSTFT round trip against
+    the oracle - clip lengths from one sample to several transforms (incl. len <= n_fft / 2, where the reflect padding folds
+    more than once), the sample rates 16 / 20 / 22.05 / 24 kHz (truncating int() of audio.py:128-129), window lengths."""
+    for n, sr, fl, nf in cases:
+        over = {"min_level_db": -100, "sample_rate": sr, "frame_length_ms": fl, "num_freq": nf}
+        ohp = _load(**over)
+        n_fft, hop, win = ao._stft_parameters(ohp)
+        if win > n_fft:
+            with pytest.raises(ValueError):
+                audio._stft(speechlike(max(n, 2), 1))
+            continue
+        wav = speechlike(n, n % 97, sr=sr)
+        D = audio._stft(wav)
+        Dref = ao._stft(wav.astype(np.float64), ohp)
+        assert D.shape == Dref.shape == (nf, 1 + n // hop), (n, sr, fl, nf)
+        # short clips are (near-)constant after the reflection: the spectrum spans > 100 dB and only its large bins carry a relative bound
+        tol = 1e-5 if n > 100 else 1e-4
+        assert ao.rel_l2(D, Dref) < tol, (n, sr, fl, nf, ao.rel_l2(D, Dref))
+        lin, mel = audio.spectrogram_and_mel(wav)
+        ftol = 1e-5 if n > 100 else 5e-3
+        assert ao.rel_l2(lin, ao.spectrogram(wav, ohp)) < ftol, (n, sr, fl, nf)
+        assert ao.rel_l2(mel, ao.melspectrogram(wav, ohp)) < ftol, (n, sr, fl, nf)
+        if D.shape[1] >= 2:
+            assert ao.rel_l2(audio._istft(Dref), ao._istft(Dref, ohp)) < 1e-5, (n, sr, fl, nf)
+    hparams.load()

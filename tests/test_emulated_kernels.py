@@ -152,3 +152,12 @@ def test_api_guards(emu):
 
 def test_stale_griffin_lim_state(emu):
     pc.check_stale_griffin_lim_state(lambda a: a)          # the emulated library's "device" pointers are host pointers
+
+
+def test_tf_twin_golden(emu, golden_tf):
+    pc.check_tf_twin_golden(golden_tf)
+
+
+def test_length_and_hparams_sweep(emu):
+    pc.check_length_and_hparams_sweep([(1, 20000, 50, 1025), (700, 22050, 50, 1025), (1024, 20000, 50, 1025), (1025, 24000, 50, 1025),
+                                       (3000, 16000, 50, 1025), (2500, 20000, 25, 1025), (900, 16000, 50, 513), (4100, 20000, 120, 1025)])

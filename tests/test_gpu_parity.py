@@ -430,3 +430,46 @@ def test_two_streams_on_one_handle_are_ordered():
     h.griffin_lim(np.random.RandomState(1).rand(50, 1025).astype(np.float32), _lib.FRAME_MAJOR, [50], host, seed=1, iters=2, flags=flags, out_dtype=_lib.F64)
     torch.cuda.synchronize()
     assert torch.equal(o1, ref) and torch.equal(o2, ref) and np.isfinite(host).all()
+
+
+def test_tf_twin_golden(golden_tf):
+    pc.check_tf_twin_golden(golden_tf)
+
+
+def test_length_and_hparams_property_sweep():
+    """hypothesis over clip length x sample rate x window length x num_freq"""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import strategies as hs
+
+    @hyp.settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=list(hyp.HealthCheck))
+    @hyp.given(n=hs.one_of(hs.integers(1, 6144), hs.sampled_from([1, 2, 249, 250, 251, 1023, 1024, 1025, 2047, 2048, 2049, 4096, 6144])),
+               sr=hs.sampled_from([16000, 20000, 22050, 24000]), fl=hs.sampled_from([25, 40, 50, 64]), nf=hs.sampled_from([1025, 1025, 513, 2049]))
+    def run(n, sr, fl, nf):
+        pc.check_length_and_hparams_sweep([(n, sr, fl, nf)])
+    run()
+
+
+def test_config3_shape_through_the_streaming_kernel_vs_oracle():
+    """Two 12.5 s utterances (1000 frames, U(0,1) spectrograms, the yaml's +100 dB floor), all 60 iterations through the
+    production kernel k_gl_stream itself (forced: the automatic choice would take the tile kernel for two utterances),
+    against the oracle: SNR >= 40 dB and spectral convergence within 1 % (BASELINE.json) - no inference through the
+    bit-equality of the kernels."""
+    ohp = pc._load()
+    h = audio._handle()
+    rs = np.random.RandomState(77)
+    specs = [rs.rand(1025, 1000).astype(np.float32) for _ in range(2)]
+    phases = [np.exp(2j * np.pi * rs.rand(1025, 1000)) for _ in range(2)]
+    h.set_generic_iteration(0)
+    try:
+        launches = h.kernel_launches()
+        outs = batch.inv_spectrogram_batch(specs, init_phase=phases, layout="FT")
+        assert h.kernel_launches() - launches <= 6          # prepare, initial iSTFT, ONE iteration launch, de-emphasis
+    finally:
+        h.set_generic_iteration(-1)
+    for S, ang, y in zip(specs, phases, outs):
+        yref = ao.inv_spectrogram(S, ohp, angles=ang)
+        assert y.shape == yref.shape == (250 * 999,)
+        assert ao.snr_db(y, yref) >= 40.0, ao.snr_db(y, yref)
+        mag = ao._db_to_amp(ao._denormalize(S, ohp) + ohp.ref_level_db) ** ohp.power
+        sc, sc_ref = (ao.spectral_convergence(ao.preemphasis(v, ohp), mag, ohp) for v in (y, yref))
+        assert abs(sc - sc_ref) <= 0.01 * sc_ref
