@@ -387,7 +387,7 @@ def main():
         return max_over_ranks((time.perf_counter() - t0) * 1e3)
 
     pinned_inputs = [p_.array for p_ in pin_in]
-    e2e_stream(max(2, args.warmup // 2 + 1), pinned_inputs, 0)
+    e2e_stream(max(5, args.warmup), pinned_inputs, 0)      # (also fills the pinned result pool: four blocks are alive in steady state)
     sampler.mark()
     ms_e2e = wall_ms(lambda: e2e_stream(args.steps, pinned_inputs, 200))
     sampler.mark()
@@ -416,12 +416,12 @@ def main():
         h.check_status(st)
         assert 0.0 < float(d_mel[:1000].mean()) <= 1.0
         del d_lin, d_mel
-        # end to end from host memory on a bounded sample (every 8th clip: the full corpus would need 30 GB of page-locked results)
-        sub = list(range(0, 13100, 8))
+        # end to end from host memory on a bounded sample (every 32nd clip: the full corpus would need 30 GB of page-locked results)
+        sub = list(range(0, 13100, 32))
         offs = np.concatenate([[0], np.cumsum(ns)])
         sub_wavs = [d_wav[offs[i]:offs[i + 1]].cpu().numpy() for i in sub]
         sub_frames = sum(Tn[i] for i in sub)
-        batch.features_batch(sub_wavs[:64])
+        del batch.features_batch(sub_wavs)[:]                # warm-up of the same size: the result blocks return to the pinned pool
         t0 = time.perf_counter()
         feats = batch.features_batch(sub_wavs)
         ms_feat_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
@@ -438,7 +438,7 @@ def main():
                          "algorithmic_bytes_per_frame": feat_bytes, "traffic": NCU_FEATURES_TRAFFIC_BYTES_PER_FRAME * n_fr,
                          "traffic_source": NCU_FEATURES_TRAFFIC_SOURCE},
             "e2e": {"value": world * sub_frames / (ms_feat_e2e * 1e-3), "unit": "mel frames/s", "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(out_bytes),
-                    "sample": "every 8th clip of the corpus (%d clips, %d frames) through batch.features_batch from numpy arrays, results in pooled page-locked memory" % (len(sub), sub_frames)}}
+                    "sample": "every 32nd clip of the corpus (%d clips, %d frames) through batch.features_batch from numpy arrays, results in pooled page-locked memory" % (len(sub), sub_frames)}}
         if rank == 0 and not args.no_cpu_baseline and world == 1:
             v, cores, sample = features_cpu_baseline()
             extra["features"]["cpu_baseline"] = {"value": v, "unit": "mel frames/s", "cores": cores, "kind": "port", "sample": sample}

@@ -31,12 +31,6 @@ __device__ __forceinline__ void flag_store(int* p, int v) { __atomic_store_n(p, 
 __device__ __forceinline__ void spin_pause() { std::this_thread::yield(); }
 __device__ __forceinline__ int gflag_load(const int* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 __device__ __forceinline__ void gflag_store(int* p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
-// bulk (TMA) copies and their mbarriers, emulated: the issuing lane copies at once, waiting is the warp barrier
-__device__ __forceinline__ void mbar_init(unsigned long long* b, int) { *b = 0; }
-__device__ __forceinline__ void mbar_fence_init() {}
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long*) { memcpy(dst, src, bytes); }
-__device__ __forceinline__ void bulk_prefetch_l2(const void*, unsigned) {}
-__device__ __forceinline__ void mbar_wait(unsigned long long*, unsigned) { __syncwarp(); }
 __device__ __forceinline__ bool warp_any(bool p) {
     auto* c = nsb_emu::g_ctx;
     const int w = threadIdx.x >> 5;
@@ -74,32 +68,6 @@ __device__ __forceinline__ int gflag_load(const int* p) {
 }
 __device__ __forceinline__ void gflag_store(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ bool warp_any(bool p) { return __any_sync(0xffffffffu, p); }
-// ---- bulk asynchronous copies (the TMA unit: SASS UBLKCP) completing on an mbarrier --------------------------------------
-// One elected lane moves a whole 4 KB row global -> shared with ONE instruction; the other 31 lanes issue nothing (the
-// cp.async form costs every lane nine LDGSTS plus their address arithmetic per row).  The data comes from L2 (the TMA unit
-// does not allocate in L1): safe for the waveform that other SMs rewrite inside the launch.
-__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-// (the calling lane) order this warp's earlier generic-proxy accesses of the destination before the async-proxy write, post the
-// byte count, start the copy; dst / src 16-byte aligned, bytes a multiple of 16
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("fence.proxy.async.shared::cta;\n"
-                 "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
-                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %1, [%0];"
-                 ::"r"(b), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-                 "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(b), "r"(parity) : "memory");
-}
 #endif
 
 // 1/sqrt(x) as ONE MUFU.RSQ: plain rsqrtf() wraps the instruction in a subnormal-input rescue (FSETP + two predicated

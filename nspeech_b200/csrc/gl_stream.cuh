@@ -223,22 +223,12 @@ __device__ __forceinline__ void stage_frame(float* stage, const float* src0, int
     if (lane == 0) cp_async16(dst + 64 * (T1 - T0), src + 64 * (T1 - T0));
 }
 
-// the same as ONE bulk copy issued by lane 0 (every lane of the warp has passed its last access of the tile: __syncwarp first)
-template <int T0, int T1>
-__device__ __forceinline__ void stage_frame_bulk(float* stage, const float* src0, int lane, int& off, unsigned long long* bar) {
-    off = (int)((reinterpret_cast<uintptr_t>(src0) >> 2) & 3);
-    __syncwarp();
-    if (lane == 0) bulk_load(stage + 64 * T0, src0 - off, 4 * 64 * (T1 - T0) + 16, bar);
-}
-
 // FB: one CTA barrier after every colour step (the production mode).  It keeps the 8 warps in the same stretch of code, which
 // is what the instruction caches need, and it orders the overlap-add by itself: colour s starts when every warp has added
 // its colours < s, and a group is stored before the barrier of its last colour, so ring space is never reused before it is
 // free.  Without FB the per-warp event counters do both (kept for window/hop ratios where a group's hops need ALL colours of
 // the next group, and for the barrier experiments of profiles/r1/sweep_kernels.txt).
-// BULK: the frame's magnitude row and the next frame's samples arrive by bulk asynchronous copies (cp.async.bulk, one
-// instruction of one lane per 4 KB row, completion on a per-warp mbarrier) instead of nine cp.async per lane.
-template <int PRUNE, bool DEFCFG, bool TFM, bool FB, bool BULK = false>
+template <int PRUNE, bool DEFCFG, bool TFM, bool FB>
 __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
     NSB_DYN_SMEM(smem_raw);
     const int hop = DEFCFG ? 250 : P.plan.hop;
@@ -266,17 +256,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
     const float2* wp = wp_tab - t0 * 32;                     // wp[t*32 + lane] for t in [t0, t1)
     float* ring = reinterpret_cast<float*>(wp_tab + (t1 - t0) * 32);   // 16-byte aligned
     int* progress = reinterpret_cast<int*>(ring + ((RS + 3) & ~3));    // [kWarpsPerCta] (+ pad to 16 ints)
-    unsigned long long* mbar_all = reinterpret_cast<unsigned long long*>(progress + 16);   // [kWarpsPerCta][2]: magnitude row, staged samples
-    float2* scratch_all = reinterpret_cast<float2*>(progress + 16 + 4 * kWarpsPerCta);
+    float2* scratch_all = reinterpret_cast<float2*>(progress + 16);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float2* scratch = scratch_all + warp * kScratchF2;
     float* stage = reinterpret_cast<float*>(scratch);
-    unsigned long long* mb_mag = mbar_all + 2 * warp;
-    unsigned long long* mb_stage = mb_mag + 1;
-    unsigned ph_mag = 0, ph_stage = 0;              // parity of the next completion of each barrier (warp-uniform)
-    if (BULK && threadIdx.x < 2 * kWarpsPerCta) mbar_init(mbar_all + threadIdx.x, 1);
-    if (BULK) mbar_fence_init();
     if (P.trace && threadIdx.x == 0) { P.trace[3 * blockIdx.x] = sm_id(); P.trace[3 * blockIdx.x + 1] = global_ns(); }
 
     load_twiddle_pairs(tw_s, P.plan.tw);
@@ -367,19 +351,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
             const bool active = (k >= 0 && k <= k_hi);        // warp-uniform
             const bool next_active = (s + 1 < C) && (k + 1 >= 0 && k + 1 <= k_hi);   // the group's next frame
             c2 z[32];
-            if (BULK && staged && !active) { mbar_wait(mb_stage, ph_stage); ph_stage ^= 1; }      // (cannot happen today: a staged frame is an active one; keeps the parity honest)
             if (active) {
                 // pull the NEXT frame's magnitude row towards L2 (it streams from HBM) while this frame computes
                 if (next_active) {
                     const char* nm = reinterpret_cast<const char*>(mag0 + (size_t)(k + 1) * kMagPitch);
-                    if (BULK) { if (lane == 0) bulk_prefetch_l2(nm, kMagBytes); }
-                    else { prefetch_l2(nm + lane * 128); if (lane == 0) prefetch_l2(nm + 4096); }
+                    prefetch_l2(nm + lane * 128);
+                    if (lane == 0) prefetch_l2(nm + 4096);
                 }
                 const float* magrow = mag0 + (size_t)k * kMagPitch;
                 if (staged) {
                     // samples were staged by the previous frame of this warp (see below): window them from shared memory
-                    if (BULK) { mbar_wait(mb_stage, ph_stage); ph_stage ^= 1; }
-                    else { cp_async_wait_all(); __syncwarp(); }
+                    cp_async_wait_all();
+                    __syncwarp();
                     const float* sg = stage + stage_off;
 #pragma unroll
                     for (int t = 0; t < 32; ++t) {
@@ -395,9 +378,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
 #pragma unroll
                 for (int t = 0; t < 32; ++t) z[t] = scratch[lane * kRowStride + t];
                 __syncwarp();                        // every lane has its row: the scratch tile is free
-                if (BULK) {
-                    if (lane == 0) bulk_load(scratch, magrow, kMagBytes, mb_mag);
-                } else {
+                {
                     const char* src = reinterpret_cast<const char*>(magrow);
                     char* dst = reinterpret_cast<char*>(scratch);
 #pragma unroll
@@ -410,8 +391,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
 #pragma unroll
                     for (int q = 0; q < 32; ++q) xch[q] = z[q];
                 }
-                if (BULK) { __syncwarp(); mbar_wait(mb_mag, ph_mag); ph_mag ^= 1; }
-                else { cp_async_wait_all(); __syncwarp(); }
+                cp_async_wait_all();
+                __syncwarp();
                 const float4* mrow = reinterpret_cast<const float4*>(scratch);
                 const float* mflt = reinterpret_cast<const float*>(scratch);
                 bool zero = false;
@@ -518,8 +499,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
             if (PRUNE != 0 && next_active) {
                 const long long nstart = (long long)(k + 1) * hop - origin;
                 if (nstart + 64 * t0 >= 0 && nstart + 64 * t1 <= L && ((cur.s_off + nstart) & 1) == 0) {
-                    if (BULK) stage_frame_bulk<t0, t1>(stage, yin + nstart + 64 * t0, lane, stage_off, mb_stage);
-                    else stage_frame<t0, t1>(stage, yin + nstart + 64 * t0, lane, stage_off);
+                    stage_frame<t0, t1>(stage, yin + nstart + 64 * t0, lane, stage_off);
                     staged = true;
                 }
             }

@@ -95,7 +95,6 @@ struct nsb_handle_s {
     int *d_mel_lo = nullptr, *d_mel_n = nullptr, *d_mel_ptr = nullptr;
     int* d_mel_seg = nullptr; float4* d_mel_coef = nullptr;      // the filters as line segments (null: not representable, sparse rows are used)
     int mel_lines = 1;               // A/B hook: 0 = sparse mel rows even when the line form exists, 2 = line form on the skewed magnitude row
-    int stream_bulk = 0;             // k_gl_stream at the default hparams: rows and staged samples by bulk asynchronous copies (TMA) instead of cp.async
     int* d_status = nullptr;
     std::vector<double> mel_dense;   // [num_mels][num_freq]
     // descriptors
@@ -212,7 +211,7 @@ static size_t gl_smem(int hop, int H) { return synth_smem(hop, H) + 64 + 16; }  
 static size_t stream_smem(int hop, int win, int a, int colours, int prune) {
     const int kfirst0 = (a - win >= 0) ? (a - win) / hop + 1 : -((win - a - 1) / hop + 1) + 1, klast0 = (hop - 1 + a) / hop;
     const int back = klast0 - kfirst0 < colours ? klast0 - kfirst0 : colours;
-    size_t fl = 2 * kTwF2 + (prune == 0 ? kNfft : 1024) + (((size_t)(kWarpsPerCta * colours + back) * hop + 3) & ~(size_t)3) + 16 + 4 * kWarpsPerCta;   // ... + counters + mbarriers
+    size_t fl = 2 * kTwF2 + (prune == 0 ? kNfft : 1024) + (((size_t)(kWarpsPerCta * colours + back) * hop + 3) & ~(size_t)3) + 16;
     return fl * sizeof(float) + sizeof(float2) * kScratchF2 * kWarpsPerCta;
 }
 static const size_t kSmemPerCtaTwoResident = (227 * 1024) / 2 - 1024;   // two CTAs per SM, 1 KB reserved each
@@ -443,7 +442,7 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
     SET((k_synth<SRC_MAGZERO, 0>), ss);  SET((k_synth<SRC_MAGZERO, 2>), ss);
     SET((k_gl_iter<1, true, false>), gs); SET((k_gl_iter<1, false, false>), gs); SET((k_gl_iter<0, false, false>), gs);
     SET((k_gl_iter<2, false, true>), gs); SET((k_gl_iter<0, false, true>), gs);
-    SET((k_gl_stream<1, true, false, true>), gs); SET((k_gl_stream<1, true, false, true, true>), gs); SET((k_gl_stream<1, false, false, true>), gs); SET((k_gl_stream<0, false, false, true>), gs);
+    SET((k_gl_stream<1, true, false, true>), gs); SET((k_gl_stream<1, false, false, true>), gs); SET((k_gl_stream<0, false, false, true>), gs);
     SET((k_gl_stream<2, false, true, true>), gs); SET((k_gl_stream<0, false, true, true>), gs);
     SET((k_gl_stream<1, false, false, false>), gs); SET((k_gl_stream<0, false, false, false>), gs);
     SET((k_gl_stream<2, false, true, false>), gs); SET((k_gl_stream<0, false, true, false>), gs);
@@ -511,7 +510,6 @@ extern "C" int nsb_set_option(nsb_handle_t h, int32_t key, int32_t value) {
         case NSB_OPT_WIDE_MODE: if (value < -1 || value > 1) return fail(NSB_ERR_INVALID, "wide mode %d outside [-1,1]", value); h->wide_mode = value; return NSB_OK;
         case NSB_OPT_OVERLAP_CHUNKS: h->overlap_chunks = value != 0; return NSB_OK;
         case NSB_OPT_WAVE_SCHEDULE: h->wave_schedule = value != 0; return NSB_OK;
-        case NSB_OPT_STREAM_BULK: h->stream_bulk = value != 0; return NSB_OK;
         case NSB_OPT_MEL_LINES: h->mel_lines = value < 0 ? 0 : (value > 2 ? 2 : value); return NSB_OK;
         default: return fail(NSB_ERR_INVALID, "unknown option %d", key);
     }
@@ -1041,8 +1039,7 @@ static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int t
                 if (tf) {
                     if (S.plan.prune == 2) NSB_LAUNCH((k_gl_stream<2, false, true, true>), grid, kThreads, smem, st, S);
                     else NSB_LAUNCH((k_gl_stream<0, false, true, true>), grid, kThreads, smem, st, S);
-                } else if (h->defcfg && h->stream_bulk) NSB_LAUNCH((k_gl_stream<1, true, false, true, true>), grid, kThreads, smem, st, S);
-                else if (h->defcfg) NSB_LAUNCH((k_gl_stream<1, true, false, true>), grid, kThreads, smem, st, S);
+                } else if (h->defcfg) NSB_LAUNCH((k_gl_stream<1, true, false, true>), grid, kThreads, smem, st, S);
                 else if (h->prune == 1) NSB_LAUNCH((k_gl_stream<1, false, false, true>), grid, kThreads, smem, st, S);
                 else NSB_LAUNCH((k_gl_stream<0, false, false, true>), grid, kThreads, smem, st, S);
             } else {
@@ -1842,7 +1839,7 @@ static void async_worker(nsb_handle_s* parent, nsb_async_s* A, AsyncSlot* S) {
             S->child->host_chunks = parent->host_chunks; S->child->wave_schedule = parent->wave_schedule;
             S->child->overlap_chunks = parent->overlap_chunks; S->child->use_generic_iter = parent->use_generic_iter;
             S->child->stream_sync_mode = parent->stream_sync_mode; S->child->fuse_iterations = parent->fuse_iterations;
-            S->child->wide_mode = parent->wide_mode; S->child->mel_lines = parent->mel_lines; S->child->stream_bulk = parent->stream_bulk;
+            S->child->wide_mode = parent->wide_mode; S->child->mel_lines = parent->mel_lines;
             rc = job->run(S->child);
         }
         {

@@ -31,9 +31,10 @@ def bufs(k, pinned):
     return ins, outs
 
 
-for pinned in (True, False):
-    for slots in (0, 1, 2, 3):
+for pinned, one_chunk in ((True, 0), (True, 1), (False, 0), (False, 1)):
+    for slots in ((0, 2, 3) if not one_chunk else (2, 3)):
         h = _lib.Handle(hparams.get_hparams(), 0)
+        h.set_host_chunks(1 if one_chunk else 0)
         k = max(1, slots)
         ins, outs = bufs(k, pinned)
         if slots:
@@ -56,7 +57,7 @@ for pinned in (True, False):
         t0 = time.perf_counter()
         run(steps)
         ms = (time.perf_counter() - t0) * 1e3 / steps
-        print("%-8s host buffers, %s: %.2f ms per step, %.0f audio-s/s" % ("pinned" if pinned else "pageable",
+        print("%-8s host buffers, %s, %s: %.2f ms per step, %.0f audio-s/s" % ("pinned" if pinned else "pageable", "one chunk per call" if one_chunk else "wave schedule",
               "synchronous call" if not slots else "submit/wait, %d in flight" % slots, ms, N * n_samp / 20000.0 / (ms * 1e-3)), flush=True)
         h.close()
         del ins, outs

@@ -1,8 +1,40 @@
-// Stand-alone check of the bulk-copy helpers of gl_iter.cuh (cp.async.bulk + mbarrier), the way k_gl_stream<..., BULK> uses them:
-// 8 warps per CTA, each with two mbarriers; lane 0 copies a 4112-byte row global -> shared, all lanes wait and check it.
+// Bulk asynchronous copies (cp.async.bulk = the TMA unit, SASS UBLKCP, completion on an mbarrier) for the 4 KB rows the
+// Griffin-Lim iteration kernel fetches per frame: 8 warps per CTA, each with two mbarriers; lane 0 copies a 4112-byte row
+// global -> shared, all lanes wait and check it.  All modes pass (profiles/r2/bulk_copy_micro.txt).
+// Round-2 experiment behind it (profiles/r2/sweep_bulk.txt): k_gl_stream with its magnitude rows fetched this way instead of
+// nine cp.async per lane ran 16.64 instead of 16.24 ms per 60-iteration launch (one lane's issue + the mbarrier round trip
+// are exposed where 32 lanes x LDGSTS overlapped with the FFT), and the variant that also staged the next frame's samples
+// this way hung; the kernel keeps cp.async.
 #include <cstdio>
 #include <cuda_runtime.h>
-#include "../../nspeech_b200/csrc/gl_iter.cuh"
+namespace nsb {
+// ---- bulk asynchronous copies (the TMA unit: SASS UBLKCP) completing on an mbarrier --------------------------------------
+// One elected lane moves a whole 4 KB row global -> shared with ONE instruction; the other 31 lanes issue nothing (the
+// cp.async form costs every lane nine LDGSTS plus their address arithmetic per row).  The data comes from L2 (the TMA unit
+// does not allocate in L1): safe for the waveform that other SMs rewrite inside the launch.
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// (the calling lane) order this warp's earlier generic-proxy accesses of the destination before the async-proxy write, post the
+// byte count, start the copy; dst / src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("fence.proxy.async.shared::cta;\n"
+                 "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %1, [%0];"
+                 ::"r"(b), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(b), "r"(parity) : "memory");
+}
+}  // namespace nsb
 using namespace nsb;
 
 __global__ void __launch_bounds__(256, 2) k_bulk(const float* src, int rows, int iters, int* errors, int mode) {
