@@ -315,7 +315,7 @@ def main():
 
     # ---- synthetic inputs: pinned host copies for the e2e legs, device copy for the kernel-only leg ----
     gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
-    pin_in = [_lib.PinnedArray((N_UTT, N_FRAMES, N_BINS), np.float32) for _ in range(2)]      # two batches alternate (two in flight)
+    pin_in = [_lib.PinnedArray((N_UTT, N_FRAMES, N_BINS), np.float32) for _ in range(3)]      # three batches in rotation (three in flight)
     for p_ in pin_in:
         p_.array[...] = torch.rand((N_UTT, N_FRAMES, N_BINS), generator=gen, dtype=torch.float32).numpy()
     n_samp = HOP * (N_FRAMES - 1)
@@ -370,7 +370,7 @@ def main():
     achieved_tflops = frames * FLOPS_PER_FRAME_ITER / (ms_iter * 1e-3) / 1e12
 
     # ---- end to end through the public API on host buffers: every step copies its batch in and its waveforms out ----
-    # headline: batch.inv_spectrogram_stream (nsb_griffin_lim_submit / nsb_wait, two batches in flight, results in pooled page-locked
+    # headline: batch.inv_spectrogram_stream (nsb_griffin_lim_submit / nsb_wait, three batches in flight, results in pooled page-locked
     # memory); beside it the synchronous call (round 1's e2e) and the same stream fed from PAGEABLE numpy arrays
     def e2e_stream(n_steps, inputs, seed0):
         got = 0
@@ -491,7 +491,7 @@ def main():
         "host_binding": ("every rank pinned to its GPU's %d NUMA-local CPUs" % len(host_cpus)) if host_cpus else "none",
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(pin_in[0].array.nbytes),
                 "d2h_bytes_per_step": int(pin_out.array.nbytes), "ms_per_step": ms_e2e / args.steps,
-                "api": "nspeech_b200.batch.inv_spectrogram_stream (nsb_griffin_lim_submit / nsb_wait, two batches in flight), page-locked input arrays, results in pooled page-locked memory"},
+                "api": "nspeech_b200.batch.inv_spectrogram_stream (nsb_griffin_lim_submit / nsb_wait, three batches in flight), page-locked input arrays, results in pooled page-locked memory"},
         "e2e_sync": {"value": world * audio_s_per_step * args.steps / (ms_e2e_sync * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e_sync / args.steps,
                      "api": "nspeech_b200.batch.inv_spectrogram_batch, one synchronous call per step (round 1's e2e)"},
         "e2e_pageable": {"value": world * audio_s_per_step * args.steps / (ms_e2e_pageable * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e_pageable / args.steps,

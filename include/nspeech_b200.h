@@ -17,7 +17,7 @@
  *    handle's private non-blocking stream for the (synchronous) NSB_HOST calls.  A handle's device state (descriptors,
  *    scheduling counters, workspaces) is shared by its calls: use ONE stream per handle.  A call that arrives on another
  *    stream than the previous one first waits (on the device) for the event the previous call recorded when it returned;
- *  - nsb_*_submit / nsb_wait are the asynchronous form of the NSB_HOST calls (two batches in flight per handle);
+ *  - nsb_*_submit / nsb_wait are the asynchronous form of the NSB_HOST calls (up to three batches in flight per handle);
  *  - ragged batches: per-utterance lengths are a HOST int array; utterance blocks are packed back to
  *    back in every buffer (a uniform [N,T,F] or [N,n] C-contiguous array is already in that form);
  *  - spectra are float32, 1025 = num_freq bins per frame; layout NSB_FRAME_MAJOR = [T][F] per
@@ -198,7 +198,7 @@ int nsb_features_rows(nsb_handle_t h, const float* wav, const int64_t* n_samples
                       int64_t total_rows, float* lin_out, float* mel_out, int32_t space, void* stream);
 
 /* Asynchronous NSB_HOST calls.  submit returns at once with a ticket; the call runs on one of the handle's worker slots
- * (default 2, nsb_set_async_slots before the first submit), each with private streams and workspaces, so consecutive
+ * (default 3, nsb_set_async_slots before the first submit), each with private streams and workspaces, so consecutive
  * batches overlap on the GPU and on PCIe.  Data buffers must stay valid until nsb_wait(ticket), which returns the call's
  * status (nsb_last_error has its message); lengths arrays are copied at submit.  Tickets may be waited for in any order,
  * each exactly once.  nsb_destroy runs whatever is still queued.  Caller pattern: the feeder threads of

@@ -45,13 +45,28 @@ def _frames_major(spec, num_freq, layout=None, dtype=np.float32):
     return np.ascontiguousarray(spec, dtype=dtype)
 
 
+def _pack(h, arrays, dtype):
+    """list of arrays -> one packed array; large batches are concatenated straight into pooled page-locked memory (the one host
+    copy a list input needs anyway), so that the copy to the device runs at PCIe speed"""
+    if len(arrays) == 1:
+        return arrays[0]
+    total = sum(a.shape[0] for a in arrays)
+    shape = (total,) + tuple(arrays[0].shape[1:])
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    if nbytes < (4 << 20):
+        return np.concatenate(arrays)
+    out = h.lib.pinned_pool().empty(shape, dtype)
+    np.concatenate(arrays, out=out)
+    return out
+
+
 def features_batch(wavs, device=None, want_linear=True, want_mel=True):
     """-> list of (linear [F,T] float32, mel [M,T] float32) per clip (None for a feature not requested)."""
     h = audio._handle(device)
     wavs = [audio._as_wav(w) for w in wavs]
     ns = [w.size for w in wavs]
     Ts = [h.num_frames(n) for n in ns]
-    packed = np.concatenate(wavs) if len(wavs) > 1 else wavs[0]
+    packed = _pack(h, wavs, np.float32)
     pool = h.lib.pinned_pool()             # results in pooled page-locked memory: the copy out runs at PCIe speed
     lin = pool.empty((sum(Ts), h.num_freq), np.float32) if want_linear else None
     mel = pool.empty((sum(Ts), h.num_mels), np.float32) if want_mel else None
@@ -79,7 +94,7 @@ def feeder_targets(wavs, outputs_per_step, device=None):
     ns = [w.size for w in wavs]
     Ts = [h.num_frames(n) for n in ns]
     rows = _round_up(max(Ts) + 1, outputs_per_step)
-    packed = np.concatenate(wavs) if len(wavs) > 1 else wavs[0]
+    packed = _pack(h, wavs, np.float32)
     pool = h.lib.pinned_pool()
     lin = pool.empty((len(wavs), rows, h.num_freq), np.float32)
     mel = pool.empty((len(wavs), rows, h.num_mels), np.float32)
@@ -104,7 +119,7 @@ def _gl_batch_inputs(h, specs, init_phase, layout):
     if not mats:
         raise ValueError("empty batch")
     Ts = [m.shape[0] for m in mats]
-    packed = np.concatenate(mats) if len(mats) > 1 else mats[0]
+    packed = _pack(h, mats, np.float32)
     if init_phase is not None:
         if len(init_phase) != len(mats):
             raise ValueError("init_phase has %d entries for %d spectrograms" % (len(init_phase), len(mats)))
@@ -113,7 +128,7 @@ def _gl_batch_inputs(h, specs, init_phase, layout):
             if np.shape(p) != np.shape(s):
                 raise ValueError("init_phase shape %r != spectrogram shape %r" % (np.shape(p), np.shape(s)))
             ph.append(_frames_major(p, F, layout, dtype=np.complex64))
-        init_phase = np.concatenate(ph) if len(ph) > 1 else ph[0]
+        init_phase = _pack(h, ph, np.complex64)
     return packed, Ts, init_phase
 
 
@@ -182,7 +197,7 @@ def inv_spectrogram_batch(specs, init_phase=None, seed=0, iters=None, device=Non
     return _split(out, ns)
 
 
-def inv_spectrogram_stream(batches, seed=0, iters=None, device=None, denormalize=True, deemphasis=True, layout=None, in_flight=2):
+def inv_spectrogram_stream(batches, seed=0, iters=None, device=None, denormalize=True, deemphasis=True, layout=None, in_flight=3):
     """Generator over an iterable of batches (each what ``inv_spectrogram_batch`` takes as ``specs``): yields each batch's
     list of waveforms, in order, with ``in_flight`` batches inside the library at any time (``nsb_griffin_lim_submit`` /
     ``nsb_wait``) - batch i+1 is copied in and starts while batch i finishes and is copied out.  The caller pattern is the
@@ -249,7 +264,7 @@ def feeder_groups(wavs, batch_size, outputs_per_step, rng=None, device=None):
         for j, i in enumerate(idx):
             row_off[i] = total + j * rows
         total += rows * len(idx)
-    packed = np.concatenate(wavs) if len(wavs) > 1 else wavs[0]
+    packed = _pack(h, wavs, np.float32)
     pool = h.lib.pinned_pool()
     lin = pool.empty((total, h.num_freq), np.float32)
     mel = pool.empty((total, h.num_mels), np.float32)

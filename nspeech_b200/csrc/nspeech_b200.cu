@@ -69,6 +69,8 @@ struct nsb_handle_s {
     int generic = 0;                 // n_fft != 2048: every operator runs the generic-size kernels (gen_kernels.cuh)
     GenPlan gen{}, gen_tf{};         // their plan in the librosa and the tf.contrib.signal geometry
     float2* d_wt = nullptr;          // [n_fft] exp(-2 pi i m / n_fft)
+    // pageable host input: staged through a ring of page-locked slots by the calling thread (copy_h2d)
+    void* bounce[4] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t bounce_ev[4] = {nullptr, nullptr, nullptr, nullptr}; unsigned bounce_next = 0;
     DevBuf ws_frames;                // generic path: windowed frames before the overlap-add [frames][win]
     int user_tile_hops = 0, user_stream_grid = 0;
     cudaStream_t own_stream = nullptr, copy_in = nullptr, copy_out = nullptr;
@@ -112,7 +114,7 @@ struct nsb_handle_s {
     unsigned long long launches = 0;
     unsigned long long launches_async = 0;   // kernels launched by the worker slots of the asynchronous entry points (guarded by async->m)
     struct nsb_async_s* async = nullptr;     // worker slots of nsb_*_submit / nsb_wait, created by the first submit
-    int async_slots = 2;
+    int async_slots = 3;
     std::mutex mu;
 };
 static void async_shutdown(nsb_handle_s* h);
@@ -280,6 +282,7 @@ extern "C" int nsb_destroy(nsb_handle_t h) {
     if (h->last_done) cudaEventDestroy(h->last_done);
     cudaFree(h->d_tw); cudaFree(h->d_win); cudaFree(h->d_win_tf); cudaFree(h->d_rinv); cudaFree(h->d_rinv_tf); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo); cudaFree(h->d_mel_n); cudaFree(h->d_mel_ptr); cudaFree(h->d_mel_seg); cudaFree(h->d_mel_coef);
     cudaFree(h->d_status); cudaFree(h->d_wt); h->ws_frames.release();
+    for (int i = 0; i < 4; ++i) { if (h->bounce[i]) cudaFreeHost(h->bounce[i]); if (h->bounce_ev[i]) cudaEventDestroy(h->bounce_ev[i]); }
     if (h->h_desc) cudaFreeHost(h->h_desc);
     h->d_desc.release(); h->d_trace.release(); h->d_done.release(); h->d_done2.release(); h->ws_mag.release(); h->ws_y0.release(); h->ws_y1.release();
     h->ws_in.release(); h->ws_in2.release(); h->ws_out.release(); h->ws_out2.release(); h->ws_ep.release();
@@ -655,6 +658,41 @@ static int check_launch(nsb_handle_s* h, const char* what) {
     return NSB_OK;
 }
 
+// Host -> device copy of a caller's buffer.  cudaMemcpyAsync from PAGEABLE memory is staged by the driver at a fifth of the PCIe
+// rate (11.6 against 55 GB/s here, profiles/r2/host_transfer.txt) and blocks the caller meanwhile; a drop-in caller hands plain numpy
+// arrays.  So large pageable sources go through the handle's own ring of four 8 MB page-locked slots: memcpy a piece (14.7 GB/s per
+// thread), queue its DMA, reuse the slot when its DMA is done.  One call stays host-copy bound, but the asynchronous entry points
+// run up to three calls on three threads, and three memcpy streams keep PCIe fed.  Page-locked sources are copied directly.
+constexpr size_t kBounceBytes = 8u << 20;
+static bool host_is_pageable(const void* p) {
+#ifdef NSB_EMULATE
+    (void)p;
+    return false;
+#else
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+#endif
+}
+static cudaError_t copy_h2d(nsb_handle_s* h, void* dst, const void* src, size_t bytes, cudaStream_t st, bool pageable) {
+    if (!pageable || bytes < (4u << 20)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+    for (size_t off = 0; off < bytes; off += kBounceBytes) {
+        const int slot = (int)(h->bounce_next++ & 3u);
+        cudaError_t e;
+        if (!h->bounce[slot]) {
+            if ((e = cudaHostAlloc(&h->bounce[slot], kBounceBytes, cudaHostAllocDefault)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&h->bounce_ev[slot], cudaEventDisableTiming)) != cudaSuccess) return e;
+        } else if ((e = cudaEventSynchronize(h->bounce_ev[slot])) != cudaSuccess) {
+            return e;
+        }
+        const size_t n = bytes - off < kBounceBytes ? bytes - off : kBounceBytes;
+        memcpy(h->bounce[slot], static_cast<const char*>(src) + off, n);
+        if ((e = cudaMemcpyAsync(static_cast<char*>(dst) + off, h->bounce[slot], n, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(h->bounce_ev[slot], st)) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 static int grid_1d(long long n, int threads, int max_blocks) {
     long long g = (n + threads - 1) / threads;
     if (g < 1) g = 1;
@@ -768,9 +806,10 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
             CUA(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
             CUA(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
         }
+        const bool pageable = host_is_pageable(wav);
         for (int c = 0; c < n_chunks; ++c) {                     // all input copies are queued up front, in chunk order
             const long long s0 = h->h_samp_off[cuts[c]], s1 = h->h_samp_off[cuts[c + 1]];
-            CUA(cudaMemcpyAsync(reinterpret_cast<float*>(h->ws_in.p) + s0, wav + s0, sizeof(float) * (size_t)(s1 - s0), cudaMemcpyHostToDevice, h->copy_in));
+            CUA(copy_h2d(h, reinterpret_cast<float*>(h->ws_in.p) + s0, wav + s0, sizeof(float) * (size_t)(s1 - s0), h->copy_in, pageable));
             CUA(cudaEventRecord(ev_in[c], h->copy_in));
         }
     }
@@ -1262,14 +1301,14 @@ static int griffin_lim_impl(nsb_handle_t h, const float* spec, int32_t layout, c
             CUE(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
         }
         // all input copies are queued up front on the copy-in stream, in chunk order
+        const bool pg_spec = host_is_pageable(spec), pg_phase = init_phase && host_is_pageable(init_phase);
         for (int c = 0; c < n_chunks; ++c) {
             const size_t f0 = h->h_frame_off[cuts[c]], f1 = h->h_frame_off[cuts[c + 1]];
             const size_t Fb = h->F;
-            CUE(cudaMemcpyAsync(reinterpret_cast<float*>(h->ws_in.p) + f0 * Fb, spec + f0 * Fb, sizeof(float) * (f1 - f0) * Fb,
-                                cudaMemcpyHostToDevice, h->copy_in));
+            CUE(copy_h2d(h, reinterpret_cast<float*>(h->ws_in.p) + f0 * Fb, spec + f0 * Fb, sizeof(float) * (f1 - f0) * Fb, h->copy_in, pg_spec));
             if (init_phase)
-                CUE(cudaMemcpyAsync(reinterpret_cast<float2*>(h->ws_in2.p) + f0 * Fb, reinterpret_cast<const float2*>(init_phase) + f0 * Fb,
-                                    sizeof(float2) * (f1 - f0) * Fb, cudaMemcpyHostToDevice, h->copy_in));
+                CUE(copy_h2d(h, reinterpret_cast<float2*>(h->ws_in2.p) + f0 * Fb, reinterpret_cast<const float2*>(init_phase) + f0 * Fb,
+                             sizeof(float2) * (f1 - f0) * Fb, h->copy_in, pg_phase));
             CUE(cudaEventRecord(ev_in[c], h->copy_in));
         }
     }
@@ -1786,7 +1825,7 @@ extern "C" int nsb_device_copy(int device, void* dst, const void* src, uint64_t 
 //
 // A synchronous NSB_HOST call keeps its caller inside the library for the whole batch, so consecutive batches cannot overlap
 // one's copy-out and pipeline tail with the next one's copy-in and ramp.  The asynchronous entry points hand the call to one
-// of `slots` (default 2) worker threads of the handle.  Every slot owns a CHILD handle - private streams, descriptors,
+// of `slots` (default 3) worker threads of the handle.  Every slot owns a CHILD handle - private streams, descriptors,
 // scheduling counters and workspaces, nothing shared with its siblings - and runs the ordinary synchronous call on it, so two
 // batches are in flight on the GPU at once: the second one's H2D copies and first waves fill what the first one's tail leaves
 // idle.  The caller's buffers must stay valid until nsb_wait(ticket) returns; n_frames / n_samples are copied at submit.
@@ -1926,6 +1965,10 @@ extern "C" int nsb_griffin_lim_submit(nsb_handle_t h, const float* spec, int32_t
     if (!spec || !n_frames || !wav_out || batch < 1) return fail(NSB_ERR_INVALID, "null/empty argument");
     std::vector<int32_t> nf(n_frames, n_frames + batch);
     return async_submit(h, [=](nsb_handle_s* c) {
+        // with several batches in flight the overlap comes from the neighbours: one chunk per call (copy in, ONE launch of all
+        // iterations, copy out) beats the wave schedule, whose small first launches only pay when a call runs alone
+        // (profiles/r2/e2e_async.txt: 17.45 against 18.67 ms per step)
+        if (c->host_chunks == 0) c->host_chunks = 1;
         return nsb_griffin_lim(c, spec, layout, nf.data(), batch, init_phase_complex, seed, iters, flags, wav_out, out_dtype, NSB_HOST, nullptr);
     }, ticket);
 }
@@ -1947,6 +1990,7 @@ extern "C" int nsb_synthesize_submit(nsb_handle_t h, const float* spec, const in
     if (!spec || !n_frames || !wav_out || !endpoints || batch < 1) return fail(NSB_ERR_INVALID, "null/empty argument");
     std::vector<int32_t> nf(n_frames, n_frames + batch);
     return async_submit(h, [=](nsb_handle_s* c) {
+        if (c->host_chunks == 0) c->host_chunks = 1;
         return nsb_synthesize_ex(c, spec, nf.data(), batch, iters, threshold_db, min_silence_sec, flags, wav_out, out_dtype, endpoints, NSB_HOST, nullptr);
     }, ticket);
 }
