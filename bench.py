@@ -10,13 +10,18 @@ phase renormalise, iSTFT) -> de-emphasis).  With N GPUs every rank runs its own 
 no collective on the data path; weak scaling) and the value is the whole-job aggregate.
 
   value : device-resident inputs/outputs, CUDA events on the launching stream, max over ranks
-  e2e   : the public Python API (nspeech_b200.batch.inv_spectrogram_batch) on pinned HOST buffers, H2D and
-          D2H inside the timed region
+  e2e   : the public Python API on HOST buffers, H2D and D2H of every step inside the timed region:
+          nspeech_b200.batch.inv_spectrogram_stream (nsb_griffin_lim_submit / nsb_wait, three batches in flight) on page-locked
+          input arrays; beside it `e2e_sync` (one synchronous inv_spectrogram_batch call per step, round 1's e2e) and
+          `e2e_pageable` (the same stream fed from plain numpy arrays)
   roofline : the Griffin-Lim iteration kernel (k_gl_stream; one launch runs all 60 iterations) timed alone with CUDA events;
           algorithmic bytes = 6,100 B per frame per iteration (SURVEY.md section 8d) against MEASURED_PEAKS.json's HBM copy bandwidth;
           the FP32-side numbers are reported beside it because the fused iteration is FP32-bound
   cpu_baseline : the numpy oracle (a port of the reference's librosa path; the reference itself cannot be
           imported here) on this box's host cores, on a bounded sample of the same workload
+  features : the second BASELINE metric, mel frames/s of spectrogram + melspectrogram over BASELINE config 2 (13,100
+          LJSpeech-shaped clips), with its own roofline, e2e and cpu_baseline
+  configs  : BASELINE configs 1 (single-utterance latency), 4 (the synthesis stage at batch 32) and 5 (batch x iterations sweep)
 
 ``--impl reference`` times that CPU path as the arm of its own (all host cores, one utterance per process, the
 parallelism of the reference's datasets/process.py:11-18).
@@ -43,10 +48,10 @@ FLOPS_PER_FRAME_ITER = 2 * 56320 + 12 * N_BINS         # 2 real 2048-FFTs (2.5 N
 BYTES_PER_FRAME_FULL = (ITERS + 1) * 4 * N_BINS + (2 * ITERS + 1) * 4 * HOP + 8 * HOP + 4 * N_BINS
 FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_gl_iter launch, from the committed ncu --set full capture
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 20.580e9 + 3.885e9
-NCU_TRAFFIC_SOURCE = "profiles/r1/ncu_full_k_gl_stream_fused60.txt (dram__bytes_read.sum + dram__bytes_write.sum of one 60-iteration launch)"
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 20.579e9 + 3.884e9
+NCU_TRAFFIC_SOURCE = "profiles/r2/ncu_full_k_gl_stream_fused60.txt (dram__bytes_read.sum + dram__bytes_write.sum of one 60-iteration launch)"
 # the feature kernel: DRAM bytes per frame of one k_analysis<FEATURES> launch (268,734 frames) from the committed ncu --set full capture
-NCU_FEATURES_TRAFFIC_BYTES_PER_FRAME = (270.27e6 + 1130.87e6) / 268734
+NCU_FEATURES_TRAFFIC_BYTES_PER_FRAME = (270.38e6 + 1130.41e6) / 268734
 NCU_FEATURES_TRAFFIC_SOURCE = "profiles/r2/ncu_full_k_analysis_features.txt (dram__bytes_read.sum + dram__bytes_write.sum per frame of a 268,734-frame launch, scaled to this launch's frames)"
 
 
@@ -399,9 +404,8 @@ def main():
     sync_steps(1)
     ms_e2e_sync = wall_ms(lambda: sync_steps(args.steps))
     pageable_inputs = [np.array(p_.array) for p_ in pin_in]          # plain numpy memory, what a drop-in caller holds
-    n_pg = max(2, args.steps // 2)
-    e2e_stream(2, pageable_inputs, 0)
-    ms_e2e_pageable = wall_ms(lambda: e2e_stream(n_pg, pageable_inputs, 400)) * args.steps / n_pg
+    e2e_stream(3, pageable_inputs, 0)
+    ms_e2e_pageable = wall_ms(lambda: e2e_stream(args.steps, pageable_inputs, 400))
     barrier()
 
     extra = {}

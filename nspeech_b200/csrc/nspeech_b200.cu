@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -70,7 +71,7 @@ struct nsb_handle_s {
     GenPlan gen{}, gen_tf{};         // their plan in the librosa and the tf.contrib.signal geometry
     float2* d_wt = nullptr;          // [n_fft] exp(-2 pi i m / n_fft)
     // pageable host input: staged through a ring of page-locked slots by the calling thread (copy_h2d)
-    void* bounce[4] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t bounce_ev[4] = {nullptr, nullptr, nullptr, nullptr}; unsigned bounce_next = 0;
+    void* bounce[8] = {}; cudaEvent_t bounce_ev[8] = {};
     DevBuf ws_frames;                // generic path: windowed frames before the overlap-add [frames][win]
     int user_tile_hops = 0, user_stream_grid = 0;
     cudaStream_t own_stream = nullptr, copy_in = nullptr, copy_out = nullptr;
@@ -282,7 +283,7 @@ extern "C" int nsb_destroy(nsb_handle_t h) {
     if (h->last_done) cudaEventDestroy(h->last_done);
     cudaFree(h->d_tw); cudaFree(h->d_win); cudaFree(h->d_win_tf); cudaFree(h->d_rinv); cudaFree(h->d_rinv_tf); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo); cudaFree(h->d_mel_n); cudaFree(h->d_mel_ptr); cudaFree(h->d_mel_seg); cudaFree(h->d_mel_coef);
     cudaFree(h->d_status); cudaFree(h->d_wt); h->ws_frames.release();
-    for (int i = 0; i < 4; ++i) { if (h->bounce[i]) cudaFreeHost(h->bounce[i]); if (h->bounce_ev[i]) cudaEventDestroy(h->bounce_ev[i]); }
+    for (int i = 0; i < 8; ++i) { if (h->bounce[i]) cudaFreeHost(h->bounce[i]); if (h->bounce_ev[i]) cudaEventDestroy(h->bounce_ev[i]); }
     if (h->h_desc) cudaFreeHost(h->h_desc);
     h->d_desc.release(); h->d_trace.release(); h->d_done.release(); h->d_done2.release(); h->ws_mag.release(); h->ws_y0.release(); h->ws_y1.release();
     h->ws_in.release(); h->ws_in2.release(); h->ws_out.release(); h->ws_out2.release(); h->ws_ep.release();
@@ -659,11 +660,13 @@ static int check_launch(nsb_handle_s* h, const char* what) {
 }
 
 // Host -> device copy of a caller's buffer.  cudaMemcpyAsync from PAGEABLE memory is staged by the driver at a fifth of the PCIe
-// rate (11.6 against 55 GB/s here, profiles/r2/host_transfer.txt) and blocks the caller meanwhile; a drop-in caller hands plain numpy
-// arrays.  So large pageable sources go through the handle's own ring of four 8 MB page-locked slots: memcpy a piece (14.7 GB/s per
-// thread), queue its DMA, reuse the slot when its DMA is done.  One call stays host-copy bound, but the asynchronous entry points
-// run up to three calls on three threads, and three memcpy streams keep PCIe fed.  Page-locked sources are copied directly.
-constexpr size_t kBounceBytes = 8u << 20;
+// rate (11.6 against 55 GB/s here, profiles/r2/host_transfer.txt) and blocks the caller meanwhile - and a drop-in caller hands plain
+// numpy arrays.  So large pageable sources go through the handle's own page-locked slots: four short-lived threads (one memcpy
+// stream moves 14.7 GB/s, PCIe needs four) each copy every fourth 4 MB piece into one of their two slots and queue its DMA; a
+// slot is reused when its DMA is done.  The pieces reach the stream in any order; the caller's event behind the call orders them.
+// Page-locked sources are copied directly.
+constexpr size_t kBounceBytes = 4u << 20;
+constexpr int kBounceThreads = 4;
 static bool host_is_pageable(const void* p) {
 #ifdef NSB_EMULATE
     (void)p;
@@ -675,21 +678,34 @@ static bool host_is_pageable(const void* p) {
 #endif
 }
 static cudaError_t copy_h2d(nsb_handle_s* h, void* dst, const void* src, size_t bytes, cudaStream_t st, bool pageable) {
-    if (!pageable || bytes < (4u << 20)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
-    for (size_t off = 0; off < bytes; off += kBounceBytes) {
-        const int slot = (int)(h->bounce_next++ & 3u);
-        cudaError_t e;
-        if (!h->bounce[slot]) {
-            if ((e = cudaHostAlloc(&h->bounce[slot], kBounceBytes, cudaHostAllocDefault)) != cudaSuccess) return e;
-            if ((e = cudaEventCreateWithFlags(&h->bounce_ev[slot], cudaEventDisableTiming)) != cudaSuccess) return e;
-        } else if ((e = cudaEventSynchronize(h->bounce_ev[slot])) != cudaSuccess) {
-            return e;
+    if (!pageable || bytes < (8u << 20)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+    for (int i = 0; i < 2 * kBounceThreads; ++i)
+        if (!h->bounce[i]) {
+            cudaError_t e;
+            if ((e = cudaHostAlloc(&h->bounce[i], kBounceBytes, cudaHostAllocDefault)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&h->bounce_ev[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(h->bounce_ev[i], st)) != cudaSuccess) return e;
         }
-        const size_t n = bytes - off < kBounceBytes ? bytes - off : kBounceBytes;
-        memcpy(h->bounce[slot], static_cast<const char*>(src) + off, n);
-        if ((e = cudaMemcpyAsync(static_cast<char*>(dst) + off, h->bounce[slot], n, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
-        if ((e = cudaEventRecord(h->bounce_ev[slot], st)) != cudaSuccess) return e;
-    }
+    const size_t pieces = (bytes + kBounceBytes - 1) / kBounceBytes;
+    cudaError_t errs[kBounceThreads];
+    auto work = [&](int t) {
+        cudaError_t e = cudaSetDevice(h->device);
+        unsigned turn = 0;
+        for (size_t i = (size_t)t; i < pieces && e == cudaSuccess; i += kBounceThreads, ++turn) {
+            const int slot = 2 * t + (int)(turn & 1u);
+            if ((e = cudaEventSynchronize(h->bounce_ev[slot])) != cudaSuccess) break;
+            const size_t off = i * kBounceBytes, n = bytes - off < kBounceBytes ? bytes - off : kBounceBytes;
+            memcpy(h->bounce[slot], static_cast<const char*>(src) + off, n);
+            if ((e = cudaMemcpyAsync(static_cast<char*>(dst) + off, h->bounce[slot], n, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+            e = cudaEventRecord(h->bounce_ev[slot], st);
+        }
+        errs[t] = e;
+    };
+    std::thread th[kBounceThreads - 1];
+    for (int t = 1; t < kBounceThreads; ++t) th[t - 1] = std::thread(work, t);
+    work(0);
+    for (int t = 1; t < kBounceThreads; ++t) th[t - 1].join();
+    for (int t = 0; t < kBounceThreads; ++t) if (errs[t] != cudaSuccess) return errs[t];
     return cudaSuccess;
 }
 
