@@ -115,6 +115,8 @@ __device__ __forceinline__ void load_frame(c2 (&z)[32], const float* __restrict_
     const bool interior = (first >= (PREEMPH ? 1 : 0)) && (last <= L);
     if (interior) {
         const float* xs = x + start + lane;
+        // (x[n-1] for the pre-emphasis by rotating the loaded samples one lane - two shuffles instead of two more loads per 64 samples -
+        // measured slower: 0.954 vs 0.901 ms, the shuffle sits between the load and its first use; profiles/r2/features_ab_shuffle_preemphasis.txt)
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
             if (t >= t0 && t < t1) {
@@ -160,7 +162,7 @@ struct AnalysisParams {
     // _normalize(_amp_to_db(amp) - ref) = clip(log2(max(1e-5, amp)) * db_scale + db_offset, 0, 1) with
     // db_scale = 20 log10(2) / (-min_level_db), db_offset = (-ref - min_level_db) / (-min_level_db) (host, from double)
     float db_scale, db_offset_lin, db_offset_mel;
-    int mel_skew;          // 1: magnitude row with a pad word per 32 bins (A/B: NSB_OPT_MEL_LINES 2)
+    int mel_skew;          // 1: magnitude row with a pad word per 32 bins (production; NSB_OPT_MEL_LINES 1 is the A/B switch without it)
     int* status;           // device flag: bit0 = non-finite input
 };
 
@@ -224,7 +226,7 @@ template <bool SKEW> __device__ __forceinline__ int mag_skew(int kb) { return SK
 // MUFU operations of a bin no longer depend on each other.
 template <bool LIN, bool SKEW>
 __device__ __forceinline__ void feature_epilogue(const AnalysisParams& P, c2 (&z)[32], int lane, float2* scratch, float* o_lin, float* o_mel,
-                                                 float db_scale, float db_off_lin, float db_off_mel, bool& bad) {
+                                                 float db_scale, float db_off_lin, float db_off_mel, bool& bad, const float4* coef_s) {
     float* magrow = reinterpret_cast<float*>(scratch);
     float* mom = magrow + kMagSkewLen;                             // [num_mels + 1][2] (the host checks that it fits the scratch tile)
     float2* xch = reinterpret_cast<float2*>(magrow + kMagSkewLen + 2 * 96 + 4);   // lane 0's 32 slots (8-byte aligned: 1256 floats in)
@@ -288,7 +290,7 @@ __device__ __forceinline__ void feature_epilogue(const AnalysisParams& P, c2 (&z
         }
         __syncwarp();
         for (int m = lane; m < M; m += 32) {
-            const float4 c = __ldg(P.plan.mel_coef + m);
+            const float4 c = coef_s ? coef_s[m] : __ldg(P.plan.mel_coef + m);
             const float2 r = *reinterpret_cast<const float2*>(mom + 2 * m), f = *reinterpret_cast<const float2*>(mom + 2 * m + 2);
             float acc = c.x * r.x;
             acc = fmaf(c.y, r.y, acc); acc = fmaf(c.z, f.x, acc); acc = fmaf(c.w, f.y, acc);
@@ -312,6 +314,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
     float* win_s = reinterpret_cast<float*>(tw_s + kTwF2);
     float2* scratch_all = reinterpret_cast<float2*>(win_s + kNfft);
+    // the mel rows' line coefficients, once per CTA (a load from L2 per row and frame otherwise: 4 % of the stall samples)
+    float4* coef_s = reinterpret_cast<float4*>(scratch_all + kScratchF2 * kWarpsPerCta);
+    const bool mel_tables = MODE == ANALYSIS_FEATURES && P.plan.mel_seg && P.plan.num_mels <= 96;
+    if (mel_tables)
+        for (int i = threadIdx.x; i < P.plan.num_mels; i += kThreads) coef_s[i] = P.plan.mel_coef[i];
     load_twiddle_pairs(tw_s, P.plan.tw);
     const float4* tw4 = reinterpret_cast<const float4*>(tw_s);
     const float2* tw31 = tw_s + 15 * 64;
@@ -362,11 +369,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
             float* o_lin = P.out_lin ? P.out_lin + (size_t)orow * kBins : nullptr;
             float* o_mel = P.out_mel ? P.out_mel + (size_t)orow * P.plan.num_mels : nullptr;
             if (P.mel_skew) {
-                if (o_lin) feature_epilogue<true, true>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad);
-                else feature_epilogue<false, true>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad);
+                if (o_lin) feature_epilogue<true, true>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad, mel_tables ? coef_s : nullptr);
+                else feature_epilogue<false, true>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad, mel_tables ? coef_s : nullptr);
             } else {
-                if (o_lin) feature_epilogue<true, false>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad);
-                else feature_epilogue<false, false>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad);
+                if (o_lin) feature_epilogue<true, false>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad, mel_tables ? coef_s : nullptr);
+                else feature_epilogue<false, false>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad, mel_tables ? coef_s : nullptr);
             }
         }
     }

@@ -97,7 +97,7 @@ struct nsb_handle_s {
     float* d_mel_w = nullptr;
     int *d_mel_lo = nullptr, *d_mel_n = nullptr, *d_mel_ptr = nullptr;
     int* d_mel_seg = nullptr; float4* d_mel_coef = nullptr;      // the filters as line segments (null: not representable, sparse rows are used)
-    int mel_lines = 1;               // A/B hook: 0 = sparse mel rows even when the line form exists, 2 = line form on the skewed magnitude row
+    int mel_lines = 2;               // 2 = line segments on the skewed magnitude row (production), 1 = on the plain row, 0 = sparse mel rows (A/B hooks)
     int* d_status = nullptr;
     std::vector<double> mel_dense;   // [num_mels][num_freq]
     // descriptors
@@ -203,7 +203,9 @@ static int set_smem(K kernel, size_t bytes) {
     return NSB_OK;
 }
 
-static size_t analysis_smem() { return sizeof(float2) * kTwF2 + sizeof(float) * kNfft + sizeof(float2) * kScratchF2 * kWarpsPerCta; }
+static size_t analysis_smem() {
+    return sizeof(float2) * kTwF2 + sizeof(float) * kNfft + sizeof(float2) * kScratchF2 * kWarpsPerCta + sizeof(float4) * 96;   // ... + mel line coefficients
+}
 static size_t synth_smem(int hop, int H) {
     size_t fl = 2 * kTwF2 + kNfft + hop + (size_t)H * hop;
     fl = (fl + 3) & ~(size_t)3;
