@@ -3,11 +3,11 @@
 // The fused kernels of kernels.cuh / gl_iter.cuh / gl_stream.cuh are specialised for the yaml's n_fft = 2048 (64 x 32 in
 // registers).  Every other num_freq - 513 (n_fft 1024), 2049 (4096), the yaml's commented alternative 2048 (n_fft 4094 =
 // 2 * 23 * 89), 401 (800 = 2^5 * 5^2) ... - runs here: one CTA per frame, the frame's real transform as a complex FFT of
-// length M = n_fft / 2 in shared memory (Stockham autosort, MIXED RADIX: every stage is a radix-r pass for a factor r of M
-// - 8, 4, 2, then the odd primes - computed as a direct r-point DFT per output with twiddles from one table
-// exp(-2 pi i m / n_fft)) plus the real-split pass.  O(M * sum of the factors) per frame: 30 k complex multiply-adds for
-// n_fft 4096, 230 k for 4094.  Correct first, fast second: the spectrum of an iteration crosses shared memory only, but
-// frames, magnitudes and the windowed frames of the overlap-add go through HBM, and the overlap-add is a gather kernel of
+// length M = n_fft / 2 in shared memory (Stockham autosort, MIXED RADIX: the host factors M into 8s, 4s, 2s and its odd
+// primes; the power-of-two factors run as butterfly passes - one thread per butterfly, the R-point DFT in registers - an odd
+// prime r as a direct r-point DFT per output, twiddles from one table exp(-2 pi i m / n_fft) that sits in shared memory when
+// it fits) plus the real-split pass.  The spectrum of an iteration crosses shared memory only, but frames, magnitudes and the
+// windowed frames of the overlap-add go through HBM, and the overlap-add is a gather kernel of
 // its own (sum over the covering frames in ascending frame order: deterministic, no atomics).
 //
 // Replaces, for those hparams: librosa.stft / istft / filters.mel as called from audio.py:108, 113, 147 and the
@@ -25,37 +25,70 @@ struct GenPlan {
     int n_stages;
     int radix[kGenMaxStages];        // product = M
     const float2* wt;                // [n_fft] exp(-2 pi i m / n_fft), rounded from double
+    int wt_in_smem;                  // 1: the kernels keep a copy of the table in shared memory (it fits beside the frame)
     const float* win;                // [n_fft] window in the frame (librosa: padded centrally; tf: at the start)
     int hop, win_len, lo, origin, norm_wss;
     // sparse mel rows (the Plan's, built for F bins)
     const float* mel_w; const int* mel_lo; const int* mel_n; const int* mel_ptr; int num_mels;
 };
 
+// radix-R butterfly pass for R = 2, 4, 8: one thread per butterfly - R inputs, R - 1 twiddle multiplications, the R-point DFT in
+// registers (FftC of fft_core.cuh, packed fp32) - instead of R multiply-adds per OUTPUT: 5 x fewer operations at radix 8
+template <int DIR, int R>
+__device__ __forceinline__ void gen_stage_pow2(const GenPlan& G, const float2* wt, const float2* a, float2* b, int Ns) {
+    const int Mr = G.M / R;
+    const int tstep = G.n_fft / (Ns * R);                        // exp(-2 pi i / (Ns R)) = wt[tstep]
+    for (int j = threadIdx.x; j < Mr; j += blockDim.x) {
+        const int k = j % Ns;
+        c2 v[R], y[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = a[j + q * Mr];
+        if (k) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) {
+                const float2 w = wt[q * k * tstep];               // q k < Ns R: the index stays below n_fft
+                v[q] = DIR > 0 ? cmul_conj(v[q], w) : cmul(v[q], w);
+            }
+        }
+        FftC<R, DIR, 1>::run(v, y);
+        float2* o = b + (j / Ns) * Ns * R + k;
+#pragma unroll
+        for (int t = 0; t < R; ++t) o[t * Ns] = y[t];
+    }
+}
+
 // complex FFT of length M: `a` holds the input, `b` is scratch; returns the array that holds the result (natural order).
 // DIR = -1: sum x e^{-i...} (forward), +1: conjugate twiddles (unnormalised inverse).  All threads of the CTA.
+// Factors 8, 4, 2 run as butterfly passes; an odd prime factor r as a direct r-point DFT per output (r multiply-adds, the
+// twiddle index advanced by a modular add - no per-radix code).
 template <int DIR>
-__device__ float2* gen_cfft(const GenPlan& G, float2* a, float2* b) {
+__device__ float2* gen_cfft(const GenPlan& G, const float2* wt, float2* a, float2* b) {
     const int M = G.M;
     int Ns = 1;
     for (int s = 0; s < G.n_stages; ++s) {
         const int r = G.radix[s], Mr = M / r;
-        const int tstep = G.n_fft / (Ns * r);                    // exp(-2 pi i / (Ns r)) = wt[tstep]
-        for (int o = threadIdx.x; o < M; o += blockDim.x) {
-            const int t = o / Mr, j = o - t * Mr;
-            const int k = j % Ns;
-            const int step = (k + t * Ns) * tstep;               // < n_fft: the twiddle index advances by this per input
-            int idx = 0;
-            float ax = 0.f, ay = 0.f;
-            for (int q = 0; q < r; ++q) {
-                const float2 v = a[j + q * Mr];
-                float2 w = __ldg(G.wt + idx);
-                if (DIR > 0) w.y = -w.y;
-                ax = fmaf(v.x, w.x, fmaf(-v.y, w.y, ax));
-                ay = fmaf(v.x, w.y, fmaf(v.y, w.x, ay));
-                idx += step;
-                if (idx >= G.n_fft) idx -= G.n_fft;
+        if (r == 8) gen_stage_pow2<DIR, 8>(G, wt, a, b, Ns);
+        else if (r == 4) gen_stage_pow2<DIR, 4>(G, wt, a, b, Ns);
+        else if (r == 2) gen_stage_pow2<DIR, 2>(G, wt, a, b, Ns);
+        else {
+            const int tstep = G.n_fft / (Ns * r);                    // exp(-2 pi i / (Ns r)) = wt[tstep]
+            for (int o = threadIdx.x; o < M; o += blockDim.x) {
+                const int t = o / Mr, j = o - t * Mr;
+                const int k = j % Ns;
+                const int step = (k + t * Ns) * tstep;               // < n_fft: the twiddle index advances by this per input
+                int idx = 0;
+                float ax = 0.f, ay = 0.f;
+                for (int q = 0; q < r; ++q) {
+                    const float2 v = a[j + q * Mr];
+                    float2 w = wt[idx];
+                    if (DIR > 0) w.y = -w.y;
+                    ax = fmaf(v.x, w.x, fmaf(-v.y, w.y, ax));
+                    ay = fmaf(v.x, w.y, fmaf(v.y, w.x, ay));
+                    idx += step;
+                    if (idx >= G.n_fft) idx -= G.n_fft;
+                }
+                b[(j / Ns) * Ns * r + k + t * Ns] = make_float2(ax, ay);
             }
-            b[(j / Ns) * Ns * r + k + t * Ns] = make_float2(ax, ay);
         }
         __syncthreads();
         float2* tmp = a; a = b; b = tmp;
@@ -64,26 +97,35 @@ __device__ float2* gen_cfft(const GenPlan& G, float2* a, float2* b) {
     return a;
 }
 
+// the twiddle table the CTA reads: a shared-memory copy behind the frame's arrays when it fits (4 to 8 table reads per butterfly
+// otherwise go to L1 / L2), else the global one
+__device__ __forceinline__ const float2* gen_twiddles(const GenPlan& G, float2* smem_copy) {
+    if (!G.wt_in_smem) return G.wt;
+    for (int i = threadIdx.x; i < G.n_fft; i += blockDim.x) smem_copy[i] = __ldg(G.wt + i);
+    __syncthreads();
+    return smem_copy;
+}
+
 // rfft of the packed frame z[m] = (x[2m], x[2m+1]) after gen_cfft: X[k], k = 0..M
-__device__ __forceinline__ float2 gen_split_fwd(const GenPlan& G, const float2* Z, int k) {
+__device__ __forceinline__ float2 gen_split_fwd(const GenPlan& G, const float2* wt, const float2* Z, int k) {
     const int M = G.M;
     const float2 zk = Z[k == M ? 0 : k];
     const float2 zc = Z[k == 0 ? 0 : M - k];                    // Z[M - k] (conjugated below)
     const float ex = 0.5f * (zk.x + zc.x), ey = 0.5f * (zk.y - zc.y);         // E = (Z[k] + conj Z[M-k]) / 2
     const float dx = zk.x - zc.x, dy = zk.y + zc.y;                            // D = Z[k] - conj Z[M-k]
     const float ox = 0.5f * dy, oy = -0.5f * dx;                               // O = -i D / 2
-    const float2 w = __ldg(G.wt + k);                                          // exp(-2 pi i k / n_fft), k <= M < n_fft
+    const float2 w = wt[k];                                                    // exp(-2 pi i k / n_fft), k <= M < n_fft
     return make_float2(ex + (ox * w.x - oy * w.y), ey + (ox * w.y + oy * w.x));
 }
 // the packed spectrum whose inverse complex FFT is (x[2m], x[2m+1]) * M, from the Hermitian half X[0..M] (function of k)
 template <typename GetX>
-__device__ __forceinline__ float2 gen_split_inv(const GenPlan& G, GetX X, int k) {
+__device__ __forceinline__ float2 gen_split_inv(const GenPlan& G, const float2* wt, GetX X, int k) {
     const int M = G.M;
     float2 xk = X(k), xc = X(M - k);
     if (k == 0) { xk.y = 0.f; xc.y = 0.f; }                    // DC and Nyquist are real (irfft ignores their imaginary parts)
     const float ex = 0.5f * (xk.x + xc.x), ey = 0.5f * (xk.y - xc.y);         // E = (X[k] + conj X[M-k]) / 2
     const float dx = 0.5f * (xk.x - xc.x), dy = 0.5f * (xk.y + xc.y);         // (X[k] - conj X[M-k]) / 2
-    const float2 w = __ldg(G.wt + k);
+    const float2 w = wt[k];
     const float ox = dx * w.x + dy * w.y, oy = dy * w.x - dx * w.y;            // O = conj(w) * that
     return make_float2(ex - oy, ey + ox);                                      // Z = E + i O
 }
@@ -138,18 +180,19 @@ __global__ void __launch_bounds__(kGenThreads) k_gen_analysis(GenAnalysisParams 
     const GenPlan& G = P.plan;
     float2* a = reinterpret_cast<float2*>(smem_raw);
     float2* b = a + G.M;
+    const float2* wt = gen_twiddles(G, b + G.M);
     bool bad = false;
     for (int f = P.batch.frame_base + (int)blockIdx.x; f < P.batch.frame_base + P.total_frames; f += (int)gridDim.x) {
         const GenFrameLoc loc = gen_locate(P.batch, f);
         const long long start = (long long)loc.k * G.hop - G.origin;
         if (P.preemph_on) gen_load_frame<true>(G, a, P.wav + loc.s_off, loc.L, start, P.preemph);
         else gen_load_frame<false>(G, a, P.wav + loc.s_off, loc.L, start, 0.f);
-        float2* Z = gen_cfft<-1>(G, a, b);
+        float2* Z = gen_cfft<-1>(G, wt, a, b);
         float2* other = (Z == a) ? b : a;
         if (P.out_complex) {
             float2* o = P.out_complex + (size_t)f * G.F;
             for (int k = threadIdx.x; k <= G.M; k += blockDim.x) {
-                const float2 X = gen_split_fwd(G, Z, k);
+                const float2 X = gen_split_fwd(G, wt, Z, k);
                 bad |= !(isfinite(X.x) && isfinite(X.y));
                 o[k] = X;
             }
@@ -159,7 +202,7 @@ __global__ void __launch_bounds__(kGenThreads) k_gen_analysis(GenAnalysisParams 
             float* magrow = reinterpret_cast<float*>(other);                  // F <= 2 M floats
             float* o_lin = P.out_lin ? P.out_lin + (size_t)orow * G.F : nullptr;
             for (int k = threadIdx.x; k <= G.M; k += blockDim.x) {
-                const float2 X = gen_split_fwd(G, Z, k);
+                const float2 X = gen_split_fwd(G, wt, Z, k);
                 const float mg = sqrtf(fmaf(X.x, X.x, X.y * X.y));
                 bad |= !isfinite(mg);
                 magrow[k] = mg;
@@ -206,15 +249,16 @@ __global__ void __launch_bounds__(kGenThreads) k_gen_synth(GenSynthParams P) {
     float2* a = reinterpret_cast<float2*>(smem_raw);
     float2* b = a + M;
     float2* X = b + M;                                     // [F] the frame's spectrum
+    const float2* wt = gen_twiddles(G, X + G.F);
     bool bad = false;
     for (int f = P.batch.frame_base + (int)blockIdx.x; f < P.batch.frame_base + P.total_frames; f += (int)gridDim.x) {
         const GenFrameLoc loc = gen_locate(P.batch, f);
         const float* mrow = P.mag ? P.mag + (size_t)f * G.F : nullptr;
         if (P.src == SRC_Y) {
             gen_load_frame<false>(G, a, P.y_in + loc.s_off, loc.L, (long long)loc.k * G.hop - G.origin, 0.f);
-            const float2* Z = gen_cfft<-1>(G, a, b);
+            const float2* Z = gen_cfft<-1>(G, wt, a, b);
             for (int k = threadIdx.x; k <= M; k += blockDim.x) {
-                c2 z = gen_split_fwd(G, Z, k);
+                c2 z = gen_split_fwd(G, wt, Z, k);
                 const float S = __ldg(mrow + k);
                 if (k == 0 || k == M) z.y = 0.f;
                 if (P.tf_renorm) {
@@ -250,9 +294,9 @@ __global__ void __launch_bounds__(kGenThreads) k_gen_synth(GenSynthParams P) {
         }
         __syncthreads();
         for (int k = threadIdx.x; k < M; k += blockDim.x)
-            a[k] = gen_split_inv(G, [&](int i) { return X[i]; }, k);
+            a[k] = gen_split_inv(G, wt, [&](int i) { return X[i]; }, k);
         __syncthreads();
-        const float2* z = gen_cfft<+1>(G, a, b);
+        const float2* z = gen_cfft<+1>(G, wt, a, b);
         // x[2m] = Re z[m] / M, x[2m+1] = Im z[m] / M; keep the window's support, windowed
         float* o = P.frames_out + (size_t)f * G.win_len;
         const float inv = 1.0f / (float)M;

@@ -428,6 +428,7 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
         CUB(cudaMalloc(&h->d_wt, sizeof(float2) * n_fft));
         CUB(cudaMemcpy(h->d_wt, wt.data(), sizeof(float2) * n_fft, cudaMemcpyHostToDevice));
         G.wt = h->d_wt; G.hop = hop; G.win_len = win; G.num_mels = hp->num_mels;
+        G.wt_in_smem = ((size_t)(3 * G.M + 1 + n_fft) * sizeof(float2) <= 100 * 1024) ? 1 : 0;          // (up to n_fft = 4096: 81 KB, two CTAs per SM)
         G.mel_w = h->d_mel_w; G.mel_lo = h->d_mel_lo; G.mel_n = h->d_mel_n; G.mel_ptr = h->d_mel_ptr;
         h->gen_tf = G;
         G.win = h->d_win; G.lo = h->lo; G.origin = n_fft / 2; G.norm_wss = 1;
@@ -719,10 +720,12 @@ static int grid_1d(long long n, int threads, int max_blocks) {
 }
 
 // ---- generic-size path (gen_kernels.cuh): launch helpers ----
-static size_t gen_smem_analysis(const GenPlan& G) { return (size_t)2 * G.M * sizeof(float2); }
-static size_t gen_smem_synth(const GenPlan& G) { return (size_t)(3 * G.M + 1) * sizeof(float2); }
+static size_t gen_smem_analysis(const GenPlan& G) { return (size_t)(2 * G.M + (G.wt_in_smem ? G.n_fft : 0)) * sizeof(float2); }
+static size_t gen_smem_synth(const GenPlan& G) { return (size_t)(3 * G.M + 1 + (G.wt_in_smem ? G.n_fft : 0)) * sizeof(float2); }
+// threads per frame: a quarter of the complex length (a radix-8 pass has M / 8 butterflies), 64 to 256
+static int gen_threads(const GenPlan& G) { int t = G.M / 4; t = (t + 31) & ~31; return t < 64 ? 64 : (t > kGenThreads ? kGenThreads : t); }
 static int gen_grid(const nsb_handle_s* h, long long frames) {
-    const long long cap = 8LL * h->num_sms;
+    const long long cap = 16LL * h->num_sms;
     return (int)(frames < 1 ? 1 : (frames < cap ? frames : cap));
 }
 // frames of the (sub-)batch B from `src` -> windowed inverse transforms -> overlap-add into y_out (packed samples of the batch)
@@ -734,7 +737,7 @@ static int gen_synthesize(nsb_handle_s* h, const GenPlan& G, const Batch& B, int
     S.plan = G; S.batch = B; S.src = src; S.y_in = y_in; S.mag = mag; S.spec = spec; S.spec_bin_major = spec_bin_major;
     S.frames_out = reinterpret_cast<float*>(h->ws_frames.p) - (size_t)B.frame_base * G.win_len;     // indexed by the GLOBAL frame number
     S.total_frames = frames; S.tf_renorm = tf_renorm; S.seed = seed; S.status = h->d_status;
-    NSB_LAUNCH(k_gen_synth, gen_grid(h, frames), kGenThreads, gen_smem_synth(G), st, S);
+    NSB_LAUNCH(k_gen_synth, gen_grid(h, frames), gen_threads(G), gen_smem_synth(G), st, S);
     if ((rc = check_launch(h, "k_gen_synth"))) return rc;
     GenOlaParams O{};
     O.plan = G; O.batch = B; O.frames = S.frames_out; O.y_out = y_out; O.total_samples = total_samples;
@@ -850,7 +853,7 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
             Q.out_mel = mode == ANALYSIS_COMPLEX ? nullptr : d_mel;
             Q.preemph_on = preemph ? 1 : 0; Q.preemph = P.preemph;
             Q.db_scale = P.db_scale; Q.db_offset_lin = P.db_offset_lin; Q.db_offset_mel = P.db_offset_mel; Q.status = h->d_status;
-            NSB_LAUNCH(k_gen_analysis, gen_grid(h, P.total_frames), kGenThreads, gen_smem_analysis(Q.plan), st, Q);
+            NSB_LAUNCH(k_gen_analysis, gen_grid(h, P.total_frames), gen_threads(Q.plan), gen_smem_analysis(Q.plan), st, Q);
         } else if (mode == ANALYSIS_COMPLEX) {
             if (preemph) {
                 if (prune == 1) NSB_LAUNCH((k_analysis<ANALYSIS_COMPLEX, true, 1>), grid, kThreads, smem, st, P);
