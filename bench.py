@@ -473,11 +473,12 @@ def main():
                                                "what": "audio.inv_spectrogram on one [1025,401] spectrogram, 60 iterations, supplied initial phase"}
         lin4 = _lib.PinnedArray((32, 1500, N_BINS), np.float32)
         lin4.array[...] = torch.rand((32, 1500, N_BINS), generator=gen, dtype=torch.float32).numpy()
-        audio.synthesize_waveforms(lin4.array)
+        for _ in range(3):          # the same call as the timed one: workspaces, the int16 staging buffer and the pooled result block exist afterwards
+            audio.synthesize_waveforms(lin4.array, peak_normalize=True, dtype=np.int16)
         t0 = time.perf_counter()
-        for _ in range(3):
+        for _ in range(5):
             w4 = audio.synthesize_waveforms(lin4.array, peak_normalize=True, dtype=np.int16)
-        ms4 = max_over_ranks((time.perf_counter() - t0) / 3 * 1e3)
+        ms4 = max_over_ranks((time.perf_counter() - t0) / 5 * 1e3)
         cfgs["config4_synthesis_stage_batch32"] = {"ms_per_batch": ms4, "audio_s_per_s": world * 32 * (HOP * 1499 + 1000) / SR / (ms4 * 1e-3),
                                                    "what": "audio.synthesize_waveforms on [32,1500,1025] from host memory: TF-twin Griffin-Lim (60 iterations) + de-emphasis + "
                                                            "find_endpoint + save_wav scaling to int16, the stage after the network in synthesizer.py:51-53 / eval.py:43"}

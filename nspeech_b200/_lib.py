@@ -21,7 +21,7 @@ F32, F64, I16 = 0, 1, 2
 SYNTH_PEAK_NORMALIZE = 1
 EW_AMP_TO_DB, EW_DB_TO_AMP, EW_NORMALIZE, EW_DENORMALIZE = range(4)
 GL_DENORMALIZE, GL_DEEMPHASIS, GL_TF_TWIN = 1, 2, 4
-OPT_STREAM_SYNC_MODE, OPT_FUSE_ITERATIONS, OPT_WIDE_MODE, OPT_OVERLAP_CHUNKS, OPT_WAVE_SCHEDULE, OPT_MEL_LINES = 1, 2, 3, 4, 5, 6
+OPT_STREAM_SYNC_MODE, OPT_FUSE_ITERATIONS, OPT_WIDE_MODE, OPT_OVERLAP_CHUNKS, OPT_WAVE_SCHEDULE, OPT_MEL_LINES, OPT_SPECIALIZE = 1, 2, 3, 4, 5, 6, 7
 
 
 class ParameterError(ValueError):

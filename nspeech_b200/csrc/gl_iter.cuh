@@ -15,7 +15,7 @@
 //     256-byte exchange area instead of running on one lane while 31 idle;
 //   * branch-free renormalisation (the magnitudes are pre-scaled by a power of two in k_prepare_mag so the
 //     squares cannot overflow; exact zeros are fixed up in a rare warp-uniform path);
-//   * DEFCFG folds hop/win/lo of the reference's default hparams (250/1000/524) into immediates.
+//   * DEFCFG folds hop/win/lo of the reference's default hparams (250/1000/524; lo = 0 for the TF twin) into immediates.
 #pragma once
 #include "kernels.cuh"
 
@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
     NSB_DYN_SMEM(smem_raw);
     const int hop = DEFCFG ? 250 : P.plan.hop;
     const int win = DEFCFG ? 1000 : P.plan.win_len;
-    const int lo = DEFCFG ? 524 : P.plan.lo;
+    constexpr int LO = TFM ? 0 : 524;                // DEFCFG: librosa pads the window centrally, tf.contrib.signal on the right
+    const int lo = DEFCFG ? LO : P.plan.lo;
     const int C = DEFCFG ? 4 : P.colours;
     const int H = P.tile_hops;                       // a multiple of C (host guarantees it)
     float2* tw_s = reinterpret_cast<float2*>(smem_raw);
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float2* scratch = scratch_all + warp * kScratchF2;
-    const int origin = DEFCFG ? kNfft / 2 : P.plan.origin;
+    const int origin = DEFCFG ? (TFM ? 0 : kNfft / 2) : P.plan.origin;
     const int a = origin - lo;
     // first frame (possibly negative = does not exist) whose window support can reach hop h is h + kfirst0
     const int kfirst0 = (a - win >= 0) ? (a - win) / hop + 1 : -((win - a - 1) / hop + 1) + 1;
@@ -461,25 +462,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(GlParams P) {
                 constexpr int t0 = PruneRange<PRUNE>::t0, t1 = PruneRange<PRUNE>::t1;
                 const bool inside = (base + lo >= 0) && (base + lo + win <= n_out);
                 if (DEFCFG && inside) {
-                    // default hparams: the support n in [524, 1524) is known at compile time; (acc[n], acc[n+32]) and the
+                    // default hparams: the support n in [LO, LO + 1000) is known at compile time; (acc[n], acc[n+32]) and the
                     // two window values ride in register pairs so the accumulate is one FFMA2
-                    float* ap = acc + base + lane;
-#pragma unroll
-                    for (int t = 0; t < 32; ++t) {
-                        if (t >= t0 && t < t1) {
-                            if (t == 8) {
-                                if (lane >= 12) ap[64 * t] = fmaf(z[t].x, win_s[64 * t + lane], ap[64 * t]);
-                                ap[64 * t + 32] = fmaf(z[t].y, win_s[64 * t + 32 + lane], ap[64 * t + 32]);
-                            } else if (t == 23) {
-                                ap[64 * t] = fmaf(z[t].x, win_s[64 * t + lane], ap[64 * t]);
-                                if (lane < 20) ap[64 * t + 32] = fmaf(z[t].y, win_s[64 * t + 32 + lane], ap[64 * t + 32]);
-                            } else {
-                                c2 r = p_fma(z[t], mk2(win_s[64 * t + lane], win_s[64 * t + 32 + lane]), mk2(ap[64 * t], ap[64 * t + 32]));
-                                ap[64 * t] = r.x;
-                                ap[64 * t + 32] = r.y;
-                            }
-                        }
-                    }
+                    ola_fixed_support<LO, t0, t1>(acc + base + lane, z, lane,
+                                                  [&](int t) { return mk2(win_s[64 * t + lane], win_s[64 * t + 32 + lane]); });
                 } else {
                     // window support [lo, lo+win) clipped to the tile -> per-lane bitmasks of the valid t
                     // (n = 64 t + lane [+32]).  Touching nothing outside the support makes the plain RMW race-free.

@@ -233,9 +233,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
     NSB_DYN_SMEM(smem_raw);
     const int hop = DEFCFG ? 250 : P.plan.hop;
     const int win = DEFCFG ? 1000 : P.plan.win_len;
-    const int lo = DEFCFG ? 524 : P.plan.lo;
+    constexpr int LO = TFM ? 0 : 524;                // DEFCFG: librosa pads the window centrally, tf.contrib.signal on the right
+    const int lo = DEFCFG ? LO : P.plan.lo;
     const int C = DEFCFG ? 4 : P.colours;
-    const int origin = DEFCFG ? kNfft / 2 : P.plan.origin;
+    const int origin = DEFCFG ? (TFM ? 0 : kNfft / 2) : P.plan.origin;
     const int a = origin - lo;                       // frame k's window support starts at sample k*hop - a
     // hop h is touched by the frames h + kfirst0 .. h + klast0
     const int kfirst0 = (a - win >= 0) ? (a - win) / hop + 1 : -((win - a - 1) / hop + 1) + 1;
@@ -521,26 +522,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
                 if (q0 < 0) q0 += RS;
                 const bool inside = (base + lo >= xmin) && (base + lo + win <= L);
                 if (DEFCFG && inside && q0 + win <= RS) {
-                    // default hparams: the support n in [524, 1524) is known at compile time; (acc[n], acc[n+32]) and the
+                    // default hparams: the support n in [LO, LO + 1000) is known at compile time; (acc[n], acc[n+32]) and the
                     // two window values ride in register pairs so the accumulate is one FFMA2
-                    float* ap = ring + (q0 - lo) + lane;
-#pragma unroll
-                    for (int t = 0; t < 32; ++t) {
-                        if (t >= t0 && t < t1) {
-                            const c2 w = wp[t * 32 + lane];
-                            if (t == 8) {
-                                if (lane >= 12) ap[64 * t] = fmaf(z[t].x, w.x, ap[64 * t]);
-                                ap[64 * t + 32] = fmaf(z[t].y, w.y, ap[64 * t + 32]);
-                            } else if (t == 23) {
-                                ap[64 * t] = fmaf(z[t].x, w.x, ap[64 * t]);
-                                if (lane < 20) ap[64 * t + 32] = fmaf(z[t].y, w.y, ap[64 * t + 32]);
-                            } else {
-                                c2 rr = p_fma(z[t], w, mk2(ap[64 * t], ap[64 * t + 32]));
-                                ap[64 * t] = rr.x;
-                                ap[64 * t + 32] = rr.y;
-                            }
-                        }
-                    }
+                    ola_fixed_support<LO, t0, t1>(ring + (q0 - lo) + lane, z, lane, [&](int t) { return wp[t * 32 + lane]; });
                 } else {
                     // window support [lo, lo+win) clipped to the piece -> per-lane bitmasks of the valid t
                     // (n = 64 t + lane [+32]); indices wrap around the ring.  Touching nothing outside the support

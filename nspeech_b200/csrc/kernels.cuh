@@ -69,6 +69,31 @@ struct Plan {                    // device tables owned by the handle
 
 template <int PRUNE> struct PruneRange { static constexpr int t0 = PRUNE == 1 ? 8 : 0, t1 = PRUNE == 1 ? 24 : (PRUNE == 2 ? 16 : 32); };
 
+// Overlap-add of one frame whose window support n in [LO, LO + 1000) is a compile-time fact (the reference's default
+// hparams: LO = 524 for the librosa geometry, 0 for the tf.contrib.signal one).  Lane l holds the samples n = 64 t + l (.x)
+// and 64 t + 32 + l (.y); ap = accumulator address of sample n = lane.  Slots fully inside the support are one packed
+// multiply-add on (acc[n], acc[n+32]); the two edge slots predicate on the lane.  win_at(t) = (w[64 t + l], w[64 t + 32 + l]).
+template <int LO, int T0, int T1, typename WinAt>
+__device__ __forceinline__ void ola_fixed_support(float* ap, const c2 (&z)[32], int lane, WinAt win_at) {
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+        if (t >= T0 && t < T1) {
+            const int r0 = LO - 64 * t, r1 = r0 + 1000;      // lanes whose .x sample is inside the support: [r0, r1)
+            const int i0 = r0 - 32, i1 = r1 - 32;            // ... .y sample
+            const bool fre = (r0 <= 0 && r1 >= 32), fim = (i0 <= 0 && i1 >= 32);
+            const c2 w = win_at(t);
+            if (fre && fim) {
+                const c2 rr = p_fma(z[t], w, mk2(ap[64 * t], ap[64 * t + 32]));
+                ap[64 * t] = rr.x;
+                ap[64 * t + 32] = rr.y;
+            } else {
+                if (r1 > 0 && r0 < 32 && (fre || (lane >= r0 && lane < r1))) ap[64 * t] = fmaf(z[t].x, w.x, ap[64 * t]);
+                if (i1 > 0 && i0 < 32 && (fim || (lane >= i0 && lane < i1))) ap[64 * t + 32] = fmaf(z[t].y, w.y, ap[64 * t + 32]);
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ int find_segment(const int* __restrict__ off, int n, int v) {
     // largest b in [0,n) with off[b] <= v
     int lo = 0, hi = n;

@@ -94,6 +94,7 @@ struct nsb_handle_s {
     int fuse_iterations = 1;         // all Griffin-Lim iterations of a call in ONE launch (0: one launch per iteration, A/B hook)
     int stream_ctas_per_sm = 1;      // resident k_gl_stream CTAs per SM (occupancy query at creation)
     int prune_tf = 0, colours_tf = 0;
+    int specialize = 1;              // NSB_OPT_SPECIALIZE: 1 = the instantiations with the default hparams' geometry as immediates when it applies (defcfg), 0 = never
     float* d_mel_w = nullptr;
     int *d_mel_lo = nullptr, *d_mel_n = nullptr, *d_mel_ptr = nullptr;
     int* d_mel_seg = nullptr; float4* d_mel_coef = nullptr;      // the filters as line segments (null: not representable, sparse rows are used)
@@ -448,9 +449,9 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
     SET((k_synth<SRC_MAGRAND, 0>), ss);  SET((k_synth<SRC_MAGRAND, 1>), ss);
     SET((k_synth<SRC_MAGZERO, 0>), ss);  SET((k_synth<SRC_MAGZERO, 2>), ss);
     SET((k_gl_iter<1, true, false>), gs); SET((k_gl_iter<1, false, false>), gs); SET((k_gl_iter<0, false, false>), gs);
-    SET((k_gl_iter<2, false, true>), gs); SET((k_gl_iter<0, false, true>), gs);
+    SET((k_gl_iter<2, false, true>), gs); SET((k_gl_iter<0, false, true>), gs); SET((k_gl_iter<2, true, true>), gs);
     SET((k_gl_stream<1, true, false, true>), gs); SET((k_gl_stream<1, false, false, true>), gs); SET((k_gl_stream<0, false, false, true>), gs);
-    SET((k_gl_stream<2, false, true, true>), gs); SET((k_gl_stream<0, false, true, true>), gs);
+    SET((k_gl_stream<2, false, true, true>), gs); SET((k_gl_stream<0, false, true, true>), gs); SET((k_gl_stream<2, true, true, true>), gs);
     SET((k_gl_stream<1, false, false, false>), gs); SET((k_gl_stream<0, false, false, false>), gs);
     SET((k_gl_stream<2, false, true, false>), gs); SET((k_gl_stream<0, false, true, false>), gs);
     {
@@ -517,6 +518,7 @@ extern "C" int nsb_set_option(nsb_handle_t h, int32_t key, int32_t value) {
         case NSB_OPT_WIDE_MODE: if (value < -1 || value > 1) return fail(NSB_ERR_INVALID, "wide mode %d outside [-1,1]", value); h->wide_mode = value; return NSB_OK;
         case NSB_OPT_OVERLAP_CHUNKS: h->overlap_chunks = value != 0; return NSB_OK;
         case NSB_OPT_WAVE_SCHEDULE: h->wave_schedule = value != 0; return NSB_OK;
+        case NSB_OPT_SPECIALIZE: h->specialize = value != 0; return NSB_OK;
         case NSB_OPT_MEL_LINES: h->mel_lines = value < 0 ? 0 : (value > 2 ? 2 : value); return NSB_OK;
         default: return fail(NSB_ERR_INVALID, "unknown option %d", key);
     }
@@ -1046,6 +1048,8 @@ static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int t
     DevBuf& d_done = done_buf ? *done_buf : h->d_done;     // scheduling counters of this stream's launches
     float* y[2] = {reinterpret_cast<float*>(h->ws_y0.p), reinterpret_cast<float*>(h->ws_y1.p)};
     if (total_tiles <= 0) return NSB_OK;
+    // hop 250 / window 1000 / 4 colours as immediates (the window sits at n = 524 in the librosa geometry, at 0 in the TF twin's)
+    const bool defcfg = h->defcfg && h->specialize;
     // automatic choice: the streaming kernel wins from about 7,000 groups (28k frames) per launch on; below that the tile
     // kernel, which has less to set up per work item (measured: profiles/r1/sweep_kernels.txt)
     int which = h->use_generic_iter;
@@ -1097,9 +1101,10 @@ static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int t
             // default hparams) and no barrier experiment is selected
             if (fb) {
                 if (tf) {
-                    if (S.plan.prune == 2) NSB_LAUNCH((k_gl_stream<2, false, true, true>), grid, kThreads, smem, st, S);
+                    if (defcfg && S.plan.prune == 2) NSB_LAUNCH((k_gl_stream<2, true, true, true>), grid, kThreads, smem, st, S);
+                    else if (S.plan.prune == 2) NSB_LAUNCH((k_gl_stream<2, false, true, true>), grid, kThreads, smem, st, S);
                     else NSB_LAUNCH((k_gl_stream<0, false, true, true>), grid, kThreads, smem, st, S);
-                } else if (h->defcfg) NSB_LAUNCH((k_gl_stream<1, true, false, true>), grid, kThreads, smem, st, S);
+                } else if (defcfg) NSB_LAUNCH((k_gl_stream<1, true, false, true>), grid, kThreads, smem, st, S);
                 else if (h->prune == 1) NSB_LAUNCH((k_gl_stream<1, false, false, true>), grid, kThreads, smem, st, S);
                 else NSB_LAUNCH((k_gl_stream<0, false, false, true>), grid, kThreads, smem, st, S);
             } else {
@@ -1147,9 +1152,10 @@ static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int t
         const long long items = (long long)n * total_tiles;
         const int grid = items < 2LL * h->num_sms ? (int)items : 2 * h->num_sms;   // persistent: 2 CTAs per SM
         if (tf) {
-            if (G.plan.prune == 2) NSB_LAUNCH((k_gl_iter<2, false, true>), grid, kThreads, smem, st, G);
+            if (defcfg && G.plan.prune == 2) NSB_LAUNCH((k_gl_iter<2, true, true>), grid, kThreads, smem, st, G);
+            else if (G.plan.prune == 2) NSB_LAUNCH((k_gl_iter<2, false, true>), grid, kThreads, smem, st, G);
             else NSB_LAUNCH((k_gl_iter<0, false, true>), grid, kThreads, smem, st, G);
-        } else if (h->defcfg) NSB_LAUNCH((k_gl_iter<1, true, false>), grid, kThreads, smem, st, G);
+        } else if (defcfg) NSB_LAUNCH((k_gl_iter<1, true, false>), grid, kThreads, smem, st, G);
         else if (h->prune == 1) NSB_LAUNCH((k_gl_iter<1, false, false>), grid, kThreads, smem, st, G);
         else NSB_LAUNCH((k_gl_iter<0, false, false>), grid, kThreads, smem, st, G);
         if ((rc = check_launch(h, "k_gl_iter"))) return rc;
@@ -1896,7 +1902,7 @@ static void async_worker(nsb_handle_s* parent, nsb_async_s* A, AsyncSlot* S) {
         }
         if (!rc) {
             // the tuning state of the parent at the time the job runs
-            S->child->host_chunks = parent->host_chunks; S->child->wave_schedule = parent->wave_schedule;
+            S->child->host_chunks = parent->host_chunks; S->child->wave_schedule = parent->wave_schedule; S->child->specialize = parent->specialize;
             S->child->overlap_chunks = parent->overlap_chunks; S->child->use_generic_iter = parent->use_generic_iter;
             S->child->stream_sync_mode = parent->stream_sync_mode; S->child->fuse_iterations = parent->fuse_iterations;
             S->child->wide_mode = parent->wide_mode; S->child->mel_lines = parent->mel_lines;

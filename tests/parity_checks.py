@@ -266,8 +266,17 @@ def check_streaming_rounds(T=150, iters=2, tf=False):
         outs["tile"] = run()
         h.set_option(_lib.OPT_WIDE_MODE, 1)             # ... and in its wide (low-latency) mode: one frame per warp and step
         outs["tile_wide"] = run()
+        # the instantiations with run-time geometry (what other hop / window lengths use) against the ones with the
+        # default hparams folded into immediates
+        h.set_option(_lib.OPT_SPECIALIZE, 0)
+        h.set_option(_lib.OPT_WIDE_MODE, 0)
+        outs["tile_general"] = run()
+        h.set_generic_iteration(0)
+        h.set_stream_grid(2)
+        outs["stream_general"] = run()
     finally:
         h.set_stream_grid(0); h.set_tile_hops(0); h.set_generic_iteration(-1); h.set_option(_lib.OPT_WIDE_MODE, -1)
+        h.set_option(_lib.OPT_SPECIALIZE, 1)
     ref = outs.pop("grid1")
     for name, o in outs.items():
         np.testing.assert_array_equal(o, ref, err_msg=name)
