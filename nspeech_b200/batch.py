@@ -60,17 +60,81 @@ def _pack(h, arrays, dtype):
     return out
 
 
-def features_batch(wavs, device=None, want_linear=True, want_mel=True):
-    """-> list of (linear [F,T] float32, mel [M,T] float32) per clip (None for a feature not requested)."""
+_copy_pool = None
+
+
+def _copy_many(out, arrays, offsets):
+    """out[offsets[i] : offsets[i] + len(arrays[i])] = arrays[i] on a few host threads (numpy's copies release the GIL; one
+    thread's memcpy moves ~10 GB/s, a PCIe 5 link takes 55)."""
+    global _copy_pool
+    if len(arrays) < 8:
+        for a, o in zip(arrays, offsets):
+            out[o:o + a.shape[0]] = a
+        return
+    if _copy_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _copy_pool = ThreadPoolExecutor(max_workers=4, thread_name_prefix="nsb-pack")
+    n = len(arrays)
+    cuts = [n * i // 4 for i in range(5)]
+
+    def part(i):
+        for a, o in zip(arrays[cuts[i]:cuts[i + 1]], offsets[cuts[i]:cuts[i + 1]]):
+            out[o:o + a.shape[0]] = a
+    for f in [_copy_pool.submit(part, i) for i in range(4)]:
+        f.result()
+
+
+def _group_cuts(sizes, n_groups):
+    """cut a list into at most n_groups contiguous runs of about equal total size -> boundaries [0, ..., len(sizes)]"""
+    total = float(sum(sizes))
+    cuts, acc = [0], 0
+    for i, sz in enumerate(sizes):
+        acc += sz
+        if len(cuts) < n_groups and acc >= total * len(cuts) / n_groups and i + 1 < len(sizes):
+            cuts.append(i + 1)
+    cuts.append(len(sizes))
+    return cuts
+
+
+def features_batch(wavs, device=None, want_linear=True, want_mel=True, in_flight=3, group_bytes=96 << 20):
+    """-> list of (linear [F,T] float32, mel [M,T] float32) per clip (None for a feature not requested).
+    Large batches run as a pipeline of clip groups through ``nsb_features_submit`` / ``nsb_wait``: while group g is being
+    packed into page-locked memory on the host, group g-1 is copied in and transformed and the results of group g-2 are
+    copied out (groups of about ``group_bytes`` of results, at most 16, ``in_flight`` of them submitted at a time;
+    ``in_flight=0``: one synchronous call)."""
     h = audio._handle(device)
     wavs = [audio._as_wav(w) for w in wavs]
     ns = [w.size for w in wavs]
     Ts = [h.num_frames(n) for n in ns]
-    packed = _pack(h, wavs, np.float32)
     pool = h.lib.pinned_pool()             # results in pooled page-locked memory: the copy out runs at PCIe speed
     lin = pool.empty((sum(Ts), h.num_freq), np.float32) if want_linear else None
     mel = pool.empty((sum(Ts), h.num_mels), np.float32) if want_mel else None
-    h.features(packed, ns, lin, mel)
+    out_bytes = 4 * sum(Ts) * ((h.num_freq if want_linear else 0) + (h.num_mels if want_mel else 0))
+    n_groups = min(len(wavs) // 8, int(out_bytes // max(1, group_bytes)), 16)
+    if n_groups < 2 or in_flight < 1:
+        h.features(_pack(h, wavs, np.float32), ns, lin, mel)
+    else:
+        soff = np.concatenate([[0], np.cumsum(ns)]).tolist()
+        foff = np.concatenate([[0], np.cumsum(Ts)]).tolist()
+        packed = pool.empty((soff[-1],), np.float32)
+        cuts = _group_cuts(ns, n_groups)
+        pending = collections.deque()
+        try:
+            for g0, g1 in zip(cuts[:-1], cuts[1:]):
+                _copy_many(packed, wavs[g0:g1], soff[g0:g1])
+                pending.append(h.features_submit(packed[soff[g0]:soff[g1]], ns[g0:g1],
+                                                 lin[foff[g0]:foff[g1]] if want_linear else None,
+                                                 mel[foff[g0]:foff[g1]] if want_mel else None))
+                if len(pending) >= in_flight:
+                    h.wait(pending.popleft())
+            while pending:
+                h.wait(pending.popleft())
+        finally:
+            while pending:                 # an error above: the calls still in flight hold pointers into these buffers
+                try:
+                    h.wait(pending.popleft())
+                except (_lib.NativeError, _lib.ParameterError):
+                    pass
     out, off = [], 0
     for T in Ts:
         out.append((lin[off:off + T].T if want_linear else None, mel[off:off + T].T if want_mel else None))

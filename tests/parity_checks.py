@@ -603,6 +603,26 @@ def check_generic_tf_twin_and_stages():
         audio.inv_spectrogram(np.full((F, 4), np.inf, np.float32), iters=1)
 
 
+def check_features_pipeline():
+    """batch.features_batch as a pipeline of clip groups (nsb_features_submit / nsb_wait, packing on host threads) against
+    the single synchronous call: identical bits whatever the grouping."""
+    from nspeech_b200 import batch
+    ohp = _load(min_level_db=-100)
+    many = [speechlike(600 + 37 * i, i) for i in range(34)]
+    one = batch.features_batch(many, in_flight=0)
+    for kw in ({"group_bytes": 1 << 14}, {"group_bytes": 1 << 16, "in_flight": 1}, {"group_bytes": 1 << 14, "want_linear": False}):
+        piped = batch.features_batch(many, **kw)
+        assert len(piped) == len(one)
+        for (l0, m0), (l1, m1) in zip(one, piped):
+            if kw.get("want_linear", True):
+                np.testing.assert_array_equal(l0, l1)
+            else:
+                assert l1 is None
+            np.testing.assert_array_equal(m0, m1)
+    assert ao.rel_l2(one[5][0], ao.spectrogram(many[5], ohp)) < 1e-5 and ao.rel_l2(one[33][1], ao.melspectrogram(many[33], ohp)) < 1e-5
+    assert batch._group_cuts([5] * 34, 4) == [0, 9, 17, 26, 34] and batch._group_cuts([3, 1], 16) == [0, 1, 2]
+
+
 def check_tf_twin_golden(golden_tf):
     """Fixtures written by the reference's OWN TF-twin functions (tests/golden/make_golden_tf.py: audio.py:51-58, 90-123 run
     unmodified on an eager numpy stand-in for tf) through the kernels and the oracle."""

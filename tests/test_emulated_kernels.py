@@ -150,6 +150,10 @@ def test_api_guards(emu):
     pc.check_api_guards()
 
 
+def test_features_pipeline(emu):
+    pc.check_features_pipeline()
+
+
 def test_stale_griffin_lim_state(emu):
     pc.check_stale_griffin_lim_state(lambda a: a)          # the emulated library's "device" pointers are host pointers
 
