@@ -452,7 +452,7 @@ def main():
                          "algorithmic_bytes_per_frame": feat_bytes, "traffic": NCU_FEATURES_TRAFFIC_BYTES_PER_FRAME * n_fr,
                          "traffic_source": NCU_FEATURES_TRAFFIC_SOURCE},
             "e2e": {"value": world * sub_frames / (ms_feat_e2e * 1e-3), "unit": "mel frames/s", "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(out_bytes),
-                    "sample": "every 32nd clip of the corpus (%d clips, %d frames) through batch.features_batch from numpy arrays, results in pooled page-locked memory" % (len(sub), sub_frames)}}
+                    "sample": "every 32nd clip of the corpus (%d clips, %d frames) through batch.features_batch from numpy arrays (pipeline of clip groups: nsb_features_submit / nsb_wait), results in pooled page-locked memory" % (len(sub), sub_frames)}}
         if rank == 0 and not args.no_cpu_baseline and world == 1:
             v, cores, sample = features_cpu_baseline()
             extra["features"]["cpu_baseline"] = {"value": v, "unit": "mel frames/s", "cores": cores, "kind": "port", "sample": sample}
