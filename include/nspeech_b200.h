@@ -230,7 +230,7 @@ int nsb_set_tile_hops(nsb_handle_t h, int32_t tile_hops);       /* 0 = automatic
 int nsb_set_host_chunks(nsb_handle_t h, int32_t n);             /* pipelining of NSB_HOST calls (Griffin-Lim, features, STFT): 0 = automatic (Griffin-Lim: wave schedule on long batches, else a few chunks; analysis: ~24 MB of results per chunk), n = force n equal chunks of whole utterances */
 int nsb_set_generic_iteration(nsb_handle_t h, int32_t on);     /* A/B hook: Griffin-Lim iterations with 0 = k_gl_stream (production), 1 = the generic k_synth<SRC_Y>, 2 = the tile kernel k_gl_iter */
 enum {                          /* nsb_set_option keys: A/B switches of the iteration kernels (defaults are the production settings) */
-    NSB_OPT_STREAM_SYNC_MODE = 1,   /* k_gl_stream: 2 = CTA barrier per colour step (default); 0 none, 1 per round, 3 per half CTA (+4: no pacing) use the event counters */
+    NSB_OPT_STREAM_SYNC_MODE = 1,   /* k_gl_stream: 2 = CTA barrier per colour step (default), 10 = the same barrier split-phase (publish after the overlap-add, wait before the next one); 0 none, 1 per round, 3 per half CTA (+4: no pacing) use the event counters */
     NSB_OPT_FUSE_ITERATIONS = 2,    /* 1 = all iterations of a call in one launch (default), 0 = one launch per iteration */
     NSB_OPT_WIDE_MODE = 3,          /* k_gl_iter one-frame-per-warp tiles: -1 automatic for a few utterances (default), 0 off, 1 forced */
     NSB_OPT_OVERLAP_CHUNKS = 4,     /* NSB_HOST Griffin-Lim chunk pipeline: 1 = consecutive chunks on two streams so that tails and ramps overlap, 0 = one stream (default) */

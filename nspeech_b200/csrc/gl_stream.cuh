@@ -506,7 +506,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
             }
             // ---- overlap-add ordering ----
             if (FB) {
-                // nothing to wait for: the barriers order everything
+                // the barrier at the end of the previous step ordered everything - or, split-phase (sync_mode bit 3): every warp
+                // published its finished steps in progress[], and only now, with the frame's transforms done, waits for the others
+                if (P.sync_mode & 8) {
+                    if (lane < kWarpsPerCta) while (flag_load(progress + lane) < (i >> 3) * C + s) spin_pause();
+                    __syncwarp();
+                }
             } else if (s == 0) {
                 // ring reuse: this group writes where positions i-8 (this warp) and i-9 (the right-hand warp) stored
                 if (i >= 9) wait_events(progress + wr, E * (((i - 9) >> 3) + 1), lane);
@@ -550,7 +555,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_stream(GlStreamParams P) {
             }
             if (FB) {
                 if (s == C - 1) { __syncwarp(); store_group(); }      // the lanes read each other's accumulates
-                __syncthreads();
+                if (P.sync_mode & 8) {
+                    __syncwarp();
+                    if (lane == 0) flag_store(progress + warp, (i >> 3) * C + s + 1);
+                } else {
+                    __syncthreads();
+                }
             } else {
                 __syncwarp();
                 if (lane == 0) flag_store(progress + warp, E * r + s + 1);

@@ -513,7 +513,7 @@ extern "C" int nsb_set_stream_grid(nsb_handle_t h, int32_t n) {
 extern "C" int nsb_set_option(nsb_handle_t h, int32_t key, int32_t value) {
     if (!h) return fail(NSB_ERR_INVALID, "null handle");
     switch (key) {
-        case NSB_OPT_STREAM_SYNC_MODE: if (value < 0 || value > 7) return fail(NSB_ERR_INVALID, "sync mode %d outside [0,7]", value); h->stream_sync_mode = value; return NSB_OK;
+        case NSB_OPT_STREAM_SYNC_MODE: if (value < 0 || (value > 7 && value != 10)) return fail(NSB_ERR_INVALID, "sync mode %d outside [0,7] and not 10", value); h->stream_sync_mode = value; return NSB_OK;
         case NSB_OPT_FUSE_ITERATIONS: h->fuse_iterations = value != 0; return NSB_OK;
         case NSB_OPT_WIDE_MODE: if (value < -1 || value > 1) return fail(NSB_ERR_INVALID, "wide mode %d outside [-1,1]", value); h->wide_mode = value; return NSB_OK;
         case NSB_OPT_OVERLAP_CHUNKS: h->overlap_chunks = value != 0; return NSB_OK;
@@ -1083,7 +1083,7 @@ static int gl_iterations(nsb_handle_s* h, const Batch& B, int total_tiles, int t
         {
             const int a = S.plan.origin - S.plan.lo, hop = h->hop, win = h->win;
             const int kfirst0 = (a - win >= 0) ? (a - win) / hop + 1 : -((win - a - 1) / hop + 1) + 1, klast0 = (hop - 1 + a) / hop;
-            fb = (klast0 - kfirst0 <= h->colours - 1) && h->stream_sync_mode == 2;
+            fb = (klast0 - kfirst0 <= h->colours - 1) && (h->stream_sync_mode & 7) == 2;
         }
         const int per_launch = h->fuse_iterations ? iters : 1;
         for (int it = 0; it < iters; it += per_launch) {

@@ -274,7 +274,13 @@ def check_streaming_rounds(T=150, iters=2, tf=False):
         h.set_generic_iteration(0)
         h.set_stream_grid(2)
         outs["stream_general"] = run()
+        h.set_option(_lib.OPT_SPECIALIZE, 1)
+        h.set_option(_lib.OPT_STREAM_SYNC_MODE, 10)     # split-phase barrier: publish after the overlap-add, wait before the next one
+        outs["stream_split_phase"] = run()
+        h.set_stream_grid(0)
+        outs["stream_split_phase_grid0"] = run()
     finally:
+        h.set_option(_lib.OPT_STREAM_SYNC_MODE, 2)
         h.set_stream_grid(0); h.set_tile_hops(0); h.set_generic_iteration(-1); h.set_option(_lib.OPT_WIDE_MODE, -1)
         h.set_option(_lib.OPT_SPECIALIZE, 1)
     ref = outs.pop("grid1")
