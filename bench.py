@@ -436,9 +436,11 @@ def main():
         sub_wavs = [d_wav[offs[i]:offs[i + 1]].cpu().numpy() for i in sub]
         sub_frames = sum(Tn[i] for i in sub)
         del batch.features_batch(sub_wavs)[:]                # warm-up of the same size: the result blocks return to the pinned pool
+        del batch.features_batch(sub_wavs)[:]
         t0 = time.perf_counter()
-        feats = batch.features_batch(sub_wavs)
-        ms_feat_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        for _ in range(3):
+            feats = batch.features_batch(sub_wavs)
+        ms_feat_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3 / 3)
         in_bytes, out_bytes = 4 * sum(len(w) for w in sub_wavs), 4 * sub_frames * (N_BINS + 80)
         del feats, d_wav
         feat_bytes = 4 * HOP + 4 * N_BINS + 4 * 80
