@@ -1,7 +1,7 @@
 """Silence trimming of the preprocessing path - the mirror of ``neural_speech/datasets/process.py:39-68`` (``trim_wav``,
-``trim_silence``, ``_find_start``, ``_find_end``) and of the two librosa 0.6.0 calls behind them
+``trim_silence`` and its two interval searches) and of the two librosa 0.6.0 calls behind them
 (``librosa.effects.split``, ``librosa.feature.rmse``).  The per-frame energies (the only pass over the samples) come from
-the GPU (``nsb_frame_energy``); the interval logic on the handful of frame values is the reference's own, on the host."""
+the GPU (``nsb_frame_energy``); the interval logic on the handful of frame values runs on the host."""
 import numpy as np
 
 from . import audio
@@ -31,36 +31,32 @@ def _split(wav, top_db, frame_length, hop_length):
     return edges.reshape((-1, 2))
 
 
-def _find_start(splits, min_samples=2000):
-    # reference datasets/process.py:57-61
-    for split_start, split_end in splits:
-        if split_end - split_start > min_samples:
-            return max(0, split_start - min_samples)
-    return 0
-
-
-def _find_end(splits, num_samples, min_samples=2000):
-    # reference datasets/process.py:64-68
-    for split_start, split_end in reversed(splits):
-        if split_end - split_start > min_samples:
-            return min(num_samples, split_end + min_samples)
-    return num_samples
+def _trim_bounds(splits, num_samples, min_samples=2000):
+    """[start, end) that ``trim_wav`` keeps: from the first to the last non-silent interval longer than ``min_samples``, widened by
+    ``min_samples`` on either side and clipped to the clip (what the reference's two interval searches, datasets/process.py:57-68,
+    return); the whole clip when no interval is that long."""
+    splits = np.asarray(splits, dtype=np.int64).reshape(-1, 2)
+    keep = np.flatnonzero(splits[:, 1] - splits[:, 0] > min_samples)
+    if keep.size == 0:
+        return 0, num_samples
+    return max(0, int(splits[keep[0], 0]) - min_samples), min(num_samples, int(splits[keep[-1], 1]) + min_samples)
 
 
 def trim_wav(wav, threshold_db=25):
-    '''Trims silence from the ends of the wav (reference datasets/process.py:39-42)'''
-    splits = _split(wav, threshold_db, frame_length=1024, hop_length=512)
-    return wav[_find_start(splits):_find_end(splits, len(wav))]
+    """Silence off both ends of the clip (reference datasets/process.py:39-42): energies of the centred 1024-sample frames every 512
+    samples from the GPU, the interval logic of ``librosa.effects.split`` and of the reference on those few values."""
+    start, end = _trim_bounds(_split(wav, threshold_db, frame_length=1024, hop_length=512), len(wav))
+    return wav[start:end]
 
 
 def trim_silence(wav, threshold, frame_length=2048):
-    '''Removes silence at the beginning and end of a sample (reference datasets/process.py:45-54).'''
-    if wav.size < frame_length:
-        frame_length = wav.size
-    energy = np.sqrt(frame_energy(wav, frame_length))
-    indices = np.nonzero(energy > threshold)[0] * 512
-    # Note: indices can be an empty array, if the whole audio was silence.
-    return wav[indices[0]:indices[-1]] if indices.size else wav[:0]
+    """Everything before the first and from the last frame whose RMS exceeds ``threshold`` goes (reference
+    datasets/process.py:45-54: ``librosa.feature.rmse`` at hop 512, ``frames_to_samples``); an all-silent clip becomes empty."""
+    frame_length = min(frame_length, wav.size)
+    loud = np.flatnonzero(np.sqrt(frame_energy(wav, frame_length)) > threshold)
+    if loud.size == 0:
+        return wav[:0]
+    return wav[512 * int(loud[0]):512 * int(loud[-1])]
 
 
 def process_utterance_arrays(wav):
