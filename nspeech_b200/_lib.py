@@ -168,29 +168,40 @@ class PinnedPool(object):
     """Result buffers in page-locked memory, recycled.  A device-to-host copy into pageable numpy memory is staged by the
     driver at a fraction of PCIe bandwidth (measured: 37.6 vs 25 ms for BASELINE config 4), and cudaHostAlloc itself costs
     milliseconds, so the batch front end hands out arrays backed by pooled pinned blocks: when the last view of such an
-    array is garbage-collected the block returns to the pool (at most ``max_bytes`` are kept)."""
+    array is garbage-collected the block returns to the pool.  At most ``max_bytes`` of free blocks are kept; over that the
+    blocks that have been free the longest go first (a workload that changes its sizes must not end up allocating and
+    freeing on every call because blocks of its old sizes fill the pool).  A request takes the smallest free block that
+    holds it without wasting more than half."""
 
     def __init__(self, lib, max_bytes=2 << 30, granule=1 << 20):
         self.lib, self.max_bytes, self.granule = lib, max_bytes, granule
-        self.free, self.kept, self.lock = {}, 0, threading.Lock()
+        self.free, self.kept, self.lock = [], 0, threading.Lock()        # free: [(size, ptr)], oldest first
 
     def _release(self, ptr, size):
+        evict = []
         with self.lock:
-            if self.kept + size <= self.max_bytes:
-                self.free.setdefault(size, []).append(ptr)
-                self.kept += size
-                return
-        self.lib.dll.nsb_free_pinned(ctypes.c_void_p(ptr))
+            self.free.append((size, ptr))
+            self.kept += size
+            while self.kept > self.max_bytes and self.free:
+                sz, p = self.free.pop(0)
+                self.kept -= sz
+                evict.append(p)
+        for p in evict:
+            self.lib.dll.nsb_free_pinned(ctypes.c_void_p(p))
 
     def empty(self, shape, dtype):
         import weakref
         dtype = np.dtype(dtype)
         count = int(np.prod(shape))
         size = max(self.granule, -(-count * dtype.itemsize // self.granule) * self.granule)
+        ptr = None
         with self.lock:
-            blocks = self.free.get(size)
-            ptr = blocks.pop() if blocks else None
-            if ptr is not None:
+            best = -1
+            for i, (sz, _) in enumerate(self.free):
+                if size <= sz <= 2 * size and (best < 0 or sz < self.free[best][0]):
+                    best = i
+            if best >= 0:
+                size, ptr = self.free.pop(best)
                 self.kept -= size
         if ptr is None:
             p = ctypes.c_void_p()
