@@ -39,7 +39,7 @@ __device__ __forceinline__ void gen_stage_pow2(const GenPlan& G, const float2* w
     const int Mr = G.M / R;
     const int tstep = G.n_fft / (Ns * R);                        // exp(-2 pi i / (Ns R)) = wt[tstep]
     for (int j = threadIdx.x; j < Mr; j += blockDim.x) {
-        const int k = j % Ns;
+        const int k = j & (Ns - 1);                              // the power-of-two factors come first: Ns is a power of two here
         c2 v[R], y[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) v[q] = a[j + q * Mr];
@@ -51,7 +51,7 @@ __device__ __forceinline__ void gen_stage_pow2(const GenPlan& G, const float2* w
             }
         }
         FftC<R, DIR, 1>::run(v, y);
-        float2* o = b + (j / Ns) * Ns * R + k;
+        float2* o = b + (j - k) * R + k;                         // (j / Ns) * Ns * R + k
 #pragma unroll
         for (int t = 0; t < R; ++t) o[t * Ns] = y[t];
     }
