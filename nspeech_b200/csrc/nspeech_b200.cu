@@ -691,6 +691,11 @@ static cudaError_t copy_h2d(nsb_handle_s* h, void* dst, const void* src, size_t 
             if ((e = cudaEventCreateWithFlags(&h->bounce_ev[i], cudaEventDisableTiming)) != cudaSuccess) return e;
             if ((e = cudaEventRecord(h->bounce_ev[i], st)) != cudaSuccess) return e;
         }
+    // one staging at a time per process: when several calls arrive together (the first batches of an asynchronous stream) their
+    // memcpy threads would only share the cores and the memory bus, and the first batch - the one the GPU waits for - would be
+    // ready last
+    static std::mutex staging_mu;
+    std::lock_guard<std::mutex> staging(staging_mu);
     const size_t pieces = (bytes + kBounceBytes - 1) / kBounceBytes;
     cudaError_t errs[kBounceThreads];
     auto work = [&](int t) {
