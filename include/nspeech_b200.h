@@ -234,7 +234,7 @@ enum {                          /* nsb_set_option keys: A/B switches of the iter
     NSB_OPT_FUSE_ITERATIONS = 2,    /* 1 = all iterations of a call in one launch (default), 0 = one launch per iteration */
     NSB_OPT_WIDE_MODE = 3,          /* k_gl_iter one-frame-per-warp tiles: -1 automatic for a few utterances (default), 0 off, 1 forced */
     NSB_OPT_OVERLAP_CHUNKS = 4,     /* NSB_HOST Griffin-Lim chunk pipeline: 1 = consecutive chunks on two streams so that tails and ramps overlap, 0 = one stream (default) */
-    NSB_OPT_MEL_LINES = 6,          /* mel projection: 2 = filters as line segments, two moments per band, on a magnitude row with one pad word per 32 bins (default when representable), 1 = the same on the plain row, 0 = sparse rows */
+    NSB_OPT_MEL_LINES = 6,          /* mel projection: 3 = filters as line segments, two moments per band, on a magnitude row with one pad word per 32 bins, the long segments cut in two so that the lanes run equally long (default when representable), 2 = whole segments, 1 = 2 on the plain row, 0 = sparse rows */
     NSB_OPT_SPECIALIZE = 7,         /* Griffin-Lim iteration kernels: 1 = at the reference's default hparams (hop 250, window 1000, n_fft 2048) run the instantiations with that geometry as immediates (default), 0 = the general ones; results are identical bit for bit */
     NSB_OPT_WAVE_SCHEDULE = 5       /* NSB_HOST Griffin-Lim on long batches: 1 = wave schedule (chunk g joins at wave g, every launch runs all chunks in flight; default), 0 = plain chunk pipeline */
 };

@@ -58,6 +58,10 @@ struct Plan {                    // device tables owned by the handle
     // c.x + c.y (mel_seg[m+1] - k) and falls on segment m+1 as c.z + c.w (mel_seg[m+2] - k).  Null: use the sparse rows.
     const int* mel_seg;          // [num_mels + 2]
     const float4* mel_coef;      // [num_mels]
+    // the same segments cut into at most 96 pieces of balanced length (long segments in two): piece p = bins [x, y), z = float bits of
+    // (its segment's end - y); mel_segp[m] = (first, second piece of segment m, first, second piece of segment m+1), 96 = an all-zero slot
+    const int4* mel_piece;       // [96] or null
+    const int4* mel_segp;        // [num_mels]
     int n_fft, hop, win_len, lo; // window support is n in [lo, lo + win_len) of the n_fft-long frame
     int origin;                  // frame k starts at sample k*hop - origin
     int norm_wss;                // 1: divide the overlap-add by the summed squared window (librosa.istft), 0: do not (tf inverse_stft)
@@ -187,6 +191,7 @@ struct AnalysisParams {
     // _normalize(_amp_to_db(amp) - ref) = clip(log2(max(1e-5, amp)) * db_scale + db_offset, 0, 1) with
     // db_scale = 20 log10(2) / (-min_level_db), db_offset = (-ref - min_level_db) / (-min_level_db) (host, from double)
     float db_scale, db_offset_lin, db_offset_mel;
+    int mel_split;         // 1: the moment loop over the balanced pieces (NSB_OPT_MEL_LINES 3)
     int mel_skew;          // 1: magnitude row with a pad word per 32 bins (production; NSB_OPT_MEL_LINES 1 is the A/B switch without it)
     int* status;           // device flag: bit0 = non-finite input
 };
@@ -251,7 +256,8 @@ template <bool SKEW> __device__ __forceinline__ int mag_skew(int kb) { return SK
 // MUFU operations of a bin no longer depend on each other.
 template <bool LIN, bool SKEW>
 __device__ __forceinline__ void feature_epilogue(const AnalysisParams& P, c2 (&z)[32], int lane, float2* scratch, float* o_lin, float* o_mel,
-                                                 float db_scale, float db_off_lin, float db_off_mel, bool& bad, const float4* coef_s) {
+                                                 float db_scale, float db_off_lin, float db_off_mel, bool& bad, const float4* coef_s,
+                                                 const int4* piece_s = nullptr, const int4* segp_s = nullptr) {
     float* magrow = reinterpret_cast<float*>(scratch);
     float* mom = magrow + kMagSkewLen;                             // [num_mels + 1][2] (the host checks that it fits the scratch tile)
     float2* xch = reinterpret_cast<float2*>(magrow + kMagSkewLen + 2 * 96 + 4);   // lane 0's 32 slots (8-byte aligned: 1256 floats in)
@@ -306,6 +312,31 @@ __device__ __forceinline__ void feature_epilogue(const AnalysisParams& P, c2 (&z
         // a1 = sum of the running sums = sum (k1 - k) |D[k]|: the first moment counted from the segment's END costs one add
         // per bin; the host folds the change of origin into the coefficients.  The adds run in bin order whatever the unrolling.
         const int M = P.plan.num_mels;
+        if (piece_s) {
+            // balanced form: three pieces per lane, piece p = lane + 32 r (the host sorted them by length, so the lanes of a round
+            // run about equally long); a piece of a segment cut in two measures its first moment from its own end and moves it
+            // to the segment's end with one multiply-add.  Row m then adds the (at most two) pieces of its two segments.
+            float2* pm = reinterpret_cast<float2*>(mom);
+#pragma unroll 1
+            for (int r = 0; r < 3; ++r) {
+                const int4 t = piece_s[lane + 32 * r];
+                float a0 = 0.f, a1 = 0.f;
+                for (int kb = t.x; kb < t.y; ++kb) { a0 += magrow[mag_skew<SKEW>(kb)]; a1 += a0; }
+                pm[lane + 32 * r] = make_float2(a0, fmaf(__int_as_float(t.z), a0, a1));
+            }
+            if (lane == 0) pm[96] = make_float2(0.f, 0.f);
+            __syncwarp();
+            for (int m = lane; m < M; m += 32) {
+                const float4 c = coef_s[m];
+                const int4 q = segp_s[m];
+                const float2 r0 = pm[q.x], r1 = pm[q.y], f0 = pm[q.z], f1 = pm[q.w];
+                float acc = c.x * (r0.x + r1.x);
+                acc = fmaf(c.y, r0.y + r1.y, acc); acc = fmaf(c.z, f0.x + f1.x, acc); acc = fmaf(c.w, f0.y + f1.y, acc);
+                o_mel[m] = amp_to_db_norm_fast(fmaxf(acc, 0.f), db_scale, db_off_mel);
+            }
+            __syncwarp();
+            return;
+        }
         for (int j = lane; j <= M; j += 32) {
             const int k0 = __ldg(P.plan.mel_seg + j), k1 = __ldg(P.plan.mel_seg + j + 1);
             float a0 = 0.f, a1 = 0.f;
@@ -342,8 +373,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
     // the mel rows' line coefficients, once per CTA (a load from L2 per row and frame otherwise: 4 % of the stall samples)
     float4* coef_s = reinterpret_cast<float4*>(scratch_all + kScratchF2 * kWarpsPerCta);
     const bool mel_tables = MODE == ANALYSIS_FEATURES && P.plan.mel_seg && P.plan.num_mels <= 96;
+    int4* piece_s = reinterpret_cast<int4*>(coef_s + 96);
+    int4* segp_s = piece_s + 96;
+    const bool mel_split = mel_tables && P.mel_split && P.plan.mel_piece;
     if (mel_tables)
         for (int i = threadIdx.x; i < P.plan.num_mels; i += kThreads) coef_s[i] = P.plan.mel_coef[i];
+    if (mel_split) {
+        for (int i = threadIdx.x; i < 96; i += kThreads) piece_s[i] = P.plan.mel_piece[i];
+        for (int i = threadIdx.x; i < P.plan.num_mels; i += kThreads) segp_s[i] = P.plan.mel_segp[i];
+    }
     load_twiddle_pairs(tw_s, P.plan.tw);
     const float4* tw4 = reinterpret_cast<const float4*>(tw_s);
     const float2* tw31 = tw_s + 15 * 64;
@@ -394,11 +432,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_analysis(AnalysisParams P) {
             float* o_lin = P.out_lin ? P.out_lin + (size_t)orow * kBins : nullptr;
             float* o_mel = P.out_mel ? P.out_mel + (size_t)orow * P.plan.num_mels : nullptr;
             if (P.mel_skew) {
-                if (o_lin) feature_epilogue<true, true>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad, mel_tables ? coef_s : nullptr);
-                else feature_epilogue<false, true>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad, mel_tables ? coef_s : nullptr);
+                if (o_lin) feature_epilogue<true, true>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad, mel_tables ? coef_s : nullptr, mel_split ? piece_s : nullptr, segp_s);
+                else feature_epilogue<false, true>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad, mel_tables ? coef_s : nullptr, mel_split ? piece_s : nullptr, segp_s);
             } else {
-                if (o_lin) feature_epilogue<true, false>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad, mel_tables ? coef_s : nullptr);
-                else feature_epilogue<false, false>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad, mel_tables ? coef_s : nullptr);
+                if (o_lin) feature_epilogue<true, false>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad, mel_tables ? coef_s : nullptr, mel_split ? piece_s : nullptr, segp_s);
+                else feature_epilogue<false, false>(P, z, lane, scratch, o_lin, o_mel, db_scale, db_off_lin, db_off_mel, bad, mel_tables ? coef_s : nullptr, mel_split ? piece_s : nullptr, segp_s);
             }
         }
     }

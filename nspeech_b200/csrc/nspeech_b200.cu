@@ -1,4 +1,5 @@
 // C-ABI implementation: handle, plans, workspaces, launches.  See include/nspeech_b200.h.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdarg>
@@ -97,8 +98,9 @@ struct nsb_handle_s {
     int specialize = 1;              // NSB_OPT_SPECIALIZE: 1 = the instantiations with the default hparams' geometry as immediates when it applies (defcfg), 0 = never
     float* d_mel_w = nullptr;
     int *d_mel_lo = nullptr, *d_mel_n = nullptr, *d_mel_ptr = nullptr;
+    int4* d_mel_piece = nullptr; int4* d_mel_segp = nullptr;     // the segments as 96 balanced pieces (null: no such cut exists)
     int* d_mel_seg = nullptr; float4* d_mel_coef = nullptr;      // the filters as line segments (null: not representable, sparse rows are used)
-    int mel_lines = 2;               // 2 = line segments on the skewed magnitude row (production), 1 = on the plain row, 0 = sparse mel rows (A/B hooks)
+    int mel_lines = 3;               // 3 = line segments on the skewed magnitude row, long segments cut in two (production; 2 where no such cut exists), 2 = whole segments, 1 = on the plain row, 0 = sparse mel rows (A/B hooks)
     int* d_status = nullptr;
     std::vector<double> mel_dense;   // [num_mels][num_freq]
     // descriptors
@@ -125,6 +127,7 @@ static Plan make_plan(nsb_handle_s* h, bool tf = false) {
     Plan p;
     p.tw = h->d_tw; p.mel_w = h->d_mel_w; p.mel_lo = h->d_mel_lo; p.mel_n = h->d_mel_n; p.mel_ptr = h->d_mel_ptr;
     p.mel_seg = h->mel_lines ? h->d_mel_seg : nullptr; p.mel_coef = h->d_mel_coef;
+    p.mel_piece = h->d_mel_piece; p.mel_segp = h->d_mel_segp;
     p.n_fft = h->n_fft; p.hop = h->hop; p.win_len = h->win; p.num_mels = h->num_mels;
     if (tf) { p.win = h->d_win_tf; p.rinv = h->d_rinv_tf; p.lo = 0; p.origin = 0; p.norm_wss = 0; p.prune = h->prune_tf; }
     else { p.win = h->d_win; p.rinv = h->d_rinv; p.lo = h->lo; p.origin = h->n_fft / 2; p.norm_wss = 1; p.prune = h->prune; }
@@ -198,6 +201,41 @@ static bool build_mel_lines(int sr, int n_fft, int n_mels, const std::vector<dou
     return true;
 }
 
+// The segments of build_mel_lines cut into at most 96 pieces (three per lane) so that the lanes of the moment loop run about equally
+// long: the longest segments (the top mel bands: 42 bins at the default hparams, where the first 32 have 4 or 5) are cut in two.
+// Pieces sorted by length, longest first: piece p goes to lane p % 32 in round p / 32.  false: no cut with <= 2 pieces per segment fits.
+static bool build_mel_pieces(const std::vector<int>& seg, int n_mels, std::vector<int4>& piece, std::vector<int4>& segp) {
+    const int S = n_mels + 1;                                      // segments 0 .. n_mels
+    int lmax = 0;
+    for (int limit = 1; limit <= 4096 && !lmax; ++limit) {         // smallest cap on the piece length that needs <= 96 pieces
+        int n = 0;
+        bool ok = true;
+        for (int j = 0; j < S; ++j) { const int len = seg[j + 1] - seg[j]; if (len > 2 * limit) ok = false; n += len > limit ? 2 : 1; }
+        if (ok && n <= 96) lmax = limit;
+    }
+    if (!lmax) return false;
+    struct Pc { int k0, k1, end, segment; };
+    std::vector<Pc> pcs;
+    for (int j = 0; j < S; ++j) {
+        const int k0 = seg[j], k1 = seg[j + 1], len = k1 - k0;
+        if (len > lmax) { const int kc = k0 + (len + 1) / 2; pcs.push_back({k0, kc, k1, j}); pcs.push_back({kc, k1, k1, j}); }
+        else pcs.push_back({k0, k1, k1, j});
+    }
+    std::stable_sort(pcs.begin(), pcs.end(), [](const Pc& a, const Pc& b) { return a.k1 - a.k0 > b.k1 - b.k0; });
+    piece.assign(96, make_int4(0, 0, 0, 0));
+    std::vector<int> first(S, 96), second(S, 96);                  // 96 = the all-zero slot
+    for (size_t p = 0; p < pcs.size(); ++p) {
+        const float shift = (float)(pcs[p].end - pcs[p].k1);
+        int bits;
+        std::memcpy(&bits, &shift, sizeof(bits));
+        piece[p] = make_int4(pcs[p].k0, pcs[p].k1, bits, pcs[p].segment);
+        if (first[pcs[p].segment] == 96) first[pcs[p].segment] = (int)p; else second[pcs[p].segment] = (int)p;
+    }
+    segp.resize(n_mels);
+    for (int m = 0; m < n_mels; ++m) segp[m] = make_int4(first[m], second[m], first[m + 1], second[m + 1]);
+    return true;
+}
+
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -205,7 +243,7 @@ static int set_smem(K kernel, size_t bytes) {
 }
 
 static size_t analysis_smem() {
-    return sizeof(float2) * kTwF2 + sizeof(float) * kNfft + sizeof(float2) * kScratchF2 * kWarpsPerCta + sizeof(float4) * 96;   // ... + mel line coefficients
+    return sizeof(float2) * kTwF2 + sizeof(float) * kNfft + sizeof(float2) * kScratchF2 * kWarpsPerCta + sizeof(float4) * 96 + sizeof(int4) * 192;   // ... + mel line coefficients + piece tables
 }
 static size_t synth_smem(int hop, int H) {
     size_t fl = 2 * kTwF2 + kNfft + hop + (size_t)H * hop;
@@ -284,7 +322,7 @@ extern "C" int nsb_destroy(nsb_handle_t h) {
     if (h->chunk_fork) cudaEventDestroy(h->chunk_fork);
     if (h->chunk_join) cudaEventDestroy(h->chunk_join);
     if (h->last_done) cudaEventDestroy(h->last_done);
-    cudaFree(h->d_tw); cudaFree(h->d_win); cudaFree(h->d_win_tf); cudaFree(h->d_rinv); cudaFree(h->d_rinv_tf); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo); cudaFree(h->d_mel_n); cudaFree(h->d_mel_ptr); cudaFree(h->d_mel_seg); cudaFree(h->d_mel_coef);
+    cudaFree(h->d_tw); cudaFree(h->d_win); cudaFree(h->d_win_tf); cudaFree(h->d_rinv); cudaFree(h->d_rinv_tf); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo); cudaFree(h->d_mel_n); cudaFree(h->d_mel_ptr); cudaFree(h->d_mel_seg); cudaFree(h->d_mel_coef); cudaFree(h->d_mel_piece); cudaFree(h->d_mel_segp);
     cudaFree(h->d_status); cudaFree(h->d_wt); h->ws_frames.release();
     for (int i = 0; i < 8; ++i) { if (h->bounce[i]) cudaFreeHost(h->bounce[i]); if (h->bounce_ev[i]) cudaEventDestroy(h->bounce_ev[i]); }
     if (h->h_desc) cudaFreeHost(h->h_desc);
@@ -405,6 +443,13 @@ extern "C" int nsb_create(const nsb_hparams* hp, int device, nsb_handle_t* out) 
             CUB(cudaMemcpy(h->d_mel_seg, seg.data(), sizeof(int) * seg.size(), cudaMemcpyHostToDevice));
             CUB(cudaMalloc(&h->d_mel_coef, sizeof(float) * coef.size()));
             CUB(cudaMemcpy(h->d_mel_coef, coef.data(), sizeof(float) * coef.size(), cudaMemcpyHostToDevice));
+            std::vector<int4> piece, segp;
+            if (build_mel_pieces(seg, hp->num_mels, piece, segp)) {
+                CUB(cudaMalloc(&h->d_mel_piece, sizeof(int4) * piece.size()));
+                CUB(cudaMemcpy(h->d_mel_piece, piece.data(), sizeof(int4) * piece.size(), cudaMemcpyHostToDevice));
+                CUB(cudaMalloc(&h->d_mel_segp, sizeof(int4) * segp.size()));
+                CUB(cudaMemcpy(h->d_mel_segp, segp.data(), sizeof(int4) * segp.size(), cudaMemcpyHostToDevice));
+            }
         }
     }
     CUB(cudaMalloc(&h->d_status, sizeof(int)));
@@ -519,7 +564,7 @@ extern "C" int nsb_set_option(nsb_handle_t h, int32_t key, int32_t value) {
         case NSB_OPT_OVERLAP_CHUNKS: h->overlap_chunks = value != 0; return NSB_OK;
         case NSB_OPT_WAVE_SCHEDULE: h->wave_schedule = value != 0; return NSB_OK;
         case NSB_OPT_SPECIALIZE: h->specialize = value != 0; return NSB_OK;
-        case NSB_OPT_MEL_LINES: h->mel_lines = value < 0 ? 0 : (value > 2 ? 2 : value); return NSB_OK;
+        case NSB_OPT_MEL_LINES: h->mel_lines = value < 0 ? 0 : (value > 3 ? 3 : value); return NSB_OK;
         default: return fail(NSB_ERR_INVALID, "unknown option %d", key);
     }
 }
@@ -799,7 +844,7 @@ static int run_analysis(nsb_handle_s* h, int mode, bool preemph, const float* wa
     AnalysisParams P;
     P.plan = make_plan(h, tf); P.batch = d.dev; P.wav = d_wav; P.out_complex = d_c; P.out_lin = d_lin; P.out_mel = d_mel;
     P.total_frames = d.total_frames; P.preemph = (float)h->hp.preemphasis; P.rows_per_utt = rows_per_utt;
-    P.ref_level_db = (float)h->hp.ref_level_db; P.min_level_db = (float)h->hp.min_level_db; P.status = h->d_status; P.mel_skew = h->mel_lines == 2;
+    P.ref_level_db = (float)h->hp.ref_level_db; P.min_level_db = (float)h->hp.min_level_db; P.status = h->d_status; P.mel_skew = h->mel_lines >= 2; P.mel_split = h->mel_lines == 3;
     {
         const double inv = 1.0 / (-h->hp.min_level_db);
         P.db_scale = (float)(20.0 * 0.30102999566398119521 * inv);      // 20 log10(2) / (-min_level_db)

@@ -1,5 +1,5 @@
 """Device-resident feature extraction (spectrogram + melspectrogram, BASELINE config 2 sample) with the mel projection as
-sparse rows (NSB_OPT_MEL_LINES 0) against line segments / two moments per band on the plain (1) and the skewed (2, production) magnitude row, plus the differences."""
+sparse rows (NSB_OPT_MEL_LINES 0) against line segments / two moments per band on the plain (1) and the skewed (2) magnitude row and over balanced pieces of the segments (3, production), plus the differences."""
 import os
 import sys
 
@@ -21,7 +21,7 @@ wav = (0.3 * np.sin(2 * np.pi * 180 * t) * (1 + 0.5 * np.sin(2 * np.pi * 3 * t))
 Tn = [h.num_frames(n) for n in ns]
 d_wav = torch.from_numpy(wav).cuda()
 outs = {}
-for mode in (2, 1, 0, 2, 1, 2, 1):
+for mode in (3, 2, 1, 0, 3, 2, 3, 2):
     h.set_option(_lib.OPT_MEL_LINES, mode)
     d_lin = torch.empty((sum(Tn), 1025), dtype=torch.float32, device="cuda")
     d_mel = torch.empty((sum(Tn), 80), dtype=torch.float32, device="cuda")
@@ -41,4 +41,6 @@ a, b = outs[0].astype(np.float64), outs[1].astype(np.float64)
 assert np.array_equal(outs[1], outs[2])        # the pad words change addresses, not the order of the adds
 print("rows vs lines: rel-L2 %.3g, max abs %.3g (normalised dB scale, min_level_db=-100; fraction of values strictly inside (0,1): %.2f)" % (
     np.linalg.norm(a - b) / np.linalg.norm(a), np.abs(a - b).max(), float(((a > 0) & (a < 1)).mean())))
-h.set_option(_lib.OPT_MEL_LINES, 2)
+c = outs[3].astype(np.float64)
+print("balanced pieces (3) vs whole segments (2): rel-L2 %.3g, max abs %.3g" % (np.linalg.norm(c - b) / np.linalg.norm(b), np.abs(c - b).max()))
+h.set_option(_lib.OPT_MEL_LINES, 3)

@@ -609,6 +609,28 @@ def check_generic_tf_twin_and_stages():
         audio.inv_spectrogram(np.full((F, 4), np.inf, np.float32), iters=1)
 
 
+def check_mel_projection_modes():
+    """The mel projection's four forms (NSB_OPT_MEL_LINES: sparse rows, line segments on the plain / the skewed magnitude row, the
+    segments cut into balanced pieces) against the oracle; the two row layouts add in the same order (identical bits)."""
+    ohp = _load(min_level_db=-100)
+    h = audio._handle()
+    wavs = [speechlike(9000, 3), (0.4 * np.random.RandomState(5).randn(5000)).astype(np.float32), speechlike(777, 9)]
+    want = [(ao.spectrogram(w, ohp), ao.melspectrogram(w, ohp)) for w in wavs]
+    got = {}
+    try:
+        for mode in (0, 1, 2, 3):
+            h.set_option(_lib.OPT_MEL_LINES, mode)
+            got[mode] = [audio.spectrogram_and_mel(w) for w in wavs]
+            for (lin, mel), (wl, wm) in zip(got[mode], want):
+                assert ao.rel_l2(lin, wl) < 1e-5 and ao.rel_l2(mel, wm) < 1e-5, mode
+    finally:
+        h.set_option(_lib.OPT_MEL_LINES, 3)
+    for i in range(len(wavs)):
+        np.testing.assert_array_equal(got[1][i][1], got[2][i][1])
+        np.testing.assert_array_equal(got[0][i][0], got[3][i][0])          # the linear feature does not depend on the mode
+        assert ao.rel_l2(got[3][i][1], got[2][i][1]) < 1e-6
+
+
 def check_features_pipeline():
     """batch.features_batch as a pipeline of clip groups (nsb_features_submit / nsb_wait, packing on host threads) against
     the single synchronous call: identical bits whatever the grouping."""

@@ -154,6 +154,10 @@ def test_features_pipeline(emu):
     pc.check_features_pipeline()
 
 
+def test_mel_projection_modes(emu):
+    pc.check_mel_projection_modes()
+
+
 def test_stale_griffin_lim_state(emu):
     pc.check_stale_griffin_lim_state(lambda a: a)          # the emulated library's "device" pointers are host pointers
 

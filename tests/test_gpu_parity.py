@@ -96,6 +96,10 @@ def test_features_pipeline():
     pc.check_features_pipeline()
 
 
+def test_mel_projection_modes():
+    pc.check_mel_projection_modes()
+
+
 def test_stale_griffin_lim_state():
     torch = pytest.importorskip("torch")
     pc.check_stale_griffin_lim_state(lambda a: torch.from_numpy(a).cuda(), torch.cuda.current_stream().cuda_stream)
