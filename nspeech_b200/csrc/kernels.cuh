@@ -321,6 +321,8 @@ __device__ __forceinline__ void feature_epilogue(const AnalysisParams& P, c2 (&z
             for (int r = 0; r < 3; ++r) {
                 const int4 t = piece_s[lane + 32 * r];
                 float a0 = 0.f, a1 = 0.f;
+                // (the piece as two pointer walks, up to the row's next pad word and after it, instead of the skewed index per bin: measured
+                //  slower, 0.954 vs 0.846 ms - two loops of divergent trip counts; profiles/r2/features_ab_pieces_pointer_walk.txt)
                 for (int kb = t.x; kb < t.y; ++kb) { a0 += magrow[mag_skew<SKEW>(kb)]; a1 += a0; }
                 pm[lane + 32 * r] = make_float2(a0, fmaf(__int_as_float(t.z), a0, a1));
             }
