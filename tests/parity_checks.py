@@ -232,7 +232,7 @@ def check_tf_twin_vs_oracle(over):
     assert ao.rel_l2(audio._denormalize_tensorflow(S[0] * 1.2 - 0.1), tfo._denormalize_tensorflow(S[0] * 1.2 - 0.1, ohp)) < 1e-6
 
 
-def check_streaming_rounds(T=150, iters=2, tf=False):
+def check_streaming_rounds(T=150, iters=2, tf=False, emulated=False):
     """k_gl_stream on long pieces: one CTA walks many rounds of its 8-group ring (slot reuse, wrap-around of the
     accumulate, the warp-7 -> warp-0 dependency across rounds), against the oracle and bit-for-bit against every
     other partition of the same batch and against the older kernels."""
@@ -254,18 +254,20 @@ def check_streaming_rounds(T=150, iters=2, tf=False):
     outs = {}
     try:
         h.set_generic_iteration(0)           # k_gl_stream
-        for grid in (1, 2, 3, 0):
+        for grid in ((1, 2, 0) if emulated else (1, 2, 3, 0)):       # (the CPU emulation runs a reduced set: every run is seconds there)
             h.set_stream_grid(grid)
             outs["grid%d" % grid] = run()
-        h.set_stream_grid(1)
-        h.set_tile_hops(12)
-        outs["piece3"] = run()
+        if not emulated:
+            h.set_stream_grid(1)
+            h.set_tile_hops(12)
+            outs["piece3"] = run()
         h.set_tile_hops(0)
         h.set_generic_iteration(2)           # the tile kernel adds in the same colour order: identical bits
         h.set_option(_lib.OPT_WIDE_MODE, 0)             # ... with C consecutive frames per warp
         outs["tile"] = run()
-        h.set_option(_lib.OPT_WIDE_MODE, 1)             # ... and in its wide (low-latency) mode: one frame per warp and step
-        outs["tile_wide"] = run()
+        if not emulated:
+            h.set_option(_lib.OPT_WIDE_MODE, 1)         # ... and in its wide (low-latency) mode: one frame per warp and step
+            outs["tile_wide"] = run()
         # the instantiations with run-time geometry (what other hop / window lengths use) against the ones with the
         # default hparams folded into immediates
         h.set_option(_lib.OPT_SPECIALIZE, 0)
@@ -276,7 +278,8 @@ def check_streaming_rounds(T=150, iters=2, tf=False):
         outs["stream_general"] = run()
         h.set_option(_lib.OPT_SPECIALIZE, 1)
         h.set_option(_lib.OPT_STREAM_SYNC_MODE, 10)     # split-phase barrier: publish after the overlap-add, wait before the next one
-        outs["stream_split_phase"] = run()
+        if not emulated:                                # (its spin-waits are what OS threads are worst at: one run is enough on the CPU)
+            outs["stream_split_phase"] = run()
         h.set_stream_grid(0)
         outs["stream_split_phase_grid0"] = run()
     finally:
@@ -412,7 +415,7 @@ def check_save_wav_scaling_and_int16(golden=None):
         assert n == lin.shape[1] and spec.flags.f_contiguous
         np.testing.assert_array_equal(spec, lin)
     # fused: ragged list, trimmed at the endpoint, scaled by the peak of the TRIMMED waveform
-    Ts = [140, 33, 90]
+    Ts = [140, 33, 60]
     specs = [rs.rand(T, 1025).astype(np.float32) for T in Ts]
     specs[0][50:] = 0.0
     plain = audio.synthesize_waveforms(specs, iters=3)

@@ -86,7 +86,7 @@ def test_tf_twin_vs_oracle(emu, over):
 
 @pytest.mark.parametrize("tf", [False, True])
 def test_streaming_rounds(emu, tf):
-    pc.check_streaming_rounds(T=110, iters=2, tf=tf)
+    pc.check_streaming_rounds(T=110, iters=2, tf=tf, emulated=True)
 
 
 def test_find_endpoint_and_synthesis_stage(emu, golden):
@@ -115,7 +115,7 @@ def test_pinned_result_pool_lifecycle(emu):
     import gc
     from nspeech_b200 import batch
     hparams.load()
-    specs = np.random.RandomState(0).rand(3, 400, 1025).astype(np.float32)
+    specs = np.random.RandomState(0).rand(3, 180, 1025).astype(np.float32)      # results just over the 1 MB from which the pool is used
     pool = audio._handle().lib.pinned_pool()
     gc.collect()
     kept0 = pool.kept
