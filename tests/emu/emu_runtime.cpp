@@ -19,27 +19,30 @@ void launch(unsigned grid, unsigned block, size_t smem, const std::function<void
     if (smem > sizeof g_smem) abort();
     std::lock_guard<std::mutex> lk(g_launch_mu);
     const unsigned nwarps = (block + 31) / 32;
-    for (unsigned b = 0; b < grid; ++b) {
-        BlockCtx ctx;
-        ctx.block_bar.reset(new std::barrier<>(block));
-        ctx.xchg.resize(nwarps);
-        for (unsigned w = 0; w < nwarps; ++w) {
-            unsigned n = std::min(32u, block - 32 * w);
-            ctx.warp_bar.emplace_back(new std::barrier<>(n));
-        }
-        std::vector<std::thread> th;
-        th.reserve(block);
-        for (unsigned t = 0; t < block; ++t)
-            th.emplace_back([&, t, b] {
-                g_ctx = &ctx;
-                g_tid = uint3{t, 0, 0};
-                g_bid = uint3{b, 0, 0};
-                g_bdim = dim3(block);
-                g_gdim = dim3(grid);
-                body();
-            });
-        for (auto& x : th) x.join();
+    // one set of OS threads per launch: thread t plays CUDA thread t of block 0, then of block 1, ... (the blocks run one after
+    // another anyway - the shared memory exists once - and creating `block` threads per block dominated launches of many small blocks)
+    BlockCtx ctx;
+    ctx.block_bar.reset(new std::barrier<>(block));
+    ctx.xchg.resize(nwarps);
+    for (unsigned w = 0; w < nwarps; ++w) {
+        unsigned n = std::min(32u, block - 32 * w);
+        ctx.warp_bar.emplace_back(new std::barrier<>(n));
     }
+    std::vector<std::thread> th;
+    th.reserve(block);
+    for (unsigned t = 0; t < block; ++t)
+        th.emplace_back([&, t] {
+            g_ctx = &ctx;
+            g_tid = uint3{t, 0, 0};
+            g_bdim = dim3(block);
+            g_gdim = dim3(grid);
+            for (unsigned b = 0; b < grid; ++b) {
+                g_bid = uint3{b, 0, 0};
+                body();
+                ctx.block_bar->arrive_and_wait();      // every thread has left block b before anyone touches shared memory as block b + 1
+            }
+        });
+    for (auto& x : th) x.join();
 }
 }  // namespace nsb_emu
 
