@@ -261,15 +261,19 @@ def inv_spectrogram_batch(specs, init_phase=None, seed=0, iters=None, device=Non
     return _split(out, ns)
 
 
-def inv_spectrogram_stream(batches, seed=0, iters=None, device=None, denormalize=True, deemphasis=True, layout=None, in_flight=3):
+def inv_spectrogram_stream(batches, seed=0, iters=None, device=None, denormalize=True, deemphasis=True, layout=None, in_flight=3, dtype=None):
     """Generator over an iterable of batches (each what ``inv_spectrogram_batch`` takes as ``specs``): yields each batch's
     list of waveforms, in order, with ``in_flight`` batches inside the library at any time (``nsb_griffin_lim_submit`` /
     ``nsb_wait``) - batch i+1 is copied in and starts while batch i finishes and is copied out.  The caller pattern is the
     reference's synthesis loops (eval.py:36-59: sentence after sentence) and feeder threads (datasets/datafeeder.py:110-152).
-    The phase is drawn on the device (Philox, ``seed`` + the batch's index)."""
+    The phase is drawn on the device (Philox, ``seed`` + the batch's index).  ``dtype``: the waveforms' type - None = the
+    reference's (float64 after ``inv_preemphasis``, float32 without it); ``np.float32`` halves the bytes that come back, which
+    is what bounds the end-to-end rate when several GPUs share one host."""
     h = audio._handle(device)
     flags = (_lib.GL_DENORMALIZE if denormalize else 0) | (_lib.GL_DEEMPHASIS if deemphasis else 0)
-    dt = np.float64 if deemphasis else np.float32
+    dt = np.dtype(np.float64 if deemphasis else np.float32) if dtype is None else np.dtype(dtype)
+    if dt not in (np.dtype(np.float32), np.dtype(np.float64)):
+        raise ValueError("dtype must be float32 or float64")
     pending = collections.deque()
 
     def collect():
@@ -283,7 +287,7 @@ def inv_spectrogram_stream(batches, seed=0, iters=None, device=None, denormalize
             ns = [h.num_samples(T) for T in Ts]
             out = _gl_out_buffer(h, ns, dt, None)
             t = h.griffin_lim_submit(packed, _lib.FRAME_MAJOR, Ts, out, seed=seed + i, iters=-1 if iters is None else iters,
-                                     flags=flags, out_dtype=_lib.F64 if deemphasis else _lib.F32)
+                                     flags=flags, out_dtype=_lib.F64 if dt == np.dtype(np.float64) else _lib.F32)
             pending.append((t, out, ns, packed))
             if len(pending) >= max(1, in_flight):
                 yield collect()

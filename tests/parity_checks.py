@@ -507,6 +507,14 @@ def check_async_submit_wait():
         ref = batch.inv_spectrogram_batch(b, seed=11 + i, iters=2, layout="FT")
         for a, c in zip(outs, ref):
             np.testing.assert_array_equal(a, c)
+    # float32 results (half the bytes back): the de-emphasised float64 waveform rounded once
+    got32 = list(batch.inv_spectrogram_stream(batches[:2], seed=11, iters=2, layout="FT", dtype=np.float32))
+    for outs32, outs64 in zip(got32, got):
+        for a, c in zip(outs32, outs64):
+            assert a.dtype == np.float32
+            np.testing.assert_array_equal(a, c.astype(np.float32))
+    with pytest.raises(ValueError):
+        list(batch.inv_spectrogram_stream(batches[:1], dtype=np.int16))
 
 
 def check_api_guards():
