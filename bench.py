@@ -387,9 +387,9 @@ def main():
     # ---- end to end through the public API on host buffers: every step copies its batch in and its waveforms out ----
     # headline: batch.inv_spectrogram_stream (nsb_griffin_lim_submit / nsb_wait, three batches in flight, results in pooled page-locked
     # memory); beside it the synchronous call (round 1's e2e) and the same stream fed from PAGEABLE numpy arrays
-    def e2e_stream(n_steps, inputs, seed0):
+    def e2e_stream(n_steps, inputs, seed0, dtype=None):
         got = 0
-        for outs in batch.inv_spectrogram_stream((inputs[i % len(inputs)] for i in range(n_steps)), seed=seed0, iters=ITERS):
+        for outs in batch.inv_spectrogram_stream((inputs[i % len(inputs)] for i in range(n_steps)), seed=seed0, iters=ITERS, dtype=dtype):
             got += len(outs)
             last = outs[-1]
         assert got == n_steps * N_UTT and np.isfinite(last[:1000]).all()
@@ -413,6 +413,10 @@ def main():
             batch.inv_spectrogram_batch(pin_in[0].array, seed=300 + i, iters=ITERS, out=pin_out.array)
     sync_steps(1)
     ms_e2e_sync = wall_ms(lambda: sync_steps(args.steps))
+    # the same stream with float32 waveforms back (NOT the reference's dtype, so not the headline): half the device-to-host bytes,
+    # which is what the end-to-end rate of several ranks on one host is bound by
+    e2e_stream(3, pinned_inputs, 0, np.float32)
+    ms_e2e_f32 = wall_ms(lambda: e2e_stream(args.steps, pinned_inputs, 300, np.float32))
     pageable_inputs = [np.array(p_.array) for p_ in pin_in]          # plain numpy memory, what a drop-in caller holds
     e2e_stream(3, pageable_inputs, 0)
     ms_e2e_pageable = wall_ms(lambda: e2e_stream(args.steps, pageable_inputs, 400))
@@ -513,6 +517,9 @@ def main():
                 "api": "nspeech_b200.batch.inv_spectrogram_stream (nsb_griffin_lim_submit / nsb_wait, three batches in flight), page-locked input arrays, results in pooled page-locked memory"},
         "e2e_sync": {"value": world * audio_s_per_step * args.steps / (ms_e2e_sync * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e_sync / args.steps,
                      "api": "nspeech_b200.batch.inv_spectrogram_batch, one synchronous call per step (round 1's e2e)"},
+        "e2e_float32_out": {"value": world * audio_s_per_step * args.steps / (ms_e2e_f32 * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e_f32 / args.steps,
+                            "d2h_bytes_per_step": int(pin_out.array.nbytes) // 2,
+                            "api": "the headline stream with dtype=np.float32: waveforms come back as float32 (the reference returns float64 - not the headline)"},
         "e2e_pageable": {"value": world * audio_s_per_step * args.steps / (ms_e2e_pageable * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e_pageable / args.steps,
                          "api": "the same stream fed from pageable numpy arrays (what a drop-in caller holds)"},
         "gpu_launches": int(launches),
