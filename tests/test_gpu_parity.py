@@ -174,6 +174,47 @@ def test_full_size_properties():
     assert errs[2] < errs[1] < errs[0]
 
 
+def test_features_full_size_properties():
+    """BASELINE config 2 at its full size (13,100 LJSpeech-shaped clips, 6.8 M frames, 37 GB of device buffers) through ONE
+    feature pass on device arrays: sampled clips against the oracle and against one-at-a-time calls (identical bits), every
+    value finite and inside [0, 1], and the whole result identical under another launch of the same pass."""
+    torch = pytest.importorskip("torch")
+    import bench
+    ohp = pc._load(min_level_db=-100)
+    h = audio._handle()
+    dev = torch.device("cuda:0")
+    free, _ = torch.cuda.mem_get_info()
+    n_clips = 13100 if free > (60 << 30) else 1310
+    d_wav, ns = bench.speechlike_corpus(torch, dev, n_clips)
+    Ts = [h.num_frames(n) for n in ns]
+    tot = sum(Ts)
+    d_lin = torch.empty((tot, 1025), dtype=torch.float32, device=dev)
+    d_mel = torch.empty((tot, 80), dtype=torch.float32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    h.features(d_wav, ns, d_lin, d_mel, space=_lib.DEVICE, stream=st)
+    h.check_status(st)
+    assert tot == sum(1 + n // h.hop for n in ns)
+    assert bool(torch.isfinite(d_mel).all()) and float(d_mel.min()) >= 0.0 and float(d_mel.max()) <= 1.0
+    for lo in range(0, tot, 1 << 20):                                   # (the linear feature in slices: no second 28 GB temporary)
+        blk = d_lin[lo:lo + (1 << 20)]
+        assert bool(torch.isfinite(blk).all()) and float(blk.min()) >= 0.0 and float(blk.max()) <= 1.0
+    assert 0.0 < float(d_mel.mean()) < 1.0                             # min_level_db = -100: not saturated
+    soff = np.concatenate([[0], np.cumsum(ns)])
+    foff = np.concatenate([[0], np.cumsum(Ts)])
+    for i in (0, 1, n_clips // 3, n_clips // 2 + 1, n_clips - 1):
+        w = d_wav[soff[i]:soff[i + 1]].cpu().numpy()
+        lin = d_lin[foff[i]:foff[i + 1]].cpu().numpy().T
+        mel = d_mel[foff[i]:foff[i + 1]].cpu().numpy().T
+        assert ao.rel_l2(lin, ao.spectrogram(w, ohp)) < 1e-5 and ao.rel_l2(mel, ao.melspectrogram(w, ohp)) < 1e-5
+        l1, m1 = audio.spectrogram_and_mel(w)                          # the clip alone, from host memory
+        np.testing.assert_array_equal(lin, l1)
+        np.testing.assert_array_equal(mel, m1)
+    ck = (d_mel.double().sum().item(), d_lin[: 1 << 22].double().sum().item())
+    h.features(d_wav, ns, d_lin, d_mel, space=_lib.DEVICE, stream=st)
+    h.check_status(st)
+    assert ck == (d_mel.double().sum().item(), d_lin[: 1 << 22].double().sum().item())
+
+
 def test_device_pointer_api_with_torch():
     """NSB_DEVICE entry points on torch-owned memory and torch's current stream."""
     torch = pytest.importorskip("torch")
