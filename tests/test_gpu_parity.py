@@ -215,6 +215,34 @@ def test_features_full_size_properties():
     assert ck == (d_mel.double().sum().item(), d_lin[: 1 << 22].double().sum().item())
 
 
+def test_largest_sweep_batch_matches_single_calls():
+    """BASELINE config 5's largest point (1024 utterances x 1000 frames = 1.02 M frames in one call, device-resident, supplied
+    phase): sampled utterances equal one-at-a-time calls bit for bit - the streaming kernel's chunking, its item counters and
+    the 32-bit frame / 64-bit sample offsets at the largest size the benchmark uses."""
+    torch = pytest.importorskip("torch")
+    pc._load(min_level_db=-100)
+    h = audio._handle()
+    free, _ = torch.cuda.mem_get_info()
+    N, T = (1024 if free > (60 << 30) else 128), 1000
+    g = torch.Generator(device="cuda").manual_seed(5)
+    spec = torch.rand((N * T, 1025), device="cuda", generator=g)
+    ang = torch.rand((N * T, 1025), device="cuda", generator=g) * (2 * np.pi)
+    phase = torch.polar(torch.ones_like(ang), ang)                      # complex64 [frames, 1025]
+    del ang
+    ns = h.num_samples(T)
+    out = torch.empty(N * ns, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    h.griffin_lim(spec, _lib.FRAME_MAJOR, [T] * N, out, init_phase=phase, iters=3, flags=3, out_dtype=_lib.F64, space=_lib.DEVICE, stream=st)
+    h.check_status(st)
+    assert bool(torch.isfinite(out).all())
+    for i in (0, 1, N // 2 + 3, N - 1):
+        one = torch.empty(ns, dtype=torch.float64, device="cuda")
+        h.griffin_lim(spec[i * T:(i + 1) * T], _lib.FRAME_MAJOR, [T], one, init_phase=phase[i * T:(i + 1) * T], iters=3, flags=3,
+                      out_dtype=_lib.F64, space=_lib.DEVICE, stream=st)
+        h.check_status(st)
+        assert torch.equal(one, out[i * ns:(i + 1) * ns]), i
+
+
 def test_device_pointer_api_with_torch():
     """NSB_DEVICE entry points on torch-owned memory and torch's current stream."""
     torch = pytest.importorskip("torch")
