@@ -69,6 +69,17 @@ def _as_wav(y):
     return np.ascontiguousarray(y, dtype=np.float32)
 
 
+def _lfilter_input(x):
+    """what scipy.signal.lfilter (audio.py:32, 36) accepts where librosa's valid_audio does not: any real dtype and an empty
+    array (-> an empty float64 result)"""
+    x = np.asarray(x)
+    if x.ndim != 1:
+        raise ParameterError('Invalid shape for monophonic audio: ndim={:d}, shape={}'.format(x.ndim, x.shape))
+    if np.iscomplexobj(x) or not (np.issubdtype(x.dtype, np.number) or x.dtype == np.bool_):
+        raise ParameterError('data must be real-valued')
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
 def _spec_layout(S, dtype):
     """Return (buffer, layout) for a [F, T] array without copying when it is either Fortran- or C-ordered."""
     S = np.asarray(S)
@@ -133,9 +144,10 @@ def preemphasis(x):
     # reference audio.py:31-32 -> float64, like scipy.signal.lfilter
     if _buffers.is_device_array(x):
         return _dev_emph(x, False)
-    x = _as_wav(x)
+    x = _lfilter_input(x)
     out = np.empty(x.shape, dtype=np.float64)
-    _handle().preemphasis(x, [x.size], out, _lib.F64)
+    if x.size:
+        _handle().preemphasis(x, [x.size], out, _lib.F64)
     return out
 
 
@@ -143,9 +155,10 @@ def inv_preemphasis(x):
     # reference audio.py:35-36
     if _buffers.is_device_array(x):
         return _dev_emph(x, True)
-    x = _as_wav(x)
+    x = _lfilter_input(x)
     out = np.empty(x.shape, dtype=np.float64)
-    _handle().preemphasis(x, [x.size], out, _lib.F64, inverse=True)
+    if x.size:
+        _handle().preemphasis(x, [x.size], out, _lib.F64, inverse=True)
     return out
 
 

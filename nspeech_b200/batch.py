@@ -104,6 +104,8 @@ def features_batch(wavs, device=None, want_linear=True, want_mel=True, in_flight
     ``in_flight=0``: one synchronous call)."""
     h = audio._handle(device)
     wavs = [audio._as_wav(w) for w in wavs]
+    if not wavs:
+        raise ValueError("empty batch")
     ns = [w.size for w in wavs]
     Ts = [h.num_frames(n) for n in ns]
     pool = h.lib.pinned_pool()             # results in pooled page-locked memory: the copy out runs at PCIe speed

@@ -161,6 +161,18 @@ def check_errors_and_edge_cases():
     with pytest.raises(audio.ParameterError):
         audio._stft(np.zeros((2, 100), np.float32))
     with pytest.raises(ValueError):
+        audio.spectrogram(np.zeros(0, np.float32))                         # librosa cannot reflect-pad an empty signal either
+    # scipy.signal.lfilter (audio.py:32, 36) takes an empty array and integer samples
+    for f, of in ((audio.preemphasis, ao.preemphasis), (audio.inv_preemphasis, ao.inv_preemphasis)):
+        e = f(np.zeros(0, np.float32))
+        assert e.shape == (0,) and e.dtype == np.float64
+        ints = np.arange(-50, 50, dtype=np.int16)
+        assert np.abs(f(ints) - of(ints.astype(np.float32), make_hp(min_level_db=-100))).max() < 1e-9
+    from nspeech_b200 import batch as _batch
+    with pytest.raises(ValueError):
+        _batch.features_batch([])
+    assert audio.find_endpoint(np.zeros(0)) == 0 and audio.peak_normalize(np.zeros(0)).shape == (0,)
+    with pytest.raises(ValueError):
         audio.inv_spectrogram(np.zeros((1025, 1), np.float32))
     with pytest.raises(ValueError):
         audio.inv_spectrogram(np.zeros((513, 10), np.float32))
