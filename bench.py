@@ -48,10 +48,10 @@ FLOPS_PER_FRAME_ITER = 2 * 56320 + 12 * N_BINS         # 2 real 2048-FFTs (2.5 N
 BYTES_PER_FRAME_FULL = (ITERS + 1) * 4 * N_BINS + (2 * ITERS + 1) * 4 * HOP + 8 * HOP + 4 * N_BINS
 FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_gl_iter launch, from the committed ncu --set full capture
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 20.579e9 + 3.884e9
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 20.584e9 + 3.885e9
 NCU_TRAFFIC_SOURCE = "profiles/r2/ncu_full_k_gl_stream_fused60.txt (dram__bytes_read.sum + dram__bytes_write.sum of one 60-iteration launch)"
 # the feature kernel: DRAM bytes per frame of one k_analysis<FEATURES> launch (268,734 frames) from the committed ncu --set full capture
-NCU_FEATURES_TRAFFIC_BYTES_PER_FRAME = (270.38e6 + 1130.41e6) / 268734
+NCU_FEATURES_TRAFFIC_BYTES_PER_FRAME = (270.52e6 + 1130.54e6) / 268734
 NCU_FEATURES_TRAFFIC_SOURCE = "profiles/r2/ncu_full_k_analysis_features.txt (dram__bytes_read.sum + dram__bytes_write.sum per frame of a 268,734-frame launch, scaled to this launch's frames)"
 
 
